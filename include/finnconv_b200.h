@@ -1,0 +1,153 @@
+/* finnconv_b200.h -- C ABI of the B200-native FINN-style quantized non-square
+ * convolution layer (sliding window + MVAU MAC array + activation [+ pool]).
+ *
+ * This header is the drop-in boundary for the reference's HLS top functions.
+ * The reference has no FFI layer; its boundary is the HLS top-function
+ * signature over hls::stream<ap_uint<W>> (conv_nonsquare_top.cpp:282,288,295)
+ * and the template parameter sets of conv2d<> (conv_nonsquare_top.cpp:198-215),
+ * deconv522<> (:71-81), ConvLayer_Batch (convlayer.h:89-111) and
+ * ThresholdsActivation (activations.hpp:168-169).  Every entry point below
+ * names the reference interface it replaces.
+ *
+ * DATA LAYOUTS (accepted verbatim):
+ *  - "ap-word container": the memory image of one ap_uint<W>/ap_int<W>:
+ *    little-endian, 1 byte (W<=8), 2 (W<=16), 4 (W<=32), 8 (W<=64), else
+ *    8*ceil(W/64) bytes.  Only the low W bits are read; writers zero the rest.
+ *  - stream: numReps images back to back; per image ifm_y rows (y-major) of
+ *    ifm_x pixels (x fastest); one word ap_uint<ifm_ch*in_bits> per pixel;
+ *    channel c occupies bits [c*in_bits, (c+1)*in_bits) (lane 0 at the LSB:
+ *    interpret.hpp:211, conv3_nonsquare_tb.cpp:807-808).
+ *  - weights: image of FixedPointWeights::m_weights[PE][TILES]
+ *    (weights.hpp:113) -- words ap_uint<SIMD*w_bits>, pe-major; lane `simd` of
+ *    [pe][tile] is W[ch = nf*PE + pe][k = sf*SIMD + simd], tile = nf*SF + sf,
+ *    k = (ky*Kx + kx)*ifm_ch + c (mvau.hpp:101-148, slidingwindow.h:1302-1313).
+ *    BinaryWeights::m_weights[PE][TILES] (weights.hpp:69): words ap_uint<SIMD>.
+ *  - thresholds: image of ThresholdsActivation::m_thresholds[PE][NF][NumTH]
+ *    (activations.hpp:172), each an ap-word container of acc_bits.
+ *  - bias: image of FixedPointWeights<1,ap_int<8>,1,OFM>::m_weights[1][OFM]
+ *    (memdata_nonsquare.h:16-22): ofm_ch bytes, signed.
+ *
+ * All functions return FCB_OK (0) or a negative fcb_status; the message of the
+ * last failure on the calling thread is available through fcb_last_error().
+ * The reference instead prints and exit(-1)s (CASSERT_DATAFLOW,
+ * bnn-library.h:55); this library never exits the process.
+ *
+ * There is NO CPU fallback: every run entry point executes CUDA kernels built
+ * for sm_100a and fails with FCB_ERR_CUDA when no such device is usable.
+ */
+#ifndef FINNCONV_B200_H
+#define FINNCONV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define FCB_API
+#else
+#define FCB_API __attribute__((visibility("default")))
+#endif
+
+typedef enum fcb_status {
+  FCB_OK = 0,
+  FCB_ERR_INVALID_ARG = -1, /* null pointer, bad struct_size, bad enum */
+  FCB_ERR_SHAPE = -2,       /* violates a reference CASSERT (IFM_CH % SIMD, OFM_CH % PE, geometry) */
+  FCB_ERR_UNSUPPORTED = -3, /* valid in the reference, not implemented here */
+  FCB_ERR_CUDA = -4,        /* CUDA runtime/driver failure, or no sm_100 device */
+  FCB_ERR_NOMEM = -5
+} fcb_status;
+
+/* conv2d<> (conv_nonsquare_top.cpp:198-280) vs deconv522<> (:71-195) */
+typedef enum fcb_layer_kind { FCB_KIND_CONV = 0, FCB_KIND_DECONV522 = 1 } fcb_layer_kind;
+
+/* weights.hpp:110-150 FixedPointWeights | weights.hpp:66-98 BinaryWeights with
+ * Recast<XnorMul> activations (interpret.hpp:57-73) | BinaryWeights with
+ * Recast<Binary> weights, +-1 (interpret.hpp:75-108) */
+typedef enum fcb_weight_kind { FCB_W_FIXED = 0, FCB_W_BINARY_XNOR = 1, FCB_W_BINARY_PM1 = 2 } fcb_weight_kind;
+
+/* activations.hpp:127-134 | conv_nonsquare_top.cpp:267-278 | activations.hpp:168-190 */
+typedef enum fcb_act_kind { FCB_ACT_PASSTHROUGH = 0, FCB_ACT_BIAS_RELU = 1, FCB_ACT_THRESHOLDS = 2 } fcb_act_kind;
+
+/* comp::less (default: thr < acc), greater, less_equal, greater_equal -- activations.hpp:57-99;
+ * evaluated as Compare()(threshold, accu) (activations.hpp:185) */
+typedef enum fcb_cmp { FCB_CMP_LESS = 0, FCB_CMP_GREATER = 1, FCB_CMP_LESS_EQUAL = 2, FCB_CMP_GREATER_EQUAL = 3 } fcb_cmp;
+
+/* Run-time mirror of the reference's compile-time parameter set. */
+typedef struct fcb_layer_desc {
+  uint32_t struct_size; /* = sizeof(fcb_layer_desc) */
+  uint32_t kind;        /* fcb_layer_kind */
+  /* geometry: KERNEL_DIM_X/Y, IFM/OFM_Channels, IFMDim_x/y, OFMDim_x/y, STRIDE_x/y, PADDING */
+  uint32_t kernel_x, kernel_y;
+  uint32_t ifm_ch, ofm_ch;
+  uint32_t ifm_x, ifm_y; /* x = fast (row-of-pixels) axis, the reference's "ROW" (768-side) */
+  uint32_t ofm_x, ofm_y; /* conv output extent BEFORE pooling; must equal the geometry's */
+  uint32_t stride_x, stride_y;
+  uint32_t pad; /* zeros added on each side (FMPadding total = 2*pad, streamtools.h:374-379) */
+  /* folding (only defines the weight/threshold image layout) */
+  uint32_t simd, pe;
+  /* numerics */
+  uint32_t in_bits;     /* INPUT_PRECISION */
+  uint32_t in_signed;   /* TSrcI = Slice<ap_int<>> (1) or Slice<ap_uint<>> (0) */
+  uint32_t w_bits;      /* WIDTH of FixedPointWeights lanes; 1 for binary kinds */
+  uint32_t weight_kind; /* fcb_weight_kind */
+  uint32_t acc_bits;    /* TA = decltype(activation.init(0,0)) width (mvau.hpp:112) */
+  uint32_t acc_signed;  /* TA signedness */
+  uint32_t act_kind;    /* fcb_act_kind */
+  uint32_t out_bits;    /* TDstI lane width / ACTIVATION_PRECISION / TR width (unsigned) */
+  uint32_t num_th;      /* NumTH (thresholds only) */
+  int32_t act_val;      /* ActVal */
+  uint32_t cmp;         /* fcb_cmp */
+  uint32_t pool;        /* 0 or 1: none; k>=2: k x k, stride k max pool on the out_bits lanes
+                           (StreamingMaxPool_Precision, maxpool.h:137-185; OR for out_bits==1, :66-96) */
+  uint32_t reserved[6]; /* must be zero */
+} fcb_layer_desc;
+
+typedef struct fcb_layer fcb_layer; /* opaque: one layer resident on one device */
+typedef struct fcb_net fcb_net;     /* opaque: chain of layers, activations stay on device */
+
+/* --- library ---------------------------------------------------------------- */
+FCB_API const char* fcb_version(void);
+FCB_API const char* fcb_last_error(void);
+/* number of usable sm_100 devices (0 if none); never fails */
+FCB_API int fcb_device_count(void);
+/* bytes of one ap-word container of `bits` bits (1,2,4,8,16,24,...) */
+FCB_API size_t fcb_word_bytes(uint32_t bits);
+/* Validate a descriptor exactly as the reference's CASSERTs would (slidingwindow.h:1259,
+ * streamtools.h:472,505, mvau.hpp:101-105) and report the stream sizes. Any out pointer may be NULL. */
+FCB_API int fcb_layer_query(const fcb_layer_desc* desc, size_t* in_bytes_per_image, size_t* out_bytes_per_image,
+                            size_t* weight_bytes, size_t* threshold_bytes, size_t* bias_bytes);
+
+/* --- one layer: replaces conv2d<>/deconv522<> instantiations such as conv2d_layer0
+ * (conv_nonsquare_top.cpp:282) and deconv2d_layer4 (:288), and ConvLayer_Batch (convlayer.h:106-125).
+ * `weights` is the m_weights image, `thresholds` the m_thresholds image (FCB_ACT_THRESHOLDS) and
+ * `bias` the bias image (FCB_ACT_BIAS_RELU); unused ones may be NULL. Images are copied and
+ * re-laid-out on `device`; the caller may free them on return. */
+FCB_API int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void* thresholds, const void* bias,
+                             int device, fcb_layer** out);
+FCB_API void fcb_layer_destroy(fcb_layer* layer);
+/* Host-buffer call: in_words -> H2D -> kernels -> D2H -> out_words, numReps images, synchronous.
+ * Mirrors `top(in_stream, out_stream, numReps)`. */
+FCB_API int fcb_layer_run(fcb_layer* layer, const void* in_words, void* out_words, uint32_t numReps);
+/* Device-buffer call on `stream` (a cudaStream_t, or NULL for the default stream); asynchronous.
+ * d_in/d_out hold the same word images in device memory of layer's device. */
+FCB_API int fcb_layer_run_device(fcb_layer* layer, const void* d_in, void* d_out, uint32_t numReps, void* stream);
+/* Which kernel family serves this layer: "umma_i8", "imad", "xnor_popc" (diagnostics / tests). */
+FCB_API const char* fcb_layer_engine(const fcb_layer* layer);
+/* Number of kernel launches issued by this layer since creation. */
+FCB_API uint64_t fcb_layer_launches(const fcb_layer* layer);
+
+/* --- layer chain: replaces eight_layers_net (conv_nonsquare_top.cpp:295-357).
+ * Layer i's output word width must equal layer i+1's input word width. */
+FCB_API int fcb_net_create(fcb_layer* const* layers, uint32_t n_layers, fcb_net** out); /* borrows the layers */
+FCB_API void fcb_net_destroy(fcb_net* net);
+FCB_API int fcb_net_run(fcb_net* net, const void* in_words, void* out_words, uint32_t numReps);
+FCB_API int fcb_net_run_device(fcb_net* net, const void* d_in, void* d_out, uint32_t numReps, void* stream);
+FCB_API uint64_t fcb_net_launches(const fcb_net* net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FINNCONV_B200_H */

@@ -1,0 +1,101 @@
+"""oracle/cases.py -- TEST INFRASTRUCTURE ONLY.
+
+The parity cases: one LayerDesc per instantiation in oracle/ref_layers.cpp (same names), plus the
+seeded synthetic tensors each case is fed (SURVEY.md 8(d) seeding rule).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from simple_image_compression_network_b200 import pack, synth
+from simple_image_compression_network_b200.desc import (ACT_BIAS_RELU, ACT_THRESHOLDS, KIND_CONV, KIND_DECONV522, W_BINARY_XNOR,
+                                      W_FIXED, LayerDesc)
+
+
+def _c2d(kx, ky, simd, pe, wb, c, ofm, ix, iy, s, p, inb, actb):
+    return LayerDesc(kind=KIND_CONV, kernel_x=kx, kernel_y=ky, ifm_ch=c, ofm_ch=ofm, ifm_x=ix, ifm_y=iy, stride_x=s,
+                     stride_y=s, pad=p, simd=simd, pe=pe, in_bits=inb, w_bits=wb, acc_bits=actb, acc_signed=0,
+                     act_kind=ACT_BIAS_RELU, out_bits=actb)
+
+
+def _dc(ix, iy, c, ofm, simd, pe, wb):
+    return LayerDesc(kind=KIND_DECONV522, kernel_x=5, kernel_y=5, ifm_ch=c, ofm_ch=ofm, ifm_x=ix, ifm_y=iy, stride_x=2,
+                     stride_y=2, pad=2, simd=simd, pe=pe, in_bits=8, w_bits=wb, acc_bits=8, acc_signed=0,
+                     act_kind=ACT_BIAS_RELU, out_bits=8)
+
+
+def _th(k, simd, pe, wb, c, ofm, ix, iy, p, inb, nth, tab, trb, av, pool=0):
+    return LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=ix, ifm_y=iy, stride_x=1,
+                     stride_y=1, pad=p, simd=simd, pe=pe, in_bits=inb, w_bits=wb, acc_bits=tab, acc_signed=1,
+                     act_kind=ACT_THRESHOLDS, out_bits=trb, num_th=nth, act_val=av, pool=pool)
+
+
+def _xn(k, simd, pe, c, ofm, ix, iy, tab):
+    return LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=ix, ifm_y=iy, stride_x=1,
+                     stride_y=1, pad=0, simd=simd, pe=pe, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR, acc_bits=tab,
+                     acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=1, num_th=1, act_val=0)
+
+
+# name -> LayerDesc ; names and parameters mirror the X-macro tables of ref_layers.cpp
+CASES = {
+    "c2d_a": _c2d(5, 5, 2, 3, 4, 4, 6, 12, 8, 2, 2, 8, 8),
+    "c2d_b": _c2d(5, 5, 8, 8, 4, 16, 32, 40, 24, 2, 2, 8, 8),
+    "c2d_c": _c2d(5, 5, 3, 8, 4, 3, 16, 32, 20, 2, 2, 8, 8),
+    "c2d_d": _c2d(3, 3, 16, 4, 8, 32, 32, 20, 12, 1, 1, 8, 8),
+    "c2d_e": _c2d(5, 5, 8, 16, 4, 128, 128, 48, 32, 2, 2, 8, 8),
+    "c2d_f": _c2d(3, 3, 4, 2, 4, 8, 8, 10, 6, 1, 1, 8, 16),
+    "c2d_g": _c2d(5, 5, 8, 24, 4, 128, 192, 24, 16, 2, 2, 8, 8),
+    "c2d_L1band": _c2d(5, 5, 8, 16, 4, 128, 128, 384, 32, 2, 2, 8, 8),
+    "c2d_L1": _c2d(5, 5, 8, 16, 4, 128, 128, 384, 256, 2, 2, 8, 8),
+    "dc_a": _dc(6, 4, 4, 6, 2, 3, 4),
+    "dc_b": _dc(12, 8, 16, 16, 8, 8, 4),
+    "dc_c": _dc(24, 16, 128, 128, 8, 16, 4),
+    "dc_d": _dc(24, 16, 128, 3, 8, 3, 4),
+    "dc_e": _dc(12, 8, 192, 128, 12, 16, 4),
+    "dc_L4": _dc(48, 32, 192, 128, 12, 16, 4),
+    "th_a": _th(3, 4, 2, 4, 8, 8, 10, 6, 1, 8, 15, 24, 4, 0),
+    "th_b": _th(3, 16, 8, 4, 32, 32, 16, 12, 1, 8, 255, 24, 8, 0),
+    "th_c": _th(3, 8, 4, 4, 16, 16, 9, 7, 0, 8, 3, 16, 2, 0),
+    "th_d": _th(3, 3, 8, 4, 3, 16, 16, 12, 1, 8, 255, 24, 8, 0),
+    "th_cfg4": _th(3, 32, 32, 4, 256, 256, 64, 48, 1, 8, 255, 24, 8, 0),
+    "xn_a": _xn(3, 8, 4, 8, 8, 12, 10, 16),
+    "xn_b": _xn(3, 64, 16, 64, 64, 16, 12, 16),
+    "xn_c": _xn(3, 32, 8, 64, 32, 20, 9, 16),
+}
+
+# cases that take long in the reference C-simulation (seconds): excluded from the quick sets
+SLOW = {"c2d_L1": 30, "c2d_L1band": 4, "dc_L4": 12, "th_cfg4": 8, "xn_b": 30, "dc_c": 5}
+
+
+def make_inputs(d: LayerDesc, seed_shift: int = 0, num_reps: int = 1, relu_range: bool = False):
+    """Seeded synthetic tensors for a case -> dict of logical arrays and packed images."""
+    k = d.k_total
+    x = synth.lanes(synth.SEED_INPUT + seed_shift, (num_reps, d.ifm_y, d.ifm_x, d.ifm_ch), d.in_bits,
+                    signed=bool(d.in_signed), mask=(0x7F if (relu_range and d.in_bits == 8) else None))
+    w = synth.weights(synth.SEED_WEIGHTS + seed_shift, d.ofm_ch, k, d.w_bits)
+    out = {"x": x, "w": w, "in_words": pack.pack_stream(x, d.in_bits), "weights": pack.pack_weights(w, d.simd, d.pe, d.w_bits),
+           "bias": None, "thresholds": None, "b": None, "t": None}
+    if d.act_kind == ACT_BIAS_RELU:
+        b = synth.bias(synth.SEED_BIAS + seed_shift, d.ofm_ch)
+        out["b"], out["bias"] = b, pack.pack_bias(b)
+    if d.act_kind == ACT_THRESHOLDS:
+        if d.weight_kind == W_BINARY_XNOR:
+            # matches ~ Binomial(K, 1/2): thresholds around K/2 +- 2 sigma discriminate
+            lo, hi = int(k / 2 - k ** 0.5), int(k / 2 + k ** 0.5)
+        else:
+            # thresholds where they discriminate: mean +- 2.5 sigma of sum_k w_k*a_k for uniform lanes
+            av = np.arange(1 << d.in_bits, dtype=np.float64) - ((1 << (d.in_bits - 1)) if d.in_signed else 0)
+            wv = np.arange(1 << d.w_bits, dtype=np.float64) - (1 << (d.w_bits - 1))
+            mean = k * wv.mean() * av.mean()
+            sigma = (k * ((wv ** 2).mean() * (av ** 2).mean() - (wv.mean() * av.mean()) ** 2)) ** 0.5
+            lo, hi = int(mean - 2.5 * sigma), int(mean + 2.5 * sigma)
+        lim = (1 << (d.acc_bits - 1)) - 1
+        lo, hi = max(lo, -lim - 1), min(hi, lim)
+        t = synth.thresholds(synth.SEED_THRESH + seed_shift, d.ofm_ch, d.num_th, lo, hi)
+        out["t"], out["thresholds"] = t, pack.pack_thresholds(t, d.pe, d.acc_bits)
+    return out
+
+
+def third_image(inp):
+    """The bias-or-threshold image the ref_* entry points take as their third argument."""
+    return inp["bias"] if inp["bias"] is not None else inp["thresholds"]

@@ -1,0 +1,139 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-ends for (a) the plain-C restatement libfinn_oracle.so and (b), when it has been
+built in a container that has /root/reference, the reference's own templates in
+_ref/libref_layers.so.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class FoSizes(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("k_total", "sf", "nf", "out_x", "out_y")] + [
+        (n, ctypes.c_size_t) for n in ("in_word_bytes", "out_word_bytes", "in_bytes_per_image", "out_bytes_per_image",
+                                       "weight_word_bytes", "weight_bytes", "threshold_bytes", "bias_bytes")]
+
+
+_lib = None
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement (and the reference-linked libraries when /root/reference exists)."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"] + (["-B"] if force else []))
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "libfinn_oracle.so")
+        if not os.path.exists(path):
+            build()
+        _lib = ctypes.CDLL(path)
+        _lib.fo_layer_query.argtypes = [ctypes.c_void_p, ctypes.POINTER(FoSizes)]
+        _lib.fo_layer_run.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5 + [ctypes.c_uint32]
+        _lib.fo_maxpool.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_uint32] * 5
+        _lib.fo_word_bytes.restype = ctypes.c_size_t
+        _lib.fo_word_bytes.argtypes = [ctypes.c_uint32]
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def set_threads(n: int) -> None:
+    lib().fo_set_threads(int(n))
+
+
+def query(desc) -> FoSizes:
+    s = FoSizes()
+    c = desc.to_c()
+    rc = lib().fo_layer_query(ctypes.byref(c), ctypes.byref(s))
+    if rc:
+        raise ValueError(f"oracle rejects descriptor: rc={rc}")
+    return s
+
+
+def run_layer(desc, in_words, weights, thresholds=None, bias=None, num_reps: int = 1) -> np.ndarray:
+    """CPU restatement of one layer on packed byte images; returns the packed output stream (uint8)."""
+    s = query(desc)
+    in_words = np.ascontiguousarray(in_words, dtype=np.uint8)
+    assert in_words.size == s.in_bytes_per_image * num_reps, (in_words.size, s.in_bytes_per_image, num_reps)
+    weights = np.ascontiguousarray(weights, dtype=np.uint8)
+    assert weights.size == s.weight_bytes, (weights.size, s.weight_bytes)
+    if thresholds is not None:
+        thresholds = np.ascontiguousarray(thresholds, dtype=np.uint8)
+        assert thresholds.size == s.threshold_bytes
+    if bias is not None:
+        bias = np.ascontiguousarray(bias, dtype=np.uint8)
+        assert bias.size == s.bias_bytes
+    out = np.zeros(s.out_bytes_per_image * num_reps, dtype=np.uint8)
+    c = desc.to_c()
+    rc = lib().fo_layer_run(ctypes.byref(c), _ptr(in_words), _ptr(weights), _ptr(thresholds), _ptr(bias), _ptr(out), num_reps)
+    if rc:
+        raise RuntimeError(f"fo_layer_run rc={rc}")
+    return out
+
+
+def maxpool(in_words, dim_x, dim_y, pool, ch, bits) -> np.ndarray:
+    in_words = np.ascontiguousarray(in_words, dtype=np.uint8)
+    wb = lib().fo_word_bytes(ch * bits)
+    out = np.zeros(wb * (dim_x // pool) * (dim_y // pool), dtype=np.uint8)
+    rc = lib().fo_maxpool(_ptr(in_words), _ptr(out), dim_x, dim_y, pool, ch, bits)
+    if rc:
+        raise RuntimeError(f"fo_maxpool rc={rc}")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own templates (oracle/_ref/libref_layers.so) -- present only where it was built
+# ---------------------------------------------------------------------------------------------
+_ref = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_layers.so"))
+
+
+def ref_lib() -> ctypes.CDLL:
+    global _ref
+    if _ref is None:
+        _ref = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_layers.so"))
+    return _ref
+
+
+def ref_run(case: str, in_words, weights, third, out_bytes: int):
+    """Run reference case `case` (see ref_layers.cpp); `third` is the bias or threshold image.
+    Returns (packed output, seconds spent inside the reference's layer function)."""
+    fn = getattr(ref_lib(), "ref_" + case)
+    fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.POINTER(ctypes.c_double)]
+    in_words = np.ascontiguousarray(in_words, dtype=np.uint8)
+    weights = np.ascontiguousarray(weights, dtype=np.uint8)
+    third = np.ascontiguousarray(third, dtype=np.uint8)
+    out = np.zeros(out_bytes, dtype=np.uint8)
+    secs = ctypes.c_double(0.0)
+    rc = fn(_ptr(in_words), _ptr(weights), _ptr(third), _ptr(out), ctypes.byref(secs))
+    if rc:
+        raise RuntimeError(f"ref_{case} rc={rc}")
+    return out, secs.value
+
+
+def ref_pool(name: str, in_words, out_bytes: int) -> np.ndarray:
+    fn = getattr(ref_lib(), "ref_" + name)
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    in_words = np.ascontiguousarray(in_words, dtype=np.uint8)
+    out = np.zeros(out_bytes, dtype=np.uint8)
+    rc = fn(_ptr(in_words), _ptr(out))
+    if rc:
+        raise RuntimeError(f"ref_{name} rc={rc}")
+    return out

@@ -1,0 +1,298 @@
+// oracle/ref_layers.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Builds the REFERENCE's own templates (conv2d<> / deconv522<> from
+// conv_nonsquare_top.cpp:71-280, and the library path
+// FMPadding_nonsquare + StreamingDataWidthConverter_Batch +
+// ConvolutionInputGenerator_NonSquare + Matrix_Vector_Activate_Batch +
+// ThresholdsActivation / BinaryWeights / StreamingMaxPool*) into a shared
+// library with a plain C interface, compiled from the sources where they lie
+// under /root/reference against oracle/shim/.  Output: oracle/_ref/libref_layers.so
+// (git-ignored).  Nothing of the reference is copied: this file only
+// #includes it.
+//
+// Every entry point speaks the same packed byte images as include/finnconv_b200.h
+// (stream words / m_weights[PE][TILES] / m_thresholds[PE][NF][NumTH] /
+// bias m_weights[1][OFM] in "ap-word containers": 1,2,4,8 bytes for widths
+// <=8,16,32,64, else 8*ceil(W/64), little-endian), so the reference, the C
+// restatement (finn_oracle.c) and the CUDA library can be fed identical bytes.
+//
+// The 2.4 MB memdata_nonsquare.h is skipped here (guard PARAMS_HPP,
+// memdata_nonsquare.h:1-2) and PARAM:: is declared empty: weights are
+// caller-supplied.  The fixture weights are used by oracle/ref_net.cpp.
+#include <cstdint>
+#include <cstring>
+#include <chrono>
+
+#define AP_INT_MAX_W 16384
+#include <hls_stream.h>
+#include "ap_int.h"
+#include "weights.hpp"
+#include "config_nonsquare.h"
+
+#define PARAMS_HPP
+namespace PARAM {
+static FixedPointWeights<CONV_0_SIMD, ap_int<CONV_0_W_BIT>, CONV_0_PE, CONV_0_W_TILES> weights_layer0;
+static FixedPointWeights<CONV_1_SIMD, ap_int<CONV_1_W_BIT>, CONV_1_PE, CONV_1_W_TILES> weights_layer1;
+static FixedPointWeights<CONV_2_SIMD, ap_int<CONV_2_W_BIT>, CONV_2_PE, CONV_2_W_TILES> weights_layer2;
+static FixedPointWeights<CONV_3_SIMD, ap_int<CONV_3_W_BIT>, CONV_3_PE, CONV_3_W_TILES> weights_layer3;
+static FixedPointWeights<CONV_4_SIMD, ap_int<CONV_4_W_BIT>, CONV_4_PE, CONV_4_W_TILES> weights_layer4;
+static FixedPointWeights<CONV_5_SIMD, ap_int<CONV_5_W_BIT>, CONV_5_PE, CONV_5_W_TILES> weights_layer5;
+static FixedPointWeights<CONV_6_SIMD, ap_int<CONV_6_W_BIT>, CONV_6_PE, CONV_6_W_TILES> weights_layer6;
+static FixedPointWeights<CONV_7_SIMD, ap_int<CONV_7_W_BIT>, CONV_7_PE, CONV_7_W_TILES> weights_layer7;
+static FixedPointWeights<1, ap_int<8>, 1, CONV_0_OFM_CH> bias_layer0;
+static FixedPointWeights<1, ap_int<8>, 1, CONV_1_OFM_CH> bias_layer1;
+static FixedPointWeights<1, ap_int<8>, 1, CONV_2_OFM_CH> bias_layer2;
+static FixedPointWeights<1, ap_int<8>, 1, CONV_3_OFM_CH> bias_layer3;
+static FixedPointWeights<1, ap_int<8>, 1, CONV_4_OFM_CH> bias_layer4;
+static FixedPointWeights<1, ap_int<8>, 1, CONV_5_OFM_CH> bias_layer5;
+static FixedPointWeights<1, ap_int<8>, 1, CONV_6_OFM_CH> bias_layer6;
+static FixedPointWeights<1, ap_int<8>, 1, CONV_7_OFM_CH> bias_layer7;
+}  // namespace PARAM
+
+#include "conv_nonsquare_top.cpp"  // the reference top, unmodified (templates conv2d<>, deconv522<>)
+
+namespace {
+
+constexpr int container_bytes(int w) { return w <= 8 ? 1 : w <= 16 ? 2 : w <= 32 ? 4 : w <= 64 ? 8 : 8 * ((w + 63) / 64); }
+
+template <int W> ap_uint<W> load_word(const uint8_t* p) {
+  ap_uint<W> v = 0;
+  for (int b = 0; b < W; b += 8) {
+    int n = (W - b) < 8 ? (W - b) : 8;
+    v(b + n - 1, b) = (unsigned long long)(p[b / 8] & ((1u << n) - 1u));
+  }
+  return v;
+}
+template <int W> void store_word(uint8_t* p, const ap_uint<W>& v) {
+  std::memset(p, 0, container_bytes(W));
+  for (int b = 0; b < W; b += 8) {
+    int n = (W - b) < 8 ? (W - b) : 8;
+    p[b / 8] = (uint8_t)(unsigned long long)v(b + n - 1, b);
+  }
+}
+// signed scalar (thresholds): low W bits of the container, sign-extended by the ap_int ctor
+template <int W> ap_int<W> load_sword(const uint8_t* p) {
+  ap_uint<W> u = load_word<W>(p);
+  ap_int<W> s;
+  s(W - 1, 0) = u(W - 1, 0);
+  return s;
+}
+
+template <int W> void fill_stream(hls::stream<ap_uint<W> >& s, const uint8_t* bytes, size_t nwords) {
+  s.reserve(nwords);
+  for (size_t i = 0; i < nwords; i++) s.write(load_word<W>(bytes + i * container_bytes(W)));
+}
+template <int W> int drain_stream(hls::stream<ap_uint<W> >& s, uint8_t* bytes, size_t nwords) {
+  if (s.size() != nwords) return -2;
+  for (size_t i = 0; i < nwords; i++) store_word<W>(bytes + i * container_bytes(W), s.read());
+  return 0;
+}
+
+template <unsigned SIMD, typename WT, unsigned PE, unsigned TILES>
+void load_weights(FixedPointWeights<SIMD, WT, PE, TILES>& w, const uint8_t* bytes) {
+  const int cb = container_bytes(SIMD * WT::width);
+  for (unsigned pe = 0; pe < PE; pe++)
+    for (unsigned t = 0; t < TILES; t++) w.m_weights[pe][t] = load_word<SIMD * WT::width>(bytes + (size_t)(pe * TILES + t) * cb);
+}
+template <unsigned SIMD, unsigned PE, unsigned TILES>
+void load_bweights(BinaryWeights<SIMD, PE, TILES>& w, const uint8_t* bytes) {
+  const int cb = container_bytes(SIMD);
+  for (unsigned pe = 0; pe < PE; pe++)
+    for (unsigned t = 0; t < TILES; t++) w.m_weights[pe][t] = load_word<SIMD>(bytes + (size_t)(pe * TILES + t) * cb);
+}
+template <unsigned NF, unsigned PE, unsigned NTH, int TAB, typename TR, int AV>
+void load_thresholds(ThresholdsActivation<NF, PE, NTH, ap_int<TAB>, TR, AV>& a, const uint8_t* bytes) {
+  const int cb = container_bytes(TAB);
+  for (unsigned pe = 0; pe < PE; pe++)
+    for (unsigned nf = 0; nf < NF; nf++)
+      for (unsigned i = 0; i < NTH; i++) a.m_thresholds[pe][nf][i] = load_sword<TAB>(bytes + (size_t)((pe * NF + nf) * NTH + i) * cb);
+}
+
+// ---- conv2d<> (conv_nonsquare_top.cpp:198-280) ---------------------------------
+template <unsigned KX, unsigned KY, unsigned SIMD, unsigned PE, unsigned WB, unsigned C, unsigned OFM, unsigned IX, unsigned IY,
+          unsigned OX, unsigned OY, unsigned SX, unsigned SY, unsigned PAD, unsigned INB, unsigned ACTB>
+int run_conv2d(const uint8_t* in, const uint8_t* wts, const uint8_t* bias, uint8_t* out, double* secs) {
+  constexpr unsigned TILES = (KX * KY * C / SIMD) * (OFM / PE);
+  static FixedPointWeights<SIMD, ap_int<WB>, PE, TILES> w;
+  static FixedPointWeights<1, ap_int<8>, 1, OFM> b;
+  load_weights(w, wts);
+  load_weights(b, bias);
+  hls::stream<ap_uint<C * INB> > s_in("in");
+  hls::stream<ap_uint<OFM * ACTB> > s_out("out");
+  fill_stream<C * INB>(s_in, in, (size_t)IX * IY);
+  auto t0 = std::chrono::steady_clock::now();
+  conv2d<KX, KY, SIMD, PE, WB, C, OFM, IX, IY, OX, OY, SX, SY, PAD, INB, TILES, ACTB>(w, b, s_in, s_out, 1);
+  auto t1 = std::chrono::steady_clock::now();
+  if (secs) *secs = std::chrono::duration<double>(t1 - t0).count();
+  return drain_stream<OFM * ACTB>(s_out, out, (size_t)OX * OY);
+}
+
+// ---- deconv522<> (conv_nonsquare_top.cpp:71-195) -------------------------------
+template <unsigned IX, unsigned IY, unsigned C, unsigned OFM, unsigned SIMD, unsigned PE, unsigned WB>
+int run_deconv(const uint8_t* in, const uint8_t* wts, const uint8_t* bias, uint8_t* out, double* secs) {
+  constexpr unsigned TILES = (25 * C / SIMD) * (OFM / PE);
+  static FixedPointWeights<SIMD, ap_int<WB>, PE, TILES> w;
+  static FixedPointWeights<1, ap_int<8>, 1, OFM> b;
+  load_weights(w, wts);
+  load_weights(b, bias);
+  hls::stream<ap_uint<C * 8> > s_in("in");
+  hls::stream<ap_uint<OFM * 8> > s_out("out");
+  fill_stream<C * 8>(s_in, in, (size_t)IX * IY);
+  auto t0 = std::chrono::steady_clock::now();
+  deconv522<IX, IY, C, OFM, SIMD, PE, 8, 8, WB, TILES>(w, b, s_in, s_out, 1);
+  auto t1 = std::chrono::steady_clock::now();
+  if (secs) *secs = std::chrono::duration<double>(t1 - t0).count();
+  return drain_stream<OFM * 8>(s_out, out, (size_t)(2 * IX) * (2 * IY));
+}
+
+// ---- library path, as the commented Testbench_conv_nonsquare composes it
+//      (conv_nonsquare_top.cpp:361-379), plus FMPadding_nonsquare in front
+//      (streamtools.h:361-406) when PAD > 0: fixed-point weights + ThresholdsActivation.
+template <unsigned K, unsigned SIMD, unsigned PE, unsigned WB, unsigned C, unsigned OFM, unsigned IX, unsigned IY, unsigned PAD,
+          unsigned INB, unsigned NTH, int TAB, unsigned TRB, int AV>
+int run_thresh(const uint8_t* in, const uint8_t* wts, const uint8_t* thr, uint8_t* out, double* secs) {
+  constexpr unsigned PX = IX + 2 * PAD, PY = IY + 2 * PAD, OX = PX - K + 1, OY = PY - K + 1;
+  constexpr unsigned MW = K * K * C, MH = OFM, SF = MW / SIMD, NF = MH / PE;
+  static FixedPointWeights<SIMD, ap_int<WB>, PE, SF * NF> w;
+  static ThresholdsActivation<NF, PE, NTH, ap_int<TAB>, ap_uint<TRB>, AV> act;
+  load_weights(w, wts);
+  load_thresholds(act, thr);
+  hls::stream<ap_uint<C * INB> > s_in("in"), s_pad("pad");
+  hls::stream<ap_uint<SIMD * INB> > s_wa("wa"), s_win("win");
+  hls::stream<ap_uint<PE * TRB> > s_mv("mv");
+  hls::stream<ap_uint<OFM * TRB> > s_out("out");
+  fill_stream<C * INB>(s_in, in, (size_t)IX * IY);
+  auto t0 = std::chrono::steady_clock::now();
+  FMPadding_nonsquare<PX, PY, 2 * PAD, 2 * PAD, C, C, ap_uint<INB> >(s_in, s_pad);
+  StreamingDataWidthConverter_Batch<C * INB, SIMD * INB, PX * PY>(s_pad, s_wa, 1);
+  ConvolutionInputGenerator_NonSquare<K, K, C, INB, PX, PY, OX, OY, SIMD, 1, 1>(s_wa, s_win, 1, ap_resource_dflt());
+  Matrix_Vector_Activate_Batch<MW, MH, SIMD, PE, 1, Slice<ap_uint<INB> >, Slice<ap_uint<TRB> >, Identity>(
+      s_win, s_mv, w, act, OX * OY, ap_resource_dsp());
+  StreamingDataWidthConverter_Batch<PE * TRB, OFM * TRB, OX * OY * NF>(s_mv, s_out, 1);
+  auto t1 = std::chrono::steady_clock::now();
+  if (secs) *secs = std::chrono::duration<double>(t1 - t0).count();
+  return drain_stream<OFM * TRB>(s_out, out, (size_t)OX * OY);
+}
+
+// ---- 1-bit path: BinaryWeights + Recast<XnorMul> + ThresholdsActivation (NumTH=1, TR=ap_uint<1>)
+//      weights.hpp:66-98, interpret.hpp:57-73,126-175, activations.hpp:168-190; no padding (ConvLayer_Batch semantics)
+template <unsigned K, unsigned SIMD, unsigned PE, unsigned C, unsigned OFM, unsigned IX, unsigned IY, int TAB>
+int run_xnor(const uint8_t* in, const uint8_t* wts, const uint8_t* thr, uint8_t* out, double* secs) {
+  constexpr unsigned OX = IX - K + 1, OY = IY - K + 1;
+  constexpr unsigned MW = K * K * C, MH = OFM, SF = MW / SIMD, NF = MH / PE;
+  static BinaryWeights<SIMD, PE, SF * NF> w;
+  static ThresholdsActivation<NF, PE, 1, ap_int<TAB>, ap_uint<1> > act;
+  load_bweights(w, wts);
+  load_thresholds(act, thr);
+  hls::stream<ap_uint<C> > s_in("in");
+  hls::stream<ap_uint<SIMD> > s_wa("wa"), s_win("win");
+  hls::stream<ap_uint<PE> > s_mv("mv");
+  hls::stream<ap_uint<OFM> > s_out("out");
+  fill_stream<C>(s_in, in, (size_t)IX * IY);
+  auto t0 = std::chrono::steady_clock::now();
+  StreamingDataWidthConverter_Batch<C, SIMD, IX * IY>(s_in, s_wa, 1);
+  ConvolutionInputGenerator_NonSquare<K, K, C, 1, IX, IY, OX, OY, SIMD, 1, 1>(s_wa, s_win, 1, ap_resource_dflt());
+  Matrix_Vector_Activate_Batch<MW, MH, SIMD, PE, 1, Recast<XnorMul>, Slice<ap_uint<1> >, Identity>(
+      s_win, s_mv, w, act, OX * OY, ap_resource_lut());
+  StreamingDataWidthConverter_Batch<PE, OFM, OX * OY * NF>(s_mv, s_out, 1);
+  auto t1 = std::chrono::steady_clock::now();
+  if (secs) *secs = std::chrono::duration<double>(t1 - t0).count();
+  return drain_stream<OFM>(s_out, out, (size_t)OX * OY);
+}
+
+// ---- pooling (maxpool.h:66-96, 137-185); the reference is square-only
+template <unsigned DIM, unsigned PD, unsigned C, unsigned B>
+int run_pool_prec(const uint8_t* in, uint8_t* out) {
+  hls::stream<ap_uint<C * B> > s_in("in"), s_out("out");
+  fill_stream<C * B>(s_in, in, (size_t)DIM * DIM);
+  StreamingMaxPool_Precision<DIM, PD, C, ap_uint<B>, 0>(s_in, s_out);
+  return drain_stream<C * B>(s_out, out, (size_t)(DIM / PD) * (DIM / PD));
+}
+template <unsigned DIM, unsigned PD, unsigned C>
+int run_pool_bin(const uint8_t* in, uint8_t* out) {
+  hls::stream<ap_uint<C> > s_in("in"), s_out("out");
+  fill_stream<C>(s_in, in, (size_t)DIM * DIM);
+  StreamingMaxPool<DIM, PD, C>(s_in, s_out);
+  return drain_stream<C>(s_out, out, (size_t)(DIM / PD) * (DIM / PD));
+}
+
+}  // namespace
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+// conv2d<> instantiations.  Name, KX,KY, SIMD,PE, WB, C,OFM, IX,IY, OX,OY, S, PAD, INB, ACTB
+#define CONV2D_CASES(X)                                                   \
+  X(c2d_a, 5, 5, 2, 3, 4, 4, 6, 12, 8, 6, 4, 2, 2, 8, 8)                  \
+  X(c2d_b, 5, 5, 8, 8, 4, 16, 32, 40, 24, 20, 12, 2, 2, 8, 8)             \
+  X(c2d_c, 5, 5, 3, 8, 4, 3, 16, 32, 20, 16, 10, 2, 2, 8, 8)              \
+  X(c2d_d, 3, 3, 16, 4, 8, 32, 32, 20, 12, 20, 12, 1, 1, 8, 8)            \
+  X(c2d_e, 5, 5, 8, 16, 4, 128, 128, 48, 32, 24, 16, 2, 2, 8, 8)          \
+  X(c2d_f, 3, 3, 4, 2, 4, 8, 8, 10, 6, 10, 6, 1, 1, 8, 16)                \
+  X(c2d_g, 5, 5, 8, 24, 4, 128, 192, 24, 16, 12, 8, 2, 2, 8, 8)           \
+  X(c2d_L1band, 5, 5, 8, 16, 4, 128, 128, 384, 32, 192, 16, 2, 2, 8, 8)   \
+  X(c2d_L1, 5, 5, 8, 16, 4, 128, 128, 384, 256, 192, 128, 2, 2, 8, 8)
+
+#define X(name, KX, KY, SIMD, PE, WB, C, OFM, IX, IY, OX, OY, S, PAD, INB, ACTB)                               \
+  REF_API int ref_##name(const uint8_t* in, const uint8_t* w, const uint8_t* b, uint8_t* out, double* secs) {  \
+    return run_conv2d<KX, KY, SIMD, PE, WB, C, OFM, IX, IY, OX, OY, S, S, PAD, INB, ACTB>(in, w, b, out, secs); \
+  }
+CONV2D_CASES(X)
+#undef X
+
+// deconv522<> instantiations.  Name, IX,IY, C,OFM, SIMD,PE, WB
+#define DECONV_CASES(X)                        \
+  X(dc_a, 6, 4, 4, 6, 2, 3, 4)                 \
+  X(dc_b, 12, 8, 16, 16, 8, 8, 4)              \
+  X(dc_c, 24, 16, 128, 128, 8, 16, 4)          \
+  X(dc_d, 24, 16, 128, 3, 8, 3, 4)             \
+  X(dc_e, 12, 8, 192, 128, 12, 16, 4)          \
+  X(dc_L4, 48, 32, 192, 128, 12, 16, 4)
+
+#define X(name, IX, IY, C, OFM, SIMD, PE, WB)                                                                  \
+  REF_API int ref_##name(const uint8_t* in, const uint8_t* w, const uint8_t* b, uint8_t* out, double* secs) {  \
+    return run_deconv<IX, IY, C, OFM, SIMD, PE, WB>(in, w, b, out, secs);                                       \
+  }
+DECONV_CASES(X)
+#undef X
+
+// threshold path.  Name, K, SIMD,PE, WB, C,OFM, IX,IY, PAD, INB, NTH, TAB, TRB, ActVal
+#define THRESH_CASES(X)                                            \
+  X(th_a, 3, 4, 2, 4, 8, 8, 10, 6, 1, 8, 15, 24, 4, 0)             \
+  X(th_b, 3, 16, 8, 4, 32, 32, 16, 12, 1, 8, 255, 24, 8, 0)        \
+  X(th_c, 3, 8, 4, 4, 16, 16, 9, 7, 0, 8, 3, 16, 2, 0)             \
+  X(th_d, 3, 3, 8, 4, 3, 16, 16, 12, 1, 8, 255, 24, 8, 0)          \
+  X(th_cfg4, 3, 32, 32, 4, 256, 256, 64, 48, 1, 8, 255, 24, 8, 0)
+
+#define X(name, K, SIMD, PE, WB, C, OFM, IX, IY, PAD, INB, NTH, TAB, TRB, AV)                                   \
+  REF_API int ref_##name(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double* secs) {  \
+    return run_thresh<K, SIMD, PE, WB, C, OFM, IX, IY, PAD, INB, NTH, TAB, TRB, AV>(in, w, t, out, secs);       \
+  }
+THRESH_CASES(X)
+#undef X
+
+// xnor path.  Name, K, SIMD,PE, C,OFM, IX,IY, TAB
+#define XNOR_CASES(X)                          \
+  X(xn_a, 3, 8, 4, 8, 8, 12, 10, 16)           \
+  X(xn_b, 3, 64, 16, 64, 64, 16, 12, 16)       \
+  X(xn_c, 3, 32, 8, 64, 32, 20, 9, 16)
+
+#define X(name, K, SIMD, PE, C, OFM, IX, IY, TAB)                                                              \
+  REF_API int ref_##name(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double* secs) {  \
+    return run_xnor<K, SIMD, PE, C, OFM, IX, IY, TAB>(in, w, t, out, secs);                                     \
+  }
+XNOR_CASES(X)
+#undef X
+
+REF_API int ref_pool_prec_8_2_8(const uint8_t* in, uint8_t* out) { return run_pool_prec<8, 2, 8, 8>(in, out); }
+REF_API int ref_pool_prec_12_2_16(const uint8_t* in, uint8_t* out) { return run_pool_prec<12, 2, 16, 8>(in, out); }
+REF_API int ref_pool_prec_12_3_4(const uint8_t* in, uint8_t* out) { return run_pool_prec<12, 3, 4, 4>(in, out); }
+REF_API int ref_pool_bin_8_2_16(const uint8_t* in, uint8_t* out) { return run_pool_bin<8, 2, 16>(in, out); }
+REF_API int ref_pool_bin_12_2_64(const uint8_t* in, uint8_t* out) { return run_pool_bin<12, 2, 64>(in, out); }
+
+REF_API const char* ref_layers_cases(void) {
+  return
+#define X(name, ...) #name " "
+      CONV2D_CASES(X) DECONV_CASES(X) THRESH_CASES(X) XNOR_CASES(X)
+#undef X
+      ;
+}

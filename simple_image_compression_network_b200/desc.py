@@ -1,0 +1,91 @@
+"""Run-time mirror of the reference's compile-time layer parameters (ctypes view of fcb_layer_desc).
+
+Field meaning follows conv2d<> (conv_nonsquare_top.cpp:198-215), deconv522<> (:71-81),
+ConvLayer_Batch (convlayer.h:89-105) and ThresholdsActivation (activations.hpp:168-169).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+KIND_CONV, KIND_DECONV522 = 0, 1
+W_FIXED, W_BINARY_XNOR, W_BINARY_PM1 = 0, 1, 2
+ACT_PASSTHROUGH, ACT_BIAS_RELU, ACT_THRESHOLDS = 0, 1, 2
+CMP_LESS, CMP_GREATER, CMP_LESS_EQUAL, CMP_GREATER_EQUAL = 0, 1, 2, 3
+
+
+class CLayerDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "struct_size", "kind", "kernel_x", "kernel_y", "ifm_ch", "ofm_ch", "ifm_x", "ifm_y", "ofm_x", "ofm_y",
+        "stride_x", "stride_y", "pad", "simd", "pe", "in_bits", "in_signed", "w_bits", "weight_kind",
+        "acc_bits", "acc_signed", "act_kind", "out_bits", "num_th")] + [
+        ("act_val", ctypes.c_int32), ("cmp", ctypes.c_uint32), ("pool", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32 * 6)]
+
+
+@dataclass(frozen=True)
+class LayerDesc:
+    kind: int = KIND_CONV
+    kernel_x: int = 5
+    kernel_y: int = 5
+    ifm_ch: int = 128
+    ofm_ch: int = 128
+    ifm_x: int = 384
+    ifm_y: int = 256
+    stride_x: int = 2
+    stride_y: int = 2
+    pad: int = 2
+    simd: int = 8
+    pe: int = 16
+    in_bits: int = 8
+    in_signed: int = 0
+    w_bits: int = 4
+    weight_kind: int = W_FIXED
+    acc_bits: int = 8
+    acc_signed: int = 0
+    act_kind: int = ACT_BIAS_RELU
+    out_bits: int = 8
+    num_th: int = 0
+    act_val: int = 0
+    cmp: int = CMP_LESS
+    pool: int = 0
+
+    # ---- derived geometry (conv_nonsquare_top.cpp:238-259 / :109-169) ----
+    @property
+    def ofm_x(self) -> int:
+        if self.kind == KIND_DECONV522:
+            return 2 * self.ifm_x
+        return (self.ifm_x + 2 * self.pad - self.kernel_x) // self.stride_x + 1
+
+    @property
+    def ofm_y(self) -> int:
+        if self.kind == KIND_DECONV522:
+            return 2 * self.ifm_y
+        return (self.ifm_y + 2 * self.pad - self.kernel_y) // self.stride_y + 1
+
+    @property
+    def out_x(self) -> int:
+        return self.ofm_x // max(self.pool, 1)
+
+    @property
+    def out_y(self) -> int:
+        return self.ofm_y // max(self.pool, 1)
+
+    @property
+    def k_total(self) -> int:
+        return self.kernel_x * self.kernel_y * self.ifm_ch
+
+    @property
+    def macs_per_image(self) -> int:
+        """MACs as the reference executes them (dense, structural zeros of deconv included)."""
+        return self.ofm_x * self.ofm_y * self.ofm_ch * self.k_total
+
+    def to_c(self) -> CLayerDesc:
+        c = CLayerDesc()
+        c.struct_size = ctypes.sizeof(CLayerDesc)
+        for f in ("kind", "kernel_x", "kernel_y", "ifm_ch", "ofm_ch", "ifm_x", "ifm_y", "stride_x", "stride_y", "pad",
+                  "simd", "pe", "in_bits", "in_signed", "w_bits", "weight_kind", "acc_bits", "acc_signed", "act_kind",
+                  "out_bits", "num_th", "act_val", "cmp", "pool"):
+            setattr(c, f, getattr(self, f))
+        c.ofm_x, c.ofm_y = self.ofm_x, self.ofm_y
+        return c
