@@ -147,6 +147,10 @@ FCB_API int fcb_net_run(fcb_net* net, const void* in_words, void* out_words, uin
 FCB_API int fcb_net_run_device(fcb_net* net, const void* d_in, void* d_out, uint32_t numReps, void* stream);
 FCB_API uint64_t fcb_net_launches(const fcb_net* net);
 
+/* --- synthetic data (bench / tests): byte i of the buffer = splitmix64(seed ^ (offset + i)) & mask,
+ * the rule of SURVEY.md 8(d); d_ptr is device memory, 16-byte aligned; asynchronous on `stream`. */
+FCB_API int fcb_synth_fill(void* d_ptr, size_t n_bytes, uint64_t seed, uint32_t mask, uint64_t offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

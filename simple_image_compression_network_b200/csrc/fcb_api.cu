@@ -1,0 +1,461 @@
+// fcb_api.cu -- the C ABI of include/finnconv_b200.h: descriptor validation, parameter re-layout,
+// engine selection, host<->device plumbing.  No arithmetic of the layer happens on the host.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "fcb_internal.h"
+
+namespace fcb {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+static size_t word_bytes(uint32_t bits) {
+  if (bits <= 8) return 1;
+  if (bits <= 16) return 2;
+  if (bits <= 32) return 4;
+  if (bits <= 64) return 8;
+  return 8 * (size_t)((bits + 63) / 64);
+}
+
+// Validation mirrors the reference's preconditions: IFMChannels % SIMD (slidingwindow.h:1259),
+// DWC divisibility PE*B | OFM*B (streamtools.h:505), TILES == NF*SF (mvau.hpp:101-105,117), pool
+// divisibility (maxpool.h:140), and deconv522's hard-wired k5 s2 p2 (conv_nonsquare_top.cpp:84-86).
+int derive_geom(const fcb_layer_desc* d, Geom* g) {
+  if (!d) { set_error("descriptor is NULL"); return FCB_ERR_INVALID_ARG; }
+  if (d->struct_size != sizeof(fcb_layer_desc)) { set_error("struct_size %u != %zu", d->struct_size, sizeof(fcb_layer_desc)); return FCB_ERR_INVALID_ARG; }
+  for (int i = 0; i < 6; i++) if (d->reserved[i]) { set_error("reserved fields must be zero"); return FCB_ERR_INVALID_ARG; }
+  if (!d->simd || !d->pe || !d->ifm_ch || !d->ofm_ch || !d->kernel_x || !d->kernel_y || !d->stride_x || !d->stride_y || !d->ifm_x || !d->ifm_y) {
+    set_error("zero-sized parameter"); return FCB_ERR_INVALID_ARG;
+  }
+  if (d->kind > FCB_KIND_DECONV522 || d->weight_kind > FCB_W_BINARY_PM1 || d->act_kind > FCB_ACT_THRESHOLDS || d->cmp > FCB_CMP_GREATER_EQUAL) {
+    set_error("bad enum value"); return FCB_ERR_INVALID_ARG;
+  }
+  if (d->ifm_ch % d->simd) { set_error("IFM_CH %% SIMD != 0 (%u %% %u)", d->ifm_ch, d->simd); return FCB_ERR_SHAPE; }
+  if (d->ofm_ch % d->pe) { set_error("OFM_CH %% PE != 0 (%u %% %u)", d->ofm_ch, d->pe); return FCB_ERR_SHAPE; }
+  uint32_t ox, oy;
+  if (d->kind == FCB_KIND_DECONV522) {
+    if (d->kernel_x != 5 || d->kernel_y != 5 || d->stride_x != 2 || d->stride_y != 2 || d->pad != 2) {
+      set_error("deconv522 is k5 s2 p2 only"); return FCB_ERR_SHAPE;
+    }
+    ox = 2 * d->ifm_x; oy = 2 * d->ifm_y;
+  } else {
+    if (d->ifm_x + 2 * d->pad < d->kernel_x || d->ifm_y + 2 * d->pad < d->kernel_y) { set_error("kernel larger than padded input"); return FCB_ERR_SHAPE; }
+    ox = (d->ifm_x + 2 * d->pad - d->kernel_x) / d->stride_x + 1;
+    oy = (d->ifm_y + 2 * d->pad - d->kernel_y) / d->stride_y + 1;
+  }
+  if (ox != d->ofm_x || oy != d->ofm_y) { set_error("ofm %ux%u does not match geometry %ux%u", d->ofm_x, d->ofm_y, ox, oy); return FCB_ERR_SHAPE; }
+  if (d->weight_kind == FCB_W_BINARY_XNOR && (d->w_bits != 1 || d->in_bits != 1)) { set_error("xnor needs 1-bit weights and activations"); return FCB_ERR_SHAPE; }
+  if (d->weight_kind == FCB_W_BINARY_PM1 && d->w_bits != 1) { set_error("binary weights are 1 bit"); return FCB_ERR_SHAPE; }
+  const uint32_t pk = d->pool >= 2 ? d->pool : 1;
+  if (ox % pk || oy % pk) { set_error("OFM %% PoolDim != 0"); return FCB_ERR_SHAPE; }
+  if (d->act_kind == FCB_ACT_THRESHOLDS && d->num_th == 0) { set_error("thresholds activation with NumTH == 0"); return FCB_ERR_SHAPE; }
+  // ---- what this implementation supports (a subset of what the templates can express)
+  auto pow2 = [](uint32_t v) { return v && !(v & (v - 1)); };
+  if (!pow2(d->in_bits) || d->in_bits > 16) { set_error("in_bits %u unsupported (1,2,4,8,16)", d->in_bits); return FCB_ERR_UNSUPPORTED; }
+  if (!pow2(d->out_bits) || d->out_bits > 32) { set_error("out_bits %u unsupported (1,2,4,8,16,32)", d->out_bits); return FCB_ERR_UNSUPPORTED; }
+  if (d->w_bits < 1 || d->w_bits > 16) { set_error("w_bits %u unsupported (1..16)", d->w_bits); return FCB_ERR_UNSUPPORTED; }
+  if (d->in_bits == 16 && !d->in_signed) { /* lanes are staged as int32: fine */ }
+  if (d->acc_bits < 1 || d->acc_bits > 32 || (d->acc_bits == 32 && !d->acc_signed && d->act_kind == FCB_ACT_THRESHOLDS)) {
+    set_error("acc_bits %u unsupported (1..32)", d->acc_bits); return FCB_ERR_UNSUPPORTED;
+  }
+  if (!(pk == 1 || pk == 2 || pk == 4)) { set_error("pool %u unsupported (2 or 4)", d->pool); return FCB_ERR_UNSUPPORTED; }
+  if (d->act_kind == FCB_ACT_BIAS_RELU && d->out_bits < 2) { set_error("bias+ReLU needs out_bits >= 2"); return FCB_ERR_UNSUPPORTED; }
+
+  g->kind = d->kind; g->C = d->ifm_ch; g->OFM = d->ofm_ch; g->KX = d->kernel_x; g->KY = d->kernel_y;
+  g->IX = d->ifm_x; g->IY = d->ifm_y; g->OX = ox; g->OY = oy; g->SX = d->stride_x; g->SY = d->stride_y; g->PAD = d->pad;
+  g->simd = d->simd; g->pe = d->pe; g->K = g->KX * g->KY * g->C; g->SF = g->K / g->simd; g->NF = g->OFM / g->pe;
+  g->in_bits = d->in_bits; g->in_signed = d->in_signed ? 1 : 0; g->w_bits = d->w_bits; g->weight_kind = d->weight_kind;
+  g->acc_bits = d->acc_bits; g->acc_signed = d->acc_signed ? 1 : 0; g->act_kind = d->act_kind; g->out_bits = d->out_bits;
+  g->num_th = d->act_kind == FCB_ACT_THRESHOLDS ? d->num_th : 0; g->act_val = d->act_val; g->cmp = d->cmp; g->pool = pk;
+  g->out_x = ox / pk; g->out_y = oy / pk;
+  g->in_word_bytes = word_bytes(g->C * g->in_bits);
+  g->out_word_bytes = word_bytes(g->OFM * g->out_bits);
+  g->in_img_bytes = g->in_word_bytes * g->IX * g->IY;
+  g->out_img_bytes = g->out_word_bytes * g->out_x * g->out_y;
+  g->w_word_bytes = word_bytes(g->simd * g->w_bits);
+  g->weight_bytes = g->w_word_bytes * g->pe * (size_t)g->SF * g->NF;
+  g->threshold_bytes = g->act_kind == FCB_ACT_THRESHOLDS ? word_bytes(g->acc_bits) * g->pe * (size_t)g->NF * g->num_th : 0;
+  g->bias_bytes = g->act_kind == FCB_ACT_BIAS_RELU ? g->OFM : 0;
+  return FCB_OK;
+}
+
+static inline uint32_t get_bits(const uint8_t* p, uint64_t lo, uint32_t n) {
+  uint64_t v = 0;
+  const uint64_t byte = lo >> 3;
+  const uint32_t sh = (uint32_t)(lo & 7), need = (sh + n + 7) >> 3;
+  for (uint32_t i = 0; i < need; i++) v |= (uint64_t)p[byte + i] << (8 * i);
+  v >>= sh;
+  return (uint32_t)(n >= 32 ? v : (v & ((1ull << n) - 1ull)));
+}
+static inline int32_t wrap_host(int64_t v, int bits, int sgn) {
+  if (bits >= 32) return (int32_t)v;
+  uint32_t u = (uint32_t)v << (32 - bits);
+  return sgn ? ((int32_t)u >> (32 - bits)) : (int32_t)(u >> (32 - bits));
+}
+
+}  // namespace fcb
+
+using namespace fcb;
+
+struct fcb_layer {
+  Geom g;
+  int device = 0;
+  int engine = ENG_IMAD;
+  void* d_wt = nullptr;
+  int8_t* d_bias = nullptr;
+  int32_t* d_thr = nullptr;
+  EpiParams epi{};
+  DirectParams dp{};
+  size_t smem = 0;
+  UmmaPlan* umma = nullptr;
+  // staging for the host-buffer entry point (two slots, double buffered)
+  void* s_in[2] = {nullptr, nullptr};
+  void* s_out[2] = {nullptr, nullptr};
+  size_t s_imgs = 0;
+  cudaStream_t s_stream[2] = {nullptr, nullptr};
+  uint64_t launches = 0;
+};
+
+struct fcb_net {
+  std::vector<fcb_layer*> layers;
+  std::vector<void*> bufs;  // intermediate activations, one per layer boundary, sized for cap_imgs
+  size_t cap_imgs = 0;
+  void* s_in = nullptr;
+  void* s_out = nullptr;
+  size_t s_imgs = 0;
+  int device = 0;
+};
+
+extern "C" {
+
+const char* fcb_version(void) { return "finnconv_b200 0.1.0 (sm_100a)"; }
+const char* fcb_last_error(void) { return g_err.c_str(); }
+size_t fcb_word_bytes(uint32_t bits) { return word_bytes(bits); }
+
+int fcb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; i++) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, i) == cudaSuccess && pr.major == 10) ok++;
+  }
+  return ok;
+}
+
+int fcb_layer_query(const fcb_layer_desc* desc, size_t* in_b, size_t* out_b, size_t* w_b, size_t* t_b, size_t* b_b) {
+  Geom g;
+  int rc = derive_geom(desc, &g);
+  if (rc) return rc;
+  if (in_b) *in_b = g.in_img_bytes;
+  if (out_b) *out_b = g.out_img_bytes;
+  if (w_b) *w_b = g.weight_bytes;
+  if (t_b) *t_b = g.threshold_bytes;
+  if (b_b) *b_b = g.bias_bytes;
+  return FCB_OK;
+}
+
+void fcb_layer_destroy(fcb_layer* L) {
+  if (!L) return;
+  cudaSetDevice(L->device);
+  if (L->umma) umma_plan_destroy(L->umma);
+  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(L->s_in[i]); cudaFree(L->s_out[i]);
+    if (L->s_stream[i]) cudaStreamDestroy(L->s_stream[i]);
+  }
+  delete L;
+}
+
+int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void* thresholds, const void* bias, int device, fcb_layer** out) {
+  if (!out) { set_error("out is NULL"); return FCB_ERR_INVALID_ARG; }
+  *out = nullptr;
+  Geom g;
+  int rc = derive_geom(desc, &g);
+  if (rc) return rc;
+  if (!weights) { set_error("weights is NULL"); return FCB_ERR_INVALID_ARG; }
+  if (g.act_kind == FCB_ACT_THRESHOLDS && !thresholds) { set_error("thresholds is NULL"); return FCB_ERR_INVALID_ARG; }
+  if (g.act_kind == FCB_ACT_BIAS_RELU && !bias) { set_error("bias is NULL"); return FCB_ERR_INVALID_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    set_error("no usable CUDA device %d (this library has no CPU path)", device);
+    return FCB_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  FCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return FCB_ERR_CUDA; }
+  FCB_CUDA_OK(cudaSetDevice(device));
+
+  fcb_layer* L = new fcb_layer();
+  L->g = g;
+  L->device = device;
+
+  // ---- weights: m_weights[pe][nf*SF+sf] lanes -> W[ch][k] (mvau.hpp:117,148; weights.hpp:134-140)
+  std::vector<int32_t> W((size_t)g.OFM * g.K);
+  {
+    const uint8_t* wb = (const uint8_t*)weights;
+    for (int pe = 0; pe < g.pe; pe++)
+      for (int nf = 0; nf < g.NF; nf++)
+        for (int sf = 0; sf < g.SF; sf++) {
+          const uint8_t* word = wb + ((size_t)pe * g.NF * g.SF + (size_t)nf * g.SF + sf) * g.w_word_bytes;
+          for (int l = 0; l < g.simd; l++) {
+            const uint32_t raw = get_bits(word, (uint64_t)l * g.w_bits, g.w_bits);
+            int32_t v;
+            if (g.weight_kind == FCB_W_FIXED) v = wrap_host(raw, g.w_bits, 1);
+            else if (g.weight_kind == FCB_W_BINARY_PM1) v = raw ? 1 : -1;  // interpret.hpp:87-90
+            else v = (int32_t)raw;
+            W[(size_t)(nf * g.pe + pe) * g.K + sf * g.simd + l] = v;
+          }
+        }
+  }
+  // ---- activation parameters
+  L->epi.act_kind = g.act_kind; L->epi.acc_bits = g.acc_bits; L->epi.acc_signed = g.acc_signed; L->epi.out_bits = g.out_bits;
+  L->epi.num_th = g.num_th; L->epi.act_val = g.act_val; L->epi.cmp = g.cmp; L->epi.pool = g.pool;
+  if (g.act_kind == FCB_ACT_BIAS_RELU) {
+    FCB_CUDA_OK(cudaMalloc(&L->d_bias, g.OFM));
+    FCB_CUDA_OK(cudaMemcpy(L->d_bias, bias, g.OFM, cudaMemcpyHostToDevice));
+    L->epi.bias = L->d_bias;
+  }
+  if (g.act_kind == FCB_ACT_THRESHOLDS) {
+    std::vector<int32_t> T((size_t)g.OFM * g.num_th);
+    const uint8_t* tb = (const uint8_t*)thresholds;
+    const size_t cb = word_bytes(g.acc_bits);
+    for (int pe = 0; pe < g.pe; pe++)
+      for (int nf = 0; nf < g.NF; nf++) {
+        int32_t* row = &T[(size_t)(nf * g.pe + pe) * g.num_th];
+        for (int i = 0; i < g.num_th; i++) {
+          const uint8_t* p = tb + (((size_t)pe * g.NF + nf) * g.num_th + i) * cb;
+          uint64_t raw = 0;
+          for (size_t b = 0; b < cb && b < 8; b++) raw |= (uint64_t)p[b] << (8 * b);
+          row[i] = wrap_host((int64_t)raw, g.acc_bits, g.acc_signed);
+        }
+        std::sort(row, row + g.num_th);
+      }
+    FCB_CUDA_OK(cudaMalloc(&L->d_thr, T.size() * sizeof(int32_t)));
+    FCB_CUDA_OK(cudaMemcpy(L->d_thr, T.data(), T.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    L->epi.thr = L->d_thr;
+  }
+
+  // ---- engine selection
+  const char* force = getenv("FCB_FORCE_ENGINE");
+  int engine = ENG_IMAD;
+  const bool dense_bits = (g.in_word_bytes * 8 == (size_t)g.C * g.in_bits);
+  if (g.weight_kind == FCB_W_BINARY_XNOR && g.C % 32 == 0 && dense_bits) engine = ENG_XNOR;
+  if (umma_eligible(g)) engine = ENG_UMMA;
+  if (force && !strcmp(force, "imad")) engine = ENG_IMAD;
+  if (force && !strcmp(force, "xnor") && g.weight_kind == FCB_W_BINARY_XNOR && g.C % 32 == 0 && dense_bits) engine = ENG_XNOR;
+  L->engine = engine;
+
+  if (engine == ENG_UMMA) {
+    rc = umma_plan_create(g, W, L->epi, device, &L->umma);
+    if (rc) { fcb_layer_destroy(L); return rc; }
+  } else {
+    DirectParams& p = L->dp;
+    const int deconv = g.kind == FCB_KIND_DECONV522;
+    p.C = g.C; p.OFM = g.OFM; p.OFMp = (g.OFM + 63) / 64 * 64; p.KX = g.KX; p.KY = g.KY; p.IX = g.IX; p.IY = g.IY;
+    p.OX = g.OX; p.OY = g.OY; p.SXe = deconv ? 1 : g.SX; p.SYe = deconv ? 1 : g.SY; p.PAD = g.PAD; p.deconv = deconv;
+    p.in_bits = g.in_bits; p.in_signed = g.in_signed; p.in_word_bytes = (int)g.in_word_bytes; p.out_word_bytes = (int)g.out_word_bytes;
+    p.out_x = g.out_x; p.out_y = g.out_y; p.tiles_x = (g.OX + 15) / 16; p.tiles_y = (g.OY + 7) / 8;
+    p.patch_w = 15 * p.SXe + g.KX; p.patch_h = 7 * p.SYe + g.KY; p.mul_kind = g.weight_kind;
+    p.in_img_bytes = g.in_img_bytes; p.out_img_bytes = g.out_img_bytes; p.epi = L->epi;
+    const int cu = engine == ENG_XNOR ? g.C / 32 : g.C;
+    const size_t budget = 96 * 1024;
+    int cc = (int)(budget / ((size_t)p.patch_w * p.patch_h * 4));
+    if (cc < 1) { set_error("kernel %dx%d stride %d: patch does not fit shared memory", g.KX, g.KY, g.SX); fcb_layer_destroy(L); return FCB_ERR_UNSUPPORTED; }
+    p.CC = std::min(cc, cu);
+    L->smem = direct_smem_bytes(engine, p.patch_w, p.patch_h, p.CC);
+    if (engine == ENG_XNOR) {
+      const int KW = g.KX * g.KY * (g.C / 32);
+      std::vector<uint32_t> Wb((size_t)KW * p.OFMp, 0u);
+      for (int ch = 0; ch < g.OFM; ch++)
+        for (int k = 0; k < g.K; k++) {
+          const int tap = k / g.C, c = k % g.C;
+          if (W[(size_t)ch * g.K + k]) Wb[(size_t)(tap * (g.C / 32) + c / 32) * p.OFMp + ch] |= 1u << (c & 31);
+        }
+      FCB_CUDA_OK(cudaMalloc(&L->d_wt, Wb.size() * 4));
+      FCB_CUDA_OK(cudaMemcpy(L->d_wt, Wb.data(), Wb.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+      std::vector<int16_t> Wt((size_t)g.K * p.OFMp, 0);
+      for (int ch = 0; ch < g.OFM; ch++)
+        for (int k = 0; k < g.K; k++) Wt[(size_t)k * p.OFMp + ch] = (int16_t)W[(size_t)ch * g.K + k];
+      FCB_CUDA_OK(cudaMalloc(&L->d_wt, Wt.size() * 2));
+      FCB_CUDA_OK(cudaMemcpy(L->d_wt, Wt.data(), Wt.size() * 2, cudaMemcpyHostToDevice));
+    }
+    p.wt = L->d_wt;
+  }
+  *out = L;
+  return FCB_OK;
+}
+
+const char* fcb_layer_engine(const fcb_layer* L) {
+  if (!L) return "";
+  return L->engine == ENG_UMMA ? "umma_i8" : L->engine == ENG_XNOR ? "xnor_popc" : "imad";
+}
+uint64_t fcb_layer_launches(const fcb_layer* L) { return L ? L->launches : 0; }
+
+int fcb_layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, void* stream) {
+  if (!L || !d_in || !d_out) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  if (numReps == 0) return FCB_OK;
+  FCB_CUDA_OK(cudaSetDevice(L->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L->engine == ENG_UMMA) return umma_run(L->umma, d_in, d_out, (int)numReps, st, &L->launches);
+  // containers with padding bits (e.g. ap_uint<24> in 4 bytes): writers zero them
+  if (L->g.out_word_bytes * 8 != (size_t)L->g.OFM * L->g.out_bits) {
+    FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, L->g.out_img_bytes * numReps, st));
+  }
+  DirectParams p = L->dp;
+  p.in = (const uint8_t*)d_in;
+  p.out = (uint8_t*)d_out;
+  int rc = launch_direct(p, L->engine, (int)numReps, L->smem, st);
+  if (rc == FCB_OK) L->launches += (numReps + 65534) / 65535;
+  return rc;
+}
+
+int fcb_layer_run(fcb_layer* L, const void* in_words, void* out_words, uint32_t numReps) {
+  if (!L || !in_words || !out_words) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  if (numReps == 0) return FCB_OK;
+  FCB_CUDA_OK(cudaSetDevice(L->device));
+  // chunk so that one slot stays <= 256 MiB of input; two slots overlap copy and compute
+  size_t chunk = std::max<size_t>(1, ((size_t)256 << 20) / std::max(L->g.in_img_bytes, L->g.out_img_bytes));
+  chunk = std::min<size_t>(chunk, numReps);
+  if (L->s_imgs < chunk) {
+    for (int i = 0; i < 2; i++) {
+      cudaFree(L->s_in[i]); cudaFree(L->s_out[i]);
+      L->s_in[i] = L->s_out[i] = nullptr;
+      FCB_CUDA_OK(cudaMalloc(&L->s_in[i], L->g.in_img_bytes * chunk));
+      FCB_CUDA_OK(cudaMalloc(&L->s_out[i], L->g.out_img_bytes * chunk));
+      if (!L->s_stream[i]) FCB_CUDA_OK(cudaStreamCreateWithFlags(&L->s_stream[i], cudaStreamNonBlocking));
+    }
+    L->s_imgs = chunk;
+  }
+  int slot = 0;
+  for (size_t n0 = 0; n0 < numReps; n0 += chunk, slot ^= 1) {
+    const size_t nb = std::min<size_t>(chunk, numReps - n0);
+    cudaStream_t st = L->s_stream[slot];
+    FCB_CUDA_OK(cudaMemcpyAsync(L->s_in[slot], (const uint8_t*)in_words + n0 * L->g.in_img_bytes, nb * L->g.in_img_bytes, cudaMemcpyHostToDevice, st));
+    int rc = fcb_layer_run_device(L, L->s_in[slot], L->s_out[slot], (uint32_t)nb, st);
+    if (rc) return rc;
+    FCB_CUDA_OK(cudaMemcpyAsync((uint8_t*)out_words + n0 * L->g.out_img_bytes, L->s_out[slot], nb * L->g.out_img_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  FCB_CUDA_OK(cudaStreamSynchronize(L->s_stream[0]));
+  FCB_CUDA_OK(cudaStreamSynchronize(L->s_stream[1]));
+  return FCB_OK;
+}
+
+// ---- layer chain ------------------------------------------------------------------------
+int fcb_net_create(fcb_layer* const* layers, uint32_t n, fcb_net** out) {
+  if (!layers || !n || !out) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  for (uint32_t i = 0; i < n; i++) {
+    if (!layers[i]) { set_error("layer %u is NULL", i); return FCB_ERR_INVALID_ARG; }
+    if (layers[i]->device != layers[0]->device) { set_error("layers live on different devices"); return FCB_ERR_INVALID_ARG; }
+    if (i + 1 < n) {
+      const Geom &a = layers[i]->g, &b = layers[i + 1]->g;
+      if (a.OFM * a.out_bits != b.C * b.in_bits || a.out_x != b.IX || a.out_y != b.IY) {
+        set_error("layer %u output (%dx%d, %d bits) does not feed layer %u input (%dx%d, %d bits)", i, a.out_x, a.out_y,
+                  a.OFM * a.out_bits, i + 1, b.IX, b.IY, b.C * b.in_bits);
+        return FCB_ERR_SHAPE;
+      }
+    }
+  }
+  fcb_net* N = new fcb_net();
+  N->layers.assign(layers, layers + n);
+  N->bufs.assign(n > 1 ? n - 1 : 0, nullptr);
+  N->device = layers[0]->device;
+  *out = N;
+  return FCB_OK;
+}
+
+void fcb_net_destroy(fcb_net* N) {
+  if (!N) return;
+  cudaSetDevice(N->device);
+  for (void* b : N->bufs) cudaFree(b);
+  cudaFree(N->s_in); cudaFree(N->s_out);
+  delete N;
+}
+
+static int net_reserve(fcb_net* N, size_t imgs) {
+  if (N->cap_imgs >= imgs) return FCB_OK;
+  for (size_t i = 0; i < N->bufs.size(); i++) {
+    cudaFree(N->bufs[i]);
+    N->bufs[i] = nullptr;
+    FCB_CUDA_OK(cudaMalloc(&N->bufs[i], N->layers[i]->g.out_img_bytes * imgs));
+  }
+  N->cap_imgs = imgs;
+  return FCB_OK;
+}
+
+int fcb_net_run_device(fcb_net* N, const void* d_in, void* d_out, uint32_t numReps, void* stream) {
+  if (!N || !d_in || !d_out) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  if (!numReps) return FCB_OK;
+  FCB_CUDA_OK(cudaSetDevice(N->device));
+  // bound the intermediates: process in chunks of images
+  size_t biggest = 1;
+  for (size_t i = 0; i + 1 < N->layers.size(); i++) biggest = std::max(biggest, N->layers[i]->g.out_img_bytes);
+  size_t chunk = std::max<size_t>(1, ((size_t)1 << 30) / biggest);
+  chunk = std::min<size_t>(chunk, numReps);
+  int rc = net_reserve(N, chunk);
+  if (rc) return rc;
+  const size_t in_b = N->layers.front()->g.in_img_bytes, out_b = N->layers.back()->g.out_img_bytes;
+  for (size_t n0 = 0; n0 < numReps; n0 += chunk) {
+    const uint32_t nb = (uint32_t)std::min<size_t>(chunk, numReps - n0);
+    const void* src = (const uint8_t*)d_in + n0 * in_b;
+    for (size_t i = 0; i < N->layers.size(); i++) {
+      void* dst = (i + 1 == N->layers.size()) ? (void*)((uint8_t*)d_out + n0 * out_b) : N->bufs[i];
+      rc = fcb_layer_run_device(N->layers[i], src, dst, nb, stream);
+      if (rc) return rc;
+      src = dst;
+    }
+  }
+  return FCB_OK;
+}
+
+int fcb_net_run(fcb_net* N, const void* in_words, void* out_words, uint32_t numReps) {
+  if (!N || !in_words || !out_words) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  if (!numReps) return FCB_OK;
+  FCB_CUDA_OK(cudaSetDevice(N->device));
+  const size_t in_b = N->layers.front()->g.in_img_bytes, out_b = N->layers.back()->g.out_img_bytes;
+  size_t chunk = std::max<size_t>(1, ((size_t)256 << 20) / std::max(in_b, out_b));
+  chunk = std::min<size_t>(chunk, numReps);
+  if (N->s_imgs < chunk) {
+    cudaFree(N->s_in); cudaFree(N->s_out);
+    N->s_in = N->s_out = nullptr;
+    FCB_CUDA_OK(cudaMalloc(&N->s_in, in_b * chunk));
+    FCB_CUDA_OK(cudaMalloc(&N->s_out, out_b * chunk));
+    N->s_imgs = chunk;
+  }
+  for (size_t n0 = 0; n0 < numReps; n0 += chunk) {
+    const size_t nb = std::min<size_t>(chunk, numReps - n0);
+    FCB_CUDA_OK(cudaMemcpyAsync(N->s_in, (const uint8_t*)in_words + n0 * in_b, nb * in_b, cudaMemcpyHostToDevice, 0));
+    int rc = fcb_net_run_device(N, N->s_in, N->s_out, (uint32_t)nb, nullptr);
+    if (rc) return rc;
+    FCB_CUDA_OK(cudaMemcpyAsync((uint8_t*)out_words + n0 * out_b, N->s_out, nb * out_b, cudaMemcpyDeviceToHost, 0));
+  }
+  FCB_CUDA_OK(cudaStreamSynchronize(0));
+  return FCB_OK;
+}
+
+uint64_t fcb_net_launches(const fcb_net* N) {
+  uint64_t s = 0;
+  if (N) for (auto* l : N->layers) s += l->launches;
+  return s;
+}
+
+int fcb_synth_fill(void* d_ptr, size_t n_bytes, uint64_t seed, uint32_t mask, uint64_t offset, void* stream) {
+  if (!d_ptr) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  return synth_fill(d_ptr, n_bytes, seed, mask, offset, (cudaStream_t)stream);
+}
+
+}  // extern "C"

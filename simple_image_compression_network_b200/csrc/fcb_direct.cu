@@ -1,0 +1,177 @@
+// fcb_direct.cu -- direct (CUDA-core) convolution engines: "imad" and "xnor_popc".
+//
+// imad      : the universal integer path (any lane width <= 16 bits, +-1 / xnor weights, any activation).
+//             north_star: "IMAD for wider types".  Replaces, in one kernel,
+//             FMPadding_nonsquare (streamtools.h:361-406), the zero-insertion of deconv522
+//             (conv_nonsquare_top.cpp:109-156), ConvolutionInputGenerator_NonSquare
+//             (slidingwindow.h:1254-1353), Matrix_Vector_Activate_Batch (mvau.hpp:87-179) and the
+//             activation / bias-ReLU / pool stages.
+// xnor_popc : BinaryWeights + Recast<XnorMul> (weights.hpp:66-98, interpret.hpp:57-73) on bit-packed
+//             lanes: acc = sum over 32-bit words of popc(~(a ^ w)).
+//
+// Work decomposition (both): one CTA = 16x8 pre-pool output pixels x 64 output channels of one
+// image; a warp owns a 4x4 pixel block, a lane owns channels {l, l+32}; the input patch of the tile
+// is staged once in shared memory (zero padding / zero insertion resolved while staging), weights
+// are read through L1 as [k][channel] rows so a warp's 32 lanes load 32 consecutive values.
+#include "fcb_epilogue.cuh"
+
+namespace fcb {
+
+constexpr int TX = 16, TY = 8, PXB = 4;  // tile and per-warp pixel block
+constexpr int CH_PER_CTA = 64;
+
+__device__ __forceinline__ int32_t load_lane(const uint8_t* word, int c, int bits, int sgn) {
+  // bits in {1,2,4,8,16}: a lane never straddles a byte pair boundary beyond 16 bits
+  const size_t bit = (size_t)c * bits;
+  uint32_t v;
+  if (bits == 8) v = word[bit >> 3];
+  else if (bits == 16) v = (uint32_t)word[bit >> 3] | ((uint32_t)word[(bit >> 3) + 1] << 8);
+  else v = (word[bit >> 3] >> (bit & 7)) & ((1u << bits) - 1u);
+  if (sgn) {
+    const uint32_t m = 1u << (bits - 1);
+    return (int32_t)((v ^ m) - m);
+  }
+  return (int32_t)v;
+}
+
+// Maps a coordinate of the virtual padded frame to the input image; false = structural zero.
+__device__ __forceinline__ bool map_coord(int v, int pad, int deconv, int extent, int* src) {
+  if (!deconv) {
+    const int s = v - pad;
+    *src = s;
+    return s >= 0 && s < extent;
+  }
+  const int s = v - 2;  // deconv522: Z(2i,2j) = a(i,j), frame padded by 2
+  *src = s >> 1;
+  return s >= 0 && !(s & 1) && (s >> 1) < extent;
+}
+
+template <int ENGINE>
+__global__ void __launch_bounds__(256) direct_conv_kernel(const DirectParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+  const int img = blockIdx.z;
+  const int ch0 = blockIdx.y * CH_PER_CTA + lane;
+  const int ox0 = tx * TX, oy0 = ty * TY;
+  const int wx = (warp & 3) * PXB, wy = (warp >> 2) * PXB;  // this warp's 4x4 pixel block in the tile
+  const uint8_t* in = p.in + (size_t)img * p.in_img_bytes;
+
+  int32_t acc[PXB * PXB][2];
+#pragma unroll
+  for (int i = 0; i < PXB * PXB; i++) acc[i][0] = acc[i][1] = 0;
+
+  const int vx0 = ox0 * p.SXe, vy0 = oy0 * p.SYe;  // tile origin in the padded frame
+  // channel units: imad = lanes, xnor = 32-bit words of packed lanes
+  const int CU = (ENGINE == ENG_XNOR) ? (p.C >> 5) : p.C;
+
+  for (int c0 = 0; c0 < CU; c0 += p.CC) {
+    const int cc = min(p.CC, CU - c0);
+    // ---- stage the patch ------------------------------------------------------------
+    const int total = p.patch_h * p.patch_w * cc;
+    for (int idx = tid; idx < total; idx += blockDim.x) {
+      const int c = idx % cc, pix = idx / cc;
+      const int px = pix % p.patch_w, py = pix / p.patch_w;
+      int sx, sy;
+      const bool okx = map_coord(vx0 + px, p.PAD, p.deconv, p.IX, &sx);
+      const bool oky = map_coord(vy0 + py, p.PAD, p.deconv, p.IY, &sy);
+      if (ENGINE == ENG_XNOR) {
+        uint32_t v = 0;
+        if (okx && oky) v = reinterpret_cast<const uint32_t*>(in + ((size_t)sy * p.IX + sx) * p.in_word_bytes)[c0 + c];
+        reinterpret_cast<uint32_t*>(smem_raw)[idx] = v;
+      } else {
+        int32_t v = 0;
+        if (okx && oky) v = load_lane(in + ((size_t)sy * p.IX + sx) * p.in_word_bytes, c0 + c, p.in_bits, p.in_signed);
+        reinterpret_cast<int32_t*>(smem_raw)[idx] = v;
+      }
+    }
+    __syncthreads();
+    // ---- multiply-accumulate ----------------------------------------------------------
+    for (int ky = 0; ky < p.KY; ky++)
+      for (int kx = 0; kx < p.KX; kx++) {
+        const int kbase = (ky * p.KX + kx) * CU + c0;
+        for (int c = 0; c < cc; c++) {
+          const size_t wrow = (size_t)(kbase + c) * p.OFMp + ch0;
+          if (ENGINE == ENG_XNOR) {
+            const uint32_t* wt = reinterpret_cast<const uint32_t*>(p.wt);
+            const uint32_t w0 = __ldg(wt + wrow), w1 = __ldg(wt + wrow + 32);
+            const uint32_t* patch = reinterpret_cast<const uint32_t*>(smem_raw);
+#pragma unroll
+            for (int i = 0; i < PXB * PXB; i++) {
+              const int ly = wy + (i >> 2), lx = wx + (i & 3);
+              const uint32_t a = patch[((ly * p.SYe + ky) * p.patch_w + (lx * p.SXe + kx)) * cc + c];
+              acc[i][0] += __popc(~(a ^ w0));
+              acc[i][1] += __popc(~(a ^ w1));
+            }
+          } else {
+            const int16_t* wt = reinterpret_cast<const int16_t*>(p.wt);
+            const int32_t w0 = __ldg(wt + wrow), w1 = __ldg(wt + wrow + 32);
+            const int32_t* patch = reinterpret_cast<const int32_t*>(smem_raw);
+#pragma unroll
+            for (int i = 0; i < PXB * PXB; i++) {
+              const int ly = wy + (i >> 2), lx = wx + (i & 3);
+              const int32_t a = patch[((ly * p.SYe + ky) * p.patch_w + (lx * p.SXe + kx)) * cc + c];
+              if (p.mul_kind == FCB_W_BINARY_XNOR) {
+                acc[i][0] += (a == w0);
+                acc[i][1] += (a == w1);
+              } else {
+                acc[i][0] += a * w0;
+                acc[i][1] += a * w1;
+              }
+            }
+          }
+        }
+      }
+    __syncthreads();
+  }
+
+  // ---- activation, pool, store -----------------------------------------------------------
+  const int pk = p.epi.pool >= 2 ? p.epi.pool : 1;
+  uint8_t* out = p.out + (size_t)img * p.out_img_bytes;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int ch = ch0 + 32 * j;
+    const bool chv = ch < p.OFM;
+    uint32_t val[PXB * PXB];
+#pragma unroll
+    for (int i = 0; i < PXB * PXB; i++) val[i] = chv ? activate(p.epi, ch, acc[i][j]) : 0u;
+    for (int by = 0; by < PXB; by += pk)
+      for (int bx = 0; bx < PXB; bx += pk) {
+        const int oy = oy0 + wy + by, ox = ox0 + wx + bx;  // pre-pool pixel (warp-uniform)
+        if (oy >= p.OY || ox >= p.OX) continue;
+        uint32_t m = 0;
+        for (int dy = 0; dy < pk; dy++)
+          for (int dx = 0; dx < pk; dx++) m = max(m, val[(by + dy) * PXB + bx + dx]);
+        uint8_t* word = out + ((size_t)(oy / pk) * p.out_x + (ox / pk)) * p.out_word_bytes;
+        store_lane(word, ch, chv, m, p.epi.out_bits);
+      }
+  }
+}
+
+size_t direct_smem_bytes(int engine, int patch_w, int patch_h, int cc) {
+  (void)engine;
+  return (size_t)patch_w * patch_h * cc * 4;
+}
+
+int launch_direct(const DirectParams& p, int engine, int n_images, size_t smem_bytes, cudaStream_t st) {
+  dim3 grid(p.tiles_x * p.tiles_y, (p.OFM + CH_PER_CTA - 1) / CH_PER_CTA, 1);
+  // grid.z is limited to 65535 images per launch
+  for (int n0 = 0; n0 < n_images; n0 += 65535) {
+    DirectParams q = p;
+    const int nb = n_images - n0 < 65535 ? n_images - n0 : 65535;
+    q.in = p.in + (size_t)n0 * p.in_img_bytes;
+    q.out = p.out + (size_t)n0 * p.out_img_bytes;
+    grid.z = nb;
+    if (engine == ENG_XNOR) {
+      FCB_CUDA_OK(cudaFuncSetAttribute(direct_conv_kernel<ENG_XNOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      direct_conv_kernel<ENG_XNOR><<<grid, 256, smem_bytes, st>>>(q);
+    } else {
+      FCB_CUDA_OK(cudaFuncSetAttribute(direct_conv_kernel<ENG_IMAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      direct_conv_kernel<ENG_IMAD><<<grid, 256, smem_bytes, st>>>(q);
+    }
+    FCB_CUDA_OK(cudaGetLastError());
+  }
+  return FCB_OK;
+}
+
+}  // namespace fcb

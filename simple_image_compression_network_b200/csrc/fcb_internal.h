@@ -1,0 +1,69 @@
+// fcb_internal.h -- shared declarations of libfinnconv_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/finnconv_b200.h"
+
+namespace fcb {
+
+// ---- error plumbing ---------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define FCB_CUDA_OK(expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      fcb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return FCB_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+// ---- derived geometry -------------------------------------------------------------
+struct Geom {
+  int kind, C, OFM, KX, KY, IX, IY, OX, OY, SX, SY, PAD;
+  int simd, pe, SF, NF, K;
+  int in_bits, in_signed, w_bits, weight_kind;
+  int acc_bits, acc_signed, act_kind, out_bits, num_th, act_val, cmp, pool;
+  int out_x, out_y;  // after pooling
+  size_t in_word_bytes, out_word_bytes, in_img_bytes, out_img_bytes;
+  size_t w_word_bytes, weight_bytes, threshold_bytes, bias_bytes;
+};
+int derive_geom(const fcb_layer_desc* d, Geom* g);  // validates like the reference's CASSERTs
+
+// ---- epilogue parameters (device-visible POD) -----------------------------------------
+struct EpiParams {
+  int act_kind, acc_bits, acc_signed, out_bits, num_th, act_val, cmp, pool;
+  const int8_t* bias;    // [OFM]            (FCB_ACT_BIAS_RELU)
+  const int32_t* thr;    // [OFM][num_th] sorted ascending, wrapped to TA (FCB_ACT_THRESHOLDS)
+};
+
+// ---- engines ----------------------------------------------------------------------
+enum Engine { ENG_IMAD = 0, ENG_XNOR = 1, ENG_UMMA = 2 };
+
+struct DirectParams {  // imad / xnor_popc direct convolution
+  const uint8_t* in;
+  uint8_t* out;
+  const void* wt;  // imad: int16 [K][OFMp]; xnor: uint32 [KW][OFMp]
+  EpiParams epi;
+  int C, OFM, OFMp, KX, KY, IX, IY, OX, OY, SXe, SYe, PAD, deconv;
+  int in_bits, in_signed, in_word_bytes, out_word_bytes, out_x, out_y;
+  int tiles_x, tiles_y, CC, patch_w, patch_h, mul_kind;
+  unsigned long long in_img_bytes, out_img_bytes;
+};
+int launch_direct(const DirectParams& p, int engine, int n_images, size_t smem_bytes, cudaStream_t st);
+size_t direct_smem_bytes(int engine, int patch_w, int patch_h, int cc);
+
+// tcgen05 implicit GEMM (fcb_umma.cu)
+struct UmmaPlan;  // opaque to the API file
+int umma_eligible(const Geom& g);
+int umma_plan_create(const Geom& g, const std::vector<int32_t>& W /*[OFM][K]*/, const EpiParams& epi, int device, UmmaPlan** out);
+void umma_plan_destroy(UmmaPlan* p);
+int umma_run(UmmaPlan* p, const void* d_in, void* d_out, int n_images, cudaStream_t st, uint64_t* launches);
+
+// synthetic data (fcb_synth.cu)
+int synth_fill(void* d_ptr, size_t n_bytes, uint64_t seed, uint32_t mask, uint64_t offset, cudaStream_t st);
+
+}  // namespace fcb

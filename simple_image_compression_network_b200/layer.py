@@ -1,0 +1,125 @@
+"""Host-side mirror of the reference's layer interface over the C ABI.
+
+`ConvLayer` stands where an instantiation of conv2d<> / deconv522<> (conv_nonsquare_top.cpp:71-280)
+or ConvLayer_Batch (convlayer.h:89-125) stands in the reference: it is built from the same
+parameter set and the same packed weight / threshold / bias images, and `run(in_words, numReps)`
+has the meaning of `top(in_stream, out_stream, numReps)`.  `Net` chains layers the way
+eight_layers_net does (conv_nonsquare_top.cpp:295-357).  All compute happens in
+libfinnconv_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .desc import LayerDesc
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class ConvLayer:
+    def __init__(self, desc: LayerDesc, weights, thresholds=None, bias=None, device: int = 0):
+        L = _lib.lib()
+        self.desc = desc
+        self.device = device
+        c = desc.to_c()
+        sizes = [ctypes.c_size_t() for _ in range(5)]
+        _lib.check(L.fcb_layer_query(ctypes.byref(c), *[ctypes.byref(s) for s in sizes]))
+        self.in_bytes, self.out_bytes, self.weight_bytes, self.threshold_bytes, self.bias_bytes = [s.value for s in sizes]
+        w = np.ascontiguousarray(weights, dtype=np.uint8)
+        if w.size != self.weight_bytes:
+            raise ValueError(f"weight image is {w.size} bytes, expected {self.weight_bytes}")
+        t = None if thresholds is None else np.ascontiguousarray(thresholds, dtype=np.uint8)
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.uint8)
+        if t is not None and t.size != self.threshold_bytes:
+            raise ValueError(f"threshold image is {t.size} bytes, expected {self.threshold_bytes}")
+        if b is not None and b.size != self.bias_bytes:
+            raise ValueError(f"bias image is {b.size} bytes, expected {self.bias_bytes}")
+        h = ctypes.c_void_p()
+        _lib.check(L.fcb_layer_create(ctypes.byref(c), _ptr(w), _ptr(t), _ptr(b), device, ctypes.byref(h)))
+        self._h = h
+
+    @property
+    def engine(self) -> str:
+        return _lib.lib().fcb_layer_engine(self._h).decode()
+
+    @property
+    def launches(self) -> int:
+        return int(_lib.lib().fcb_layer_launches(self._h))
+
+    def run(self, in_words, num_reps: int = 1) -> np.ndarray:
+        """Host buffers in, host buffers out (H2D + kernels + D2H inside)."""
+        x = np.ascontiguousarray(in_words, dtype=np.uint8).reshape(-1)
+        if x.size != self.in_bytes * num_reps:
+            raise ValueError(f"input stream is {x.size} bytes, expected {self.in_bytes * num_reps}")
+        out = np.empty(self.out_bytes * num_reps, dtype=np.uint8)
+        _lib.check(_lib.lib().fcb_layer_run(self._h, _ptr(x), _ptr(out), num_reps))
+        return out
+
+    def run_raw(self, in_ptr: int, out_ptr: int, num_reps: int) -> None:
+        """Host pointers (e.g. pinned memory) -- the same call as run() without numpy."""
+        _lib.check(_lib.lib().fcb_layer_run(self._h, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), num_reps))
+
+    def run_device(self, d_in: int, d_out: int, num_reps: int, stream: int = 0) -> None:
+        """Device pointers, asynchronous on `stream` (a cudaStream_t handle as int)."""
+        _lib.check(_lib.lib().fcb_layer_run_device(self._h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), num_reps,
+                                                   ctypes.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().fcb_layer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Net:
+    """A chain of layers whose intermediate streams stay in device memory."""
+
+    def __init__(self, layers):
+        self.layers = list(layers)
+        arr = (ctypes.c_void_p * len(self.layers))(*[l._h for l in self.layers])
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().fcb_net_create(arr, len(self.layers), ctypes.byref(h)))
+        self._h = h
+        self.in_bytes = self.layers[0].in_bytes
+        self.out_bytes = self.layers[-1].out_bytes
+
+    @property
+    def launches(self) -> int:
+        return int(_lib.lib().fcb_net_launches(self._h))
+
+    def run(self, in_words, num_reps: int = 1) -> np.ndarray:
+        x = np.ascontiguousarray(in_words, dtype=np.uint8).reshape(-1)
+        if x.size != self.in_bytes * num_reps:
+            raise ValueError(f"input stream is {x.size} bytes, expected {self.in_bytes * num_reps}")
+        out = np.empty(self.out_bytes * num_reps, dtype=np.uint8)
+        _lib.check(_lib.lib().fcb_net_run(self._h, _ptr(x), _ptr(out), num_reps))
+        return out
+
+    def run_device(self, d_in: int, d_out: int, num_reps: int, stream: int = 0) -> None:
+        _lib.check(_lib.lib().fcb_net_run_device(self._h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), num_reps,
+                                                 ctypes.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().fcb_net_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def synth_fill(d_ptr: int, n_bytes: int, seed: int, mask: int = 0xFF, offset: int = 0, stream: int = 0) -> None:
+    _lib.check(_lib.lib().fcb_synth_fill(ctypes.c_void_p(d_ptr), n_bytes, seed, mask, offset, ctypes.c_void_p(stream)))

@@ -1,0 +1,217 @@
+"""Parity tests proper: the CUDA library (through the C ABI) against the plain-C oracle on identical packed
+bytes -- bit exact (all arithmetic is integer) -- and against the reference-made golden vectors."""
+import dataclasses
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _layer(d, inp, device=0):
+    from simple_image_compression_network_b200.layer import ConvLayer
+    return ConvLayer(d, inp["weights"], thresholds=inp["thresholds"], bias=inp["bias"], device=device)
+
+
+def _diff(a, b):
+    bad = np.flatnonzero(a != b)
+    return f"{bad.size}/{a.size} bytes differ; first at {bad[:8].tolist()}: got {a[bad[:8]].tolist()} want {b[bad[:8]].tolist()}"
+
+
+@pytest.mark.parametrize("name", [n for n in cases.CASES if n != "c2d_L1"])
+def test_layer_matches_oracle_and_golden(name, fcb_lib, oracle_mod):
+    assert fcb_lib.fcb_device_count() >= 1, "no sm_100 device: the CUDA path cannot be exercised"
+    d = cases.CASES[name]
+    inp = cases.make_inputs(d)
+    L = _layer(d, inp)
+    got = L.run(inp["in_words"])
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"])
+    assert np.array_equal(got, want), f"{name} [{L.engine}]: {_diff(got, want)}"
+    g = np.load(os.path.join(GOLD, f"layer_{name}.npz"))
+    assert _sha(got) == str(g["out_sha"]), f"{name}: differs from the reference-made golden"
+    assert L.launches >= 1
+
+
+@pytest.mark.parametrize("name", ["c2d_b", "c2d_e", "c2d_g", "dc_c", "dc_e", "th_b", "c2d_d"])
+def test_engines_agree(name, fcb_lib, oracle_mod, monkeypatch):
+    """The tensor-core engine and the universal IMAD engine give identical bytes."""
+    d = cases.CASES[name]
+    inp = cases.make_inputs(d, seed_shift=3, num_reps=3)
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=3)
+    L = _layer(d, inp)
+    got = L.run(inp["in_words"], 3)
+    assert np.array_equal(got, want), f"{name} [{L.engine}]: {_diff(got, want)}"
+    monkeypatch.setenv("FCB_FORCE_ENGINE", "imad")
+    L2 = _layer(d, inp)
+    assert L2.engine == "imad"
+    got2 = L2.run(inp["in_words"], 3)
+    assert np.array_equal(got2, want), f"{name} [imad]: {_diff(got2, want)}"
+
+
+def test_expected_engines(fcb_lib):
+    exp = {"c2d_e": "umma_i8", "c2d_g": "umma_i8", "dc_c": "umma_i8", "th_cfg4": "umma_i8", "c2d_c": "imad", "dc_d": "imad",
+           "xn_b": "xnor_popc", "xn_c": "xnor_popc", "xn_a": "imad", "c2d_L1band": "umma_i8"}
+    for name, eng in exp.items():
+        d = cases.CASES[name]
+        inp = cases.make_inputs(d)
+        assert _layer(d, inp).engine == eng, name
+
+
+@pytest.mark.parametrize("name,pool", [("th_b", 2), ("th_cfg4", 2), ("th_a", 2), ("xn_c", 0), ("th_d", 2), ("th_d", 4)])
+def test_fused_pool(name, pool, fcb_lib, oracle_mod):
+    """Threshold activation with the max pool fused into the epilogue (config 4)."""
+    d = dataclasses.replace(cases.CASES[name], pool=pool)
+    inp = cases.make_inputs(d, seed_shift=5)
+    L = _layer(d, inp)
+    got = L.run(inp["in_words"])
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"])
+    assert np.array_equal(got, want), f"{name} pool={pool} [{L.engine}]: {_diff(got, want)}"
+
+
+@pytest.mark.parametrize("cmp", [0, 1, 2, 3])
+def test_threshold_compare_variants(cmp, fcb_lib, oracle_mod):
+    d = dataclasses.replace(cases.CASES["th_a"], cmp=cmp)
+    inp = cases.make_inputs(d, seed_shift=cmp)
+    got = _layer(d, inp).run(inp["in_words"])
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], None)
+    assert np.array_equal(got, want)
+
+
+def test_unsorted_thresholds(fcb_lib, oracle_mod):
+    """Threshold order does not matter to the reference (it counts); the library sorts a private copy."""
+    from simple_image_compression_network_b200 import pack
+    d = cases.CASES["th_b"]
+    inp = cases.make_inputs(d)
+    rng = np.random.default_rng(1)
+    t = inp["t"].copy()
+    for row in t:
+        rng.shuffle(row)
+    timg = pack.pack_thresholds(t, d.pe, d.acc_bits)
+    from simple_image_compression_network_b200.layer import ConvLayer
+    got = ConvLayer(d, inp["weights"], thresholds=timg).run(inp["in_words"])
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], timg, None)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], None))
+
+
+def test_passthrough_and_signed_inputs(fcb_lib, oracle_mod):
+    from simple_image_compression_network_b200.desc import ACT_PASSTHROUGH
+    d = dataclasses.replace(cases.CASES["c2d_f"], act_kind=ACT_PASSTHROUGH, acc_bits=16, acc_signed=1, out_bits=16, in_signed=1)
+    inp = cases.make_inputs(d)
+    got = _layer(d, inp).run(inp["in_words"])
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], None, None)
+    assert np.array_equal(got, want)
+
+
+def test_pm1_binary_weights(fcb_lib, oracle_mod):
+    from simple_image_compression_network_b200.desc import ACT_PASSTHROUGH, W_BINARY_PM1
+    d = dataclasses.replace(cases.CASES["c2d_f"], weight_kind=W_BINARY_PM1, w_bits=1, act_kind=ACT_PASSTHROUGH, acc_bits=16,
+                            acc_signed=1, out_bits=16)
+    inp = cases.make_inputs(d)
+    got = _layer(d, inp).run(inp["in_words"])
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], None, None)
+    assert np.array_equal(got, want)
+
+
+def test_ragged_and_edge_shapes(fcb_lib, oracle_mod):
+    """Extents that do not fill the 128-pixel tiles / 16x8 CTAs, 1x1 kernels, single-row images."""
+    base = cases.CASES["c2d_e"]
+    for ix, iy in ((50, 34), (16, 2), (130, 6)):
+        d = dataclasses.replace(base, ifm_x=ix, ifm_y=iy)
+        inp = cases.make_inputs(d, seed_shift=ix)
+        L = _layer(d, inp)
+        got = L.run(inp["in_words"])
+        want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], None, inp["bias"])
+        assert np.array_equal(got, want), f"{ix}x{iy} [{L.engine}]: {_diff(got, want)}"
+    d = dataclasses.replace(cases.CASES["c2d_d"], kernel_x=1, kernel_y=1, pad=0, simd=16, ifm_x=7, ifm_y=1)
+    inp = cases.make_inputs(d)
+    assert np.array_equal(_layer(d, inp).run(inp["in_words"]), oracle_mod.run_layer(d, inp["in_words"], inp["weights"], None, inp["bias"]))
+
+
+def test_zero_reps_and_bad_sizes(fcb_lib):
+    d = cases.CASES["c2d_a"]
+    inp = cases.make_inputs(d)
+    L = _layer(d, inp)
+    assert L.run(np.zeros(0, np.uint8), 0).size == 0
+    with pytest.raises(ValueError):
+        L.run(inp["in_words"][:-1])
+
+
+def test_batch_images_are_independent(fcb_lib, oracle_mod):
+    """numReps images = numReps single-image applications; checks image boundaries inside tiles."""
+    d = cases.CASES["c2d_g"]
+    inp = cases.make_inputs(d, num_reps=5)
+    L = _layer(d, inp)
+    got = L.run(inp["in_words"], 5)
+    per = L.in_bytes
+    for n in (0, 4):
+        one = L.run(inp["in_words"][n * per:(n + 1) * per], 1)
+        assert np.array_equal(one, got[n * L.out_bytes:(n + 1) * L.out_bytes])
+    assert np.array_equal(got, oracle_mod.run_layer(d, inp["in_words"], inp["weights"], None, inp["bias"], num_reps=5))
+
+
+def test_conv1_full_size_properties(fcb_lib, oracle_mod):
+    """CONV_1 (config_nonsquare.h:18-33) at full size: golden digest of image 0 + per-image independence +
+    linearity-style property (zero input -> relu(bias))."""
+    d = cases.CASES["c2d_L1"]
+    inp = cases.make_inputs(d)
+    L = _layer(d, inp)
+    assert L.engine == "umma_i8"
+    got = L.run(inp["in_words"])
+    g = np.load(os.path.join(GOLD, "layer_c2d_L1.npz"))
+    assert np.array_equal(got[:4096], g["head"])
+    assert _sha(got) == str(g["out_sha"])
+    zero = L.run(np.zeros(L.in_bytes, np.uint8))
+    b = inp["b"] % 256
+    exp = np.where(b >= 128, 0, b).astype(np.uint8)
+    assert np.array_equal(zero.reshape(-1, 128), np.broadcast_to(exp, (d.ofm_x * d.ofm_y, 128)))
+
+
+def test_net_chain_matches_layerwise_oracle(fcb_lib, oracle_mod):
+    """Net (eight_layers_net-style chain, intermediates on device) == oracle applied layer by layer."""
+    from simple_image_compression_network_b200.layer import Net
+    d1 = cases.CASES["c2d_e"]                                   # 128ch 48x32 -> 24x16
+    d2 = dataclasses.replace(cases.CASES["dc_c"], ifm_x=24, ifm_y=16)  # deconv back to 48x32
+    i1, i2 = cases.make_inputs(d1, num_reps=2, relu_range=True), cases.make_inputs(d2, seed_shift=9)
+    L1, L2 = _layer(d1, i1), _layer(d2, i2)
+    net = Net([L1, L2])
+    got = net.run(i1["in_words"], 2)
+    mid = oracle_mod.run_layer(d1, i1["in_words"], i1["weights"], None, i1["bias"], num_reps=2)
+    want = oracle_mod.run_layer(d2, mid, i2["weights"], None, i2["bias"], num_reps=2)
+    assert np.array_equal(got, want)
+    assert net.launches >= 2
+
+
+def test_device_synth_matches_host(fcb_lib):
+    import torch
+    from simple_image_compression_network_b200 import synth
+    from simple_image_compression_network_b200.layer import synth_fill
+    n = 1 << 16
+    buf = torch.empty(n + 5, dtype=torch.uint8, device="cuda")
+    synth_fill(buf.data_ptr(), n + 5, synth.SEED_INPUT, 0x7F, offset=123)
+    torch.cuda.synchronize()
+    want = synth.lanes(synth.SEED_INPUT, (n + 5,), 8, mask=0x7F, offset=123).astype(np.uint8)
+    assert np.array_equal(buf.cpu().numpy(), want)
+
+
+def test_run_device_pointers(fcb_lib, oracle_mod):
+    """fcb_layer_run_device on torch-owned device memory (the bench's device-resident path)."""
+    import torch
+    d = cases.CASES["c2d_e"]
+    inp = cases.make_inputs(d, num_reps=2)
+    L = _layer(d, inp)
+    x = torch.from_numpy(inp["in_words"]).cuda()
+    y = torch.empty(L.out_bytes * 2, dtype=torch.uint8, device="cuda")
+    L.run_device(x.data_ptr(), y.data_ptr(), 2, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], None, inp["bias"], num_reps=2)
+    assert np.array_equal(y.cpu().numpy(), want)
