@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: conv-layer images/sec at 1/2/4/8 B200).
+
+Workload (config[1] of BASELINE.json): the CONV_1 layer of config_nonsquare.h:18-33 (128->128 channels,
+384x256 -> 192x128, K5 S2 P2, u8 activations x s4 weights, 8-bit wrap + bias + ReLU) on a batch of 4096
+synthetic images per GPU, images sharded over the GPUs with no collective (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (torchrun for N > 1)
+  python bench.py --impl reference [...]                         the reference's own CPU implementation
+
+One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = images/s through
+the host-buffer C-ABI call (pinned host memory, H2D + kernel + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "conv_layer_images_per_sec"
+UNIT = "images/s"
+IMAGES_PER_GPU = 4096
+E2E_IMAGES = 512
+WORKLOAD = ("CONV_1 of config_nonsquare.h (128->128 ch, 384x256 -> 192x128, K5 S2 P2, u8 x s4, wrap8+bias+ReLU), "
+            "synthetic images, batch sharded over GPUs")
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own conv2d<> (oracle/_ref, built from /root/reference)
+# ---------------------------------------------------------------------------------------------------
+def _ref_band_worker(_):
+    """One CONV_1 band (384x32 input rows -> 192x16 output = 1/8 image) through the reference's conv2d<>."""
+    from oracle import cases, oracle
+    d = cases.CASES["c2d_L1band"]
+    inp = cases.make_inputs(d)
+    s = oracle.query(d)
+    if oracle.ref_available():
+        _, secs = oracle.ref_run("c2d_L1band", inp["in_words"], inp["weights"], inp["bias"], s.out_bytes_per_image)
+        return secs, "reference"
+    t0 = time.perf_counter()
+    oracle.set_threads(1)
+    oracle.run_layer(d, inp["in_words"], inp["weights"], None, inp["bias"])
+    return time.perf_counter() - t0, "port"
+
+
+def cpu_reference_step(pool, cores: int):
+    """One step = `cores` bands in parallel (one process per core). Returns (images/s, wall seconds, kind)."""
+    t0 = time.perf_counter()
+    res = pool.map(_ref_band_worker, range(cores))
+    wall = time.perf_counter() - t0
+    return cores * (1.0 / 8.0) / wall, wall, res[0][1]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_reference_step(pool, cores)
+        t0 = time.perf_counter()
+        kind = "reference"
+        for _ in range(args.steps):
+            _, _, kind = cpu_reference_step(pool, cores)
+        total = time.perf_counter() - t0
+    value = args.steps * cores * (1.0 / 8.0) / total
+    sample = (f"per step: {cores} bands of CONV_1 (384x32 input rows -> 192x16 output rows, 1/8 image each), one process per core, "
+              f"through the reference's conv2d<> template ({'oracle/_ref' if kind == 'reference' else 'oracle C port'})")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_step": cores / 8.0},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from simple_image_compression_network_b200 import configs, synth
+    from simple_image_compression_network_b200.layer import ConvLayer, synth_fill
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    d = configs.net_layer(1)  # CONV_1
+    inp = configs.synthetic_params(d)  # weights / bias (the input is generated on the device)
+    layer = ConvLayer(d, inp["weights"], bias=inp["bias"], device=local)
+    n_img = args.images
+    free, _ = torch.cuda.mem_get_info()
+    need = n_img * (layer.in_bytes + layer.out_bytes)
+    if need > free * 0.9:
+        n_img = max(1, int(free * 0.9 // (layer.in_bytes + layer.out_bytes)))
+    x = torch.empty(n_img * layer.in_bytes, dtype=torch.uint8, device="cuda")
+    y = torch.empty(n_img * layer.out_bytes, dtype=torch.uint8, device="cuda")
+    # this rank's images: global indices [rank*n_img, (rank+1)*n_img); lanes 0..127 (post-ReLU range of the previous layer)
+    synth_fill(x.data_ptr(), x.numel(), synth.SEED_INPUT, 0x7F, offset=rank * n_img * layer.in_bytes)
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    sh = stream.cuda_stream
+
+    def step():
+        layer.run_device(x.data_ptr(), y.data_ptr(), n_img, sh)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = layer.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = layer.launches - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n_img * args.steps / (ms_max / 1000.0)
+
+    # spot check on the device-generated data: image 0 of this rank against the oracle is done in tests; here a cheap
+    # sanity: output bytes are in 0..127 (ReLU on the wrapped 8-bit value)
+    assert int(y[: layer.out_bytes].max().item()) <= 127
+
+    # ---- e2e: host buffers (pinned) -> C-ABI host call -> host buffers, copies inside the timed region
+    e_img = min(args.e2e_images, n_img)
+    hx = torch.empty(e_img * layer.in_bytes, dtype=torch.uint8, pin_memory=True)
+    hy = torch.empty(e_img * layer.out_bytes, dtype=torch.uint8, pin_memory=True)
+    hx.copy_(x[: e_img * layer.in_bytes])
+    torch.cuda.synchronize()
+    e_steps = max(2, min(args.steps, 5))
+    layer.run_raw(hx.data_ptr(), hy.data_ptr(), e_img)  # warm-up (allocates the staging slots)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        layer.run_raw(hx.data_ptr(), hy.data_ptr(), e_img)
+    e_s = time.perf_counter() - t0
+    te = torch.tensor([e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e_img * e_steps / float(te.item())
+    assert torch.equal(hy[: layer.out_bytes].cuda(), y[: layer.out_bytes])
+
+    # ---- roofline of the dominant kernel (the only kernel in the step)
+    peaks, src = _peaks()
+    kernel_ms = ms / args.steps  # one launch per step, back to back on one stream
+    ops = 2.0 * d.macs_per_image * n_img
+    achieved = ops / (kernel_ms / 1000.0) / 1e12
+    peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "umma_conv_kernel<stride2>", "kernel_ms": kernel_ms,
+                "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({src}); dense int8 tensor rate is 2x bf16 on sm_100; "
+                               "ops are int8 MACs x 2 (TOP/s)",
+                "frac_of_spec_4500_TOPs": achieved / 4500.0,
+                "algorithmic_bytes_per_image": layer.in_bytes + layer.out_bytes,
+                "hbm_GBs_at_this_rate": (layer.in_bytes + layer.out_bytes) * n_img / (kernel_ms / 1000.0) / 1e9}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu": n_img, "engine": layer.engine,
+                       "l2": f"inputs ({n_img * layer.in_bytes / 1e9:.1f} GB per GPU) are larger than L2; no flush needed",
+                       "parallelism": f"batch sharding x{world}, no collective"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e_img * layer.in_bytes,
+                    "d2h_bytes_per_step": e_img * layer.out_bytes, "images_per_step": e_img, "steps": e_steps},
+            "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = max(1, min(os.cpu_count() or 1, 64))
+        with mp.get_context("spawn").Pool(cores) as pool:
+            cpu_reference_step(pool, cores)  # warm (library load)
+            v, wall, kind = cpu_reference_step(pool, cores)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{cores} bands of CONV_1 (1/8 image each) in parallel, one process per core, {wall:.1f} s wall"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=IMAGES_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--e2e-images", type=int, default=E2E_IMAGES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

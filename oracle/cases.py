@@ -69,30 +69,9 @@ SLOW = {"c2d_L1": 30, "c2d_L1band": 4, "dc_L4": 12, "th_cfg4": 8, "xn_b": 30, "d
 
 def make_inputs(d: LayerDesc, seed_shift: int = 0, num_reps: int = 1, relu_range: bool = False):
     """Seeded synthetic tensors for a case -> dict of logical arrays and packed images."""
-    k = d.k_total
-    x = synth.lanes(synth.SEED_INPUT + seed_shift, (num_reps, d.ifm_y, d.ifm_x, d.ifm_ch), d.in_bits,
-                    signed=bool(d.in_signed), mask=(0x7F if (relu_range and d.in_bits == 8) else None))
-    w = synth.weights(synth.SEED_WEIGHTS + seed_shift, d.ofm_ch, k, d.w_bits)
-    out = {"x": x, "w": w, "in_words": pack.pack_stream(x, d.in_bits), "weights": pack.pack_weights(w, d.simd, d.pe, d.w_bits),
-           "bias": None, "thresholds": None, "b": None, "t": None}
-    if d.act_kind == ACT_BIAS_RELU:
-        b = synth.bias(synth.SEED_BIAS + seed_shift, d.ofm_ch)
-        out["b"], out["bias"] = b, pack.pack_bias(b)
-    if d.act_kind == ACT_THRESHOLDS:
-        if d.weight_kind == W_BINARY_XNOR:
-            # matches ~ Binomial(K, 1/2): thresholds around K/2 +- 2 sigma discriminate
-            lo, hi = int(k / 2 - k ** 0.5), int(k / 2 + k ** 0.5)
-        else:
-            # thresholds where they discriminate: mean +- 2.5 sigma of sum_k w_k*a_k for uniform lanes
-            av = np.arange(1 << d.in_bits, dtype=np.float64) - ((1 << (d.in_bits - 1)) if d.in_signed else 0)
-            wv = np.arange(1 << d.w_bits, dtype=np.float64) - (1 << (d.w_bits - 1))
-            mean = k * wv.mean() * av.mean()
-            sigma = (k * ((wv ** 2).mean() * (av ** 2).mean() - (wv.mean() * av.mean()) ** 2)) ** 0.5
-            lo, hi = int(mean - 2.5 * sigma), int(mean + 2.5 * sigma)
-        lim = (1 << (d.acc_bits - 1)) - 1
-        lo, hi = max(lo, -lim - 1), min(hi, lim)
-        t = synth.thresholds(synth.SEED_THRESH + seed_shift, d.ofm_ch, d.num_th, lo, hi)
-        out["t"], out["thresholds"] = t, pack.pack_thresholds(t, d.pe, d.acc_bits)
+    from simple_image_compression_network_b200 import configs
+    out = configs.synthetic_params(d, seed_shift)
+    out["x"], out["in_words"] = configs.synthetic_input(d, seed_shift, num_reps, relu_range)
     return out
 
 
