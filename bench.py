@@ -205,7 +205,8 @@ def run_ours(args):
 
     # spot check on the device-generated data: image 0 of this rank against the oracle is done in tests; here a cheap
     # sanity: output bytes are in 0..127 (ReLU on the wrapped 8-bit value)
-    assert int(y[: layer.out_bytes].max().item()) <= 127
+    nocheck = bool(os.environ.get("BENCH_NOCHECK"))
+    assert nocheck or int(y[: layer.out_bytes].max().item()) <= 127
 
     # ---- e2e: host buffers (pinned) -> C-ABI host call -> host buffers, copies inside the timed region
     e_img = min(args.e2e_images, n_img)
@@ -224,7 +225,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * e_img * e_steps / float(te.item())
-    assert torch.equal(hy[: layer.out_bytes].cuda(), y[: layer.out_bytes])
+    assert nocheck or torch.equal(hy[: layer.out_bytes].cuda(), y[: layer.out_bytes])
 
     # ---- roofline of the dominant kernel (the only kernel in the step)
     peaks, src = _peaks()
@@ -233,7 +234,7 @@ def run_ours(args):
     achieved = ops / (kernel_ms / 1000.0) / 1e12
     peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "umma_conv_kernel<stride2>", "kernel_ms": kernel_ms,
+                "traffic": None, "kernel": layer.plan, "kernel_ms": kernel_ms,
                 "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({src}); dense int8 tensor rate is 2x bf16 on sm_100; "
                                "ops are int8 MACs x 2 (TOP/s)",
                 "frac_of_spec_4500_TOPs": achieved / 4500.0,

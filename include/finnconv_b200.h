@@ -136,6 +136,8 @@ FCB_API int fcb_layer_run(fcb_layer* layer, const void* in_words, void* out_word
 FCB_API int fcb_layer_run_device(fcb_layer* layer, const void* d_in, void* d_out, uint32_t numReps, void* stream);
 /* Which kernel family serves this layer: "umma_i8", "imad", "xnor_popc" (diagnostics / tests). */
 FCB_API const char* fcb_layer_engine(const fcb_layer* layer);
+/* Human-readable tiling plan of the layer (tile shape, shared-memory planes, pipeline depth). */
+FCB_API const char* fcb_layer_plan(const fcb_layer* layer);
 /* Number of kernel launches issued by this layer since creation. */
 FCB_API uint64_t fcb_layer_launches(const fcb_layer* layer);
 

@@ -41,6 +41,8 @@ def lib() -> ctypes.CDLL:
     L.fcb_layer_run_device.argtypes = [vp, vp, vp, u32, vp]
     L.fcb_layer_engine.argtypes = [vp]
     L.fcb_layer_engine.restype = ctypes.c_char_p
+    L.fcb_layer_plan.argtypes = [vp]
+    L.fcb_layer_plan.restype = ctypes.c_char_p
     L.fcb_layer_launches.argtypes = [vp]
     L.fcb_layer_launches.restype = u64
     L.fcb_net_create.argtypes = [ctypes.POINTER(vp), u32, ctypes.POINTER(vp)]

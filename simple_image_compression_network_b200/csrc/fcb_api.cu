@@ -304,6 +304,10 @@ const char* fcb_layer_engine(const fcb_layer* L) {
   if (!L) return "";
   return L->engine == ENG_UMMA ? "umma_i8" : L->engine == ENG_XNOR ? "xnor_popc" : "imad";
 }
+const char* fcb_layer_plan(const fcb_layer* L) {
+  if (!L) return "";
+  return L->engine == ENG_UMMA ? umma_plan_describe(L->umma) : "direct 16x8-pixel x 64-channel CTA tiles";
+}
 uint64_t fcb_layer_launches(const fcb_layer* L) { return L ? L->launches : 0; }
 
 int fcb_layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, void* stream) {

@@ -163,10 +163,10 @@ int launch_direct(const DirectParams& p, int engine, int n_images, size_t smem_b
     q.out = p.out + (size_t)n0 * p.out_img_bytes;
     grid.z = nb;
     if (engine == ENG_XNOR) {
-      FCB_CUDA_OK(cudaFuncSetAttribute(direct_conv_kernel<ENG_XNOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      FCB_CUDA_OK(cudaFuncSetAttribute(direct_conv_kernel<ENG_XNOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       direct_conv_kernel<ENG_XNOR><<<grid, 256, smem_bytes, st>>>(q);
     } else {
-      FCB_CUDA_OK(cudaFuncSetAttribute(direct_conv_kernel<ENG_IMAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      FCB_CUDA_OK(cudaFuncSetAttribute(direct_conv_kernel<ENG_IMAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       direct_conv_kernel<ENG_IMAD><<<grid, 256, smem_bytes, st>>>(q);
     }
     FCB_CUDA_OK(cudaGetLastError());

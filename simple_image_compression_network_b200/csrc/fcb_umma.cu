@@ -23,6 +23,7 @@
 
 #include "fcb_epilogue.cuh"
 #include "fcb_sm100.cuh"
+#include "fcb_umma_common.h"
 
 namespace fcb {
 
@@ -64,6 +65,9 @@ struct UmmaPlan {
   UmmaParams p;
   size_t smem = 0;
   int num_sms = 148;
+  int w_copies = 1;
+  Umma2Plan* v2 = nullptr;  // shared-memory-resident-patch main loop (fcb_umma2.cu) when the layer qualifies
+  char desc[160] = "v1 per-tap TMA";
 };
 
 // ------------------------------------------------------------------------------------------
@@ -252,7 +256,7 @@ static PFN_encodeTiled get_encode() {
   }
   return fn;
 }
-static int encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+int umma_encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FCB_ERR_CUDA; }
   cuuint64_t gd[5], gs[4];
@@ -356,25 +360,39 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   P->num_sms = prop.multiProcessorCount;
 
   // weights: s8 [N][K], K contiguous (k = (ky*KX+kx)*C + c) -- the implicit-GEMM B operand
+  // Replicated so that the 148 CTAs streaming the same K-blocks do not all hit the same L2 lines.
+  const int copies = getenv("FCB_W_COPIES") ? std::max(1, atoi(getenv("FCB_W_COPIES"))) : 1;
+  P->w_copies = copies;
   std::vector<int8_t> w8((size_t)p.N * g.K);
   for (size_t i = 0; i < w8.size(); i++) w8[i] = (int8_t)W[i];
-  FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size()));
-  FCB_CUDA_OK(cudaMemcpy(P->d_w, w8.data(), w8.size(), cudaMemcpyHostToDevice));
+  FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size() * copies));
+  for (int c = 0; c < copies; c++) FCB_CUDA_OK(cudaMemcpy(P->d_w + (size_t)c * w8.size(), w8.data(), w8.size(), cudaMemcpyHostToDevice));
   {
-    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)p.N};
+    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)p.N * copies};
     const uint64_t strides[1] = {(uint64_t)g.K};
     const uint32_t box[2] = {(uint32_t)KCH, (uint32_t)p.N};
-    int rc = encode_map(&P->tmB, P->d_w, 2, dims, strides, box);
+    int rc = umma_encode_map(&P->tmB, P->d_w, 2, dims, strides, box);
     if (rc) { umma_plan_destroy(P); return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem));
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem));
+  {
+    const char* v1only = getenv("FCB_UMMA_V1");
+    if (!(v1only && v1only[0] == '1')) {
+      int rc2 = umma2_plan_create(g, &P->tmB, epi, P->num_sms, P->w_copies, &P->v2);
+      if (rc2 == FCB_OK) umma2_describe(P->v2, P->desc, sizeof(P->desc));
+      else if (rc2 != FCB_ERR_UNSUPPORTED) { umma_plan_destroy(P); return rc2; }
+    }
+  }
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = P;
   return FCB_OK;
 }
 
+const char* umma_plan_describe(const UmmaPlan* P) { return P ? P->desc : ""; }
+
 void umma_plan_destroy(UmmaPlan* P) {
   if (!P) return;
+  if (P->v2) umma2_plan_destroy(P->v2);
   cudaFree(P->d_w);
   delete P;
 }
@@ -383,6 +401,11 @@ int umma_run(UmmaPlan* P, const void* d_in, void* d_out, int n_images, cudaStrea
   const Geom& g = P->g;
   UmmaParams p = P->p;
   if (((uintptr_t)d_in & 15) || ((uintptr_t)d_out & 15)) { set_error("device buffers must be 16-byte aligned"); return FCB_ERR_INVALID_ARG; }
+  if (P->v2) {
+    int rc2 = umma2_run(P->v2, d_in, d_out, n_images, st);
+    if (rc2 == FCB_OK && launches) (*launches)++;
+    return rc2;
+  }
   p.out = (uint8_t*)d_out;
   p.n_images = n_images;
   CUtensorMap tmA;
@@ -393,13 +416,13 @@ int umma_run(UmmaPlan* P, const void* d_in, void* d_out, int n_images, cudaStrea
     const uint64_t dims[5] = {2 * C, X / 2, 2, Y / 2, (uint64_t)n_images};
     const uint64_t strides[4] = {2 * C, X * C, 2 * X * C, X * Y * C};
     const uint32_t box[5] = {(uint32_t)KCH, (uint32_t)p.BW, 1, (uint32_t)p.BH, 1};
-    rc = encode_map(&tmA, const_cast<void*>(d_in), 5, dims, strides, box);
+    rc = umma_encode_map(&tmA, const_cast<void*>(d_in), 5, dims, strides, box);
   } else {
     const uint64_t C = g.C, X = g.IX, Y = g.IY;
     const uint64_t dims[4] = {C, X, Y, (uint64_t)n_images};
     const uint64_t strides[3] = {C, X * C, X * Y * C};
     const uint32_t box[4] = {(uint32_t)KCH, (uint32_t)p.BW, (uint32_t)p.BH, 1};
-    rc = encode_map(&tmA, const_cast<void*>(d_in), 4, dims, strides, box);
+    rc = umma_encode_map(&tmA, const_cast<void*>(d_in), 4, dims, strides, box);
   }
   if (rc) return rc;
   const long long total = (long long)p.nphases * p.tiles_x * p.tiles_y * n_images;

@@ -48,6 +48,10 @@ class ConvLayer:
         return _lib.lib().fcb_layer_engine(self._h).decode()
 
     @property
+    def plan(self) -> str:
+        return _lib.lib().fcb_layer_plan(self._h).decode()
+
+    @property
     def launches(self) -> int:
         return int(_lib.lib().fcb_layer_launches(self._h))
 

@@ -35,7 +35,7 @@ def test_layer_matches_oracle_and_golden(name, fcb_lib, oracle_mod):
     L = _layer(d, inp)
     got = L.run(inp["in_words"])
     want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"])
-    assert np.array_equal(got, want), f"{name} [{L.engine}]: {_diff(got, want)}"
+    assert np.array_equal(got, want), f"{name} [{L.engine}: {L.plan}]: {_diff(got, want)}"
     g = np.load(os.path.join(GOLD, f"layer_{name}.npz"))
     assert _sha(got) == str(g["out_sha"]), f"{name}: differs from the reference-made golden"
     assert L.launches >= 1
@@ -55,6 +55,24 @@ def test_engines_agree(name, fcb_lib, oracle_mod, monkeypatch):
     assert L2.engine == "imad"
     got2 = L2.run(inp["in_words"], 3)
     assert np.array_equal(got2, want), f"{name} [imad]: {_diff(got2, want)}"
+
+
+@pytest.mark.parametrize("name", ["c2d_e", "c2d_g", "dc_c", "th_cfg4", "c2d_L1band", "c2d_d"])
+def test_umma_generations_agree(name, fcb_lib, oracle_mod, monkeypatch):
+    """Resident-patch main loop (fcb_umma2.cu) and per-tap-TMA main loop (fcb_umma.cu) against the oracle."""
+    d = cases.CASES[name]
+    if not (d.ifm_ch % 128 == 0 and d.ofm_ch % 32 == 0):
+        pytest.skip("not a tensor-core shape")
+    inp = cases.make_inputs(d, seed_shift=11, num_reps=2)
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=2)
+    L = _layer(d, inp)
+    got = L.run(inp["in_words"], 2)
+    assert np.array_equal(got, want), f"{name} [{L.engine}: {L.plan}]: {_diff(got, want)}"
+    monkeypatch.setenv("FCB_UMMA_V1", "1")
+    L1 = _layer(d, inp)
+    assert L1.plan.startswith("v1")
+    got1 = L1.run(inp["in_words"], 2)
+    assert np.array_equal(got1, want), f"{name} [{L1.engine}: {L1.plan}]: {_diff(got1, want)}"
 
 
 def test_expected_engines(fcb_lib):
