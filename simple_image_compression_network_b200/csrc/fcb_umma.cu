@@ -65,7 +65,6 @@ struct UmmaPlan {
   UmmaParams p;
   size_t smem = 0;
   int num_sms = 148;
-  int w_copies = 1;
   Umma2Plan* v2 = nullptr;  // shared-memory-resident-patch main loop (fcb_umma2.cu) when the layer qualifies
   char desc[160] = "v1 per-tap TMA";
 };
@@ -360,9 +359,7 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   P->num_sms = prop.multiProcessorCount;
 
   // weights: s8 [N][K], K contiguous (k = (ky*KX+kx)*C + c) -- the implicit-GEMM B operand
-  // Replicated so that the 148 CTAs streaming the same K-blocks do not all hit the same L2 lines.
-  const int copies = getenv("FCB_W_COPIES") ? std::max(1, atoi(getenv("FCB_W_COPIES"))) : 1;
-  P->w_copies = copies;
+  const int copies = 1;
   std::vector<int8_t> w8((size_t)p.N * g.K);
   for (size_t i = 0; i < w8.size(); i++) w8[i] = (int8_t)W[i];
   FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size() * copies));
@@ -377,7 +374,7 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   {
     const char* v1only = getenv("FCB_UMMA_V1");
     if (!(v1only && v1only[0] == '1')) {
-      int rc2 = umma2_plan_create(g, &P->tmB, epi, P->num_sms, P->w_copies, &P->v2);
+      int rc2 = umma2_plan_create(g, P->d_w, epi, P->num_sms, &P->v2);
       if (rc2 == FCB_OK) umma2_describe(P->v2, P->desc, sizeof(P->desc));
       else if (rc2 != FCB_ERR_UNSUPPORTED) { umma_plan_destroy(P); return rc2; }
     }

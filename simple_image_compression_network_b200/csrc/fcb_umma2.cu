@@ -1,30 +1,33 @@
-// fcb_umma2.cu -- "umma_i8" second-generation main loop: shared-memory-RESIDENT input patch.
+// fcb_umma2.cu -- "umma_i8" main loop with a shared-memory-RESIDENT input patch, pixels on the MMA N axis.
 //
-// The first-generation kernel (fcb_umma.cu) re-fetches a 128-pixel A tile from L2 for every filter tap, so a
-// 5x5 layer pulls each input byte ~6x through the L2->SM path and sits at ~35 % tensor-pipe utilisation with the
-// SM fill rate (~37 B/clk/SM measured) as the limiter (profiles/r01_v1_ncu_full_summary.txt).  Here the patch of
-// input pixels that a tile of R x WT output pixels needs is loaded ONCE per tile into "planes" and every tap's A
-// operand is just a different 128-byte-row offset into a plane:
+// Why not the first-generation kernel (fcb_umma.cu)?  It re-fetches a 128-pixel A tile from L2 for every filter
+// tap (each input byte crosses L2->SM ~6x for a 5x5 layer) and issues M=128 x N=128 x K=32 instructions, whose
+// ~100-clock per-instruction floor (profiles/r01_umma_issue_pattern_study.log) caps the tensor pipe near 50 %.
 //
-//   plane(py,px,cc)[j][i][0..127]  = 128 channels (chunk cc) of input pixel (y, x) with
+// Here (1) the patch of input pixels a tile of R x WT output pixels needs is loaded ONCE per tile into "planes":
+//
+//   plane(py,px,cc)[j][i][0..127] = 128 channels (chunk cc) of input pixel (y, x) with
 //        stride 2:  y = 2*(y0 + dy + j) + py,  x = 2*(x0 + dx + i) + px      (parity split of the NHWC image)
 //        stride 1:  y = y0 + dy + j,           x = x0 + dx + i               (also the 4 phases of deconv522)
-//   rows are P = WT + halo pixels wide and stored back to back, so the linear row index  m = r*P + xo  of output
-//   pixel (r, xo) of the tile maps, for tap (offy, offx), to plane row  m + (offy-dy)*P + (offx-dx):
-//   ONE contiguous, uniformly strided K-major SWIZZLE_128B operand per tap.  The xo >= WT columns of each row
-//   are computed and discarded (WT/P efficiency, 96 % for WT=48).  Descriptor start addresses that are multiples
-//   of 128 B (not 1024 B) are legal: the swizzle XOR is taken from the absolute smem address bits, verified on
-//   hardware by tools/umma_probe.cu (profiles/r01_umma_probe.log, "P3 ... base_offset=0 : PASS").
+//   rows are P = WT + halo pixels wide and stored back to back, so output pixel (r, xo) of the tile, linear index
+//   m = r*P + xo, reads for tap (offy, offx) plane row  m + (offy-dy)*P + (offx-dx): ONE contiguous, uniformly
+//   strided K-major SWIZZLE_128B operand per tap -- the sliding window (slidingwindow.h:1254-1353) is a descriptor
+//   offset.  Columns xo >= WT of each row are computed and discarded (WT/P efficiency).  Operand start addresses
+//   that are multiples of 128 B (not 1024 B) are legal: the swizzle XOR uses absolute smem address bits, verified
+//   on hardware (tools/umma_probe.cu, profiles/r01_umma_probe.log "P3 ... base_offset=0 : PASS").
 //
-// Same replacement table as fcb_umma.cu (padding = TMA OOB zero fill, sliding window = plane offsets, deconv zero
-// insertion = 4 output phases over one shared plane set, MVAU = tcgen05.mma kind::i8, activation = epilogue).
-// Per tile the L2->SM traffic drops from taps*(16 KB + N*128 B) to planes + taps*N*128 B.
+// and (2) the GEMM is transposed:  D[ch][pixel] = W[ch][k] * Patch[pixel][k]^T  with M = 128 output channels
+// (A operand = weight tile), N = up to 256 pixels (B operand = plane window): twice the MACs per tcgen05.mma.
+// The epilogue thread then owns ONE channel (bias / thresholds are per-thread constants) and its 32-column TMEM
+// loads are 32 consecutive pixels, so the 2x2 max pool is register-local.
 //
-// Pipeline: warp 0 = TMA producer (planes + weight K-blocks), warp 1 = MMA issuer, warps 2..5 = epilogue.
-//   plane p      : full/empty mbarrier pair, one fill per tile; freed as soon as its last tap has been issued, so
-//                  the next tile's plane streams in while the remaining taps of this tile run
-//   weight ring  : WSTAGES x (N x 128 B) K-blocks
-//   accumulators : MB M-blocks of 128 rows x N columns per (tile, phase); double buffered in TMEM when they fit
+// Replacement table: FMPadding_nonsquare -> TMA OOB zero fill; SWG + stride decimation -> plane offsets; deconv522
+// zero insertion -> 4 output phases over one shared plane set; MVAU -> tcgen05.mma kind::i8 (int32 in TMEM);
+// PassThrough / bias+ReLU / Thresholds / max pool -> epilogue.
+//
+// Warps: 0 = weight TMA producer, 1 = MMA issuer (warp-uniform, one elected lane issues), 2..5 = epilogue,
+// 6 = plane TMA producer.  plane i: full/empty barrier pair, refilled for the next tile as soon as its last tap has
+// retired; weight ring of WSTAGES K-blocks; accumulator stages double buffered in TMEM when they fit.
 #include <algorithm>
 #include <vector>
 
@@ -36,10 +39,10 @@ namespace fcb {
 
 using namespace sm100;
 
-constexpr int U2_THREADS = 224;  // warps: 0 weight TMA, 1 MMA, 2..5 epilogue, 6 plane TMA
+constexpr int U2_THREADS = 224;
 constexpr int U2_MAX_KB = 64;
 constexpr int U2_MAX_PLANES = 8;
-enum { KB_LOAD = 1, KB_WAIT = 2, KB_FREE = 4 };
+enum { KB_WAIT = 2, KB_FREE = 4 };
 
 struct KB2 {
   uint16_t plane, flags;
@@ -56,12 +59,12 @@ struct Phase2 {
 struct Params2 {
   uint8_t* out;
   EpiParams epi;
-  int N, OFM, stride2, deconv, nphases, nplanes;
-  int WT, R, P, MB, tiles_x, tiles_y, PX, PY;
+  int OFM, CB, NPX, stride2, deconv, nphases, nplanes;
+  int WT, R, P, tiles_x, tiles_y, PX, PY;
   int out_x, out_y, out_word_bytes, n_images;
-  int wstages, acc_stages, acc_stride, mb_stride, tmem_cols;
+  int wstages, w_bytes, acc_stages, acc_stride, tmem_cols;
   int w_off, bar_off;
-  int debug, w_copies;  // perf-decomposition knobs (FCB_U2_DEBUG bitmask: 1 no weight TMA, 2 no plane TMA, 4 no stores, 8 no epilogue)
+  int debug;  // FCB_U2_DEBUG bitmask (perf decomposition only): 1 no weight TMA, 2 no plane TMA, 4 no stores, 8 no epilogue
   unsigned long long out_img_bytes;
   uint32_t idesc;
   Plane2 planes[U2_MAX_PLANES];
@@ -71,15 +74,31 @@ struct Params2 {
 struct Umma2Plan {
   Geom g;
   Params2 p;
-  const CUtensorMap* tmB;
+  CUtensorMap tmW;
   size_t smem;
   int num_sms;
   uint32_t box_rows[2];
 };
 
+// pixel bookkeeping of the epilogue: column m of the accumulator -> output word
+struct PixMap {
+  const Params2& p;
+  int x0, y0, px, py;
+  unsigned long long img_off;
+  __device__ __forceinline__ bool inside(int rr, int xo) const {
+    return xo < p.WT && rr < p.R && (x0 + xo) < p.PX && (y0 + rr) < p.PY;
+  }
+  // byte offset of the output word of tile pixel (rr, xo); pk = pool size
+  __device__ __forceinline__ size_t word_off(int rr, int xo, int pk) const {
+    const int gx = x0 + xo, gy = y0 + rr;
+    const int ox = p.deconv ? 2 * gx + px : gx, oy = p.deconv ? 2 * gy + py : gy;
+    return img_off + ((size_t)(oy / pk) * p.out_x + (ox / pk)) * p.out_word_bytes;
+  }
+};
+
 __global__ void __launch_bounds__(U2_THREADS, 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmB, const Params2 p) {
+                  const __grid_constant__ CUtensorMap tmW, const Params2 p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
@@ -94,12 +113,11 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
   const long long total_tiles = tiles_per_img * p.n_images;
-  const int w_bytes = p.N * 128;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmW);
     for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int i = 0; i < p.nplanes; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
     for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
@@ -119,20 +137,19 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int ph = 0; ph < p.nphases; ph++) {
           const Phase2& P = p.phases[ph];
           for (int i = 0; i < P.nkb; i++, it++) {
-            const KB2 kb = P.kb[i];
             const int s = it % p.wstages;
             mbar_wait(&wempty[s], ((it / p.wstages) & 1) ^ 1);
             if (p.debug & 1) { mbar_arrive(&wfull[s]); continue; }
-            mbar_arrive_expect_tx(&wfull[s], (uint32_t)w_bytes);
-            tma_load_2d(smem + p.w_off + s * w_bytes, &tmB, &wfull[s], kb.w_k, (int)(blockIdx.x % p.w_copies) * p.N);
+            mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);
+            tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, 0);
           }
         }
       }
     }
   } else if (warp == 6) {
     // ===================== TMA producer: input planes =====================
-    // Runs independently of the weight ring: plane i of the next tile is fetched the moment the MMAs that read
-    // plane i of the current tile have retired (aempty), i.e. while the remaining taps of the current tile execute.
+    // Independent of the weight ring: plane i of the next tile is fetched the moment the MMAs that read plane i of
+    // the current tile have retired (aempty), i.e. while the remaining taps of the current tile execute.
     if (lane == 0) {
       uint32_t tile_it = 0;
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_it++) {
@@ -152,111 +169,136 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The whole warp runs the loop in uniform control flow (so addresses and descriptors stay in uniform
-    // registers); one elected lane issues the tcgen05 instructions.
-    {
-      uint32_t it = 0, tile_it = 0, acc_it = 0;
-      const uint32_t smem_base = smem_u32(smem);
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t idesc = p.idesc;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_it++) {
-        for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
-          const Phase2& P = p.phases[ph];
-          const int acc = acc_it % p.acc_stages;
-          mbar_wait(&tempty[acc], ((acc_it / p.acc_stages) & 1) ^ 1);
+    // The whole warp runs the loop in uniform control flow (addresses and descriptors stay in uniform registers,
+    // which UTCIMMA consumes); one elected lane issues the tcgen05 instructions.
+    uint32_t it = 0, tile_it = 0, acc_it = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc = p.idesc;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_it++) {
+      for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
+        const Phase2& P = p.phases[ph];
+        const int acc = acc_it % p.acc_stages;
+        mbar_wait(&tempty[acc], ((acc_it / p.acc_stages) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.acc_stride);
+        for (int i = 0; i < P.nkb; i++, it++) {
+          const KB2 kb = P.kb[i];
+          if (kb.flags & KB_WAIT) mbar_wait(&afull[kb.plane], tile_it & 1);
+          const int s = it % p.wstages;
+          mbar_wait(&wfull[s], (it / p.wstages) & 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.acc_stride);
-          for (int i = 0; i < P.nkb; i++, it++) {
-            const KB2 kb = P.kb[i];
-            if (kb.flags & KB_WAIT) mbar_wait(&afull[kb.plane], tile_it & 1);
-            const int s = it % p.wstages;
-            mbar_wait(&wfull[s], (it / p.wstages) & 1);
-            tc_fence_after();
-            const uint64_t bdesc = make_smem_desc(smem_base + p.w_off + s * w_bytes, 128);
-            const uint64_t adesc = make_smem_desc(smem_base + p.planes[kb.plane].smem_off + (uint32_t)kb.a_off * 128u, 128);
-            const uint32_t acc_flag = i ? 1u : 0u;
-            if (elect_one_sync()) {
-              for (int mb = 0; mb < p.MB; mb++) {
-                const uint64_t ad = adesc + (uint64_t)(mb * 1024);  // +128 rows = 16 KB >> 4
-                const uint32_t dt = d_tmem + (uint32_t)(mb * p.mb_stride);
-                umma_i8(dt, ad, bdesc, idesc, acc_flag);
-                umma_i8(dt, ad + 2, bdesc + 2, idesc, 1u);
-                umma_i8(dt, ad + 4, bdesc + 4, idesc, 1u);
-                umma_i8(dt, ad + 6, bdesc + 6, idesc, 1u);
-              }
-              umma_commit(&wempty[s]);
-              if (kb.flags & KB_FREE) umma_commit(&aempty[kb.plane]);
-              if (i == P.nkb - 1) umma_commit(&tfull[acc]);
+          const uint64_t wdesc = make_smem_desc(smem_base + p.w_off + s * p.w_bytes, 128);
+          const uint64_t pdesc = make_smem_desc(smem_base + p.planes[kb.plane].smem_off + (uint32_t)kb.a_off * 128u, 128);
+          const uint32_t acc_flag = i ? 1u : 0u;
+          if (elect_one_sync()) {
+            for (int cb = 0; cb < p.CB; cb++) {
+              const uint64_t wd = wdesc + (uint64_t)(cb * 1024);  // next 128 weight rows = +16 KB (>> 4)
+              const uint32_t dt = d_tmem + (uint32_t)(cb * p.NPX);
+              umma_i8(dt, wd, pdesc, idesc, acc_flag);
+              umma_i8(dt, wd + 2, pdesc + 2, idesc, 1u);
+              umma_i8(dt, wd + 4, pdesc + 4, idesc, 1u);
+              umma_i8(dt, wd + 6, pdesc + 6, idesc, 1u);
             }
-            __syncwarp();
+            umma_commit(&wempty[s]);
+            if (kb.flags & KB_FREE) umma_commit(&aempty[kb.plane]);
+            if (i == P.nkb - 1) umma_commit(&tfull[acc]);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp < 6) {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..5): lane = output channel, TMEM column = pixel =====================
     const int q = warp & 3;
+    const int pk = p.epi.pool >= 2 ? p.epi.pool : 1;
+    const bool fast = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1;
+    // thresholds with comp::less / less_equal and a result that cannot wrap TR: monotone in the (wrapped, < 2^31) accumulator
+    const bool mono = p.epi.act_kind == FCB_ACT_THRESHOLDS && (p.epi.cmp == FCB_CMP_LESS || p.epi.cmp == FCB_CMP_LESS_EQUAL) &&
+                      p.epi.act_val >= 0 && (p.epi.out_bits >= 31 || p.epi.act_val + p.epi.num_th < (1 << p.epi.out_bits)) &&
+                      (p.epi.acc_signed || p.epi.acc_bits < 32);
     uint32_t acc_it = 0;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int img = (int)(t / tiles_per_img);
       const int r = (int)(t % tiles_per_img);
-      const int x0 = (r % p.tiles_x) * p.WT, y0 = (r / p.tiles_x) * p.R;
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
+        const PixMap pm{p, (r % p.tiles_x) * p.WT, (r / p.tiles_x) * p.R, p.phases[ph].px, p.phases[ph].py,
+                        (unsigned long long)img * p.out_img_bytes};
         const int acc = acc_it % p.acc_stages;
         mbar_wait(&tfull[acc], (acc_it / p.acc_stages) & 1);
         tc_fence_after();
-        for (int mb = 0; mb < ((p.debug & 8) ? 0 : p.MB); mb++) {
-          const int m = mb * 128 + q * 32 + lane;  // linear patch index of this thread's row
-          const int rr = m / p.P, xo = m - rr * p.P;
-          const int gx = x0 + xo, gy = y0 + rr;
-          const bool inside = xo < p.WT && rr < p.R && gx < p.PX && gy < p.PY && !(p.debug & 4);
-          const int ox = p.deconv ? 2 * gx + p.phases[ph].px : gx;
-          const int oy = p.deconv ? 2 * gy + p.phases[ph].py : gy;
-          uint8_t* word = p.out + (size_t)img * p.out_img_bytes + ((size_t)oy * p.out_x + ox) * p.out_word_bytes;
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + mb * p.mb_stride);
-          for (int c0 = 0; c0 < p.N; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + (uint32_t)c0, v);
-            tmem_ld_wait();
-            if (p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8) {
-              uint32_t w4[8];
-#pragma unroll
-              for (int j = 0; j < 8; j++) {
-                uint32_t pack = 0;
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                  uint32_t rv = (v[j * 4 + b] + (uint32_t)(int32_t)p.epi.bias[c0 + j * 4 + b]) & 0xFFu;
-                  rv = (rv & 0x80u) ? 0u : rv;
-                  pack |= rv << (8 * b);
-                }
-                w4[j] = pack;
-              }
-              if (inside) {
-                uint4* dst = reinterpret_cast<uint4*>(word + c0);
-                dst[0] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                dst[1] = make_uint4(w4[4], w4[5], w4[6], w4[7]);
-              }
-            } else {
-              uint32_t packed[32];
-#pragma unroll
-              for (int j = 0; j < 32; j++) packed[j] = 0;
-              const int ob = p.epi.out_bits;
+        // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
+        const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
+        const int xstep = (p.deconv ? 2 : 1) * p.out_word_bytes;  // bytes between horizontally adjacent tile pixels
+        for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++) {
+          const int ch = cb * 128 + q * 32 + lane;
+          const bool chv = ch < p.OFM;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
+          if (fast) {
+            // bias + ReLU on the wrapped 8-bit value (conv_nonsquare_top.cpp:267-278); one byte per lane and pixel,
+            // a warp writes 32 consecutive channel bytes of one output word per store
+            const uint32_t bias_v = chv ? (uint32_t)(int32_t)p.epi.bias[ch] : 0u;
+            int rr = 0, xo = 0;
+            uint8_t* ptr = p.out + pm.word_off(0, 0, 1) + ch;
+            for (int c0 = 0; c0 < p.NPX && rr < vrows; c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32(taddr + (uint32_t)c0, v);
+              tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 32; j++) {
-                const int ch = c0 + j;
-                const uint32_t a = (ch < p.OFM) ? activate(p.epi, ch, (int32_t)v[j]) : 0u;
-                const int bit = j * ob;
-                if (ob == 32) packed[j] = a;
-                else packed[bit >> 5] |= a << (bit & 31);
+                uint32_t rv = (v[j] + bias_v) & 0xFFu;
+                rv = (rv & 0x80u) ? 0u : rv;
+                if (chv && xo < vcols && rr < vrows) *ptr = (uint8_t)rv;
+                ptr += xstep;
+                if (++xo == p.P) { xo = 0; ++rr; ptr = p.out + pm.word_off(rr, 0, 1) + ch; }
               }
-              if (inside) {
-                const int nbytes = 4 * ob;
-                uint8_t* dst = word + ((size_t)c0 * ob >> 3);
-                const int valid_bytes = min(nbytes, (int)((((size_t)p.OFM - c0) * ob + 7) >> 3));
-                if (valid_bytes == nbytes) {
-                  for (int w = 0; w < ob; w++) reinterpret_cast<uint32_t*>(dst)[w] = packed[w];
-                } else {
-                  for (int b = 0; b < valid_bytes; b++) dst[b] = (uint8_t)(packed[b >> 2] >> (8 * (b & 3)));
+            }
+          } else if (pk == 1) {
+            int rr = 0, xo = 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < p.NPX && rr < vrows; c0 += 8) {
+              uint32_t v[8];
+              tmem_ld8(taddr + (uint32_t)c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                if (xo < vcols && rr < vrows) {  // warp-uniform
+                  const uint32_t a = chv ? activate(p.epi, ch, (int32_t)v[j]) : 0u;
+                  store_lane(p.out + pm.word_off(rr, xo, 1), ch, chv, a, p.epi.out_bits);
+                }
+                if (++xo == p.P) { xo = 0; ++rr; }
+              }
+            }
+          } else {
+            // 2x2 max pool: rows rr, rr+1 of the tile are columns m and m + P of the same thread
+#pragma unroll 1
+            for (int rr = 0; rr < vrows; rr += 2) {
+#pragma unroll 1
+              for (int xb = 0; xb < vcols; xb += 8) {
+                uint32_t va[8], vb[8];
+                tmem_ld8(taddr + (uint32_t)(rr * p.P + xb), va);
+                tmem_ld8(taddr + (uint32_t)((rr + 1) * p.P + xb), vb);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                  const int xo = xb + j;
+                  if (xo < vcols) {  // WT, R, PX, PY are even: the window is whole (warp-uniform)
+                    uint32_t a = 0;
+                    if (chv && mono) {
+                      // count-of-thresholds-below is non-decreasing in the TA-wrapped accumulator: pool first
+                      int32_t m0 = wrap_ta((int32_t)va[j], p.epi.acc_bits, p.epi.acc_signed);
+                      m0 = max(m0, wrap_ta((int32_t)va[j + 1], p.epi.acc_bits, p.epi.acc_signed));
+                      m0 = max(m0, wrap_ta((int32_t)vb[j], p.epi.acc_bits, p.epi.acc_signed));
+                      m0 = max(m0, wrap_ta((int32_t)vb[j + 1], p.epi.acc_bits, p.epi.acc_signed));
+                      a = activate(p.epi, ch, m0);
+                    } else if (chv) {
+                      a = activate(p.epi, ch, (int32_t)va[j]);
+                      a = max(a, activate(p.epi, ch, (int32_t)va[j + 1]));
+                      a = max(a, activate(p.epi, ch, (int32_t)vb[j]));
+                      a = max(a, activate(p.epi, ch, (int32_t)vb[j + 1]));
+                    }
+                    store_lane(p.out + pm.word_off(rr, xo, 2), ch, chv, a, p.epi.out_bits);
+                  }
                 }
               }
             }
@@ -276,16 +318,18 @@ static int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 struct TapH { int offx, offy, parx, pary, wtap, phase; };
 
-int umma2_plan_create(const Geom& g, const CUtensorMap* tmB, const EpiParams& epi, int num_sms, int w_copies, Umma2Plan** out) {
+int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, Umma2Plan** out) {
   *out = nullptr;
-  if (g.pool != 1) return FCB_ERR_UNSUPPORTED;  // pooled layers stay on the first-generation kernel
+  if (g.pool > 2) return FCB_ERR_UNSUPPORTED;
   const int deconv = g.kind == FCB_KIND_DECONV522;
+  if (deconv && g.pool != 1) return FCB_ERR_UNSUPPORTED;
   const int s = deconv ? 1 : g.SX;
   const int cch = g.C / 128;
-  const int N = g.OFM;
+  const int CB = (g.OFM + 127) / 128;
+  if (CB > 2) return FCB_ERR_UNSUPPORTED;
   // ---- taps
   std::vector<TapH> taps;
-  int nph = deconv ? 4 : 1;
+  const int nph = deconv ? 4 : 1;
   if (!deconv) {
     for (int ky = 0; ky < g.KY; ky++)
       for (int kx = 0; kx < g.KX; kx++) {
@@ -297,7 +341,7 @@ int umma2_plan_create(const Geom& g, const CUtensorMap* tmB, const EpiParams& ep
       for (int px = 0; px < 2; px++)
         for (int ky = 0; ky < 5; ky++)
           for (int kx = 0; kx < 5; kx++) {
-            if (((px + kx) & 1) || ((py + ky) & 1)) continue;
+            if (((px + kx) & 1) || ((py + ky) & 1)) continue;  // structural zero
             taps.push_back({(px + kx - 2) / 2, (py + ky - 2) / 2, 0, 0, ky * 5 + kx, py * 2 + px});
           }
   }
@@ -322,70 +366,69 @@ int umma2_plan_create(const Geom& g, const CUtensorMap* tmB, const EpiParams& ep
   }
   if (max_kb > U2_MAX_KB) return FCB_ERR_UNSUPPORTED;
   const int PX = deconv ? g.IX : g.OX, PY = deconv ? g.IY : g.OY;
-  int npow = 32;
-  while (npow < N) npow *= 2;
+  const int xdim = s == 2 ? g.IX / 2 : g.IX, ydim = s == 2 ? g.IY / 2 : g.IY;  // tensor extents the TMA box must fit
 
-  // ---- choose (WT, R, MB, wstages): minimise estimated clocks per useful output pixel
-  const int w_bytes = N * 128;
+  // ---- choose (WT, R, NPX, wstages): minimise estimated clocks per useful output pixel
+  const int w_bytes = CB * 128 * 128;
   const int smem_limit = 227 * 1024 - 2048;
+  const int step = g.pool == 2 ? 2 : 1;
   double best = 1e30;
-  int bWT = 0, bR = 0, bMB = 0, bWS = 0;
-  for (int MB = 1; MB <= 2; MB++) {
-    if (MB * npow > 512) continue;
-    for (int WS = 3; WS >= 2; WS--)
-      for (int WT = 2; WT <= std::min(PX + 1, 254 - halo_x); WT += 2) {
+  int bWT = 0, bR = 0, bNPX = 0, bWS = 0;
+  for (int NPX = 256; NPX >= 64; NPX /= 2) {
+    if (CB * NPX > 512) continue;
+    for (int WS = 4; WS >= 2; WS--)
+      for (int WT = step; WT <= std::min(PX + step - 1, 254 - halo_x); WT += step) {
         const int P = WT + halo_x;
-        int R = std::min((MB * 128) / P, PY);
+        if (P > xdim) continue;
+        const int budget = g.pool == 2 ? NPX - 8 : NPX;  // pooled epilogue reads 8-column groups from row starts
+        int R = std::min(budget / P, PY);
+        if (g.pool == 2) R &= ~1;
         if (R < 1) continue;
-        if (P > (s == 2 ? g.IX / 2 : g.IX)) continue;  // TMA box must fit the tensor extent
         size_t plane_bytes = 0;
+        bool ok = true;
         for (auto& h : ph4) {
           if (!h.used) continue;
           const int rows = R + (h.maxy - h.miny);
+          if (rows > 256 || rows > ydim) { ok = false; break; }
           const int a_off_max = (h.maxy - h.miny) * P + (h.maxx - h.minx);
-          size_t b = std::max<size_t>((size_t)rows * P * 128, (size_t)(a_off_max + MB * 128) * 128);
-          b = (b + 1023) / 1024 * 1024;
-          plane_bytes += b * cch;
-          if (rows > 256 || rows > (s == 2 ? g.IY / 2 : g.IY)) plane_bytes = (size_t)1 << 30;
+          size_t b = std::max<size_t>((size_t)rows * P * 128, (size_t)(a_off_max + NPX) * 128);
+          plane_bytes += (b + 1023) / 1024 * 1024 * cch;
         }
-        if (plane_bytes + (size_t)WS * w_bytes > (size_t)smem_limit) continue;
+        if (!ok || plane_bytes + (size_t)WS * w_bytes > (size_t)smem_limit) continue;
         const double tiles = (double)((PX + WT - 1) / WT) * ((PY + R - 1) / R);
-        const double useful = (double)PX * PY;
         const double nkb = (double)taps.size() * cch;  // all phases
-        const double mma_clk = nkb * MB * 4 * (N / 2.0);
-        const double fill_clk = ((double)plane_bytes + nkb * w_bytes) / 38.0;  // measured L2->SM fill rate, B/clk/SM
-        const double ws_pen = WS == 2 ? 1.03 : 1.0;
-        const double cost = tiles * std::max(mma_clk, fill_clk) * ws_pen / useful;
-        if (cost < best) { best = cost; bWT = WT; bR = R; bMB = MB; bWS = WS; }
+        const double mma_clk = nkb * CB * 4 * (NPX == 256 ? 146.0 : 102.0);  // measured clocks per instruction
+        const double fill_clk = ((double)plane_bytes + nkb * w_bytes) / 38.0;  // measured L2->SM fill, B/clk/SM
+        const double ws_pen = WS >= 3 ? 1.0 : 1.05;
+        const double cost = tiles * std::max(mma_clk, fill_clk) * ws_pen / ((double)PX * PY);
+        if (cost < best * 0.999) { best = cost; bWT = WT; bR = R; bNPX = NPX; bWS = WS; }
       }
   }
-  if (getenv("FCB_U2_FORCE")) {  // "WT,R,MB,WS" -- experiments only; the caller is responsible for it fitting
+  if (getenv("FCB_U2_FORCE")) {  // "WT,R,NPX,WS" -- experiments only; the caller is responsible for it fitting
     int a, b, c, d;
-    if (sscanf(getenv("FCB_U2_FORCE"), "%d,%d,%d,%d", &a, &b, &c, &d) == 4) { bWT = a; bR = b; bMB = c; bWS = d; }
+    if (sscanf(getenv("FCB_U2_FORCE"), "%d,%d,%d,%d", &a, &b, &c, &d) == 4) { bWT = a; bR = b; bNPX = c; bWS = d; }
   }
   if (!bWT) return FCB_ERR_UNSUPPORTED;
 
   Umma2Plan* U = new Umma2Plan();
-  U->g = g; U->tmB = tmB; U->num_sms = num_sms;
+  U->g = g; U->num_sms = num_sms;
   Params2& p = U->p;
   memset(&p, 0, sizeof(p));
   p.epi = epi;
-  p.N = N; p.OFM = g.OFM; p.stride2 = (s == 2); p.deconv = deconv; p.nphases = nph;
-  p.WT = bWT; p.R = bR; p.P = bWT + halo_x; p.MB = bMB; p.PX = PX; p.PY = PY;
+  p.OFM = g.OFM; p.CB = CB; p.NPX = bNPX; p.stride2 = (s == 2); p.deconv = deconv; p.nphases = nph;
+  p.WT = bWT; p.R = bR; p.P = bWT + halo_x; p.PX = PX; p.PY = PY;
   p.tiles_x = (PX + bWT - 1) / bWT; p.tiles_y = (PY + bR - 1) / bR;
   p.out_x = g.out_x; p.out_y = g.out_y; p.out_word_bytes = (int)g.out_word_bytes; p.out_img_bytes = g.out_img_bytes;
-  p.wstages = bWS;
-  p.mb_stride = npow;
-  p.acc_stride = bMB * npow;
+  p.wstages = bWS; p.w_bytes = w_bytes;
+  p.acc_stride = CB * bNPX;
   p.acc_stages = (2 * p.acc_stride <= 512) ? 2 : 1;
-  int cols = p.acc_stages * p.acc_stride, tc = 32;
-  while (tc < cols) tc *= 2;
+  int tc = 32;
+  while (tc < p.acc_stages * p.acc_stride) tc *= 2;
   p.tmem_cols = tc;
-  p.idesc = make_idesc_i8(128, N, g.in_signed, 1);
+  p.idesc = make_idesc_i8(128, bNPX, /*A = weights*/ 1, /*B = activations*/ g.in_signed);
   p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
-  p.w_copies = w_copies;
   // planes
-  int plane_of[4][4];  // [parity][cc]
+  int plane_of[4][4];
   int off = 0, np = 0, nmaps = 0;
   int map_rows[2] = {0, 0};
   for (int i = 0; i < 4; i++) {
@@ -399,7 +442,7 @@ int umma2_plan_create(const Geom& g, const CUtensorMap* tmB, const EpiParams& ep
       map = nmaps; map_rows[nmaps++] = rows;
     }
     const int a_off_max = (h.maxy - h.miny) * p.P + (h.maxx - h.minx);
-    size_t b = std::max<size_t>((size_t)rows * p.P * 128, (size_t)(a_off_max + bMB * 128) * 128);
+    size_t b = std::max<size_t>((size_t)rows * p.P * 128, (size_t)(a_off_max + bNPX) * 128);
     b = (b + 1023) / 1024 * 1024;
     for (int cc = 0; cc < cch; cc++) {
       Plane2& pl = p.planes[np];
@@ -417,8 +460,9 @@ int umma2_plan_create(const Geom& g, const CUtensorMap* tmB, const EpiParams& ep
   p.bar_off = off;
   off += (2 * bWS + 2 * np + 4) * 8 + 16;
   U->smem = (size_t)off + 1024;
+  if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
   // K-block lists: plane-major within each phase so planes are released progressively
-  std::vector<int> last_use(np, -1), first_use(np, -1);  // global K-block ordinal over all phases
+  std::vector<int> last_use(np, -1), first_use(np, -1);
   int ord = 0;
   for (int phs = 0; phs < nph; phs++) {
     Phase2& P = p.phases[phs];
@@ -443,9 +487,17 @@ int umma2_plan_create(const Geom& g, const CUtensorMap* tmB, const EpiParams& ep
   for (int phs = 0; phs < nph; phs++)
     for (int i = 0; i < p.phases[phs].nkb; i++, ord++) {
       KB2& kb = p.phases[phs].kb[i];
-      if (first_use[kb.plane] == ord) kb.flags |= KB_LOAD | KB_WAIT;
+      if (first_use[kb.plane] == ord) kb.flags |= KB_WAIT;
       if (last_use[kb.plane] == ord) kb.flags |= KB_FREE;
     }
+  // weights as the A operand: box = 128 B of K x CB*128 channel rows; rows >= OFM are zero-filled by TMA
+  {
+    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.OFM};
+    const uint64_t strides[1] = {(uint64_t)g.K};
+    const uint32_t box[2] = {128, (uint32_t)(CB * 128)};
+    int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
+    if (rc) { delete U; return rc; }
+  }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
@@ -455,8 +507,8 @@ void umma2_plan_destroy(Umma2Plan* U) { delete U; }
 
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   const Params2& p = U->p;
-  snprintf(buf, n, "v2 WT=%d R=%d P=%d MB=%d planes=%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT, p.R, p.P, p.MB, p.nplanes,
-           p.wstages, p.acc_stages, U->smem, p.tiles_x, p.tiles_y);
+  snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d planes=%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT, p.R,
+           p.P, p.NPX, p.CB, p.nplanes, p.wstages, p.acc_stages, U->smem, p.tiles_x, p.tiles_y);
   return buf;
 }
 
@@ -482,9 +534,11 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
     }
     if (rc) return rc;
   }
+  // sub-byte / padded output words are merged or partially written: start from zeroed words
+  if (g.out_word_bytes * 8 != (size_t)g.OFM * g.out_bits) FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, g.out_img_bytes * n_images, st));
   const long long total = (long long)p.tiles_x * p.tiles_y * n_images;
   const int grid = (int)std::min<long long>(total, U->num_sms);
-  umma2_conv_kernel<<<grid, U2_THREADS, U->smem, st>>>(tmA[0], tmA[1], *U->tmB, p);
+  umma2_conv_kernel<<<grid, U2_THREADS, U->smem, st>>>(tmA[0], tmA[1], U->tmW, p);
   FCB_CUDA_OK(cudaGetLastError());
   return FCB_OK;
 }

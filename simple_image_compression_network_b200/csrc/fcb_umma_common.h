@@ -8,7 +8,7 @@ namespace fcb {
 int umma_encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
 struct Umma2Plan;
-int umma2_plan_create(const Geom& g, const CUtensorMap* tmB, const EpiParams& epi, int num_sms, int w_copies, Umma2Plan** out);
+int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, Umma2Plan** out);
 void umma2_plan_destroy(Umma2Plan* U);
 int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStream_t st);
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n);

@@ -70,6 +70,61 @@ __global__ void __launch_bounds__(128, 1) peak1(int n, int iters, int shift_rows
   if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+
+// ---- issue-pattern study: warp-uniform loop, one elected lane issues (the structure of the conv kernel) -------------
+// mode bits: 1 = A start shifted by one 128-byte row, 2 = commit after every 8 MMAs, 4 = poll a completed mbarrier +
+// tcgen05.fence before every 8 MMAs, 8 = poll two barriers, 16 = A/B addresses vary per K-block like the conv kernel,
+// 32 = __syncwarp after each K-block
+__global__ void __launch_bounds__(128, 1) peak3(int iters, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 65536;  // 3 x 16 KB "weight stages"
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 49152);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 8);
+  fill_smem(sA, 65536 + 49152, blockIdx.x);
+  if (threadIdx.x == 0) { for (int i = 0; i < 6; i++) mbar_init(&bar[i], 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc(slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x < 32) {
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *slot, 0);
+    const uint32_t idesc = make_idesc_i8(128, 128, 0, 1);
+    const uint32_t a0 = smem_u32(sA) + ((mode & 1) ? 128 : 0), b0 = smem_u32(sB);
+    if (threadIdx.x == 0) { mbar_arrive(&bar[2]); mbar_arrive(&bar[3]); }
+    __syncwarp();
+    const int nkb = iters / 2;  // K-blocks of 8 MMAs
+    for (int kb = 0; kb < nkb; kb++) {
+      if (mode & 4) { mbar_wait(&bar[2], 0); tc_fence_after(); }
+      if (mode & 8) { mbar_wait(&bar[3], 0); tc_fence_after(); }
+      uint32_t aa = a0, bb = b0;
+      if (mode & 16) { aa += ((kb % 9) * 50 + (kb % 3)) * 128; bb += (kb % 3) * 16384; }
+      const uint64_t adesc = make_smem_desc(aa, 128), bdesc = make_smem_desc(bb, 128);
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int mb = 0; mb < 2; mb++) {
+          const uint64_t ad = adesc + (uint64_t)(mb * 1024);
+          const uint32_t dt = tmem + (uint32_t)(mb * 128 + (kb & 1) * 256);
+          umma_i8(dt, ad, bdesc, idesc, 1u);
+          umma_i8(dt, ad + 2, bdesc + 2, idesc, 1u);
+          umma_i8(dt, ad + 4, bdesc + 4, idesc, 1u);
+          umma_i8(dt, ad + 6, bdesc + 6, idesc, 1u);
+        }
+        if (mode & 2) umma_commit(&bar[4]);
+        if ((kb & 7) == 7) umma_commit(&bar[(kb >> 3) & 1]);
+      }
+      if (mode & 32) __syncwarp();
+      if ((kb & 7) == 7 && kb >= 15) mbar_wait(&bar[((kb >> 3) - 1) & 1], (((kb >> 3) - 1) >> 1) & 1);
+    }
+    const int last = (nkb >> 3) - 1;
+    mbar_wait(&bar[last & 1], (last >> 1) & 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(*slot, 512);
+}
+
 // ---- cta_group::2 -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync() {
@@ -168,6 +223,25 @@ int main(int argc, char** argv) {
         printf("N=128 A start shifted by %2d rows, pattern %d : %8.3f ms  %8.1f TOP/s  (%.1f clk/MMA at 1.965 GHz)\n", sh, pat, ms,
                ops / ms / 1e9, ms * 1e-3 * 1.965e9 / (iters * 4.0));
       }
+  }
+  {
+    const int smem3 = 65536 + 49152 + 1024 + 128;
+    CK(cudaFuncSetAttribute(peak3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    const int modes[] = {0, 1, 2, 4, 6, 12, 14, 16, 17, 30, 62, 63};
+    for (int mode : modes) {
+      peak3<<<sms, 128, smem3>>>(128, mode);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      peak3<<<sms, 128, smem3>>>(iters, mode);
+      CK(cudaEventRecord(e1));
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("peak3 mode %d failed: %s\n", mode, cudaGetErrorString(e)); return 3; }
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double ops = 2.0 * sms * (double)iters * 4 * 128.0 * 128 * 32.0;
+      printf("uniform-issue M=128 N=128 mode %2d : %8.3f ms  %8.1f TOP/s  (%.1f clk/MMA at 1.965 GHz)\n", mode, ms, ops / ms / 1e9,
+             ms * 1e-3 * 1.965e9 / (iters * 4.0));
+    }
   }
   const int ns2[2] = {128, 256};
   for (int n : ns2) {
