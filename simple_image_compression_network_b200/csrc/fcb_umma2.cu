@@ -46,8 +46,9 @@ enum { KB_WAIT = 2, KB_FREE = 4 };
 
 struct KB2 {
   uint16_t plane, flags;
-  int32_t a_off;  // plane row offset of this tap's operand (rows of 128 B)
-  int32_t w_k;    // K coordinate of the weight tile
+  int32_t a_off;   // plane row offset of this tap's operand (rows of 128 B)
+  int32_t w_k;     // K coordinate of the weight tile
+  uint32_t d_off;  // (plane smem offset + a_off*128) >> 4 : added to the base smem descriptor
 };
 struct Plane2 {
   int32_t smem_off, bytes, c0, dx, par, dy, map, pad_;
@@ -132,16 +133,19 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer: weight K-blocks =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t wphase = 1;
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         for (int ph = 0; ph < p.nphases; ph++) {
           const Phase2& P = p.phases[ph];
-          for (int i = 0; i < P.nkb; i++, it++) {
-            const int s = it % p.wstages;
-            mbar_wait(&wempty[s], ((it / p.wstages) & 1) ^ 1);
-            if (p.debug & 1) { mbar_arrive(&wfull[s]); continue; }
-            mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);
-            tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, 0);
+          for (int i = 0; i < P.nkb; i++) {
+            mbar_wait(&wempty[s], wphase);
+            if (p.debug & 1) mbar_arrive(&wfull[s]);
+            else {
+              mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);
+              tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, 0);
+            }
+            if (++s == p.wstages) { s = 0; wphase ^= 1; }
           }
         }
       }
@@ -171,40 +175,48 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ===================== MMA issuer =====================
     // The whole warp runs the loop in uniform control flow (addresses and descriptors stay in uniform registers,
     // which UTCIMMA consumes); one elected lane issues the tcgen05 instructions.
-    uint32_t it = 0, tile_it = 0, acc_it = 0;
-    const uint32_t smem_base = smem_u32(smem);
+    // Per K-block work is kept to: poll the weight stage, add two precomputed offsets to the base descriptor, issue.
+    uint32_t tile_it = 0, acc_it = 0;
+    int s = 0;
+    uint32_t wphase = 0;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t idesc = p.idesc;
+    const uint64_t desc0 = make_smem_desc(smem_u32(smem), 128);
+    const uint32_t w_d0 = (uint32_t)p.w_off >> 4, w_dstep = (uint32_t)p.w_bytes >> 4;
+    const int wstages = p.wstages, CB = p.CB, NPX = p.NPX;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_it++) {
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
         const Phase2& P = p.phases[ph];
+        const int nkb = P.nkb;
         const int acc = acc_it % p.acc_stages;
         mbar_wait(&tempty[acc], ((acc_it / p.acc_stages) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.acc_stride);
-        for (int i = 0; i < P.nkb; i++, it++) {
-          const KB2 kb = P.kb[i];
-          if (kb.flags & KB_WAIT) mbar_wait(&afull[kb.plane], tile_it & 1);
-          const int s = it % p.wstages;
-          mbar_wait(&wfull[s], (it / p.wstages) & 1);
+        for (int i = 0; i < nkb; i++) {
+          const uint32_t flags = P.kb[i].flags, plane = P.kb[i].plane;
+          const uint64_t pdesc = desc0 + P.kb[i].d_off;
+          if (flags & KB_WAIT) mbar_wait(&afull[plane], tile_it & 1);
+          mbar_wait(&wfull[s], wphase);
           tc_fence_after();
-          const uint64_t wdesc = make_smem_desc(smem_base + p.w_off + s * p.w_bytes, 128);
-          const uint64_t pdesc = make_smem_desc(smem_base + p.planes[kb.plane].smem_off + (uint32_t)kb.a_off * 128u, 128);
-          const uint32_t acc_flag = i ? 1u : 0u;
+          const uint64_t wdesc = desc0 + (w_d0 + (uint32_t)s * w_dstep);
           if (elect_one_sync()) {
-            for (int cb = 0; cb < p.CB; cb++) {
-              const uint64_t wd = wdesc + (uint64_t)(cb * 1024);  // next 128 weight rows = +16 KB (>> 4)
-              const uint32_t dt = d_tmem + (uint32_t)(cb * p.NPX);
-              umma_i8(dt, wd, pdesc, idesc, acc_flag);
-              umma_i8(dt, wd + 2, pdesc + 2, idesc, 1u);
-              umma_i8(dt, wd + 4, pdesc + 4, idesc, 1u);
-              umma_i8(dt, wd + 6, pdesc + 6, idesc, 1u);
+            umma_i8(d_tmem, wdesc, pdesc, idesc, i ? 1u : 0u);
+            umma_i8(d_tmem, wdesc + 2, pdesc + 2, idesc, 1u);
+            umma_i8(d_tmem, wdesc + 4, pdesc + 4, idesc, 1u);
+            umma_i8(d_tmem, wdesc + 6, pdesc + 6, idesc, 1u);
+            if (CB == 2) {
+              const uint32_t dt = d_tmem + (uint32_t)NPX;
+              umma_i8(dt, wdesc + 1024, pdesc, idesc, i ? 1u : 0u);  // next 128 weight rows = +16 KB (>> 4)
+              umma_i8(dt, wdesc + 1026, pdesc + 2, idesc, 1u);
+              umma_i8(dt, wdesc + 1028, pdesc + 4, idesc, 1u);
+              umma_i8(dt, wdesc + 1030, pdesc + 6, idesc, 1u);
             }
             umma_commit(&wempty[s]);
-            if (kb.flags & KB_FREE) umma_commit(&aempty[kb.plane]);
-            if (i == P.nkb - 1) umma_commit(&tfull[acc]);
+            if (flags & KB_FREE) umma_commit(&aempty[plane]);
+            if (i == nkb - 1) umma_commit(&tfull[acc]);
           }
           __syncwarp();
+          if (++s == wstages) { s = 0; wphase ^= 1; }
         }
       }
     }
@@ -212,7 +224,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ===================== epilogue (warps 2..5): lane = output channel, TMEM column = pixel =====================
     const int q = warp & 3;
     const int pk = p.epi.pool >= 2 ? p.epi.pool : 1;
-    const bool fast = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1;
+    const bool fast = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && (p.OFM % 32) == 0 && p.P >= 4;
     // thresholds with comp::less / less_equal and a result that cannot wrap TR: monotone in the (wrapped, < 2^31) accumulator
     const bool mono = p.epi.act_kind == FCB_ACT_THRESHOLDS && (p.epi.cmp == FCB_CMP_LESS || p.epi.cmp == FCB_CMP_LESS_EQUAL) &&
                       p.epi.act_val >= 0 && (p.epi.out_bits >= 31 || p.epi.act_val + p.epi.num_th < (1 << p.epi.out_bits)) &&
@@ -229,28 +241,32 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
-        const int xstep = (p.deconv ? 2 : 1) * p.out_word_bytes;  // bytes between horizontally adjacent tile pixels
         for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++) {
           const int ch = cb * 128 + q * 32 + lane;
           const bool chv = ch < p.OFM;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
           if (fast) {
-            // bias + ReLU on the wrapped 8-bit value (conv_nonsquare_top.cpp:267-278); one byte per lane and pixel,
-            // a warp writes 32 consecutive channel bytes of one output word per store
-            const uint32_t bias_v = chv ? (uint32_t)(int32_t)p.epi.bias[ch] : 0u;
-            int rr = 0, xo = 0;
-            uint8_t* ptr = p.out + pm.word_off(0, 0, 1) + ch;
-            for (int c0 = 0; c0 < p.NPX && rr < vrows; c0 += 32) {
+            // bias + ReLU on the wrapped 8-bit value (conv_nonsquare_top.cpp:267-278).  The thread owns one channel and
+            // 32 pixels; a 4x4 byte transpose across each lane quad (2 shuffles + 2 PRMT per word) turns that into
+            // 4 consecutive channel bytes of one pixel per lane, so a warp store writes 4 pixels x 32 B.
+            const uint32_t bias4 = (chv ? ((uint32_t)(int32_t)p.epi.bias[ch] & 0xFFu) : 0u) * 0x01010101u;
+            const int li = lane & 3, cgrp = cb * 128 + q * 32 + (lane & ~3);  // pixel-in-quad, first of this lane's 4 channels
+            const uint32_t selA = (lane & 1) ? 0x3715u : 0x6240u, selB = (lane & 2) ? 0x3276u : 0x5410u;
+            int rr = 0, xo = li;  // this lane's pixel after the transpose: m = c0 + 4*j + li
+            for (int c0 = 0; c0 < p.NPX && c0 < vrows * p.P; c0 += 32) {
               uint32_t v[32];
               tmem_ld32(taddr + (uint32_t)c0, v);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; j++) {
-                uint32_t rv = (v[j] + bias_v) & 0xFFu;
-                rv = (rv & 0x80u) ? 0u : rv;
-                if (chv && xo < vcols && rr < vrows) *ptr = (uint8_t)rv;
-                ptr += xstep;
-                if (++xo == p.P) { xo = 0; ++rr; ptr = p.out + pm.word_off(rr, 0, 1) + ch; }
+              for (int j = 0; j < 8; j++) {
+                const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
+                uint32_t w = __vadd4(__byte_perm(lo, hi, 0x5410), bias4);      // (acc + bias) mod 256, 4 pixels at once
+                w &= ~(((w >> 7) & 0x01010101u) * 0xFFu);                      // bit 7 set -> 0
+                const uint32_t a = __byte_perm(w, __shfl_xor_sync(0xffffffffu, w, 1), selA);
+                const uint32_t y = __byte_perm(a, __shfl_xor_sync(0xffffffffu, a, 2), selB);
+                if (xo < vcols && rr < vrows && cgrp < p.OFM) *reinterpret_cast<uint32_t*>(p.out + pm.word_off(rr, xo, 1) + cgrp) = y;
+                xo += 4;
+                if (xo >= p.P) { xo -= p.P; ++rr; }
               }
             }
           } else if (pk == 1) {
@@ -477,6 +493,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
           kb.flags = 0;
           kb.a_off = (t.offy - ph4[i].miny) * p.P + (t.offx - ph4[i].minx);
           kb.w_k = t.wtap * g.C + cc * 128;
+          kb.d_off = (uint32_t)(p.planes[kb.plane].smem_off + kb.a_off * 128) >> 4;
           if (first_use[kb.plane] < 0) first_use[kb.plane] = ord;
           last_use[kb.plane] = ord;
           ord++;

@@ -125,6 +125,46 @@ __global__ void __launch_bounds__(128, 1) peak3(int iters, int mode) {
   if (threadIdx.x < 32) tmem_dealloc(*slot, 512);
 }
 
+
+// ---- operand-alignment study: M=128 x N=256, B (N-side) and/or A start shifted by whole 128-byte rows ----------------
+__global__ void __launch_bounds__(128, 1) peak4(int iters, int a_shift, int b_shift, int n) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;           // 128 rows (+ slack)
+  uint8_t* sB = smem + 32768;   // 256 rows (+ slack)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768 + 65536);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 8);
+  fill_smem(sA, 32768 + 65536, blockIdx.x);
+  if (threadIdx.x == 0) { for (int i = 0; i < 2; i++) mbar_init(&bar[i], 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc(slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x < 32) {
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *slot, 0);
+    const uint32_t idesc = make_idesc_i8(128, n, 1, 0);
+    const uint64_t adesc = make_smem_desc(smem_u32(sA) + a_shift * 128, 128), bdesc = make_smem_desc(smem_u32(sB) + b_shift * 128, 128);
+    const int nkb = iters;  // K-blocks of 4 MMAs
+    for (int kb = 0; kb < nkb; kb++) {
+      if (elect_one_sync()) {
+        const uint32_t dt = tmem + (uint32_t)((kb & 1) * 256);
+        umma_i8(dt, adesc, bdesc, idesc, 1u);
+        umma_i8(dt, adesc + 2, bdesc + 2, idesc, 1u);
+        umma_i8(dt, adesc + 4, bdesc + 4, idesc, 1u);
+        umma_i8(dt, adesc + 6, bdesc + 6, idesc, 1u);
+        if ((kb & 15) == 15) umma_commit(&bar[(kb >> 4) & 1]);
+      }
+      __syncwarp();
+      if ((kb & 15) == 15 && kb >= 31) mbar_wait(&bar[((kb >> 4) - 1) & 1], (((kb >> 4) - 1) >> 1) & 1);
+    }
+    const int last = (nkb >> 4) - 1;
+    mbar_wait(&bar[last & 1], (last >> 1) & 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(*slot, 512);
+}
+
 // ---- cta_group::2 -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync() {
@@ -241,6 +281,26 @@ int main(int argc, char** argv) {
       const double ops = 2.0 * sms * (double)iters * 4 * 128.0 * 128 * 32.0;
       printf("uniform-issue M=128 N=128 mode %2d : %8.3f ms  %8.1f TOP/s  (%.1f clk/MMA at 1.965 GHz)\n", mode, ms, ops / ms / 1e9,
              ms * 1e-3 * 1.965e9 / (iters * 4.0));
+    }
+  }
+  {
+    const int smem4 = 32768 + 65536 + 1024 + 128;
+    CK(cudaFuncSetAttribute(peak4, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    const int cfg[][3] = {{0, 0, 256}, {0, 1, 256}, {0, 2, 256}, {0, 4, 256}, {0, 8, 256}, {0, 51, 256}, {1, 0, 256}, {3, 5, 256},
+                          {0, 0, 128}, {0, 1, 128}, {1, 0, 128}, {0, 0, 64}, {0, 3, 64}};
+    for (auto& c : cfg) {
+      peak4<<<sms, 128, smem4>>>(64, c[0], c[1], c[2]);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      peak4<<<sms, 128, smem4>>>(iters, c[0], c[1], c[2]);
+      CK(cudaEventRecord(e1));
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("peak4 failed: %s\n", cudaGetErrorString(e)); return 3; }
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double ops = 2.0 * sms * (double)iters * 4 * 128.0 * c[2] * 32.0;
+      printf("align study M=128 N=%3d A-shift %2d rows B-shift %2d rows : %8.3f ms  %8.1f TOP/s  (%.1f clk/MMA at 1.965 GHz)\n", c[2], c[0],
+             c[1], ms, ops / ms / 1e9, ms * 1e-3 * 1.965e9 / (iters * 4.0));
     }
   }
   const int ns2[2] = {128, 256};
