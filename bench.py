@@ -147,6 +147,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from simple_image_compression_network_b200 import configs, synth
+    from simple_image_compression_network_b200.shard import weak_range
     from simple_image_compression_network_b200.layer import ConvLayer, synth_fill
 
     rank = int(os.environ.get("RANK", "0"))
@@ -167,7 +168,8 @@ def run_ours(args):
     x = torch.empty(n_img * layer.in_bytes, dtype=torch.uint8, device="cuda")
     y = torch.empty(n_img * layer.out_bytes, dtype=torch.uint8, device="cuda")
     # this rank's images: global indices [rank*n_img, (rank+1)*n_img); lanes 0..127 (post-ReLU range of the previous layer)
-    synth_fill(x.data_ptr(), x.numel(), synth.SEED_INPUT, 0x7F, offset=rank * n_img * layer.in_bytes)
+    first_img, _ = weak_range(n_img, rank)
+    synth_fill(x.data_ptr(), x.numel(), synth.SEED_INPUT, 0x7F, offset=first_img * layer.in_bytes)
     torch.cuda.synchronize()
 
     stream = torch.cuda.Stream()
@@ -233,8 +235,13 @@ def run_ours(args):
     ops = 2.0 * d.macs_per_image * n_img
     achieved = ops / (kernel_ms / 1000.0) / 1e12
     peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    # DRAM traffic of this kernel from the committed `ncu --set full` capture (profiles/r01_resident_planes_ncu_full_summary.txt:
+    # 3.222 GB read + 0.789 GB written for a 256-image launch = 15.67 MB per image), scaled to this launch's image count
+    traffic = (3.222165e9 + 0.789302e9) / 256.0 * n_img if layer.plan.startswith("resident-planes") else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": layer.plan, "kernel_ms": kernel_ms,
+                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write of a 256-image launch, per image x images of this launch",
+                "kernel": layer.plan, "kernel_ms": kernel_ms,
+                "frac_of_measured_int8_mma_only_peak_4380_TOPs": achieved / 4380.0,
                 "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({src}); dense int8 tensor rate is 2x bf16 on sm_100; "
                                "ops are int8 MACs x 2 (TOP/s)",
                 "frac_of_spec_4500_TOPs": achieved / 4500.0,

@@ -1,0 +1,68 @@
+"""Per-layer and whole-network device-resident throughput of the reference network (config_nonsquare.h) and of the
+judged synthetic configs (BASELINE.json configs 3/4): images/s, TOP/s on the MACs the reference executes and on the
+non-zero MACs, achieved HBM GB/s on the algorithmic bytes.  Diagnostics, not the headline bench.
+    python tools/bench_layers.py [--images N]"""
+import argparse, dataclasses, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from simple_image_compression_network_b200 import configs, synth
+from simple_image_compression_network_b200.desc import ACT_THRESHOLDS, KIND_CONV, KIND_DECONV522, W_BINARY_XNOR, LayerDesc
+from simple_image_compression_network_b200.layer import ConvLayer, Net, synth_fill
+
+
+def timed(fn, steps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_layer(name, d, n, mask=0x7F):
+    prm = configs.synthetic_params(d)
+    L = ConvLayer(d, prm["weights"], thresholds=prm["thresholds"], bias=prm["bias"])
+    x = torch.empty(n * L.in_bytes, dtype=torch.uint8, device="cuda")
+    y = torch.empty(n * L.out_bytes, dtype=torch.uint8, device="cuda")
+    synth_fill(x.data_ptr(), x.numel(), synth.SEED_INPUT, mask)
+    ms = timed(lambda: L.run_device(x.data_ptr(), y.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+    macs = d.macs_per_image
+    nz = macs / 4 if d.kind == KIND_DECONV522 else macs
+    r = dict(layer=name, engine=L.engine, plan=L.plan, images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3),
+             TOPs_dense=round(2 * macs * n / ms / 1e9, 1), TOPs_nonzero=round(2 * nz * n / ms / 1e9, 1),
+             GBs=round((L.in_bytes + L.out_bytes) * n / ms / 1e6, 1))
+    print(json.dumps(r), flush=True)
+    return L, r
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=64)
+    a = ap.parse_args()
+    layers = []
+    for i in range(8):
+        n = a.images * (1 if i in (0, 6, 7) else 4)
+        L, _ = bench_layer(f"L{i}", configs.net_layer(i), n, 0xFF if i == 0 else 0x7F)
+        layers.append(L)
+    net = Net(layers)
+    n = a.images
+    x = torch.empty(n * net.in_bytes, dtype=torch.uint8, device="cuda")
+    y = torch.empty(n * net.out_bytes, dtype=torch.uint8, device="cuda")
+    synth_fill(x.data_ptr(), x.numel(), synth.SEED_INPUT, 0xFF)
+    ms = timed(lambda: net.run_device(x.data_ptr(), y.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+    print(json.dumps(dict(layer="eight_layers_net", images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3, 1),
+                          TOPs_nonzero=round(2 * 28.94e9 * n / ms / 1e9, 1))), flush=True)
+    # BASELINE.json config 3: 1-bit xnor 64->64 3x3 128x96 ; config 4: 4b/8b 256->256 64x48 thresholds(255) + 2x2 pool
+    c3 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=64, ofm_ch=64, ifm_x=128, ifm_y=96, stride_x=1, stride_y=1, pad=0,
+                   simd=64, pe=16, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR, acc_bits=16, acc_signed=1,
+                   act_kind=ACT_THRESHOLDS, out_bits=1, num_th=1)
+    bench_layer("cfg3_xnor", c3, a.images * 16, 0xFF)
+    c4 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=256, ofm_ch=256, ifm_x=64, ifm_y=48, stride_x=1, stride_y=1, pad=1,
+                   simd=32, pe=32, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8, num_th=255,
+                   pool=2)
+    bench_layer("cfg4_thr_pool", c4, a.images * 16, 0xFF)
+    bench_layer("cfg4_thr_nopool", dataclasses.replace(c4, pool=0), a.images * 16, 0xFF)
