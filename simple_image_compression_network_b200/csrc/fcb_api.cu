@@ -120,6 +120,12 @@ struct fcb_layer {
   DirectParams dp{};
   size_t smem = 0;
   UmmaPlan* umma = nullptr;
+  // thin-input layers (Kx*Ky*C <= 128): im2col rows in a scratch buffer, then a 1x1 layer on the tensor-core engine
+  bool lowered = false;
+  Im2colParams ip{};
+  void* d_scratch = nullptr;
+  size_t scratch_imgs = 0, scratch_img_bytes = 0;
+  char plan_desc[256] = "";
   // staging for the host-buffer entry point (two slots, double buffered)
   void* s_in[2] = {nullptr, nullptr};
   void* s_out[2] = {nullptr, nullptr};
@@ -171,7 +177,7 @@ void fcb_layer_destroy(fcb_layer* L) {
   if (!L) return;
   cudaSetDevice(L->device);
   if (L->umma) umma_plan_destroy(L->umma);
-  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr);
+  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_scratch);
   for (int i = 0; i < 2; i++) {
     cudaFree(L->s_in[i]); cudaFree(L->s_out[i]);
     if (L->s_stream[i]) cudaStreamDestroy(L->s_stream[i]);
@@ -261,8 +267,33 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
 
   if (engine == ENG_UMMA) {
     rc = umma_plan_create(g, W, L->epi, device, &L->umma);
-    if (rc) { fcb_layer_destroy(L); return rc; }
-  } else {
+    if (rc == FCB_ERR_UNSUPPORTED) { engine = L->engine = ENG_IMAD; L->umma = nullptr; }  // shape the planner cannot tile
+    else if (rc) { fcb_layer_destroy(L); return rc; }
+  }
+  // thin-input lowering: conv2d with Kx*Ky*C <= 128 bytes of window (the C = 3 first layer of the reference network)
+  if (engine == ENG_IMAD && !(force && !strcmp(force, "imad")) && g.kind == FCB_KIND_CONV && g.weight_kind == FCB_W_FIXED &&
+      g.w_bits <= 8 && g.in_bits == 8 && g.K <= 128 && g.OFM <= 256 && g.pool <= 2 && g.SX == g.SY) {
+    Geom g2 = g;
+    g2.C = 128; g2.KX = g2.KY = 1; g2.K = 128; g2.IX = g.OX; g2.IY = g.OY; g2.SX = g2.SY = 1; g2.PAD = 0;
+    g2.in_word_bytes = 128; g2.in_img_bytes = (size_t)128 * g.OX * g.OY;
+    std::vector<int32_t> W2((size_t)g.OFM * 128, 0);
+    for (int ch = 0; ch < g.OFM; ch++)
+      for (int k = 0; k < g.K; k++) W2[(size_t)ch * 128 + k] = W[(size_t)ch * g.K + k];
+    if (umma_eligible(g2)) {
+      rc = umma_plan_create(g2, W2, L->epi, device, &L->umma);
+      if (rc == FCB_OK) {
+        engine = L->engine = ENG_UMMA;
+        L->lowered = true;
+        L->scratch_img_bytes = g2.in_img_bytes;
+        Im2colParams& ip = L->ip;
+        ip.IX = g.IX; ip.IY = g.IY; ip.OX = g.OX; ip.OY = g.OY; ip.S = g.SX; ip.PAD = g.PAD; ip.K = g.K; ip.C = g.C; ip.KX = g.KX;
+        ip.in_word_bytes = (int)g.in_word_bytes; ip.in_img_bytes = g.in_img_bytes;
+        snprintf(L->plan_desc, sizeof(L->plan_desc), "im2col rows (K=%d -> 128 B) + 1x1 %s", g.K, umma_plan_describe(L->umma));
+      } else if (rc != FCB_ERR_UNSUPPORTED) { fcb_layer_destroy(L); return rc; }
+      else L->umma = nullptr;
+    }
+  }
+  if (engine != ENG_UMMA) {
     DirectParams& p = L->dp;
     const int deconv = g.kind == FCB_KIND_DECONV522;
     p.C = g.C; p.OFM = g.OFM; p.OFMp = (g.OFM + 63) / 64 * 64; p.KX = g.KX; p.KY = g.KY; p.IX = g.IX; p.IY = g.IY;
@@ -306,6 +337,7 @@ const char* fcb_layer_engine(const fcb_layer* L) {
 }
 const char* fcb_layer_plan(const fcb_layer* L) {
   if (!L) return "";
+  if (L->lowered) return L->plan_desc;
   return L->engine == ENG_UMMA ? umma_plan_describe(L->umma) : "direct 16x8-pixel x 64-channel CTA tiles";
 }
 uint64_t fcb_layer_launches(const fcb_layer* L) { return L ? L->launches : 0; }
@@ -315,6 +347,29 @@ int fcb_layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t n
   if (numReps == 0) return FCB_OK;
   FCB_CUDA_OK(cudaSetDevice(L->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (L->lowered) {
+    size_t cap = std::max<size_t>(1, ((size_t)1 << 30) / L->scratch_img_bytes);
+    cap = std::min<size_t>(cap, numReps);
+    if (L->scratch_imgs < cap) {
+      cudaFree(L->d_scratch);
+      L->d_scratch = nullptr;
+      L->scratch_imgs = 0;
+      FCB_CUDA_OK(cudaMalloc(&L->d_scratch, L->scratch_img_bytes * cap));
+      L->scratch_imgs = cap;
+    }
+    for (size_t n0 = 0; n0 < numReps; n0 += L->scratch_imgs) {
+      const int nb = (int)std::min<size_t>(L->scratch_imgs, numReps - n0);
+      Im2colParams ip = L->ip;
+      ip.in = (const uint8_t*)d_in + n0 * L->g.in_img_bytes;
+      ip.out = (uint8_t*)L->d_scratch;
+      int rc = launch_im2col(ip, nb, st);
+      if (rc) return rc;
+      L->launches++;
+      rc = umma_run(L->umma, L->d_scratch, (uint8_t*)d_out + n0 * L->g.out_img_bytes, nb, st, &L->launches);
+      if (rc) return rc;
+    }
+    return FCB_OK;
+  }
   if (L->engine == ENG_UMMA) return umma_run(L->umma, d_in, d_out, (int)numReps, st, &L->launches);
   // containers with padding bits (e.g. ap_uint<24> in 4 bytes): writers zero them
   if (L->g.out_word_bytes * 8 != (size_t)L->g.OFM * L->g.out_bits) {

@@ -64,6 +64,15 @@ void umma_plan_destroy(UmmaPlan* p);
 const char* umma_plan_describe(const UmmaPlan* p);
 int umma_run(UmmaPlan* p, const void* d_in, void* d_out, int n_images, cudaStream_t st, uint64_t* launches);
 
+// thin-input lowering (fcb_im2col.cu)
+struct Im2colParams {
+  const uint8_t* in;
+  uint8_t* out;  // [n][OY][OX][128]
+  int IX, IY, OX, OY, S, PAD, K, C, KX, in_word_bytes;
+  unsigned long long in_img_bytes;
+};
+int launch_im2col(const Im2colParams& p, int n_images, cudaStream_t st);
+
 // synthetic data (fcb_synth.cu)
 int synth_fill(void* d_ptr, size_t n_bytes, uint64_t seed, uint32_t mask, uint64_t offset, cudaStream_t st);
 

@@ -268,18 +268,23 @@ int umma_encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, 
   return FCB_OK;
 }
 
+// v1 (per-tap TMA) needs whole 128-byte channel chunks and 32-channel epilogue groups
+static int v1_eligible(const Geom& g) { return g.C % KCH == 0 && g.OFM % 32 == 0 && g.OFM >= 32 && g.OFM <= 256; }
+
 int umma_eligible(const Geom& g) {
   if (g.weight_kind != FCB_W_FIXED || g.w_bits > 8 || g.in_bits != 8) return 0;
-  if (g.C % KCH) return 0;                                   // one 128-byte swizzle row per K block
   if (g.in_word_bytes != (size_t)g.C) return 0;              // stream image == dense NHWC bytes
-  if (g.OFM % 32 || g.OFM > 256 || g.OFM < 32) return 0;     // UMMA N and the 32-column epilogue chunks
+  if (g.C % 16) return 0;                                    // TMA strides are multiples of 16 bytes
+  if (g.OFM > 256) return 0;
   if (g.KX * g.KY > MAX_TAPS) return 0;
   if ((uint64_t)g.K * 255ull * 128ull >= (1ull << 31)) return 0;  // exact int32 accumulation
   if (g.pool > 2) return 0;
   if (g.kind == FCB_KIND_DECONV522) return g.pool == 1;
   if (g.SX != g.SY) return 0;
+  // stride 1: a partial last channel chunk is zero-filled by TMA (it then multiplies the next tap's weights by 0);
+  // stride 2: the parity view packs two pixels per row, so chunks must not straddle pixels
   if (g.SX == 1) return 1;
-  if (g.SX == 2) return (g.IX % 2 == 0) && (g.IY % 2 == 0);
+  if (g.SX == 2) return (g.C % KCH == 0) && (g.IX % 2 == 0) && (g.IY % 2 == 0);
   return 0;
 }
 
@@ -292,7 +297,7 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   UmmaParams& p = P->p;
   memset(&p, 0, sizeof(p));
   p.epi = epi;
-  p.C = g.C; p.OFM = g.OFM; p.N = g.OFM; p.cchunks = g.C / KCH;
+  p.C = g.C; p.OFM = g.OFM; p.N = g.OFM; p.cchunks = (g.C + KCH - 1) / KCH;
   p.deconv = g.kind == FCB_KIND_DECONV522;
   p.stride2 = (!p.deconv && g.SX == 2);
   p.OX = g.OX; p.OY = g.OY; p.out_x = g.out_x; p.out_y = g.out_y; p.out_word_bytes = (int)g.out_word_bytes;
@@ -364,7 +369,7 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   for (size_t i = 0; i < w8.size(); i++) w8[i] = (int8_t)W[i];
   FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size() * copies));
   for (int c = 0; c < copies; c++) FCB_CUDA_OK(cudaMemcpy(P->d_w + (size_t)c * w8.size(), w8.data(), w8.size(), cudaMemcpyHostToDevice));
-  {
+  if (v1_eligible(g)) {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)p.N * copies};
     const uint64_t strides[1] = {(uint64_t)g.K};
     const uint32_t box[2] = {(uint32_t)KCH, (uint32_t)p.N};
@@ -379,6 +384,7 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
       else if (rc2 != FCB_ERR_UNSUPPORTED) { umma_plan_destroy(P); return rc2; }
     }
   }
+  if (!P->v2 && !v1_eligible(g)) { umma_plan_destroy(P); set_error("no tensor-core plan for this shape"); return FCB_ERR_UNSUPPORTED; }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = P;

@@ -64,7 +64,7 @@ struct Params2 {
   int WT, R, P, tiles_x, tiles_y, PX, PY;
   int out_x, out_y, out_word_bytes, n_images;
   int wstages, w_bytes, acc_stages, acc_stride, tmem_cols;
-  int w_off, bar_off;
+  int w_off, bar_off, stage_off;  // stage_off: 8 x 256 B staging rows of the thin-output epilogue (OFM <= 8)
   int debug;  // FCB_U2_DEBUG bitmask (perf decomposition only): 1 no weight TMA, 2 no plane TMA, 4 no stores, 8 no epilogue
   unsigned long long out_img_bytes;
   uint32_t idesc;
@@ -229,6 +229,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const bool mono = p.epi.act_kind == FCB_ACT_THRESHOLDS && (p.epi.cmp == FCB_CMP_LESS || p.epi.cmp == FCB_CMP_LESS_EQUAL) &&
                       p.epi.act_val >= 0 && (p.epi.out_bits >= 31 || p.epi.act_val + p.epi.num_th < (1 << p.epi.out_bits)) &&
                       (p.epi.acc_signed || p.epi.acc_bits < 32);
+    const bool thin = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
     uint32_t acc_it = 0;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int img = (int)(t / tiles_per_img);
@@ -241,7 +242,44 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
-        for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++) {
+        if (thin) {
+          // Thin output (OFM <= 8, e.g. the 3-channel last layer): only lanes < OFM of the first lane quarter hold data.
+          // They turn their 256 columns into bytes in a shared staging row per channel; then all 128 epilogue threads
+          // assemble and store whole output words, one pixel per thread (coalesced), instead of 3 lanes doing everything.
+          uint8_t* stage = smem + p.stage_off;
+          if (q == 0) {  // the whole warp issues the (warp-collective) TMEM loads; lanes >= OFM hold zero rows
+            const uint32_t bias4 = (lane < p.OFM ? ((uint32_t)(int32_t)p.epi.bias[lane] & 0xFFu) : 0u) * 0x01010101u;
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride);
+            for (int c0 = 0; c0 < p.NPX && c0 < vrows * p.P; c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32(taddr + (uint32_t)c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
+                uint32_t w = __vadd4(__byte_perm(lo, hi, 0x5410), bias4);
+                w &= ~(((w >> 7) & 0x01010101u) * 0xFFu);
+                if (lane < p.OFM) *reinterpret_cast<uint32_t*>(stage + lane * 256 + c0 + 4 * j) = w;
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int m = (warp - 2) * 32 + lane; m < p.NPX; m += 128) {
+            const int rr = m / p.P, xo = m - rr * p.P;
+            if (xo < vcols && rr < vrows) {
+              unsigned long long word = 0;
+              for (int c = 0; c < p.OFM; c++) word |= (unsigned long long)stage[c * 256 + m] << (8 * c);
+              uint8_t* dst = p.out + pm.word_off(rr, xo, 1);
+              if (p.out_word_bytes == 4) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)word;
+              else if (p.out_word_bytes == 8) *reinterpret_cast<unsigned long long*>(dst) = word;
+              else if (p.out_word_bytes == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)word;
+              else *dst = (uint8_t)word;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // staging rows are reused by the next accumulator
+        }
+        for (int cb = 0; cb < ((p.debug & 8) || thin ? 0 : p.CB); cb++) {
+          if (cb * 128 + q * 32 >= p.OFM) continue;  // this warp's 32 channels do not exist (warp-uniform)
           const int ch = cb * 128 + q * 32 + lane;
           const bool chv = ch < p.OFM;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
@@ -340,7 +378,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   const int deconv = g.kind == FCB_KIND_DECONV522;
   if (deconv && g.pool != 1) return FCB_ERR_UNSUPPORTED;
   const int s = deconv ? 1 : g.SX;
-  const int cch = g.C / 128;
+  const int cch = (g.C + 127) / 128;  // a partial last chunk is zero-filled by TMA (stride-1 views only)
   const int CB = (g.OFM + 127) / 128;
   if (CB > 2) return FCB_ERR_UNSUPPORTED;
   // ---- taps
@@ -386,7 +424,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
 
   // ---- choose (WT, R, NPX, wstages): minimise estimated clocks per useful output pixel
   const int w_bytes = CB * 128 * 128;
-  const int smem_limit = 227 * 1024 - 2048;
+  const int smem_limit = 227 * 1024 - 2048 - 2048;
   const int step = g.pool == 2 ? 2 : 1;
   double best = 1e30;
   int bWT = 0, bR = 0, bNPX = 0, bWS = 0;
@@ -416,7 +454,8 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
         const double mma_clk = nkb * CB * 4 * (NPX == 256 ? 146.0 : 102.0);  // measured clocks per instruction
         const double fill_clk = ((double)plane_bytes + nkb * w_bytes) / 38.0;  // measured L2->SM fill, B/clk/SM
         const double ws_pen = WS >= 3 ? 1.0 : 1.05;
-        const double cost = tiles * std::max(mma_clk, fill_clk) * ws_pen / ((double)PX * PY);
+        // ties (e.g. 1x1 layers, where every WT is equally efficient) go to wide boxes: long contiguous TMA rows
+        const double cost = tiles * std::max(mma_clk, fill_clk) * ws_pen * (1.0 + 0.0005 * R) / ((double)PX * PY);
         if (cost < best * 0.999) { best = cost; bWT = WT; bR = R; bNPX = NPX; bWS = WS; }
       }
   }
@@ -475,6 +514,9 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   off += bWS * w_bytes;
   p.bar_off = off;
   off += (2 * bWS + 2 * np + 4) * 8 + 16;
+  off = (off + 15) & ~15;
+  p.stage_off = off;
+  off += 8 * 256;
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
   // K-block lists: plane-major within each phase so planes are released progressively

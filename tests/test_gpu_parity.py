@@ -76,7 +76,7 @@ def test_umma_generations_agree(name, fcb_lib, oracle_mod, monkeypatch):
 
 
 def test_expected_engines(fcb_lib):
-    exp = {"c2d_e": "umma_i8", "c2d_g": "umma_i8", "dc_c": "umma_i8", "th_cfg4": "umma_i8", "c2d_c": "imad", "dc_d": "imad",
+    exp = {"c2d_e": "umma_i8", "c2d_g": "umma_i8", "dc_c": "umma_i8", "th_cfg4": "umma_i8", "c2d_c": "umma_i8", "c2d_a": "umma_i8", "dc_a": "imad", "dc_d": "umma_i8", "dc_e": "umma_i8", "dc_L4": "umma_i8", "c2d_b": "imad",
            "xn_b": "xnor_popc", "xn_c": "xnor_popc", "xn_a": "imad", "c2d_L1band": "umma_i8"}
     for name, eng in exp.items():
         d = cases.CASES[name]
