@@ -8,10 +8,8 @@
 
 namespace fcb {
 
-__global__ void __launch_bounds__(256) im2col_rows_kernel(const Im2colParams p, int n_images) {
-  const int lane = threadIdx.x & 31;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long pix_per_img = (long long)p.OX * p.OY, total = pix_per_img * n_images;
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const Im2colParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // this lane's 4 window bytes: tap coordinates and byte offset inside the input word are fixed
   int ky[4], kx[4], co[4];
   bool kv[4];
@@ -20,27 +18,38 @@ __global__ void __launch_bounds__(256) im2col_rows_kernel(const Im2colParams p, 
     const int k = 4 * lane + b;
     kv[b] = k < p.K;
     const int tap = kv[b] ? k / p.C : 0;
-    ky[b] = tap / p.KX; kx[b] = tap % p.KX; co[b] = kv[b] ? k - tap * p.C : 0;
+    ky[b] = tap / p.KX - p.PAD; kx[b] = tap % p.KX - p.PAD; co[b] = kv[b] ? k - tap * p.C : 0;
   }
-  for (long long w = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < total; w += warps) {
-    const int img = (int)(w / pix_per_img);
-    const int pix = (int)(w - (long long)img * pix_per_img);
-    const int oy = pix / p.OX, ox = pix - oy * p.OX;
-    const uint8_t* in = p.in + (size_t)img * p.in_img_bytes;
+  // grid = (column blocks of 8 warps x 4 pixels, output rows, images): no divisions in the pixel loop
+  const int img = blockIdx.z, oy = blockIdx.y;
+  const uint8_t* in = p.in + (size_t)img * p.in_img_bytes;
+  uint32_t* out = reinterpret_cast<uint32_t*>(p.out) + ((size_t)img * p.OY + oy) * p.OX * 32;
+  const int ox0 = (blockIdx.x * 8 + warp) * 4;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int ox = ox0 + i;
+    if (ox >= p.OX) break;
     uint32_t word = 0;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-      const int iy = oy * p.S + ky[b] - p.PAD, ix = ox * p.S + kx[b] - p.PAD;
+      const int iy = oy * p.S + ky[b], ix = ox * p.S + kx[b];
       if (kv[b] && iy >= 0 && iy < p.IY && ix >= 0 && ix < p.IX)
         word |= (uint32_t)__ldg(in + ((size_t)iy * p.IX + ix) * p.in_word_bytes + co[b]) << (8 * b);
     }
-    reinterpret_cast<uint32_t*>(p.out)[w * 32 + lane] = word;
+    out[(size_t)ox * 32 + lane] = word;
   }
 }
 
 int launch_im2col(const Im2colParams& p, int n_images, cudaStream_t st) {
-  im2col_rows_kernel<<<148 * 16, 256, 0, st>>>(p, n_images);
-  FCB_CUDA_OK(cudaGetLastError());
+  for (int n0 = 0; n0 < n_images; n0 += 65535) {
+    Im2colParams q = p;
+    const int nb = n_images - n0 < 65535 ? n_images - n0 : 65535;
+    q.in = p.in + (size_t)n0 * p.in_img_bytes;
+    q.out = p.out + (size_t)n0 * p.OX * p.OY * 128;
+    dim3 grid((p.OX + 31) / 32, p.OY, nb);
+    im2col_rows_kernel<<<grid, 256, 0, st>>>(q);
+    FCB_CUDA_OK(cudaGetLastError());
+  }
   return FCB_OK;
 }
 

@@ -364,11 +364,14 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   P->num_sms = prop.multiProcessorCount;
 
   // weights: s8 [N][K], K contiguous (k = (ky*KX+kx)*C + c) -- the implicit-GEMM B operand
+  // rows padded with zeros to whole 128-channel blocks: an all-out-of-bounds TMA box row costs as much as a real one
+  // (measured on the 3-channel last layer), a zero row in memory does not
   const int copies = 1;
-  std::vector<int8_t> w8((size_t)p.N * g.K);
-  for (size_t i = 0; i < w8.size(); i++) w8[i] = (int8_t)W[i];
-  FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size() * copies));
-  for (int c = 0; c < copies; c++) FCB_CUDA_OK(cudaMemcpy(P->d_w + (size_t)c * w8.size(), w8.data(), w8.size(), cudaMemcpyHostToDevice));
+  const int rows_pad = (g.OFM + 127) / 128 * 128;
+  std::vector<int8_t> w8((size_t)rows_pad * g.K, 0);
+  for (size_t i = 0; i < (size_t)g.OFM * g.K; i++) w8[i] = (int8_t)W[i];
+  FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size()));
+  FCB_CUDA_OK(cudaMemcpy(P->d_w, w8.data(), w8.size(), cudaMemcpyHostToDevice));
   if (v1_eligible(g)) {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)p.N * copies};
     const uint64_t strides[1] = {(uint64_t)g.K};

@@ -39,7 +39,7 @@ namespace fcb {
 
 using namespace sm100;
 
-constexpr int U2_THREADS = 224;
+constexpr int U2_THREADS = 352;  // 11 warps: 0 weight TMA, 1 MMA issue, 2..9 epilogue (2 per TMEM lane quarter), 10 plane TMA
 constexpr int U2_MAX_KB = 64;
 constexpr int U2_MAX_PLANES = 8;
 enum { KB_WAIT = 2, KB_FREE = 4 };
@@ -64,6 +64,7 @@ struct Params2 {
   int WT, R, P, tiles_x, tiles_y, PX, PY;
   int out_x, out_y, out_word_bytes, n_images;
   int wstages, w_bytes, acc_stages, acc_stride, tmem_cols;
+  int nsets, set_bytes;  // plane sets (double buffering of the input patch across tiles when shared memory allows)
   int w_off, bar_off, stage_off;  // stage_off: 8 x 256 B staging rows of the thin-output epilogue (OFM <= 8)
   int debug;  // FCB_U2_DEBUG bitmask (perf decomposition only): 1 no weight TMA, 2 no plane TMA, 4 no stores, 8 no epilogue
   unsigned long long out_img_bytes;
@@ -106,8 +107,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* wfull = bars;
   uint64_t* wempty = wfull + p.wstages;
   uint64_t* afull = wempty + p.wstages;
-  uint64_t* aempty = afull + p.nplanes;
-  uint64_t* tfull = aempty + p.nplanes;
+  uint64_t* aempty = afull + p.nsets * p.nplanes;
+  uint64_t* tfull = aempty + p.nsets * p.nplanes;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -120,8 +121,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-    for (int i = 0; i < p.nplanes; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    for (int i = 0; i < p.nsets * p.nplanes; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -150,7 +151,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     // ===================== TMA producer: input planes =====================
     // Independent of the weight ring: plane i of the next tile is fetched the moment the MMAs that read plane i of
     // the current tile have retired (aempty), i.e. while the remaining taps of the current tile execute.
@@ -160,14 +161,18 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int img = (int)(t / tiles_per_img);
         const int r = (int)(t % tiles_per_img);
         const int x0 = (r % p.tiles_x) * p.WT, y0 = (r / p.tiles_x) * p.R;
+        const int set = tile_it % p.nsets;
+        const uint32_t par = ((tile_it / p.nsets) & 1) ^ 1;
         for (int i = 0; i < p.nplanes; i++) {
           const Plane2& pl = p.planes[i];
-          mbar_wait(&aempty[i], (tile_it & 1) ^ 1);
-          if (p.debug & 2) { mbar_arrive(&afull[i]); continue; }
-          mbar_arrive_expect_tx(&afull[i], (uint32_t)pl.bytes);
+          uint64_t* fb = &afull[set * p.nplanes + i];
+          mbar_wait(&aempty[set * p.nplanes + i], par);
+          if (p.debug & 2) { mbar_arrive(fb); continue; }
+          mbar_arrive_expect_tx(fb, (uint32_t)pl.bytes);
           const CUtensorMap* m = pl.map ? &tmA1 : &tmA0;
-          if (p.stride2) tma_load_5d(smem + pl.smem_off, m, &afull[i], pl.c0, x0 + pl.dx, pl.par, y0 + pl.dy, img);
-          else tma_load_4d(smem + pl.smem_off, m, &afull[i], pl.c0, x0 + pl.dx, y0 + pl.dy, img);
+          uint8_t* dst = smem + set * p.set_bytes + pl.smem_off;
+          if (p.stride2) tma_load_5d(dst, m, fb, pl.c0, x0 + pl.dx, pl.par, y0 + pl.dy, img);
+          else tma_load_4d(dst, m, fb, pl.c0, x0 + pl.dx, y0 + pl.dy, img);
         }
       }
     }
@@ -185,6 +190,9 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint32_t w_d0 = (uint32_t)p.w_off >> 4, w_dstep = (uint32_t)p.w_bytes >> 4;
     const int wstages = p.wstages, CB = p.CB, NPX = p.NPX;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_it++) {
+      const int set = tile_it % p.nsets;
+      const uint32_t apar = (tile_it / p.nsets) & 1;
+      const uint64_t desc_set = desc0 + (uint32_t)((set * p.set_bytes) >> 4);
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
         const Phase2& P = p.phases[ph];
         const int nkb = P.nkb;
@@ -193,9 +201,9 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.acc_stride);
         for (int i = 0; i < nkb; i++) {
-          const uint32_t flags = P.kb[i].flags, plane = P.kb[i].plane;
-          const uint64_t pdesc = desc0 + P.kb[i].d_off;
-          if (flags & KB_WAIT) mbar_wait(&afull[plane], tile_it & 1);
+          const uint32_t flags = P.kb[i].flags, plane = set * p.nplanes + P.kb[i].plane;
+          const uint64_t pdesc = desc_set + P.kb[i].d_off;
+          if (flags & KB_WAIT) mbar_wait(&afull[plane], apar);
           mbar_wait(&wfull[s], wphase);
           tc_fence_after();
           const uint64_t wdesc = desc0 + (w_d0 + (uint32_t)s * w_dstep);
@@ -220,9 +228,11 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
     }
-  } else if (warp < 6) {
-    // ===================== epilogue (warps 2..5): lane = output channel, TMEM column = pixel =====================
-    const int q = warp & 3;
+  } else if (warp < 10) {
+    // ===================== epilogue (warps 2..9): lane = output channel, TMEM column = pixel =====================
+    // two warps per TMEM lane quarter; `half` splits the accumulator columns (pixels) between them
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int col_lo = half * (p.NPX / 2), col_hi = col_lo + p.NPX / 2;
     const int pk = p.epi.pool >= 2 ? p.epi.pool : 1;
     const bool fast = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && (p.OFM % 32) == 0 && p.P >= 4;
     // thresholds with comp::less / less_equal and a result that cannot wrap TR: monotone in the (wrapped, < 2^31) accumulator
@@ -250,7 +260,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (q == 0) {  // the whole warp issues the (warp-collective) TMEM loads; lanes >= OFM hold zero rows
             const uint32_t bias4 = (lane < p.OFM ? ((uint32_t)(int32_t)p.epi.bias[lane] & 0xFFu) : 0u) * 0x01010101u;
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.acc_stride);
-            for (int c0 = 0; c0 < p.NPX && c0 < vrows * p.P; c0 += 32) {
+            for (int c0 = col_lo; c0 < col_hi && c0 < vrows * p.P; c0 += 32) {
               uint32_t v[32];
               tmem_ld32(taddr + (uint32_t)c0, v);
               tmem_ld_wait();
@@ -263,8 +273,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               }
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int m = (warp - 2) * 32 + lane; m < p.NPX; m += 128) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int m = (warp - 2) * 32 + lane; m < p.NPX; m += 256) {
             const int rr = m / p.P, xo = m - rr * p.P;
             if (xo < vcols && rr < vrows) {
               unsigned long long word = 0;
@@ -276,7 +286,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               else *dst = (uint8_t)word;
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // staging rows are reused by the next accumulator
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // staging rows are reused by the next accumulator
         }
         for (int cb = 0; cb < ((p.debug & 8) || thin ? 0 : p.CB); cb++) {
           if (cb * 128 + q * 32 >= p.OFM) continue;  // this warp's 32 channels do not exist (warp-uniform)
@@ -290,8 +300,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const uint32_t bias4 = (chv ? ((uint32_t)(int32_t)p.epi.bias[ch] & 0xFFu) : 0u) * 0x01010101u;
             const int li = lane & 3, cgrp = cb * 128 + q * 32 + (lane & ~3);  // pixel-in-quad, first of this lane's 4 channels
             const uint32_t selA = (lane & 1) ? 0x3715u : 0x6240u, selB = (lane & 2) ? 0x3276u : 0x5410u;
-            int rr = 0, xo = li;  // this lane's pixel after the transpose: m = c0 + 4*j + li
-            for (int c0 = 0; c0 < p.NPX && c0 < vrows * p.P; c0 += 32) {
+            int rr = (col_lo + li) / p.P, xo = (col_lo + li) - rr * p.P;  // this lane's pixel after the transpose: m = c0 + 4*j + li
+            for (int c0 = col_lo; c0 < col_hi && c0 < vrows * p.P; c0 += 32) {
               uint32_t v[32];
               tmem_ld32(taddr + (uint32_t)c0, v);
               tmem_ld_wait();
@@ -308,9 +318,9 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               }
             }
           } else if (pk == 1) {
-            int rr = 0, xo = 0;
+            int rr = col_lo / p.P, xo = col_lo - rr * p.P;
 #pragma unroll 1
-            for (int c0 = 0; c0 < p.NPX && rr < vrows; c0 += 8) {
+            for (int c0 = col_lo; c0 < col_hi && rr < vrows; c0 += 8) {
               uint32_t v[8];
               tmem_ld8(taddr + (uint32_t)c0, v);
               tmem_ld_wait();
@@ -326,7 +336,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           } else {
             // 2x2 max pool: rows rr, rr+1 of the tile are columns m and m + P of the same thread
 #pragma unroll 1
-            for (int rr = 0; rr < vrows; rr += 2) {
+            for (int rr = 2 * half; rr < vrows; rr += 4) {  // the two warps of a lane quarter take alternate row pairs
 #pragma unroll 1
               for (int xb = 0; xb < vcols; xb += 8) {
                 uint32_t va[8], vb[8];
@@ -509,11 +519,15 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     }
   }
   p.nplanes = np;
+  p.set_bytes = off;
+  p.nsets = ((size_t)2 * off + (size_t)bWS * w_bytes + 4096 <= (size_t)227 * 1024 - 1024) ? 2 : 1;
+  if (getenv("FCB_U2_NSETS")) p.nsets = std::max(1, std::min(p.nsets, atoi(getenv("FCB_U2_NSETS"))));
+  off *= p.nsets;
   U->box_rows[0] = map_rows[0]; U->box_rows[1] = nmaps > 1 ? map_rows[1] : map_rows[0];
   p.w_off = off;
   off += bWS * w_bytes;
   p.bar_off = off;
-  off += (2 * bWS + 2 * np + 4) * 8 + 16;
+  off += (2 * bWS + 2 * np * p.nsets + 4) * 8 + 16;
   off = (off + 15) & ~15;
   p.stage_off = off;
   off += 8 * 256;
@@ -551,7 +565,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     }
   // weights as the A operand: box = 128 B of K x CB*128 channel rows; rows >= OFM are zero-filled by TMA
   {
-    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.OFM};
+    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)(CB * 128)};  // rows >= OFM are zeros in memory (fcb_umma.cu)
     const uint64_t strides[1] = {(uint64_t)g.K};
     const uint32_t box[2] = {128, (uint32_t)(CB * 128)};
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
@@ -566,8 +580,8 @@ void umma2_plan_destroy(Umma2Plan* U) { delete U; }
 
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   const Params2& p = U->p;
-  snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d planes=%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT, p.R,
-           p.P, p.NPX, p.CB, p.nplanes, p.wstages, p.acc_stages, U->smem, p.tiles_x, p.tiles_y);
+  snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT, p.R,
+           p.P, p.NPX, p.CB, p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem, p.tiles_x, p.tiles_y);
   return buf;
 }
 

@@ -42,7 +42,13 @@ def bench_layer(name, d, n, mask=0x7F):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=64)
+    ap.add_argument("--only", default="", help="comma list of net layers to time alone, e.g. L0,L6 (skips the rest)")
     a = ap.parse_args()
+    if a.only:
+        for nm in a.only.split(","):
+            i = int(nm[1:])
+            bench_layer(nm, configs.net_layer(i), a.images, 0xFF if i == 0 else 0x7F)
+        sys.exit(0)
     layers = []
     for i in range(8):
         n = a.images * (1 if i in (0, 6, 7) else 4)
