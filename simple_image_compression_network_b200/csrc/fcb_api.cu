@@ -116,6 +116,7 @@ struct fcb_layer {
   void* d_wt = nullptr;
   int8_t* d_bias = nullptr;
   int32_t* d_thr = nullptr;
+  int32_t* d_thr_cm = nullptr;
   EpiParams epi{};
   DirectParams dp{};
   size_t smem = 0;
@@ -177,7 +178,7 @@ void fcb_layer_destroy(fcb_layer* L) {
   if (!L) return;
   cudaSetDevice(L->device);
   if (L->umma) umma_plan_destroy(L->umma);
-  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_scratch);
+  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_thr_cm); cudaFree(L->d_scratch);
   for (int i = 0; i < 2; i++) {
     cudaFree(L->s_in[i]); cudaFree(L->s_out[i]);
     if (L->s_stream[i]) cudaStreamDestroy(L->s_stream[i]);
@@ -236,23 +237,37 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     L->epi.bias = L->d_bias;
   }
   if (g.act_kind == FCB_ACT_THRESHOLDS) {
-    std::vector<int32_t> T((size_t)g.OFM * g.num_th);
+    // sorted per channel (the reference result is a count), laid out threshold-major and padded to 2^k - 1 entries
+    int tn = 1;
+    while (tn - 1 < g.num_th) tn *= 2;
+    tn -= 1;
+    const int tstride = (g.OFM + 127) / 128 * 128;
+    std::vector<int32_t> T((size_t)tn * tstride, 0x7fffffff);
+    std::vector<int32_t> row(g.num_th);
     const uint8_t* tb = (const uint8_t*)thresholds;
     const size_t cb = word_bytes(g.acc_bits);
     for (int pe = 0; pe < g.pe; pe++)
       for (int nf = 0; nf < g.NF; nf++) {
-        int32_t* row = &T[(size_t)(nf * g.pe + pe) * g.num_th];
         for (int i = 0; i < g.num_th; i++) {
           const uint8_t* p = tb + (((size_t)pe * g.NF + nf) * g.num_th + i) * cb;
           uint64_t raw = 0;
           for (size_t b = 0; b < cb && b < 8; b++) raw |= (uint64_t)p[b] << (8 * b);
           row[i] = wrap_host((int64_t)raw, g.acc_bits, g.acc_signed);
         }
-        std::sort(row, row + g.num_th);
+        std::sort(row.begin(), row.end());
+        for (int i = 0; i < g.num_th; i++) T[(size_t)i * tstride + nf * g.pe + pe] = row[i];
       }
+    std::vector<int32_t> TC((size_t)tstride * (tn + 1), 0x7fffffff);  // channel-major copy
+    for (int ch = 0; ch < g.OFM; ch++)
+      for (int i = 0; i < g.num_th; i++) TC[(size_t)ch * (tn + 1) + i] = T[(size_t)i * tstride + ch];
     FCB_CUDA_OK(cudaMalloc(&L->d_thr, T.size() * sizeof(int32_t)));
     FCB_CUDA_OK(cudaMemcpy(L->d_thr, T.data(), T.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    FCB_CUDA_OK(cudaMalloc(&L->d_thr_cm, TC.size() * sizeof(int32_t)));
+    FCB_CUDA_OK(cudaMemcpy(L->d_thr_cm, TC.data(), TC.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    L->epi.thr_cm = L->d_thr_cm;
     L->epi.thr = L->d_thr;
+    L->epi.thr_n = tn;
+    L->epi.thr_stride = tstride;
   }
 
   // ---- engine selection

@@ -18,6 +18,26 @@ __device__ __forceinline__ int32_t wrap_ta(int32_t acc, int bits, int sgn) {
   return sgn ? ((int32_t)u >> (32 - bits)) : (int32_t)(u >> (32 - bits));
 }
 
+// Branch-free lower/upper bound over the per-channel sorted, INT32_MAX-padded table of thr_n = 2^k - 1 entries laid out
+// threshold-major ([i][channel]): consecutive lanes = consecutive channels read one 128-byte line at the top levels.
+// Returns the number of table entries that compare "below" the accumulator.
+__device__ __forceinline__ int thr_search(const EpiParams& e, int ch, int32_t a) {
+  const int32_t* __restrict__ t = e.thr + ch;
+  const bool strict = (e.cmp == FCB_CMP_LESS) || (e.cmp == FCB_CMP_GREATER_EQUAL);
+  int pos = 0;
+  for (int step = (e.thr_n + 1) >> 1; step; step >>= 1) {
+    const int32_t tv = __ldg(t + (size_t)(pos + step - 1) * e.thr_stride);
+    pos += (strict ? (tv < a) : (tv <= a)) ? step : 0;
+  }
+  return pos;
+}
+__device__ __forceinline__ uint32_t thr_finish(const EpiParams& e, int pos) {
+  const uint32_t omask = e.out_bits >= 32 ? 0xffffffffu : ((1u << e.out_bits) - 1u);
+  pos = min(pos, e.num_th);  // a == INT32_MAX can "pass" the padding with the non-strict compares
+  const int cnt = (e.cmp == FCB_CMP_LESS || e.cmp == FCB_CMP_LESS_EQUAL) ? pos : (e.num_th - pos);
+  return (uint32_t)(e.act_val + cnt) & omask;
+}
+
 __device__ __forceinline__ uint32_t activate(const EpiParams& e, int ch, int32_t acc) {
   const int32_t a = wrap_ta(acc, e.acc_bits, e.acc_signed);
   const uint32_t omask = e.out_bits >= 32 ? 0xffffffffu : ((1u << e.out_bits) - 1u);
@@ -26,17 +46,75 @@ __device__ __forceinline__ uint32_t activate(const EpiParams& e, int ch, int32_t
     const uint32_t r = ((uint32_t)a + (uint32_t)(int32_t)e.bias[ch]) & omask;
     return ((r >> (e.out_bits - 1)) & 1u) ? 0u : r;
   }
-  const int32_t* __restrict__ t = e.thr + (size_t)ch * e.num_th;
+  return thr_finish(e, thr_search(e, ch, a));
+}
+
+// N independent searches advanced in lock step: the N loads of one level are issued back to back, so the latency of a
+// level (the table does not fit the little L1 left beside the operand planes) is paid once per N outputs.
+// `tbl` / `stride` select the table: the global one (e.thr, e.thr_stride) or a shared-memory copy of a channel block.
+template <int N>
+__device__ __forceinline__ void activate_thrN(const EpiParams& e, const int32_t* __restrict__ tbl, int stride, const int32_t (&acc)[N],
+                                              uint32_t (&out)[N]) {
+  int32_t a[N];
+  int pos[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { a[i] = wrap_ta(acc[i], e.acc_bits, e.acc_signed); pos[i] = 0; }
   const bool strict = (e.cmp == FCB_CMP_LESS) || (e.cmp == FCB_CMP_GREATER_EQUAL);
-  int lo = 0, hi = e.num_th;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const int32_t tv = __ldg(t + mid);
-    const bool right = strict ? (tv < a) : (tv <= a);
-    if (right) lo = mid + 1; else hi = mid;
+#pragma unroll 1
+  for (int step = (e.thr_n + 1) >> 1; step; step >>= 1) {
+    int32_t tv[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) tv[i] = tbl[(size_t)(pos[i] + step - 1) * stride];
+#pragma unroll
+    for (int i = 0; i < N; i++) pos[i] += (strict ? (tv[i] < a[i]) : (tv[i] <= a[i])) ? step : 0;
   }
-  const int cnt = (e.cmp == FCB_CMP_LESS || e.cmp == FCB_CMP_LESS_EQUAL) ? lo : (e.num_th - lo);
-  return (uint32_t)(e.act_val + cnt) & omask;
+#pragma unroll
+  for (int i = 0; i < N; i++) out[i] = thr_finish(e, pos[i]);
+}
+
+// Hybrid search of the tensor-core epilogue (thread = one fixed channel).  The top `L` levels of the binary search only
+// ever probe sorted indices j * 2^(D-L) - 1 (j = 1 .. 2^L - 1; D = log2(thr_n + 1)): those 2^L - 1 entries per channel sit
+// in shared memory, threshold-major, so lane <-> bank and a probe is one conflict-free wavefront whatever index each lane
+// is at.  What remains is an aligned group of G = 2^(D-L) consecutive sorted thresholds: ONE 16-byte load per lane from the
+// channel-major global copy (G = 4), counted in registers.  A plain search in global memory costs one L1 tag-stage
+// wavefront per lane and probe (~127 per warp and output) and was the limiter at 1 wavefront/clk/SM.
+__device__ __forceinline__ int32_t lds_s32(uint32_t saddr) {
+  int32_t v;
+  asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+// top_saddr: shared-space byte address of this channel's column of the top table; row_shift: log2(bytes per table row);
+// gshift: log2(G).  32-bit shared addressing and shifts keep a level at ~5 instructions per output.
+template <int N>
+__device__ __forceinline__ void activate_thr_hybrid(const EpiParams& e, uint32_t top_saddr, int row_shift, int top_levels, int gshift,
+                                                    const int32_t* __restrict__ row_cm /*global row of the channel*/,
+                                                    const int32_t (&acc)[N], uint32_t (&out)[N]) {
+  int32_t a[N];
+  int pos[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { a[i] = wrap_ta(acc[i], e.acc_bits, e.acc_signed); pos[i] = 0; }
+  const bool strict = (e.cmp == FCB_CMP_LESS) || (e.cmp == FCB_CMP_GREATER_EQUAL);
+  int step = (e.thr_n + 1) >> 1;
+  const uint32_t base = top_saddr - (1u << row_shift);  // row (j - 1)
+#pragma unroll 1
+  for (int l = 0; l < top_levels; l++, step >>= 1) {
+    int32_t tv[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) tv[i] = lds_s32(base + ((uint32_t)((pos[i] + step) >> gshift) << row_shift));
+#pragma unroll
+    for (int i = 0; i < N; i++) pos[i] += (strict ? (tv[i] < a[i]) : (tv[i] <= a[i])) ? step : 0;
+  }
+  if (gshift == 2) {  // G = 4: entries pos, pos+1, pos+2 of the sorted row decide the last two levels
+    int4 qv[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) qv[i] = __ldg(reinterpret_cast<const int4*>(row_cm + pos[i]));
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      pos[i] += strict ? ((qv[i].x < a[i]) + (qv[i].y < a[i]) + (qv[i].z < a[i])) : ((qv[i].x <= a[i]) + (qv[i].y <= a[i]) + (qv[i].z <= a[i]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) out[i] = thr_finish(e, pos[i]);
 }
 
 // Store one output lane per thread of a warp: lane `l` holds channel ch0 + l of one pixel.

@@ -37,7 +37,11 @@ int derive_geom(const fcb_layer_desc* d, Geom* g);  // validates like the refere
 struct EpiParams {
   int act_kind, acc_bits, acc_signed, out_bits, num_th, act_val, cmp, pool;
   const int8_t* bias;    // [OFM]            (FCB_ACT_BIAS_RELU)
-  const int32_t* thr;    // [OFM][num_th] sorted ascending, wrapped to TA (FCB_ACT_THRESHOLDS)
+  const int32_t* thr;    // [thr_n][thr_stride]: threshold i of channel ch at thr[i*thr_stride + ch]; per channel sorted
+                         // ascending, wrapped to TA, padded with INT32_MAX up to thr_n = 2^k - 1 entries (FCB_ACT_THRESHOLDS)
+  int thr_n, thr_stride;
+  const int32_t* thr_cm; // [thr_stride][thr_n + 1] channel-major copy (same values, INT32_MAX padded): the bottom levels of a
+                         // search are one aligned 16-byte group of it
 };
 
 // ---- engines ----------------------------------------------------------------------

@@ -54,11 +54,29 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~10 ms pass) instead of
+// spinning.  Spinning waiters (producer / MMA warps idle during an epilogue-bound phase) were stealing issue slots from the
+// epilogue warps of the same SM sub-partition: 7 M TRYWAITs per SM in the config-4 profile.
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity))
-    if (globaltimer_ns() - t0 > 4000000000ull) __trap();  // 4 s
+  uint64_t t0 = 0;
+  for (uint32_t n = 1; !mbar_try_wait_sleep(bar, parity); ++n) {
+    if ((n & 15) == 0) {  // bounded: a protocol bug must end in a trap, not a hung GPU
+      if (!t0) t0 = globaltimer_ns();
+      else if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+    }
+  }
 }
 
 // ---- TMA ---------------------------------------------------------------------------------

@@ -64,6 +64,9 @@ struct Params2 {
   int WT, R, P, tiles_x, tiles_y, PX, PY;
   int out_x, out_y, out_word_bytes, n_images;
   int wstages, w_bytes, acc_stages, acc_stride, tmem_cols;
+  int chb;      // channel blocks the grid is split into (CTA c serves channel block c % chb); > 1 only with smem thresholds
+  int thr_off;  // smem offset of the top `thr_top` search levels of this CTA's channels, [2^thr_top - 1][CB*128] (-1: none)
+  int thr_top;
   int nsets, set_bytes;  // plane sets (double buffering of the input patch across tiles when shared memory allows)
   int w_off, bar_off, stage_off;  // stage_off: 8 x 256 B staging rows of the thin-output epilogue (OFM <= 8)
   int debug;  // FCB_U2_DEBUG bitmask (perf decomposition only): 1 no weight TMA, 2 no plane TMA, 4 no stores, 8 no epilogue
@@ -72,6 +75,8 @@ struct Params2 {
   Plane2 planes[U2_MAX_PLANES];
   Phase2 phases[4];
 };
+
+__device__ __forceinline__ bool chv_of(int ch, int ofm) { return ch < ofm; }
 
 struct Umma2Plan {
   Geom g;
@@ -115,6 +120,20 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
   const long long total_tiles = tiles_per_img * p.n_images;
+  // CTA -> (channel block, tile sequence): with chb > 1 every tile is visited once per channel block
+  const int chblk = blockIdx.x % p.chb, chbase = chblk * 128;
+  const long long cta0 = blockIdx.x / p.chb, ncta = gridDim.x / p.chb;
+  if (p.thr_off >= 0) {
+    // top levels of the threshold search for this CTA's channels, threshold-major (see activate_thr_hybrid)
+    int32_t* ts = reinterpret_cast<int32_t*>(smem + p.thr_off);
+    const int nch = p.CB * 128, ntop = (1 << p.thr_top) - 1;
+    int gshift = 0;
+    for (int t = p.epi.thr_n + 1; (t >> (p.thr_top + gshift)) > 1;) gshift++;
+    for (int idx = threadIdx.x; idx < ntop * nch; idx += blockDim.x) {
+      const int j = idx / nch + 1, c = idx - (j - 1) * nch;
+      ts[idx] = __ldg(p.epi.thr + (size_t)((j << gshift) - 1) * p.epi.thr_stride + chbase + c);
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -136,7 +155,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (lane == 0) {
       int s = 0;
       uint32_t wphase = 1;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (long long t = cta0; t < total_tiles; t += ncta) {
         for (int ph = 0; ph < p.nphases; ph++) {
           const Phase2& P = p.phases[ph];
           for (int i = 0; i < P.nkb; i++) {
@@ -144,7 +163,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             if (p.debug & 1) mbar_arrive(&wfull[s]);
             else {
               mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);
-              tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, 0);
+              tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, chbase);
             }
             if (++s == p.wstages) { s = 0; wphase ^= 1; }
           }
@@ -157,7 +176,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // the current tile have retired (aempty), i.e. while the remaining taps of the current tile execute.
     if (lane == 0) {
       uint32_t tile_it = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_it++) {
+      for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
         const int img = (int)(t / tiles_per_img);
         const int r = (int)(t % tiles_per_img);
         const int x0 = (r % p.tiles_x) * p.WT, y0 = (r / p.tiles_x) * p.R;
@@ -189,7 +208,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint64_t desc0 = make_smem_desc(smem_u32(smem), 128);
     const uint32_t w_d0 = (uint32_t)p.w_off >> 4, w_dstep = (uint32_t)p.w_bytes >> 4;
     const int wstages = p.wstages, CB = p.CB, NPX = p.NPX;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_it++) {
+    for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
       const int set = tile_it % p.nsets;
       const uint32_t apar = (tile_it / p.nsets) & 1;
       const uint64_t desc_set = desc0 + (uint32_t)((set * p.set_bytes) >> 4);
@@ -239,9 +258,11 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const bool mono = p.epi.act_kind == FCB_ACT_THRESHOLDS && (p.epi.cmp == FCB_CMP_LESS || p.epi.cmp == FCB_CMP_LESS_EQUAL) &&
                       p.epi.act_val >= 0 && (p.epi.out_bits >= 31 || p.epi.act_val + p.epi.num_th < (1 << p.epi.out_bits)) &&
                       (p.epi.acc_signed || p.epi.acc_bits < 32);
+    int gshift = 0;  // log2 of the group the shared-memory levels of the threshold search narrow down to
+    if (p.thr_off >= 0) for (int t = p.epi.thr_n + 1; (t >> (p.thr_top + gshift)) > 1;) gshift++;
     const bool thin = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
     uint32_t acc_it = 0;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (long long t = cta0; t < total_tiles; t += ncta) {
       const int img = (int)(t / tiles_per_img);
       const int r = (int)(t % tiles_per_img);
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
@@ -289,8 +310,16 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           asm volatile("bar.sync 1, 256;" ::: "memory");  // staging rows are reused by the next accumulator
         }
         for (int cb = 0; cb < ((p.debug & 8) || thin ? 0 : p.CB); cb++) {
-          if (cb * 128 + q * 32 >= p.OFM) continue;  // this warp's 32 channels do not exist (warp-uniform)
-          const int ch = cb * 128 + q * 32 + lane;
+          if (chbase + cb * 128 + q * 32 >= p.OFM) continue;  // this warp's 32 channels do not exist (warp-uniform)
+          const int ch = chbase + cb * 128 + q * 32 + lane;
+          // threshold tables of this thread's channel: top levels in shared memory + channel-major global row, or all global
+          const int chs = chv_of(ch, p.OFM) ? ch : 0;
+          const int32_t* tbl = p.epi.thr + chs;
+          const int tstride = p.epi.thr_stride;
+          const uint32_t top_s = smem_u32(smem + (p.thr_off >= 0 ? p.thr_off : 0)) + 4u * (uint32_t)(cb * 128 + q * 32 + lane);
+          const int32_t* row_cm = p.epi.thr_cm + (size_t)chs * (p.epi.thr_n + 1);
+          const bool hybrid = p.thr_off >= 0;
+          const int row_shift = p.CB == 2 ? 10 : 9;  // log2(CB * 128 channels * 4 bytes)
           const bool chv = ch < p.OFM;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
           if (fast) {
@@ -298,7 +327,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             // 32 pixels; a 4x4 byte transpose across each lane quad (2 shuffles + 2 PRMT per word) turns that into
             // 4 consecutive channel bytes of one pixel per lane, so a warp store writes 4 pixels x 32 B.
             const uint32_t bias4 = (chv ? ((uint32_t)(int32_t)p.epi.bias[ch] & 0xFFu) : 0u) * 0x01010101u;
-            const int li = lane & 3, cgrp = cb * 128 + q * 32 + (lane & ~3);  // pixel-in-quad, first of this lane's 4 channels
+            const int li = lane & 3, cgrp = chbase + cb * 128 + q * 32 + (lane & ~3);  // pixel-in-quad, first of this lane's 4 channels
             const uint32_t selA = (lane & 1) ? 0x3715u : 0x6240u, selB = (lane & 2) ? 0x3276u : 0x5410u;
             int rr = (col_lo + li) / p.P, xo = (col_lo + li) - rr * p.P;  // this lane's pixel after the transpose: m = c0 + 4*j + li
             for (int c0 = col_lo; c0 < col_hi && c0 < vrows * p.P; c0 += 32) {
@@ -320,16 +349,42 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           } else if (pk == 1) {
             int rr = col_lo / p.P, xo = col_lo - rr * p.P;
 #pragma unroll 1
-            for (int c0 = col_lo; c0 < col_hi && rr < vrows; c0 += 8) {
-              uint32_t v[8];
-              tmem_ld8(taddr + (uint32_t)c0, v);
+            for (int c0 = col_lo; c0 < col_hi && rr < vrows; c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32(taddr + (uint32_t)c0, v);
               tmem_ld_wait();
+              uint32_t act[32];
+              if (p.epi.act_kind == FCB_ACT_THRESHOLDS) {
 #pragma unroll
-              for (int j = 0; j < 8; j++) {
-                if (xo < vcols && rr < vrows) {  // warp-uniform
-                  const uint32_t a = chv ? activate(p.epi, ch, (int32_t)v[j]) : 0u;
-                  store_lane(p.out + pm.word_off(rr, xo, 1), ch, chv, a, p.epi.out_bits);
+                for (int b = 0; b < 2; b++) {
+                  int32_t a16[16];
+                  uint32_t o16[16];
+#pragma unroll
+                  for (int j = 0; j < 16; j++) a16[j] = (int32_t)v[16 * b + j];
+                  if (hybrid) {
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; h8++) {
+                      int32_t a8[8];
+                      uint32_t o8[8];
+#pragma unroll
+                      for (int j = 0; j < 8; j++) a8[j] = a16[8 * h8 + j];
+                      activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, a8, o8);
+#pragma unroll
+                      for (int j = 0; j < 8; j++) o16[8 * h8 + j] = o8[j];
+                    }
+                  } else {
+                    activate_thrN<16>(p.epi, tbl, tstride, a16, o16);
+                  }
+#pragma unroll
+                  for (int j = 0; j < 16; j++) act[16 * b + j] = o16[j];
                 }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) act[j] = chv ? activate(p.epi, ch, (int32_t)v[j]) : 0u;
+              }
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                if (xo < vcols && rr < vrows) store_lane(p.out + pm.word_off(rr, xo, 1), ch, chv, act[j], p.epi.out_bits);  // warp-uniform
                 if (++xo == p.P) { xo = 0; ++rr; }
               }
             }
@@ -338,30 +393,72 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll 1
             for (int rr = 2 * half; rr < vrows; rr += 4) {  // the two warps of a lane quarter take alternate row pairs
 #pragma unroll 1
-              for (int xb = 0; xb < vcols; xb += 8) {
-                uint32_t va[8], vb[8];
-                tmem_ld8(taddr + (uint32_t)(rr * p.P + xb), va);
-                tmem_ld8(taddr + (uint32_t)((rr + 1) * p.P + xb), vb);
-                tmem_ld_wait();
+              for (int xb = 0; xb < vcols; xb += 32) {
+                if (mono) {
+                  // count-of-thresholds-below is non-decreasing in the TA-wrapped accumulator: pool first, then ONE search
+                  int32_t m16[16];
+                  uint32_t pooled[16];
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) {
-                  const int xo = xb + j;
-                  if (xo < vcols) {  // WT, R, PX, PY are even: the window is whole (warp-uniform)
-                    uint32_t a = 0;
-                    if (chv && mono) {
-                      // count-of-thresholds-below is non-decreasing in the TA-wrapped accumulator: pool first
-                      int32_t m0 = wrap_ta((int32_t)va[j], p.epi.acc_bits, p.epi.acc_signed);
-                      m0 = max(m0, wrap_ta((int32_t)va[j + 1], p.epi.acc_bits, p.epi.acc_signed));
-                      m0 = max(m0, wrap_ta((int32_t)vb[j], p.epi.acc_bits, p.epi.acc_signed));
-                      m0 = max(m0, wrap_ta((int32_t)vb[j + 1], p.epi.acc_bits, p.epi.acc_signed));
-                      a = activate(p.epi, ch, m0);
-                    } else if (chv) {
-                      a = activate(p.epi, ch, (int32_t)va[j]);
-                      a = max(a, activate(p.epi, ch, (int32_t)va[j + 1]));
-                      a = max(a, activate(p.epi, ch, (int32_t)vb[j]));
-                      a = max(a, activate(p.epi, ch, (int32_t)vb[j + 1]));
+                  for (int g4 = 0; g4 < 4; g4++) {
+                    uint32_t va[8], vb[8];
+                    if (xb + 8 * g4 < vcols) {  // warp-uniform; 8-column groups keep reads inside the accumulator stage
+                      tmem_ld8(taddr + (uint32_t)(rr * p.P + xb + 8 * g4), va);
+                      tmem_ld8(taddr + (uint32_t)((rr + 1) * p.P + xb + 8 * g4), vb);
+                      tmem_ld_wait();
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 8; j++) va[j] = vb[j] = 0;
                     }
-                    store_lane(p.out + pm.word_off(rr, xo, 2), ch, chv, a, p.epi.out_bits);
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                      int32_t m0 = wrap_ta((int32_t)va[2 * w], p.epi.acc_bits, p.epi.acc_signed);
+                      m0 = max(m0, wrap_ta((int32_t)va[2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
+                      m0 = max(m0, wrap_ta((int32_t)vb[2 * w], p.epi.acc_bits, p.epi.acc_signed));
+                      m16[4 * g4 + w] = max(m0, wrap_ta((int32_t)vb[2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
+                    }
+                  }
+                  if (p.debug & 16) {
+#pragma unroll
+                    for (int w = 0; w < 16; w++) pooled[w] = (uint32_t)m16[w] & 0xFFu;
+                  } else if (hybrid) {
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; h8++) {
+                      int32_t a8[8];
+                      uint32_t o8[8];
+#pragma unroll
+                      for (int j = 0; j < 8; j++) a8[j] = m16[8 * h8 + j];
+                      activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, a8, o8);
+#pragma unroll
+                      for (int j = 0; j < 8; j++) pooled[8 * h8 + j] = o8[j];
+                    }
+                  } else {
+                    activate_thrN<16>(p.epi, tbl, tstride, m16, pooled);
+                  }
+#pragma unroll
+                  for (int w = 0; w < 16; w++) {
+                    const int xo = xb + 2 * w;
+                    if (xo < vcols) store_lane(p.out + pm.word_off(rr, xo, 2), ch, chv, pooled[w], p.epi.out_bits);  // whole windows
+                  }
+                } else {
+#pragma unroll 1
+                  for (int g4 = 0; g4 < 4; g4++) {
+                    uint32_t va[8], vb[8];
+                    if (xb + 8 * g4 >= vcols) break;
+                    tmem_ld8(taddr + (uint32_t)(rr * p.P + xb + 8 * g4), va);
+                    tmem_ld8(taddr + (uint32_t)((rr + 1) * p.P + xb + 8 * g4), vb);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                      uint32_t a = 0;
+                      if (chv) {
+                        a = activate(p.epi, ch, (int32_t)va[2 * w]);
+                        a = max(a, activate(p.epi, ch, (int32_t)va[2 * w + 1]));
+                        a = max(a, activate(p.epi, ch, (int32_t)vb[2 * w]));
+                        a = max(a, activate(p.epi, ch, (int32_t)vb[2 * w + 1]));
+                      }
+                      const int xo = xb + 8 * g4 + 2 * w;
+                      if (xo < vcols) store_lane(p.out + pm.word_off(rr, xo, 2), ch, chv, a, p.epi.out_bits);
+                    }
                   }
                 }
               }
@@ -432,14 +529,30 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   const int PX = deconv ? g.IX : g.OX, PY = deconv ? g.IY : g.OY;
   const int xdim = s == 2 ? g.IX / 2 : g.IX, ydim = s == 2 ? g.IY / 2 : g.IY;  // tensor extents the TMA box must fit
 
-  // ---- choose (WT, R, NPX, wstages): minimise estimated clocks per useful output pixel
-  const int w_bytes = CB * 128 * 128;
-  const int smem_limit = 227 * 1024 - 2048 - 2048;
+  // ---- choose (WT, R, NPX, wstages): minimise estimated clocks per useful output pixel.
+  // Threshold layers keep the top levels of the per-channel binary search in shared memory (activate_thr_hybrid):
+  // all D levels if they fit ~66 KB, else D-2 (the rest is one 16-byte global load per output), else none.
   const int step = g.pool == 2 ? 2 : 1;
+  const int pool2 = g.pool == 2 ? 4 : 1;
+  const bool thr = g.act_kind == FCB_ACT_THRESHOLDS;
+  int thr_top = 0, thr_bytes = 0;
+  if (thr && !getenv("FCB_U2_NO_SMEM_THR")) {
+    int D = 0;
+    while ((1 << D) < epi.thr_n + 1) D++;
+    const int cand[2] = {D, D - 2};
+    for (int c : cand) {
+      if (c < 1) continue;
+      const int bytes = ((1 << c) - 1) * CB * 128 * 4;
+      if (bytes <= 66 * 1024) { thr_top = c; thr_bytes = bytes; break; }
+    }
+  }
+  const int smem_limit = 227 * 1024 - 2048 - 2048 - (thr_bytes ? thr_bytes + 128 : 0);
+  const int w_bytes = CB * 128 * 128;
   double best = 1e30;
   int bWT = 0, bR = 0, bNPX = 0, bWS = 0;
   for (int NPX = 256; NPX >= 64; NPX /= 2) {
     if (CB * NPX > 512) continue;
+    const int acc_st = (2 * CB * NPX <= 512) ? 2 : 1;
     for (int WS = 4; WS >= 2; WS--)
       for (int WT = step; WT <= std::min(PX + step - 1, 254 - halo_x); WT += step) {
         const int P = WT + halo_x;
@@ -458,17 +571,24 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
           size_t b = std::max<size_t>((size_t)rows * P * 128, (size_t)(a_off_max + NPX) * 128);
           plane_bytes += (b + 1023) / 1024 * 1024 * cch;
         }
-        if (!ok || plane_bytes + (size_t)WS * w_bytes > (size_t)smem_limit) continue;
+        if (!ok || (long long)plane_bytes + (long long)WS * w_bytes > (long long)smem_limit) continue;
         const double tiles = (double)((PX + WT - 1) / WT) * ((PY + R - 1) / R);
         const double nkb = (double)taps.size() * cch;  // all phases
         const double mma_clk = nkb * CB * 4 * (NPX == 256 ? 146.0 : 102.0);  // measured clocks per instruction
         const double fill_clk = ((double)plane_bytes + nkb * w_bytes) / 38.0;  // measured L2->SM fill, B/clk/SM
+        // epilogue: bias/ReLU ~7 clk per pixel and channel block.  Threshold search: instruction bound, ~60 issue clocks
+        // per warp-level output (32 channels), counted with the padding of the 16-wide search batches (measured on
+        // config 4: 37 k clk for a 22x10 pooled tile, profiles/r01_cfg4_epilogue_profile.txt)
+        const double groups = g.pool == 2 ? (double)(R / 2) * ((WT + 31) / 32) * 16 : (double)((R * P + 31) / 32) * 32;
+        const double epi_clk = thr ? groups * nph * CB * 4 * 60.0 : (double)WT * R * nph * CB * 7.0;
+        const double tile_clk = acc_st == 2 ? std::max(std::max(mma_clk, fill_clk), epi_clk) : std::max(mma_clk + epi_clk, fill_clk);
         const double ws_pen = WS >= 3 ? 1.0 : 1.05;
         // ties (e.g. 1x1 layers, where every WT is equally efficient) go to wide boxes: long contiguous TMA rows
-        const double cost = tiles * std::max(mma_clk, fill_clk) * ws_pen * (1.0 + 0.0005 * R) / ((double)PX * PY);
+        const double cost = tiles * tile_clk * ws_pen * (1.0 + 0.0005 * R) / ((double)PX * PY);
         if (cost < best * 0.999) { best = cost; bWT = WT; bR = R; bNPX = NPX; bWS = WS; }
       }
   }
+  const int chb = 1, CBe = CB, bMode = 0;
   if (getenv("FCB_U2_FORCE")) {  // "WT,R,NPX,WS" -- experiments only; the caller is responsible for it fitting
     int a, b, c, d;
     if (sscanf(getenv("FCB_U2_FORCE"), "%d,%d,%d,%d", &a, &b, &c, &d) == 4) { bWT = a; bR = b; bNPX = c; bWS = d; }
@@ -480,12 +600,12 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   Params2& p = U->p;
   memset(&p, 0, sizeof(p));
   p.epi = epi;
-  p.OFM = g.OFM; p.CB = CB; p.NPX = bNPX; p.stride2 = (s == 2); p.deconv = deconv; p.nphases = nph;
+  p.OFM = g.OFM; p.CB = CBe; p.chb = chb; p.NPX = bNPX; p.stride2 = (s == 2); p.deconv = deconv; p.nphases = nph;
   p.WT = bWT; p.R = bR; p.P = bWT + halo_x; p.PX = PX; p.PY = PY;
   p.tiles_x = (PX + bWT - 1) / bWT; p.tiles_y = (PY + bR - 1) / bR;
   p.out_x = g.out_x; p.out_y = g.out_y; p.out_word_bytes = (int)g.out_word_bytes; p.out_img_bytes = g.out_img_bytes;
   p.wstages = bWS; p.w_bytes = w_bytes;
-  p.acc_stride = CB * bNPX;
+  p.acc_stride = CBe * bNPX;
   p.acc_stages = (2 * p.acc_stride <= 512) ? 2 : 1;
   int tc = 32;
   while (tc < p.acc_stages * p.acc_stride) tc *= 2;
@@ -520,7 +640,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   }
   p.nplanes = np;
   p.set_bytes = off;
-  p.nsets = ((size_t)2 * off + (size_t)bWS * w_bytes + 4096 <= (size_t)227 * 1024 - 1024) ? 2 : 1;
+  p.nsets = ((size_t)2 * off + (size_t)bWS * w_bytes + 4096 + (thr_bytes ? thr_bytes + 128 : 0) <= (size_t)227 * 1024 - 1024) ? 2 : 1;
   if (getenv("FCB_U2_NSETS")) p.nsets = std::max(1, std::min(p.nsets, atoi(getenv("FCB_U2_NSETS"))));
   off *= p.nsets;
   U->box_rows[0] = map_rows[0]; U->box_rows[1] = nmaps > 1 ? map_rows[1] : map_rows[0];
@@ -531,6 +651,13 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   off = (off + 15) & ~15;
   p.stage_off = off;
   off += 8 * 256;
+  p.thr_off = -1;
+  p.thr_top = thr_top;
+  if (thr_bytes) {
+    off = (off + 127) & ~127;
+    p.thr_off = off;
+    off += thr_bytes;
+  }
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
   // K-block lists: plane-major within each phase so planes are released progressively
@@ -567,7 +694,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)(CB * 128)};  // rows >= OFM are zeros in memory (fcb_umma.cu)
     const uint64_t strides[1] = {(uint64_t)g.K};
-    const uint32_t box[2] = {128, (uint32_t)(CB * 128)};
+    const uint32_t box[2] = {128, (uint32_t)(CBe * 128)};
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
@@ -580,8 +707,9 @@ void umma2_plan_destroy(Umma2Plan* U) { delete U; }
 
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   const Params2& p = U->p;
-  snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT, p.R,
-           p.P, p.NPX, p.CB, p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem, p.tiles_x, p.tiles_y);
+  snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d chb=%d%s planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT,
+           p.R, p.P, p.NPX, p.CB, p.chb, p.thr_off >= 0 ? " thr-top@smem" : "", p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
+           p.tiles_x, p.tiles_y);
   return buf;
 }
 
@@ -610,7 +738,7 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   // sub-byte / padded output words are merged or partially written: start from zeroed words
   if (g.out_word_bytes * 8 != (size_t)g.OFM * g.out_bits) FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, g.out_img_bytes * n_images, st));
   const long long total = (long long)p.tiles_x * p.tiles_y * n_images;
-  const int grid = (int)std::min<long long>(total, U->num_sms);
+  const int grid = (int)std::min<long long>(total, U->num_sms / p.chb) * p.chb;
   umma2_conv_kernel<<<grid, U2_THREADS, U->smem, st>>>(tmA[0], tmA[1], U->tmW, p);
   FCB_CUDA_OK(cudaGetLastError());
   return FCB_OK;

@@ -44,10 +44,21 @@ if __name__ == "__main__":
     ap.add_argument("--images", type=int, default=64)
     ap.add_argument("--only", default="", help="comma list of net layers to time alone, e.g. L0,L6 (skips the rest)")
     a = ap.parse_args()
+    c3 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=64, ofm_ch=64, ifm_x=128, ifm_y=96, stride_x=1, stride_y=1, pad=0,
+                   simd=64, pe=16, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR, acc_bits=16, acc_signed=1,
+                   act_kind=ACT_THRESHOLDS, out_bits=1, num_th=1)
+    c4 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=256, ofm_ch=256, ifm_x=64, ifm_y=48, stride_x=1, stride_y=1, pad=1,
+                   simd=32, pe=32, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8, num_th=255,
+                   pool=2)
     if a.only:
         for nm in a.only.split(","):
-            i = int(nm[1:])
-            bench_layer(nm, configs.net_layer(i), a.images, 0xFF if i == 0 else 0x7F)
+            if nm == "cfg3":
+                bench_layer("cfg3_xnor", c3, a.images, 0xFF)
+            elif nm == "cfg4":
+                bench_layer("cfg4_thr_pool", c4, a.images, 0xFF)
+            else:
+                i = int(nm[1:])
+                bench_layer(nm, configs.net_layer(i), a.images, 0xFF if i == 0 else 0x7F)
         sys.exit(0)
     layers = []
     for i in range(8):
@@ -62,13 +73,6 @@ if __name__ == "__main__":
     ms = timed(lambda: net.run_device(x.data_ptr(), y.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
     print(json.dumps(dict(layer="eight_layers_net", images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3, 1),
                           TOPs_nonzero=round(2 * 28.94e9 * n / ms / 1e9, 1))), flush=True)
-    # BASELINE.json config 3: 1-bit xnor 64->64 3x3 128x96 ; config 4: 4b/8b 256->256 64x48 thresholds(255) + 2x2 pool
-    c3 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=64, ofm_ch=64, ifm_x=128, ifm_y=96, stride_x=1, stride_y=1, pad=0,
-                   simd=64, pe=16, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR, acc_bits=16, acc_signed=1,
-                   act_kind=ACT_THRESHOLDS, out_bits=1, num_th=1)
     bench_layer("cfg3_xnor", c3, a.images * 16, 0xFF)
-    c4 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=256, ofm_ch=256, ifm_x=64, ifm_y=48, stride_x=1, stride_y=1, pad=1,
-                   simd=32, pe=32, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8, num_th=255,
-                   pool=2)
     bench_layer("cfg4_thr_pool", c4, a.images * 16, 0xFF)
     bench_layer("cfg4_thr_nopool", dataclasses.replace(c4, pool=0), a.images * 16, 0xFF)
