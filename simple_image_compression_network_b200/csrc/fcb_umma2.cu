@@ -390,10 +390,12 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             }
           } else {
             // 2x2 max pool: rows rr, rr+1 of the tile are columns m and m + P of the same thread
+            // work units = (row pair, 32-column block); the two warps of a lane quarter take alternate units
+            const int xblocks = (vcols + 31) >> 5, nunits = (vrows >> 1) * xblocks;
 #pragma unroll 1
-            for (int rr = 2 * half; rr < vrows; rr += 4) {  // the two warps of a lane quarter take alternate row pairs
-#pragma unroll 1
-              for (int xb = 0; xb < vcols; xb += 32) {
+            for (int u = half; u < nunits; u += 2) {
+              {
+                const int rr = 2 * (u / xblocks), xb = 32 * (u % xblocks);
                 if (mono) {
                   // count-of-thresholds-below is non-decreasing in the TA-wrapped accumulator: pool first, then ONE search
                   int32_t m16[16];

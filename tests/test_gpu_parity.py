@@ -233,3 +233,22 @@ def test_run_device_pointers(fcb_lib, oracle_mod):
     torch.cuda.synchronize()
     want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], None, inp["bias"], num_reps=2)
     assert np.array_equal(y.cpu().numpy(), want)
+
+
+def test_analysis_stack_stage_shapes(fcb_lib, oracle_mod):
+    """Config 5b stage shapes (K3 S1 P1 + 255 thresholds + 2x2 pool) at reduced spatial size: thin first stage (C = 3, im2col
+    lowering) and a 128 -> 192 stage, chained through Net, against the oracle applied stage by stage."""
+    from simple_image_compression_network_b200.desc import ACT_THRESHOLDS, KIND_CONV, LayerDesc
+    from simple_image_compression_network_b200.layer import Net
+
+    def stage(c, ofm, x, y, simd, pe):
+        return LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=1, stride_y=1, pad=1,
+                         simd=simd, pe=pe, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8,
+                         num_th=255, pool=2)
+    d1, d2 = stage(3, 128, 48, 32, 3, 16), stage(128, 192, 24, 16, 32, 24)
+    i1, i2 = cases.make_inputs(d1, num_reps=2), cases.make_inputs(d2, seed_shift=4)
+    L1, L2 = _layer(d1, i1), _layer(d2, i2)
+    got = Net([L1, L2]).run(i1["in_words"], 2)
+    mid = oracle_mod.run_layer(d1, i1["in_words"], i1["weights"], i1["thresholds"], None, num_reps=2)
+    want = oracle_mod.run_layer(d2, mid, i2["weights"], i2["thresholds"], None, num_reps=2)
+    assert np.array_equal(got, want), f"[{L1.engine}: {L1.plan}] [{L2.engine}: {L2.plan}]"

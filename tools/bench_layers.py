@@ -73,6 +73,26 @@ if __name__ == "__main__":
     ms = timed(lambda: net.run_device(x.data_ptr(), y.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
     print(json.dumps(dict(layer="eight_layers_net", images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3, 1),
                           TOPs_nonzero=round(2 * 28.94e9 * n / ms / 1e9, 1))), flush=True)
+    # BASELINE.json config 5b: analysis-transform-shaped stack [K3 S1 P1 conv -> 255 thresholds (u8) -> 2x2 max pool] x 4,
+    # channels 3 -> 128 -> 128 -> 128 -> 192 on 768x512; 5a = layers 0-3 of the reference net
+    def stage(c, ofm, x, y, simd, pe):
+        return LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=1, stride_y=1, pad=1,
+                         simd=simd, pe=pe, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8,
+                         num_th=255, pool=2)
+    st = [stage(3, 128, 768, 512, 3, 16), stage(128, 128, 384, 256, 32, 16), stage(128, 128, 192, 128, 32, 16), stage(128, 192, 96, 64, 32, 24)]
+    sl = []
+    for i, d in enumerate(st):
+        L, _ = bench_layer(f"stack5b_stage{i + 1}", d, a.images if i == 0 else a.images * 4, 0xFF)
+        sl.append(L)
+    for name, ls, macs in (("stack5b", sl, 20.84e9), ("stack5a_layers0-3", layers[:4], 14.47e9)):
+        net2 = Net(ls)
+        n = a.images
+        x = torch.empty(n * net2.in_bytes, dtype=torch.uint8, device="cuda")
+        y = torch.empty(n * net2.out_bytes, dtype=torch.uint8, device="cuda")
+        synth_fill(x.data_ptr(), x.numel(), synth.SEED_INPUT, 0xFF)
+        ms = timed(lambda: net2.run_device(x.data_ptr(), y.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+        print(json.dumps(dict(layer=name, images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3, 1), TOPs=round(2 * macs * n / ms / 1e9, 1))),
+              flush=True)
     bench_layer("cfg3_xnor", c3, a.images * 16, 0xFF)
     bench_layer("cfg4_thr_pool", c4, a.images * 16, 0xFF)
     bench_layer("cfg4_thr_nopool", dataclasses.replace(c4, pool=0), a.images * 16, 0xFF)
