@@ -123,6 +123,7 @@ struct fcb_layer {
   UmmaPlan* umma = nullptr;
   // thin-input layers (Kx*Ky*C <= 128): im2col rows in a scratch buffer, then a 1x1 layer on the tensor-core engine
   bool lowered = false;
+  bool lower_bits = false;  // lowering = 1-bit -> +-1 int8 expansion (instead of im2col rows)
   Im2colParams ip{};
   void* d_scratch = nullptr;
   size_t scratch_imgs = 0, scratch_img_bytes = 0;
@@ -186,6 +187,30 @@ void fcb_layer_destroy(fcb_layer* L) {
   delete L;
 }
 
+// threshold tables on the device: threshold-major [2^k - 1][stride] for the lock-step search, channel-major copy for the
+// 16-byte bottom groups of the hybrid search (fcb_epilogue.cuh)
+static int upload_thresholds(fcb_layer* L, const std::vector<std::vector<int32_t>>& rows) {
+  const int ofm = (int)rows.size(), nth = ofm ? (int)rows[0].size() : 0;
+  int tn = 1;
+  while (tn - 1 < nth) tn *= 2;
+  tn -= 1;
+  const int tstride = (ofm + 127) / 128 * 128;
+  std::vector<int32_t> T((size_t)tn * tstride, 0x7fffffff), TC((size_t)tstride * (tn + 1), 0x7fffffff);
+  for (int ch = 0; ch < ofm; ch++)
+    for (int i = 0; i < nth; i++) {
+      T[(size_t)i * tstride + ch] = rows[ch][i];
+      TC[(size_t)ch * (tn + 1) + i] = rows[ch][i];
+    }
+  cudaFree(L->d_thr); cudaFree(L->d_thr_cm);
+  L->d_thr = L->d_thr_cm = nullptr;
+  FCB_CUDA_OK(cudaMalloc(&L->d_thr, T.size() * sizeof(int32_t)));
+  FCB_CUDA_OK(cudaMemcpy(L->d_thr, T.data(), T.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  FCB_CUDA_OK(cudaMalloc(&L->d_thr_cm, TC.size() * sizeof(int32_t)));
+  FCB_CUDA_OK(cudaMemcpy(L->d_thr_cm, TC.data(), TC.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  L->epi.thr = L->d_thr; L->epi.thr_cm = L->d_thr_cm; L->epi.thr_n = tn; L->epi.thr_stride = tstride;
+  return FCB_OK;
+}
+
 int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void* thresholds, const void* bias, int device, fcb_layer** out) {
   if (!out) { set_error("out is NULL"); return FCB_ERR_INVALID_ARG; }
   *out = nullptr;
@@ -236,18 +261,15 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     FCB_CUDA_OK(cudaMemcpy(L->d_bias, bias, g.OFM, cudaMemcpyHostToDevice));
     L->epi.bias = L->d_bias;
   }
+  // thresholds: wrapped to TA and sorted per channel (the reference result is a count, activations.hpp:181-189)
+  std::vector<std::vector<int32_t>> thr_rows;
   if (g.act_kind == FCB_ACT_THRESHOLDS) {
-    // sorted per channel (the reference result is a count), laid out threshold-major and padded to 2^k - 1 entries
-    int tn = 1;
-    while (tn - 1 < g.num_th) tn *= 2;
-    tn -= 1;
-    const int tstride = (g.OFM + 127) / 128 * 128;
-    std::vector<int32_t> T((size_t)tn * tstride, 0x7fffffff);
-    std::vector<int32_t> row(g.num_th);
+    thr_rows.assign(g.OFM, std::vector<int32_t>(g.num_th));
     const uint8_t* tb = (const uint8_t*)thresholds;
     const size_t cb = word_bytes(g.acc_bits);
     for (int pe = 0; pe < g.pe; pe++)
       for (int nf = 0; nf < g.NF; nf++) {
+        std::vector<int32_t>& row = thr_rows[nf * g.pe + pe];
         for (int i = 0; i < g.num_th; i++) {
           const uint8_t* p = tb + (((size_t)pe * g.NF + nf) * g.num_th + i) * cb;
           uint64_t raw = 0;
@@ -255,19 +277,9 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
           row[i] = wrap_host((int64_t)raw, g.acc_bits, g.acc_signed);
         }
         std::sort(row.begin(), row.end());
-        for (int i = 0; i < g.num_th; i++) T[(size_t)i * tstride + nf * g.pe + pe] = row[i];
       }
-    std::vector<int32_t> TC((size_t)tstride * (tn + 1), 0x7fffffff);  // channel-major copy
-    for (int ch = 0; ch < g.OFM; ch++)
-      for (int i = 0; i < g.num_th; i++) TC[(size_t)ch * (tn + 1) + i] = T[(size_t)i * tstride + ch];
-    FCB_CUDA_OK(cudaMalloc(&L->d_thr, T.size() * sizeof(int32_t)));
-    FCB_CUDA_OK(cudaMemcpy(L->d_thr, T.data(), T.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    FCB_CUDA_OK(cudaMalloc(&L->d_thr_cm, TC.size() * sizeof(int32_t)));
-    FCB_CUDA_OK(cudaMemcpy(L->d_thr_cm, TC.data(), TC.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    L->epi.thr_cm = L->d_thr_cm;
-    L->epi.thr = L->d_thr;
-    L->epi.thr_n = tn;
-    L->epi.thr_stride = tstride;
+    rc = upload_thresholds(L, thr_rows);
+    if (rc) { fcb_layer_destroy(L); return rc; }
   }
 
   // ---- engine selection
@@ -280,7 +292,50 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   if (force && !strcmp(force, "xnor") && g.weight_kind == FCB_W_BINARY_XNOR && g.C % 32 == 0 && dense_bits) engine = ENG_XNOR;
   L->engine = engine;
 
-  if (engine == ENG_UMMA) {
+  // opt-in (FCB_XNOR_ENGINE=tensor): the 1-bit layer on the tensor cores.  With a^ = 2a-1, w^ = 2w-1 in {-1,+1}:
+  // sum_k [w_k == a_k] = (K + sum_k a^_k w^_k) / 2 (interpret.hpp:57-73), so thr < matches  <=>  2*thr - K < sum a^w^ :
+  // bits are expanded to s8 (a zero-padded border bit is an ordinary 0 activation = -1), thresholds are remapped once,
+  // and the layer runs on umma_i8.  north_star names XNOR/popc as the implementation of this path, so that stays the default.
+  const char* xeng = getenv("FCB_XNOR_ENGINE");
+  if (xeng && !strcmp(xeng, "tensor") && g.weight_kind == FCB_W_BINARY_XNOR && g.act_kind == FCB_ACT_THRESHOLDS && g.kind == FCB_KIND_CONV &&
+      dense_bits && g.SX == g.SY && g.SX == 1 && g.OFM <= 256 && g.pool <= 2 && (g.acc_bits >= 31 || g.K < (1 << (g.acc_bits - (g.acc_signed ? 1 : 0))))) {
+    const int Cp = (g.C + 15) / 16 * 16;
+    Geom g2 = g;
+    g2.C = Cp; g2.K = g.KX * g.KY * Cp; g2.IX = g.IX + 2 * g.PAD; g2.IY = g.IY + 2 * g.PAD; g2.PAD = 0;
+    g2.in_bits = 8; g2.in_signed = 1; g2.w_bits = 8; g2.weight_kind = FCB_W_FIXED; g2.acc_bits = 32; g2.acc_signed = 1;
+    g2.in_word_bytes = Cp; g2.in_img_bytes = (size_t)Cp * g2.IX * g2.IY;
+    std::vector<int32_t> W2((size_t)g.OFM * g2.K, 0);
+    for (int ch = 0; ch < g.OFM; ch++)
+      for (int tap = 0; tap < g.KX * g.KY; tap++)
+        for (int c = 0; c < g.C; c++) W2[(size_t)ch * g2.K + tap * Cp + c] = W[(size_t)ch * g.K + tap * g.C + c] ? 1 : -1;
+    std::vector<std::vector<int32_t>> rows2 = thr_rows;
+    for (auto& r : rows2)
+      for (auto& t : r) t = 2 * t - g.K;
+    if (umma_eligible(g2)) {
+      rc = upload_thresholds(L, rows2);
+      if (rc) { fcb_layer_destroy(L); return rc; }
+      EpiParams e2 = L->epi;
+      e2.acc_bits = 32; e2.acc_signed = 1;
+      rc = umma_plan_create(g2, W2, e2, device, &L->umma);
+      if (rc == FCB_OK) {
+        L->epi = e2;
+        engine = L->engine = ENG_UMMA;
+        L->lowered = true;
+        L->lower_bits = true;
+        L->scratch_img_bytes = g2.in_img_bytes;
+        Im2colParams& ip = L->ip;
+        ip.IX = g.IX; ip.IY = g.IY; ip.OX = g2.IX; ip.OY = g2.IY; ip.S = 1; ip.PAD = g.PAD; ip.K = Cp; ip.C = g.C; ip.KX = g.KX;
+        ip.in_word_bytes = (int)g.in_word_bytes; ip.in_img_bytes = g.in_img_bytes;
+        snprintf(L->plan_desc, sizeof(L->plan_desc), "xnor as +-1 int8: bit expansion (C=%d -> %d B) + %s", g.C, Cp, umma_plan_describe(L->umma));
+      } else {
+        L->umma = nullptr;
+        int rc3 = upload_thresholds(L, thr_rows);  // back to the popcount engine's tables
+        if (rc3) { fcb_layer_destroy(L); return rc3; }
+        if (rc != FCB_ERR_UNSUPPORTED) { fcb_layer_destroy(L); return rc; }
+      }
+    }
+  }
+  if (engine == ENG_UMMA && !L->lowered) {
     rc = umma_plan_create(g, W, L->epi, device, &L->umma);
     if (rc == FCB_ERR_UNSUPPORTED) { engine = L->engine = ENG_IMAD; L->umma = nullptr; }  // shape the planner cannot tile
     else if (rc) { fcb_layer_destroy(L); return rc; }
@@ -377,7 +432,7 @@ int fcb_layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t n
       Im2colParams ip = L->ip;
       ip.in = (const uint8_t*)d_in + n0 * L->g.in_img_bytes;
       ip.out = (uint8_t*)L->d_scratch;
-      int rc = launch_im2col(ip, nb, st);
+      int rc = L->lower_bits ? launch_expand_bits(ip, nb, st) : launch_im2col(ip, nb, st);
       if (rc) return rc;
       L->launches++;
       rc = umma_run(L->umma, L->d_scratch, (uint8_t*)d_out + n0 * L->g.out_img_bytes, nb, st, &L->launches);

@@ -135,6 +135,24 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const DirectParams p) 
     uint32_t val[PXB * PXB];
 #pragma unroll
     for (int i = 0; i < PXB * PXB; i++) val[i] = chv ? activate(p.epi, ch, acc[i][j]) : 0u;
+    if (p.epi.out_bits == 1 && pk == 1) {
+      // 1-bit lanes: one ballot per pixel; lane i keeps pixel i of the 4x4 block, then one store instruction for all 16
+      uint32_t mine = 0;
+#pragma unroll
+      for (int i = 0; i < PXB * PXB; i++) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, chv && (val[i] & 1u));
+        if (lane == i) mine = bits;
+      }
+      const int oy = oy0 + wy + (lane >> 2), ox = ox0 + wx + (lane & 3), c0 = ch - lane;  // c0: first channel of this warp
+      if (lane < PXB * PXB && oy < p.OY && ox < p.OX && c0 < p.OFM) {
+        uint8_t* dst = out + ((size_t)oy * p.out_x + ox) * p.out_word_bytes + (c0 >> 3);
+        if (c0 + 32 <= p.OFM && p.out_word_bytes >= 4) *reinterpret_cast<uint32_t*>(dst) = mine;
+        else
+          for (int b = 0; b < 4; b++)
+            if (c0 + 8 * b < p.OFM) dst[b] = (uint8_t)(mine >> (8 * b));
+      }
+      continue;
+    }
     for (int by = 0; by < PXB; by += pk)
       for (int bx = 0; bx < PXB; bx += pk) {
         const int oy = oy0 + wy + by, ox = ox0 + wx + bx;  // pre-pool pixel (warp-uniform)

@@ -128,7 +128,16 @@ __device__ __forceinline__ void store_lane(uint8_t* word, int ch, bool valid, ui
     if (valid) *reinterpret_cast<uint16_t*>(word + 2 * (size_t)ch) = (uint16_t)v;
   } else if (out_bits == 32) {
     if (valid) *reinterpret_cast<uint32_t*>(word + 4 * (size_t)ch) = v;
-  } else {  // 1, 2, 4 bits: 8/out_bits lanes share a byte
+  } else if (out_bits == 1) {  // one ballot gathers the warp's 32 channel bits; lane 0 stores them
+    const uint32_t vm = __ballot_sync(0xffffffffu, valid), bits = __ballot_sync(0xffffffffu, valid && (v & 1u));
+    if (lane == 0) {
+      uint8_t* dst = word + (ch >> 3);
+      if (vm == 0xffffffffu && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) *reinterpret_cast<uint32_t*>(dst) = bits;
+      else
+        for (int b = 0; b < 4; b++)
+          if ((vm >> (8 * b)) & 0xFFu) dst[b] = (uint8_t)(bits >> (8 * b));  // partially valid bytes keep zero pad bits
+    }
+  } else {  // 2, 4 bits: 8/out_bits lanes share a byte
     const int per = 8 / out_bits;
     uint32_t b = valid ? (v << ((lane % per) * out_bits)) : 0u;
     for (int s = 1; s < per; s <<= 1) b |= __shfl_xor_sync(0xffffffffu, b, s);

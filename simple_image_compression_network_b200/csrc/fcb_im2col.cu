@@ -53,4 +53,41 @@ int launch_im2col(const Im2colParams& p, int n_images, cudaStream_t st) {
   return FCB_OK;
 }
 
+// ---- 1-bit activations -> {-1,+1} bytes (tensor-core form of the xnor layer) -----------------------------------------
+__global__ void __launch_bounds__(256) expand_bits_kernel(const Im2colParams p) {
+  const int img = blockIdx.z, oy = blockIdx.y;
+  const int words_per_px = p.K >> 2;  // output u32 per pixel
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.OX * words_per_px) return;
+  const int ox = idx / words_per_px, w = idx - ox * words_per_px;
+  const int iy = oy - p.PAD, ix = ox - p.PAD;
+  uint32_t bits = 0;  // a zero-padded border bit is an ordinary 0 activation
+  if (iy >= 0 && iy < p.IY && ix >= 0 && ix < p.IX) {
+    const uint8_t* word = p.in + (size_t)img * p.in_img_bytes + ((size_t)iy * p.IX + ix) * p.in_word_bytes;
+    bits = (uint32_t)(word[(4 * w) >> 3] >> ((4 * w) & 7)) & 0xFu;
+  }
+  uint32_t out = 0;
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    const int c = 4 * w + b;
+    const uint32_t v = c < p.C ? (((bits >> b) & 1u) ? 0x01u : 0xFFu) : 0u;  // channels beyond C: 0 (weights there are 0 too)
+    out |= v << (8 * b);
+  }
+  reinterpret_cast<uint32_t*>(p.out)[(((size_t)img * p.OY + oy) * p.OX + ox) * words_per_px + w] = out;
+}
+
+int launch_expand_bits(const Im2colParams& p, int n_images, cudaStream_t st) {
+  const int per_row = p.OX * (p.K >> 2);
+  for (int n0 = 0; n0 < n_images; n0 += 65535) {
+    Im2colParams q = p;
+    const int nb = n_images - n0 < 65535 ? n_images - n0 : 65535;
+    q.in = p.in + (size_t)n0 * p.in_img_bytes;
+    q.out = p.out + (size_t)n0 * p.OX * p.OY * p.K;
+    dim3 grid((per_row + 255) / 256, p.OY, nb);
+    expand_bits_kernel<<<grid, 256, 0, st>>>(q);
+    FCB_CUDA_OK(cudaGetLastError());
+  }
+  return FCB_OK;
+}
+
 }  // namespace fcb

@@ -76,6 +76,8 @@ struct Im2colParams {
   unsigned long long in_img_bytes;
 };
 int launch_im2col(const Im2colParams& p, int n_images, cudaStream_t st);
+// 1-bit lanes -> s8 {-1,+1} NHWC with an explicit -1 border of PAD pixels; out [n][OY][OX][K] (OX = IX+2*PAD, K = padded C)
+int launch_expand_bits(const Im2colParams& p, int n_images, cudaStream_t st);
 
 // synthetic data (fcb_synth.cu)
 int synth_fill(void* d_ptr, size_t n_bytes, uint64_t seed, uint32_t mask, uint64_t offset, cudaStream_t st);

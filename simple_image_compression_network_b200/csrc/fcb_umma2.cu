@@ -382,10 +382,32 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 32; j++) act[j] = chv ? activate(p.epi, ch, (int32_t)v[j]) : 0u;
               }
+              if (p.epi.out_bits == 1) {
+                // 1-bit lanes: one ballot per pixel gathers the warp's 32 channel bits; lane j keeps pixel j's word so the
+                // 32 pixels leave in ONE store instruction (32 single-lane stores into the same few cache lines serialise)
+                uint32_t mine = 0;
+                size_t mine_off = 0;
+                bool mine_ok = false;
 #pragma unroll
-              for (int j = 0; j < 32; j++) {
-                if (xo < vcols && rr < vrows) store_lane(p.out + pm.word_off(rr, xo, 1), ch, chv, act[j], p.epi.out_bits);  // warp-uniform
-                if (++xo == p.P) { xo = 0; ++rr; }
+                for (int j = 0; j < 32; j++) {
+                  const uint32_t bits = __ballot_sync(0xffffffffu, chv && (act[j] & 1u));
+                  if (lane == j) { mine = bits; mine_ok = xo < vcols && rr < vrows; mine_off = pm.word_off(rr, xo, 1); }
+                  if (++xo == p.P) { xo = 0; ++rr; }
+                }
+                const int c0 = chbase + cb * 128 + q * 32;  // first channel of this warp
+                if (mine_ok) {
+                  uint8_t* dst = p.out + mine_off + (c0 >> 3);
+                  if (c0 + 32 <= p.OFM && p.out_word_bytes >= 4) *reinterpret_cast<uint32_t*>(dst) = mine;
+                  else
+                    for (int b = 0; b < 4; b++)
+                      if (c0 + 8 * b < p.OFM) dst[b] = (uint8_t)(mine >> (8 * b));
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                  if (xo < vcols && rr < vrows) store_lane(p.out + pm.word_off(rr, xo, 1), ch, chv, act[j], p.epi.out_bits);  // warp-uniform
+                  if (++xo == p.P) { xo = 0; ++rr; }
+                }
               }
             }
           } else {

@@ -252,3 +252,20 @@ def test_analysis_stack_stage_shapes(fcb_lib, oracle_mod):
     mid = oracle_mod.run_layer(d1, i1["in_words"], i1["weights"], i1["thresholds"], None, num_reps=2)
     want = oracle_mod.run_layer(d2, mid, i2["weights"], i2["thresholds"], None, num_reps=2)
     assert np.array_equal(got, want), f"[{L1.engine}: {L1.plan}] [{L2.engine}: {L2.plan}]"
+
+
+@pytest.mark.parametrize("name,pad,pool", [("xn_a", 0, 0), ("xn_b", 0, 0), ("xn_c", 0, 0), ("xn_c", 1, 0), ("xn_b", 1, 2)])
+def test_xnor_on_tensor_cores(name, pad, pool, fcb_lib, oracle_mod, monkeypatch):
+    """Opt-in +-1 int8 form of the xnor layer (sum [w==a] = (K + sum a^w^)/2, thresholds remapped to 2t-K) against the
+    oracle and against the default popcount engine; pad > 0 checks that border bits act as ordinary 0 activations."""
+    d = dataclasses.replace(cases.CASES[name], pad=pad, pool=pool)
+    inp = cases.make_inputs(d, seed_shift=21, num_reps=2)
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], None, num_reps=2)
+    Lp = _layer(d, inp)
+    assert Lp.engine in ("xnor_popc", "imad")
+    assert np.array_equal(Lp.run(inp["in_words"], 2), want)
+    monkeypatch.setenv("FCB_XNOR_ENGINE", "tensor")
+    Lt = _layer(d, inp)
+    assert Lt.engine == "umma_i8" and "xnor as +-1" in Lt.plan, Lt.plan
+    got = Lt.run(inp["in_words"], 2)
+    assert np.array_equal(got, want), f"{name} pad={pad} [{Lt.plan}]: {_diff(got, want)}"

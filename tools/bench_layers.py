@@ -52,7 +52,10 @@ if __name__ == "__main__":
                    pool=2)
     if a.only:
         for nm in a.only.split(","):
-            if nm == "cfg3":
+            if nm == "cfg3t":
+                os.environ["FCB_XNOR_ENGINE"] = "tensor"
+                bench_layer("cfg3_xnor_tensor", c3, a.images, 0xFF)
+            elif nm == "cfg3":
                 bench_layer("cfg3_xnor", c3, a.images, 0xFF)
             elif nm == "cfg4":
                 bench_layer("cfg4_thr_pool", c4, a.images, 0xFF)
@@ -94,5 +97,8 @@ if __name__ == "__main__":
         print(json.dumps(dict(layer=name, images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3, 1), TOPs=round(2 * macs * n / ms / 1e9, 1))),
               flush=True)
     bench_layer("cfg3_xnor", c3, a.images * 16, 0xFF)
+    os.environ["FCB_XNOR_ENGINE"] = "tensor"
+    bench_layer("cfg3_xnor_as_pm1_int8_tensor", c3, a.images * 16, 0xFF)
+    del os.environ["FCB_XNOR_ENGINE"]
     bench_layer("cfg4_thr_pool", c4, a.images * 16, 0xFF)
     bench_layer("cfg4_thr_nopool", dataclasses.replace(c4, pool=0), a.images * 16, 0xFF)
