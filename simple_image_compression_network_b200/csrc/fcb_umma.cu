@@ -256,14 +256,20 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 int umma_encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  return umma_encode_map_ex(m, base, 1, 128, rank, dims, strides_bytes, box);
+}
+// elem_bytes: 1 (u8) or 4 (u32 elements: boxes wider than 256 bytes); swizzle: 0 (dense box image) or 128
+int umma_encode_map_ex(CUtensorMap* m, void* base, int elem_bytes, int swizzle, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FCB_ERR_CUDA; }
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; i++) gs[i] = strides_bytes[i];
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, base, gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return FCB_ERR_CUDA; }
   return FCB_OK;
 }

@@ -69,6 +69,9 @@ struct Params2 {
   int thr_top;
   int nsets, set_bytes;  // plane sets (double buffering of the input patch across tiles when shared memory allows)
   int w_off, bar_off, stage_off;  // stage_off: 8 x 256 B staging rows of the thin-output epilogue (OFM <= 8)
+  // staged epilogue: the tile's output words are assembled in shared memory ([CB][NPX] rows of 128 B, stg_bufs buffers) and
+  // leave through TMA stores, one per tile row (whole 128-byte lines, clipped at the image edge by the tensor map)
+  int stg_off, stg_bufs, stg_bytes;
   int debug;  // FCB_U2_DEBUG bitmask (perf decomposition only): 1 no weight TMA, 2 no plane TMA, 4 no stores, 8 no epilogue
   unsigned long long out_img_bytes;
   uint32_t idesc;
@@ -105,7 +108,7 @@ struct PixMap {
 
 __global__ void __launch_bounds__(U2_THREADS, 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmW, const Params2 p) {
+                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params2 p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
@@ -273,6 +276,55 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
+        if (p.stg_bufs > 0) {
+          // Staged bias + ReLU epilogue (conv_nonsquare_top.cpp:267-278): thread = channel turns its 32-column TMEM loads into
+          // bytes of the tile's [pixel][channel] image in shared memory (a warp's 32 lanes write 32 consecutive bytes: one
+          // wavefront, no shuffles, no predicates); one thread then issues a TMA store per tile row.  The register path below
+          // (4-byte global stores after a quad transpose) is kept for plans whose planes leave no room for the staging tile.
+          const int sb = (int)(acc_it % (uint32_t)p.stg_bufs);
+          uint8_t* stg = smem + p.stg_off + sb * p.stg_bytes;
+          if (warp == 2 && lane == 0) {  // the buffer's previous stores must have finished reading it
+            if (p.stg_bufs == 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++) {
+            const int ch = chbase + cb * 128 + q * 32 + lane;
+            const uint32_t bias4 = ((uint32_t)(int32_t)p.epi.bias[ch] & 0xFFu) * 0x01010101u;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
+            const uint32_t srow = smem_u32(stg) + (uint32_t)(cb * p.NPX * 128 + q * 32 + lane);
+            for (int c0 = col_lo; c0 < col_hi && c0 < vrows * p.P; c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32(taddr + (uint32_t)c0, v);
+              tmem_ld_wait();
+              const uint32_t sa = srow + (uint32_t)c0 * 128u;
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
+                uint32_t w = __vadd4(__byte_perm(lo, hi, 0x5410), bias4);  // (acc + bias) mod 256, 4 pixels at once
+                w &= ~(((w >> 7) & 0x01010101u) * 0xFFu);                  // bit 7 set -> 0
+                sts_u8(sa + (4 * j + 0) * 128, w);
+                sts_u8(sa + (4 * j + 1) * 128, w >> 8);
+                sts_u8(sa + (4 * j + 2) * 128, w >> 16);
+                sts_u8(sa + (4 * j + 3) * 128, w >> 24);
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tempty[acc]);
+          fence_proxy_async();  // generic-proxy writes -> visible to the TMA engine
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (warp == 2 && lane == 0) {
+            for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++)
+              for (int rr = 0; rr < vrows; rr++) {
+                const uint8_t* src = stg + (cb * p.NPX + rr * p.P) * 128;
+                if (p.deconv) tma_store_5d(&tmO, src, pm.px * p.OFM + chbase + cb * 128, pm.x0, pm.py, pm.y0 + rr, img);
+                else tma_store_4d(&tmO, src, chbase + cb * 128, pm.x0, pm.y0 + rr, img);
+              }
+            bulk_commit();
+          }
+          continue;
+        }
         if (thin) {
           // Thin output (OFM <= 8, e.g. the 3-channel last layer): only lanes < OFM of the first lane quarter hold data.
           // They turn their 256 columns into bytes in a shared staging row per channel; then all 128 epilogue threads
@@ -494,6 +546,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
   }
+  if (warp == 2 && lane == 0 && p.stg_bufs > 0) bulk_wait<0>();  // staged stores still read shared memory
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
@@ -682,6 +735,17 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     p.thr_off = off;
     off += thr_bytes;
   }
+  // staged epilogue (bias + ReLU on whole 128-channel blocks): two buffers if they fit, else one, else the register path
+  p.stg_off = 0; p.stg_bufs = 0; p.stg_bytes = CBe * bNPX * 128;
+  const bool fast_epi = epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && g.pool <= 1 && g.OFM % 128 == 0 &&
+                        g.out_word_bytes == (size_t)g.OFM;
+  if (fast_epi && !getenv("FCB_U2_NO_STAGE")) {
+    off = (off + 127) & ~127;
+    for (int nb = 2; nb >= 1; nb--)
+      if ((size_t)off + (size_t)nb * p.stg_bytes + 1024 <= (size_t)227 * 1024) { p.stg_bufs = nb; break; }
+    p.stg_off = off;
+    off += p.stg_bufs * p.stg_bytes;
+  }
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
   // K-block lists: plane-major within each phase so planes are released progressively
@@ -732,7 +796,7 @@ void umma2_plan_destroy(Umma2Plan* U) { delete U; }
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   const Params2& p = U->p;
   snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d chb=%d%s planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT,
-           p.R, p.P, p.NPX, p.CB, p.chb, p.thr_off >= 0 ? " thr-top@smem" : "", p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
+           p.R, p.P, p.NPX, p.CB, p.chb, p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
            p.tiles_x, p.tiles_y);
   return buf;
 }
@@ -759,11 +823,28 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
     }
     if (rc) return rc;
   }
+  CUtensorMap tmO = tmA[0];
+  if (p.stg_bufs > 0) {
+    const uint64_t F = g.OFM, OX = g.out_x, OY = g.out_y;
+    int rc;
+    if (p.deconv) {  // [n][oy/2][oy%2][ox/2][(ox%2)*OFM + ch]: a phase's tile row is a dense box
+      const uint64_t dims[5] = {2 * F, OX / 2, 2, OY / 2, (uint64_t)n_images};
+      const uint64_t strides[4] = {2 * F, OX * F, 2 * OX * F, OX * OY * F};
+      const uint32_t box[5] = {128, (uint32_t)p.WT, 1, 1, 1};
+      rc = umma_encode_map_ex(&tmO, d_out, 1, 0, 5, dims, strides, box);
+    } else {
+      const uint64_t dims[4] = {F, OX, OY, (uint64_t)n_images};
+      const uint64_t strides[3] = {F, OX * F, OX * OY * F};
+      const uint32_t box[4] = {128, (uint32_t)p.WT, 1, 1};
+      rc = umma_encode_map_ex(&tmO, d_out, 1, 0, 4, dims, strides, box);
+    }
+    if (rc) return rc;
+  }
   // sub-byte / padded output words are merged or partially written: start from zeroed words
   if (g.out_word_bytes * 8 != (size_t)g.OFM * g.out_bits) FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, g.out_img_bytes * n_images, st));
   const long long total = (long long)p.tiles_x * p.tiles_y * n_images;
   const int grid = (int)std::min<long long>(total, U->num_sms / p.chb) * p.chb;
-  umma2_conv_kernel<<<grid, U2_THREADS, U->smem, st>>>(tmA[0], tmA[1], U->tmW, p);
+  umma2_conv_kernel<<<grid, U2_THREADS, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   FCB_CUDA_OK(cudaGetLastError());
   return FCB_OK;
 }

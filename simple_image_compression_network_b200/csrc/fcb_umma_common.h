@@ -6,6 +6,8 @@
 
 namespace fcb {
 int umma_encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+int umma_encode_map_ex(CUtensorMap* m, void* base, int elem_bytes, int swizzle, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box);
 
 struct Umma2Plan;
 int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, Umma2Plan** out);
