@@ -340,7 +340,22 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     if (rc == FCB_ERR_UNSUPPORTED) { engine = L->engine = ENG_IMAD; L->umma = nullptr; }  // shape the planner cannot tile
     else if (rc) { fcb_layer_destroy(L); return rc; }
   }
-  // thin-input lowering: conv2d with Kx*Ky*C <= 128 bytes of window (the C = 3 first layer of the reference network)
+  // thin-input layers (one 4-byte word per pixel, e.g. the ap_uint<24> C = 3 first layer): the sliding window is built in
+  // shared memory inside the tensor-core kernel (fcb_umma2.cu, thin-input mode); FCB_THIN=im2col keeps the two-kernel lowering
+  const char* thin_env = getenv("FCB_THIN");
+  if (engine == ENG_IMAD && !(force && !strcmp(force, "imad")) && !(thin_env && !strcmp(thin_env, "im2col")) && g.kind == FCB_KIND_CONV &&
+      g.weight_kind == FCB_W_FIXED && g.w_bits <= 8 && g.in_bits == 8 && g.in_word_bytes == 4 && g.KX * g.KY <= 32 && g.OFM <= 256 &&
+      g.pool <= 2 && g.SX == g.SY && g.SX <= 2 && g.IX % 4 == 0 && (uint64_t)g.K * 255ull * 128ull < (1ull << 31)) {
+    std::vector<int32_t> W4((size_t)g.OFM * 128, 0);
+    for (int ch = 0; ch < g.OFM; ch++)
+      for (int tap = 0; tap < g.KX * g.KY; tap++)
+        for (int c = 0; c < g.C; c++) W4[(size_t)ch * 128 + tap * 4 + c] = W[(size_t)ch * g.K + tap * g.C + c];
+    rc = umma_plan_create_thin(g, W4, L->epi, device, &L->umma);
+    if (rc == FCB_OK) engine = L->engine = ENG_UMMA;
+    else if (rc != FCB_ERR_UNSUPPORTED) { fcb_layer_destroy(L); return rc; }
+    else L->umma = nullptr;
+  }
+  // older two-kernel lowering: conv2d with Kx*Ky*C <= 128 bytes of window as im2col rows + a 1x1 layer
   if (engine == ENG_IMAD && !(force && !strcmp(force, "imad")) && g.kind == FCB_KIND_CONV && g.weight_kind == FCB_W_FIXED &&
       g.w_bits <= 8 && g.in_bits == 8 && g.K <= 128 && g.OFM <= 256 && g.pool <= 2 && g.SX == g.SY) {
     Geom g2 = g;

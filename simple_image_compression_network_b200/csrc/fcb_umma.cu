@@ -66,7 +66,7 @@ struct UmmaPlan {
   size_t smem = 0;
   int num_sms = 148;
   Umma2Plan* v2 = nullptr;  // shared-memory-resident-patch main loop (fcb_umma2.cu) when the layer qualifies
-  char desc[160] = "v1 per-tap TMA";
+  char desc[224] = "v1 per-tap TMA";
 };
 
 // ------------------------------------------------------------------------------------------
@@ -396,6 +396,26 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   if (!P->v2 && !v1_eligible(g)) { umma_plan_destroy(P); set_error("no tensor-core plan for this shape"); return FCB_ERR_UNSUPPORTED; }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  *out = P;
+  return FCB_OK;
+}
+
+// Thin-input layers (one 4-byte word per pixel): W4 is [OFM][128], k = (ky*KX + kx)*4 + lane.
+int umma_plan_create_thin(const Geom& g, const std::vector<int32_t>& W4, const EpiParams& epi, int device, UmmaPlan** out) {
+  UmmaPlan* P = new UmmaPlan();
+  P->g = g;
+  P->device = device;
+  cudaDeviceProp prop;
+  FCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  P->num_sms = prop.multiProcessorCount;
+  const int rows_pad = (g.OFM + 127) / 128 * 128;
+  std::vector<int8_t> w8((size_t)rows_pad * 128, 0);
+  for (size_t i = 0; i < (size_t)g.OFM * 128; i++) w8[i] = (int8_t)W4[i];
+  FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size()));
+  FCB_CUDA_OK(cudaMemcpy(P->d_w, w8.data(), w8.size(), cudaMemcpyHostToDevice));
+  int rc = umma2_plan_create_thin(g, P->d_w, epi, P->num_sms, &P->v2);
+  if (rc) { umma_plan_destroy(P); return rc; }
+  umma2_describe(P->v2, P->desc, sizeof(P->desc));
   *out = P;
   return FCB_OK;
 }

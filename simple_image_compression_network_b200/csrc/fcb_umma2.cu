@@ -72,6 +72,12 @@ struct Params2 {
   // staged epilogue: the tile's output words are assembled in shared memory ([CB][NPX] rows of 128 B, stg_bufs buffers) and
   // leave through TMA stores, one per tile row (whole 128-byte lines, clipped at the image edge by the tensor map)
   int stg_off, stg_bufs, stg_bytes;
+  // thin-input mode (input word = one 4-byte pixel of <= 4 lanes, e.g. the C = 3 first layer): warp 10 builds the tile's
+  // im2col rows in shared memory (one 128-byte SWIZZLE_128B row per output pixel, word (ky*KX + kx) = input pixel of that tap)
+  // from a raw patch fetched by TMA; the layer is then ONE K-block of `ksteps` MMAs per tile with resident weights.
+  int cscale;
+  int thin_in, S, pad, nw, BWp, BHp, patch_off, patch_bytes, ksteps, wstatic;
+  int toff[32];  // patch word offset of window word i: ky*BWp + kx
   int debug;  // FCB_U2_DEBUG bitmask (perf decomposition only): 1 no weight TMA, 2 no plane TMA, 4 no stores, 8 no epilogue
   unsigned long long out_img_bytes;
   uint32_t idesc;
@@ -119,6 +125,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* tfull = aempty + p.nsets * p.nplanes;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* pfull = tempty + 3;  // thin-input mode: raw patch buffers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
@@ -144,7 +151,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int i = 0; i < p.nsets * p.nplanes; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); mbar_init(&pfull[a], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -159,6 +166,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       int s = 0;
       uint32_t wphase = 1;
       for (long long t = cta0; t < total_tiles; t += ncta) {
+        if (p.wstatic && t != cta0) break;  // every K-block of the layer has its own stage: loaded once, never released
         for (int ph = 0; ph < p.nphases; ph++) {
           const Phase2& P = p.phases[ph];
           for (int i = 0; i < P.nkb; i++) {
@@ -177,7 +185,54 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ===================== TMA producer: input planes =====================
     // Independent of the weight ring: plane i of the next tile is fetched the moment the MMAs that read plane i of
     // the current tile have retired (aempty), i.e. while the remaining taps of the current tile execute.
-    if (lane == 0) {
+    if (p.thin_in) {
+      // ===== sliding window as shared-memory im2col (slidingwindow.h:1302-1313 order ky, kx, lane; FMPadding zeros = TMA OOB fill)
+      // (no lambda here: taking &tmA0 through a by-reference capture would hand TMA a local-memory copy of the tensor map)
+#define FCB_FETCH_PATCH(T_, IT_)                                                                                              \
+  do {                                                                                                                        \
+    const int img_ = (int)((T_) / tiles_per_img);                                                                             \
+    const int r_ = (int)((T_) % tiles_per_img);                                                                               \
+    const int x0_ = (r_ % p.tiles_x) * p.WT, y0_ = (r_ / p.tiles_x) * p.R;                                                    \
+    uint64_t* fb_ = &pfull[(IT_) & 1];                                                                                        \
+    if (p.debug & 32) { mbar_arrive(fb_); break; }                                                                            \
+    mbar_arrive_expect_tx(fb_, (uint32_t)(p.BWp * p.BHp * 4));                                                                \
+    tma_load_3d(smem + p.patch_off + ((IT_) & 1) * p.patch_bytes, &tmA0, fb_, ((p.S * x0_ - p.pad) & ~3) * p.cscale, p.S * y0_ - p.pad, img_);    \
+  } while (0)
+      uint32_t tile_it = 0;
+      if (lane == 0 && cta0 < total_tiles) FCB_FETCH_PATCH(cta0, 0u);
+      const int npix = p.R * p.WT, nchunk = 2 * p.ksteps;
+      for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
+        __syncwarp();
+        if (lane == 0 && t + ncta < total_tiles) FCB_FETCH_PATCH(t + ncta, tile_it + 1);  // the other buffer: its reads ended with the previous build
+        const int set = tile_it % p.nsets;
+        mbar_wait(&pfull[tile_it & 1], (tile_it >> 1) & 1);
+        mbar_wait(&aempty[set * p.nplanes], ((tile_it / p.nsets) & 1) ^ 1);
+        const uint32_t patch = smem_u32(smem + p.patch_off + (tile_it & 1) * p.patch_bytes);
+        const uint32_t rows = smem_u32(smem + set * p.set_bytes + p.planes[0].smem_off);
+        // the box starts at a multiple of 4 pixels: an un-swizzled TMA box must start 16-byte aligned in its innermost
+        // dimension (anything else is an illegal instruction: tools/tma_probe.cu, profiles/r01_tma_inner_alignment_probe.log)
+        const int xshift = (p.S * (int)((t % tiles_per_img) % p.tiles_x) * p.WT - p.pad) & 3;
+        int rr = lane / p.WT, xo = lane - rr * p.WT;
+        for (int m = lane; m < ((p.debug & 64) ? 0 : npix); m += 32) {
+          const uint32_t src = patch + 4u * (uint32_t)(rr * p.S * p.BWp + xo * p.S + xshift);
+          const uint32_t dst = rows + 128u * (uint32_t)m;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (j < nchunk) {
+              uint32_t w[4];
+#pragma unroll
+              for (int b = 0; b < 4; b++) w[b] = (4 * j + b < p.nw) ? lds_b32(src + 4u * (uint32_t)p.toff[4 * j + b]) : 0u;
+              sts_v4(dst + (uint32_t)((j ^ (m & 7)) << 4), w[0], w[1], w[2], w[3]);
+            }
+          }
+          xo += 32;
+          while (xo >= p.WT) { xo -= p.WT; ++rr; }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afull[set * p.nplanes]);
+      }
+    } else if (lane == 0) {
       uint32_t tile_it = 0;
       for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
         const int img = (int)(t / tiles_per_img);
@@ -210,7 +265,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint32_t idesc = p.idesc;
     const uint64_t desc0 = make_smem_desc(smem_u32(smem), 128);
     const uint32_t w_d0 = (uint32_t)p.w_off >> 4, w_dstep = (uint32_t)p.w_bytes >> 4;
-    const int wstages = p.wstages, CB = p.CB, NPX = p.NPX;
+    const int wstages = p.wstages, CB = p.CB, NPX = p.NPX, ksteps = p.ksteps, wstatic = p.wstatic;
     for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
       const int set = tile_it % p.nsets;
       const uint32_t apar = (tile_it / p.nsets) & 1;
@@ -230,23 +285,25 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           tc_fence_after();
           const uint64_t wdesc = desc0 + (w_d0 + (uint32_t)s * w_dstep);
           if (elect_one_sync()) {
+            if (!(p.debug & 128)) {
             umma_i8(d_tmem, wdesc, pdesc, idesc, i ? 1u : 0u);
-            umma_i8(d_tmem, wdesc + 2, pdesc + 2, idesc, 1u);
-            umma_i8(d_tmem, wdesc + 4, pdesc + 4, idesc, 1u);
-            umma_i8(d_tmem, wdesc + 6, pdesc + 6, idesc, 1u);
+            if (ksteps > 1) umma_i8(d_tmem, wdesc + 2, pdesc + 2, idesc, 1u);
+            if (ksteps > 2) umma_i8(d_tmem, wdesc + 4, pdesc + 4, idesc, 1u);
+            if (ksteps > 3) umma_i8(d_tmem, wdesc + 6, pdesc + 6, idesc, 1u);
             if (CB == 2) {
               const uint32_t dt = d_tmem + (uint32_t)NPX;
               umma_i8(dt, wdesc + 1024, pdesc, idesc, i ? 1u : 0u);  // next 128 weight rows = +16 KB (>> 4)
-              umma_i8(dt, wdesc + 1026, pdesc + 2, idesc, 1u);
-              umma_i8(dt, wdesc + 1028, pdesc + 4, idesc, 1u);
-              umma_i8(dt, wdesc + 1030, pdesc + 6, idesc, 1u);
+              if (ksteps > 1) umma_i8(dt, wdesc + 1026, pdesc + 2, idesc, 1u);
+              if (ksteps > 2) umma_i8(dt, wdesc + 1028, pdesc + 4, idesc, 1u);
+              if (ksteps > 3) umma_i8(dt, wdesc + 1030, pdesc + 6, idesc, 1u);
             }
-            umma_commit(&wempty[s]);
+            }
+            if (!wstatic) umma_commit(&wempty[s]);
             if (flags & KB_FREE) umma_commit(&aempty[plane]);
             if (i == nkb - 1) umma_commit(&tfull[acc]);
           }
           __syncwarp();
-          if (++s == wstages) { s = 0; wphase ^= 1; }
+          if (++s == wstages) { s = 0; wphase ^= wstatic ? 0u : 1u; }
         }
       }
     }
@@ -681,7 +738,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   p.WT = bWT; p.R = bR; p.P = bWT + halo_x; p.PX = PX; p.PY = PY;
   p.tiles_x = (PX + bWT - 1) / bWT; p.tiles_y = (PY + bR - 1) / bR;
   p.out_x = g.out_x; p.out_y = g.out_y; p.out_word_bytes = (int)g.out_word_bytes; p.out_img_bytes = g.out_img_bytes;
-  p.wstages = bWS; p.w_bytes = w_bytes;
+  p.wstages = bWS; p.w_bytes = w_bytes; p.ksteps = 4;
   p.acc_stride = CBe * bNPX;
   p.acc_stages = (2 * p.acc_stride <= 512) ? 2 : 1;
   int tc = 32;
@@ -724,7 +781,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   p.w_off = off;
   off += bWS * w_bytes;
   p.bar_off = off;
-  off += (2 * bWS + 2 * np * p.nsets + 4) * 8 + 16;
+  off += (2 * bWS + 2 * np * p.nsets + 8) * 8;
   off = (off + 15) & ~15;
   p.stage_off = off;
   off += 8 * 256;
@@ -791,10 +848,122 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   return FCB_OK;
 }
 
+// Thin-input plan: d_w is [CB*128][128] s8 with k = (ky*KX + kx)*4 + lane (zero beyond the window / lanes >= C).
+int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, Umma2Plan** out) {
+  *out = nullptr;
+  const int s = g.SX, nw = g.KX * g.KY;
+  if (g.kind != FCB_KIND_CONV || g.in_word_bytes != 4 || g.in_bits != 8 || nw > 32 || g.SX != g.SY || s < 1 || s > 2 || g.pool > 2 ||
+      (g.IX % 4) || g.OFM > 256)
+    return FCB_ERR_UNSUPPORTED;
+  const int CB = (g.OFM + 127) / 128;
+  const int PX = g.OX, PY = g.OY;
+  const int step = g.pool == 2 ? 2 : 1;
+  const bool thr = g.act_kind == FCB_ACT_THRESHOLDS;
+  int thr_top = 0, thr_bytes = 0;
+  if (thr && !getenv("FCB_U2_NO_SMEM_THR")) {
+    int D = 0;
+    while ((1 << D) < epi.thr_n + 1) D++;
+    // the whole search in shared memory when it fits beside the small operands of this mode, else all but the last two levels
+    const int cand[2] = {D, D - 2};
+    for (int c : cand) {
+      if (c < 1) continue;
+      const int bytes = ((1 << c) - 1) * CB * 128 * 4;
+      if (bytes <= 132 * 1024) { thr_top = c; thr_bytes = bytes; break; }
+    }
+  }
+  const int w_bytes = CB * 128 * 128;
+  const int ksteps = (nw * 4 + 31) / 32;
+  int bWT = 0, bR = 0, bNPX = 0;
+  double best = 1e30;
+  for (int NPX = 256; NPX >= 64; NPX /= 2) {
+    if (CB * NPX > 512) continue;
+    for (int WT = step; WT <= std::min(PX + step - 1, 256); WT += step) {
+      const int BWp = (s * (WT - 1) + g.KX + 3 + 3) / 4 * 4;  // + up to 3 pixels of alignment slack on the left
+      if (BWp > 256) continue;
+      const int budget = (g.pool == 2 && (WT % 8)) ? NPX - 8 : NPX;  // pooled epilogue reads 8-column groups from row starts
+      int R = std::min(budget / WT, PY);
+      if (g.pool == 2) R &= ~1;
+      if (R < 1) continue;
+      const int BHp = s * (R - 1) + g.KY;
+      if (BHp > 256) continue;
+      const size_t need = (size_t)2 * NPX * 128 + w_bytes + 2 * (((size_t)BWp * BHp * 4 + 127) / 128 * 128) + 8192 + (thr_bytes ? thr_bytes + 128 : 0);
+      if (need > (size_t)227 * 1024) continue;
+      const double tiles = (double)((PX + WT - 1) / WT) * ((PY + R - 1) / R);
+      // per tile: fixed cost ~ NPX columns of MMA/epilogue work + overheads; prefer full tiles and wide rows
+      const double cost = tiles * (NPX + 24.0) * (1.0 + 0.002 * R) / ((double)PX * PY);
+      if (cost < best * 0.999) { best = cost; bWT = WT; bR = R; bNPX = NPX; }
+    }
+  }
+  if (!bWT) return FCB_ERR_UNSUPPORTED;
+  Umma2Plan* U = new Umma2Plan();
+  U->g = g; U->num_sms = num_sms;
+  Params2& p = U->p;
+  memset(&p, 0, sizeof(p));
+  p.epi = epi;
+  p.OFM = g.OFM; p.CB = CB; p.chb = 1; p.NPX = bNPX; p.stride2 = 0; p.deconv = 0; p.nphases = 1;
+  p.WT = bWT; p.R = bR; p.P = bWT; p.PX = PX; p.PY = PY;
+  p.tiles_x = (PX + bWT - 1) / bWT; p.tiles_y = (PY + bR - 1) / bR;
+  p.out_x = g.out_x; p.out_y = g.out_y; p.out_word_bytes = (int)g.out_word_bytes; p.out_img_bytes = g.out_img_bytes;
+  p.wstages = 1; p.wstatic = 1; p.w_bytes = w_bytes; p.ksteps = ksteps;
+  p.acc_stride = CB * bNPX;
+  p.acc_stages = (2 * p.acc_stride <= 512) ? 2 : 1;
+  int tc = 32;
+  while (tc < p.acc_stages * p.acc_stride) tc *= 2;
+  p.tmem_cols = tc;
+  p.idesc = make_idesc_i8(128, bNPX, 1, g.in_signed);
+  p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
+  p.thin_in = 1; p.S = s; p.pad = g.PAD; p.nw = nw;
+  p.BWp = (s * (bWT - 1) + g.KX + 3 + 3) / 4 * 4; p.BHp = s * (bR - 1) + g.KY;
+  for (int i = 0; i < 32; i++) p.toff[i] = i < nw ? (i / g.KX) * p.BWp + (i % g.KX) : 0;
+  p.patch_bytes = (p.BWp * p.BHp * 4 + 127) / 128 * 128;
+  // shared memory: [im2col rows x 2 sets][weights][barriers][thin-output staging][thresholds][store staging][patches x 2]
+  p.nplanes = 1; p.nsets = 2; p.set_bytes = bNPX * 128;
+  p.planes[0].smem_off = 0; p.planes[0].bytes = bNPX * 128;
+  int off = 2 * p.set_bytes;
+  p.w_off = off; off += w_bytes;
+  p.bar_off = off; off += (2 * 1 + 2 * 2 + 4 + 1 + 2) * 8 + 16;
+  off = (off + 15) & ~15;
+  p.stage_off = off; off += 8 * 256;
+  p.thr_off = -1; p.thr_top = thr_top;
+  if (thr_bytes) { off = (off + 127) & ~127; p.thr_off = off; off += thr_bytes; }
+  p.stg_bytes = CB * bNPX * 128;
+  const bool fast_epi = epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && g.pool <= 1 && g.OFM % 128 == 0 &&
+                        g.out_word_bytes == (size_t)g.OFM;
+  off = (off + 127) & ~127;
+  p.stg_off = off;
+  if (fast_epi && !getenv("FCB_U2_NO_STAGE"))
+    for (int nb = 2; nb >= 1; nb--)
+      if ((size_t)off + (size_t)nb * p.stg_bytes + 2 * p.patch_bytes + 1024 <= (size_t)227 * 1024) { p.stg_bufs = nb; break; }
+  off += p.stg_bufs * p.stg_bytes;
+  p.patch_off = off; off += 2 * p.patch_bytes;
+  U->smem = (size_t)off + 1024;
+  if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
+  Phase2& P = p.phases[0];
+  P.nkb = 1; P.px = P.py = 0;
+  P.kb[0].plane = 0; P.kb[0].flags = KB_WAIT | KB_FREE; P.kb[0].a_off = 0; P.kb[0].w_k = 0; P.kb[0].d_off = 0;
+  {
+    const uint64_t dims[2] = {128, (uint64_t)(CB * 128)};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {128, (uint32_t)(CB * 128)};
+    int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
+    if (rc) { delete U; return rc; }
+  }
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  *out = U;
+  return FCB_OK;
+}
+
 void umma2_plan_destroy(Umma2Plan* U) { delete U; }
 
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   const Params2& p = U->p;
+  if (p.thin_in) {
+    snprintf(buf, n, "smem-im2col (thin input, K=%d B, %d MMA/tile, weights resident) WT=%d R=%d NPX=%d CB=%d%s patch=%dx%d smem=%zu tiles=%dx%d",
+             p.nw * 4, p.ksteps * p.CB, p.WT, p.R, p.NPX, p.CB,
+             p.thr_off >= 0 ? " thr@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.BWp, p.BHp, U->smem,
+             p.tiles_x, p.tiles_y);
+    return buf;
+  }
   snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d chb=%d%s planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT,
            p.R, p.P, p.NPX, p.CB, p.chb, p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
            p.tiles_x, p.tiles_y);
@@ -810,7 +979,21 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   const uint64_t C = g.C, X = g.IX, Y = g.IY;
   for (int m = 0; m < 2; m++) {
     int rc;
-    if (p.stride2) {
+    if (p.thin_in) {  // raw image of 4-byte pixels; the patch of a tile is one box, borders zero-filled
+      if (getenv("FCB_THIN_U8")) {
+        const uint64_t dims[3] = {X * 4, Y, (uint64_t)n_images};
+        const uint64_t strides[2] = {X * 4, X * Y * 4};
+        const uint32_t box[3] = {(uint32_t)p.BWp * 4, (uint32_t)p.BHp, 1};
+        p.cscale = 4;
+        rc = umma_encode_map_ex(&tmA[m], const_cast<void*>(d_in), 1, 0, 3, dims, strides, box);
+      } else {
+      const uint64_t dims[3] = {X, Y, (uint64_t)n_images};
+      const uint64_t strides[2] = {X * 4, X * Y * 4};
+      const uint32_t box[3] = {(uint32_t)p.BWp, (uint32_t)p.BHp, 1};
+      p.cscale = 1;
+      rc = umma_encode_map_ex(&tmA[m], const_cast<void*>(d_in), 4, 0, 3, dims, strides, box);
+      }
+    } else if (p.stride2) {
       const uint64_t dims[5] = {2 * C, X / 2, 2, Y / 2, (uint64_t)n_images};
       const uint64_t strides[4] = {2 * C, X * C, 2 * X * C, X * Y * C};
       const uint32_t box[5] = {128, (uint32_t)p.P, 1, U->box_rows[m], 1};

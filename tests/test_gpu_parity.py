@@ -269,3 +269,38 @@ def test_xnor_on_tensor_cores(name, pad, pool, fcb_lib, oracle_mod, monkeypatch)
     assert Lt.engine == "umma_i8" and "xnor as +-1" in Lt.plan, Lt.plan
     got = Lt.run(inp["in_words"], 2)
     assert np.array_equal(got, want), f"{name} pad={pad} [{Lt.plan}]: {_diff(got, want)}"
+
+
+def _thin_cases():
+    from simple_image_compression_network_b200.desc import ACT_BIAS_RELU, ACT_THRESHOLDS, KIND_CONV, LayerDesc
+
+    def mk(k, s, p, c, ofm, x, y, pe, thr=0, pool=0):
+        kw = dict(act_kind=ACT_THRESHOLDS, acc_bits=24, acc_signed=1, out_bits=8, num_th=thr, pool=pool) if thr else \
+            dict(act_kind=ACT_BIAS_RELU, acc_bits=8, acc_signed=0, out_bits=8)
+        return LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=s, stride_y=s, pad=p,
+                         simd=c, pe=pe, in_bits=8, w_bits=4, **kw)
+    return {
+        "L0_shape_multi_tile": (mk(5, 2, 2, 3, 128, 264, 40, 16), 2),       # staged TMA-store epilogue, ragged right edge
+        "L0_shape_one_row": (mk(5, 2, 2, 3, 128, 16, 2, 16), 1),
+        "stage1_thr255_pool": (mk(3, 1, 1, 3, 128, 72, 20, 16, thr=255, pool=2), 3),
+        "c4_thr15_nopool": (mk(3, 1, 1, 4, 32, 36, 10, 8, thr=15), 2),
+        "k5_s1_cb2": (mk(5, 1, 2, 3, 256, 64, 12, 32), 2),                 # two channel blocks
+        "k3_s2_ofm192": (mk(3, 2, 1, 3, 192, 40, 12, 24), 1),               # register epilogue (OFM % 128 != 0)
+    }
+
+
+@pytest.mark.parametrize("name", list(_thin_cases()))
+def test_thin_input_smem_im2col(name, fcb_lib, oracle_mod, monkeypatch):
+    """Thin-input layers (one 4-byte word per pixel): sliding window built in shared memory inside the tensor-core kernel,
+    against the oracle and against the older two-kernel im2col lowering."""
+    d, reps = _thin_cases()[name]
+    inp = cases.make_inputs(d, seed_shift=31, num_reps=reps)
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=reps)
+    L = _layer(d, inp)
+    assert L.engine == "umma_i8" and L.plan.startswith("smem-im2col"), L.plan
+    got = L.run(inp["in_words"], reps)
+    assert np.array_equal(got, want), f"{name} [{L.plan}]: {_diff(got, want)}"
+    monkeypatch.setenv("FCB_THIN", "im2col")
+    L2 = _layer(d, inp)
+    assert not L2.plan.startswith("smem-im2col")
+    assert np.array_equal(L2.run(inp["in_words"], reps), want), f"{name} [{L2.plan}]"
