@@ -350,7 +350,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     for (int ch = 0; ch < g.OFM; ch++)
       for (int tap = 0; tap < g.KX * g.KY; tap++)
         for (int c = 0; c < g.C; c++) W4[(size_t)ch * 128 + tap * 4 + c] = W[(size_t)ch * g.K + tap * g.C + c];
-    rc = umma_plan_create_thin(g, W4, L->epi, device, &L->umma);
+    rc = umma_plan_create_thin(g, W4, L->epi, g.act_kind == FCB_ACT_BIAS_RELU ? (const int8_t*)bias : nullptr, device, &L->umma);
     if (rc == FCB_OK) engine = L->engine = ENG_UMMA;
     else if (rc != FCB_ERR_UNSUPPORTED) { fcb_layer_destroy(L); return rc; }
     else L->umma = nullptr;

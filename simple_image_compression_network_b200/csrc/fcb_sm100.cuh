@@ -79,6 +79,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// pure polling (no suspend hint): lowest wake-up latency, for waits on the critical path of short tiles
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint64_t t0 = 0;
+  for (uint32_t n = 1; !mbar_try_wait(bar, parity); ++n) {
+    if ((n & 1023) == 0) {
+      if (!t0) t0 = globaltimer_ns();
+      else if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+
 // ---- TMA ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -104,6 +115,14 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+
+// 0xFF in every byte of x whose bit 7 is set, else 0x00: PTX prmt with the sign-replicate bit (msb) of each selector nibble.
+// (__byte_perm() only honours the low 3 bits of a nibble, so this has to be the PTX instruction.)
+__device__ __forceinline__ uint32_t prmt_sign_mask(uint32_t x) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(m) : "r"(x));
+  return m;
+}
 
 // ---- TMA stores (shared -> global, bulk async-group completion) ---------------------------------
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {

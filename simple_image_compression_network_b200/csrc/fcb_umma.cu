@@ -61,6 +61,7 @@ struct UmmaPlan {
   Geom g;
   int device = 0;
   int8_t* d_w = nullptr;  // [Npad][K] s8, K contiguous
+  int8_t* d_zero_bias = nullptr;  // thin-input plans with the bias folded into the weights
   CUtensorMap tmB;
   UmmaParams p;
   size_t smem = 0;
@@ -401,7 +402,7 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
 }
 
 // Thin-input layers (one 4-byte word per pixel): W4 is [OFM][128], k = (ky*KX + kx)*4 + lane.
-int umma_plan_create_thin(const Geom& g, const std::vector<int32_t>& W4, const EpiParams& epi, int device, UmmaPlan** out) {
+int umma_plan_create_thin(const Geom& g, const std::vector<int32_t>& W4, const EpiParams& epi, const int8_t* bias_host, int device, UmmaPlan** out) {
   UmmaPlan* P = new UmmaPlan();
   P->g = g;
   P->device = device;
@@ -411,9 +412,24 @@ int umma_plan_create_thin(const Geom& g, const std::vector<int32_t>& W4, const E
   const int rows_pad = (g.OFM + 127) / 128 * 128;
   std::vector<int8_t> w8((size_t)rows_pad * 128, 0);
   for (size_t i = 0; i < (size_t)g.OFM * 128; i++) w8[i] = (int8_t)W4[i];
+  // bias + ReLU on the wrapped 8-bit lane (conv_nonsquare_top.cpp:267-278): ((acc mod 256) + bias) mod 256 = (acc + bias) mod 256, so
+  // the bias can ride in the GEMM as the weight of a constant-1 activation in the first unused window word
+  const int nw = g.KX * g.KY;
+  int bias_word = -1;
+  if (bias_host && epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && (nw == 25 || nw == 9) &&
+      (uint64_t)(g.K + 1) * 255ull * 128ull < (1ull << 31) && !getenv("FCB_U2_NO_FOLD")) {
+    bias_word = nw;
+    for (int ch = 0; ch < g.OFM; ch++) w8[(size_t)ch * 128 + 4 * nw] = bias_host[ch];
+  }
   FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size()));
   FCB_CUDA_OK(cudaMemcpy(P->d_w, w8.data(), w8.size(), cudaMemcpyHostToDevice));
-  int rc = umma2_plan_create_thin(g, P->d_w, epi, P->num_sms, &P->v2);
+  EpiParams epi2 = epi;
+  if (bias_word >= 0) {  // every epilogue variant now adds a zero bias
+    FCB_CUDA_OK(cudaMalloc(&P->d_zero_bias, rows_pad));
+    FCB_CUDA_OK(cudaMemset(P->d_zero_bias, 0, rows_pad));
+    epi2.bias = P->d_zero_bias;
+  }
+  int rc = umma2_plan_create_thin(g, P->d_w, epi2, P->num_sms, bias_word, &P->v2);
   if (rc) { umma_plan_destroy(P); return rc; }
   umma2_describe(P->v2, P->desc, sizeof(P->desc));
   *out = P;
@@ -426,6 +442,7 @@ void umma_plan_destroy(UmmaPlan* P) {
   if (!P) return;
   if (P->v2) umma2_plan_destroy(P->v2);
   cudaFree(P->d_w);
+  cudaFree(P->d_zero_bias);
   delete P;
 }
 

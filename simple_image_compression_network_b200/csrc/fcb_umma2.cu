@@ -39,8 +39,9 @@ namespace fcb {
 
 using namespace sm100;
 
-constexpr int U2_THREADS = 352;  // 11 warps: 0 weight TMA, 1 MMA issue, 2..9 epilogue (2 per TMEM lane quarter), 10 plane TMA
+// warps: 0 weight TMA, 1 MMA issue, 2..9 epilogue (2 per TMEM lane quarter), 10.. plane TMA producer / im2col builders
 constexpr int U2_MAX_KB = 64;
+constexpr uint32_t U2_NPB = 4;  // raw patch buffers of the thin-input mode
 constexpr int U2_MAX_PLANES = 8;
 enum { KB_WAIT = 2, KB_FREE = 4 };
 
@@ -75,7 +76,19 @@ struct Params2 {
   // thin-input mode (input word = one 4-byte pixel of <= 4 lanes, e.g. the C = 3 first layer): warp 10 builds the tile's
   // im2col rows in shared memory (one 128-byte SWIZZLE_128B row per output pixel, word (ky*KX + kx) = input pixel of that tap)
   // from a raw patch fetched by TMA; the layer is then ONE K-block of `ksteps` MMAs per tile with resident weights.
-  int cscale;
+  int cscale, spin;
+  // swapped orientation (thin-input + bias/ReLU): pixels on the MMA M axis (D[pixel][channel]) so an epilogue thread owns ONE
+  // pixel and assembles its 128-byte output word with 16-byte shared-memory stores (the tile is store-bound: K is tiny)
+  int swap;
+  uint32_t idesc_swap;
+  // alternating epilogue groups (staged paths with two accumulator stages): warps 2..5 own accumulator stage / staging buffer 0,
+  // warps 6..9 stage 1, so one group's barriers, fences and store issue overlap the other group's TMEM reads (64 B/clk/SM:
+  // ~2048 clocks for a 256 x 128 int32 tile -- the floor of a store-bound layer)
+  int epi_alt;
+  // bias folded into the GEMM (thin-input mode): window word `bias_word` of every im2col row is the constant 1 and the weight
+  // byte there is the channel's bias, so the accumulator already is acc + bias (all arithmetic is mod 2^8); -1 = not folded
+  int bias_word;
+  unsigned long long* prof;  // FCB_U2_PROF: per-CTA clock totals [role 0 builder | 1 mma | 2 epilogue][8 segments]
   int thin_in, S, pad, nw, BWp, BHp, patch_off, patch_bytes, ksteps, wstatic;
   int toff[32];  // patch word offset of window word i: ky*BWp + kx
   int debug;  // FCB_U2_DEBUG bitmask (perf decomposition only): 1 no weight TMA, 2 no plane TMA, 4 no stores, 8 no epilogue
@@ -112,7 +125,50 @@ struct PixMap {
   }
 };
 
-__global__ void __launch_bounds__(U2_THREADS, 1)
+// Persistent-tile iterator: CTA c visits tiles c, c + ncta, ... ; (image, tile column, tile row) advance by precomputed
+// increments, so the per-tile bookkeeping of every warp role is a handful of adds instead of 32/64-bit divisions.
+struct TileIter {
+  int img, tx, ty, da, dx, dy, tiles_x, tiles_y;
+  long long t, ncta, total;
+  __device__ __forceinline__ TileIter(long long cta0, long long ncta_, int tiles_x_, int tiles_y_, int n_images)
+      : tiles_x(tiles_x_), tiles_y(tiles_y_), t(cta0), ncta(ncta_), total((long long)tiles_x_ * tiles_y_ * n_images) {
+    const uint32_t tpi = (uint32_t)(tiles_x * tiles_y), c = (uint32_t)cta0, n = (uint32_t)ncta_;
+    img = (int)(c / tpi);
+    const uint32_t r = c - (uint32_t)img * tpi;
+    ty = (int)(r / (uint32_t)tiles_x); tx = (int)(r - (uint32_t)ty * tiles_x);
+    da = (int)(n / tpi);
+    const uint32_t b = n - (uint32_t)da * tpi;
+    dy = (int)(b / (uint32_t)tiles_x); dx = (int)(b - (uint32_t)dy * tiles_x);
+  }
+  __device__ __forceinline__ bool valid() const { return t < total; }
+  __device__ __forceinline__ void next() {
+    t += ncta; tx += dx; ty += dy; img += da;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    if (ty >= tiles_y) { ty -= tiles_y; ++img; }
+  }
+};
+// rings of 1 or 2 slots: slot and phase parity of iteration `it`
+__device__ __forceinline__ uint32_t ring_idx(uint32_t it, int n) { return n == 2 ? (it & 1u) : 0u; }
+__device__ __forceinline__ uint32_t ring_par(uint32_t it, int n) { return n == 2 ? ((it >> 1) & 1u) : (it & 1u); }
+
+// One im2col row of the thin-input mode: 8*KS window words gathered from the raw patch (offsets in registers), written as 2*KS
+// 16-byte chunks of a SWIZZLE_128B row.  Straight-line: all loads are issued before the first store.
+template <int KS, int BW>
+__device__ __forceinline__ void build_row(uint32_t src, uint32_t dst, uint32_t m7, const uint32_t (&offs)[32]) {
+  uint32_t w[8 * KS];
+#pragma unroll
+  for (int i = 0; i < 8 * KS; i++) {
+    if (i == BW) w[i] = 1u;  // the constant-1 activation that multiplies the bias row of the weights
+    else if (BW >= 0 && i > BW) w[i] = 0u;
+    else w[i] = lds_b32(src + offs[i]);
+  }
+#pragma unroll
+  for (int j = 0; j < 2 * KS; j++) sts_v4(dst + (((uint32_t)j ^ m7) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+
+// NB = warps from index 10 on: 1 = plane TMA producer (resident-planes mode); 4 = im2col builders (thin-input mode)
+template <int NB>
+__global__ void __launch_bounds__(320 + 32 * NB, 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params2 p) {
   extern __shared__ uint8_t smem_raw[];
@@ -125,9 +181,18 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* tfull = aempty + p.nsets * p.nplanes;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint64_t* pfull = tempty + 3;  // thin-input mode: raw patch buffers
+  uint64_t* pfull = tempty + 3;  // thin-input mode: raw patch buffers (U2_NPB)
+  uint64_t* pempty = pfull + U2_NPB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool spin = p.spin != 0;  // short tiles: poll instead of suspending on the barriers of the tile pipeline
+#define WAITB(BAR_, PAR_) do { if (spin) mbar_wait_spin((BAR_), (PAR_)); else mbar_wait((BAR_), (PAR_)); } while (0)
+  // opt-in clock accounting: PROF_T(seg) adds the clocks since the previous PROF_T / PROF_START of this thread to segment `seg`
+  long long prof_c = 0;
+  unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_START() do { if (p.prof) prof_c = clock64(); } while (0)
+#define PROF_T(SEG_) do { if (p.prof) { const long long n_ = clock64(); prof_acc[SEG_] += (unsigned long long)(n_ - prof_c); prof_c = n_; } } while (0)
+#define PROF_FLUSH(ROLE_) do { if (p.prof) for (int i_ = 0; i_ < 8; i_++) p.prof[(blockIdx.x * 3 + (ROLE_)) * 8 + i_] = prof_acc[i_]; } while (0)
   const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
   const long long total_tiles = tiles_per_img * p.n_images;
   // CTA -> (channel block, tile sequence): with chb > 1 every tile is visited once per channel block
@@ -145,13 +210,16 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   }
 
+  if (p.swap)  // bias bytes of this CTA's channels (read as packed words by every epilogue thread)
+    for (int idx = threadIdx.x; idx < p.CB * 128; idx += blockDim.x) smem[p.stage_off + idx] = idx < p.OFM ? (uint8_t)p.epi.bias[idx] : 0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-    for (int i = 0; i < p.nsets * p.nplanes; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); mbar_init(&pfull[a], 1); }
+    for (int i = 0; i < p.nsets * p.nplanes; i++) { mbar_init(&afull[i], p.thin_in ? NB : 1); mbar_init(&aempty[i], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], p.epi_alt ? 4 : 8); }
+    for (int a = 0; a < U2_NPB; a++) { mbar_init(&pfull[a], 1); mbar_init(&pempty[a], NB); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -180,66 +248,77 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
         }
       }
+      if (p.thin_in) {
+        // ===== raw patch fetcher (thin-input mode; the weights above were loaded once): U2_NPB buffers, released by the builders
+        uint32_t it = 0;
+        for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next(), it++) {
+          const uint32_t b = it % U2_NPB;
+          if (it >= U2_NPB) WAITB(&pempty[b], ((it / U2_NPB) & 1u) ^ 1u);
+          if (p.debug & 32) { mbar_arrive(&pfull[b]); continue; }
+          mbar_arrive_expect_tx(&pfull[b], (uint32_t)(p.BWp * p.BHp * 4));
+          // the box starts at a multiple of 4 pixels: an un-swizzled TMA box must start 16-byte aligned in its innermost dimension
+          // (anything else is an illegal instruction: tools/tma_probe.cu, profiles/r01_tma_inner_alignment_probe.log)
+          tma_load_3d(smem + p.patch_off + b * p.patch_bytes, &tmA0, &pfull[b], ((p.S * ti.tx * p.WT - p.pad) & ~3) * p.cscale,
+                      p.S * ti.ty * p.R - p.pad, ti.img);
+        }
+      }
     }
-  } else if (warp == 10) {
+  } else if (warp >= 10) {
     // ===================== TMA producer: input planes =====================
     // Independent of the weight ring: plane i of the next tile is fetched the moment the MMAs that read plane i of
     // the current tile have retired (aempty), i.e. while the remaining taps of the current tile execute.
     if (p.thin_in) {
       // ===== sliding window as shared-memory im2col (slidingwindow.h:1302-1313 order ky, kx, lane; FMPadding zeros = TMA OOB fill)
-      // (no lambda here: taking &tmA0 through a by-reference capture would hand TMA a local-memory copy of the tensor map)
-#define FCB_FETCH_PATCH(T_, IT_)                                                                                              \
-  do {                                                                                                                        \
-    const int img_ = (int)((T_) / tiles_per_img);                                                                             \
-    const int r_ = (int)((T_) % tiles_per_img);                                                                               \
-    const int x0_ = (r_ % p.tiles_x) * p.WT, y0_ = (r_ / p.tiles_x) * p.R;                                                    \
-    uint64_t* fb_ = &pfull[(IT_) & 1];                                                                                        \
-    if (p.debug & 32) { mbar_arrive(fb_); break; }                                                                            \
-    mbar_arrive_expect_tx(fb_, (uint32_t)(p.BWp * p.BHp * 4));                                                                \
-    tma_load_3d(smem + p.patch_off + ((IT_) & 1) * p.patch_bytes, &tmA0, fb_, ((p.S * x0_ - p.pad) & ~3) * p.cscale, p.S * y0_ - p.pad, img_);    \
-  } while (0)
+      // builder warp bw takes rows m = 32*bw + lane (mod 32*NB).  Window word i of a row comes from patch word
+      // offs[i] = ky*BWp + kx (bytes, kept in registers); words beyond the window re-read word 0: their weights are zero.
+      const int bw = warp - 10;
+      uint32_t offs[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        offs[i] = i < p.nw ? 4u * (uint32_t)p.toff[i] : 0u;
+        asm volatile("" : "+r"(offs[i]));
+      }
+      const int npix = p.R * p.WT, ksteps = p.ksteps, bias_word = p.bias_word;
+      const uint32_t row_step = 4u * (uint32_t)(p.S * p.BWp), col_step = 4u * (uint32_t)p.S;
       uint32_t tile_it = 0;
-      if (lane == 0 && cta0 < total_tiles) FCB_FETCH_PATCH(cta0, 0u);
-      const int npix = p.R * p.WT, nchunk = 2 * p.ksteps;
-      for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
-        __syncwarp();
-        if (lane == 0 && t + ncta < total_tiles) FCB_FETCH_PATCH(t + ncta, tile_it + 1);  // the other buffer: its reads ended with the previous build
-        const int set = tile_it % p.nsets;
-        mbar_wait(&pfull[tile_it & 1], (tile_it >> 1) & 1);
-        mbar_wait(&aempty[set * p.nplanes], ((tile_it / p.nsets) & 1) ^ 1);
-        const uint32_t patch = smem_u32(smem + p.patch_off + (tile_it & 1) * p.patch_bytes);
+      PROF_START();
+      for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next(), tile_it++) {
+        const uint32_t set = ring_idx(tile_it, p.nsets), pb = tile_it % U2_NPB;
+        PROF_T(0);
+        WAITB(&pfull[pb], (tile_it / U2_NPB) & 1u);
+        PROF_T(1);
+        WAITB(&aempty[set * p.nplanes], ring_par(tile_it, p.nsets) ^ 1u);
+        PROF_T(2);
+        const uint32_t xshift = (uint32_t)((p.S * ti.tx * p.WT - p.pad) & 3);
+        const uint32_t patch = smem_u32(smem + p.patch_off + pb * p.patch_bytes) + 4u * xshift;
         const uint32_t rows = smem_u32(smem + set * p.set_bytes + p.planes[0].smem_off);
-        // the box starts at a multiple of 4 pixels: an un-swizzled TMA box must start 16-byte aligned in its innermost
-        // dimension (anything else is an illegal instruction: tools/tma_probe.cu, profiles/r01_tma_inner_alignment_probe.log)
-        const int xshift = (p.S * (int)((t % tiles_per_img) % p.tiles_x) * p.WT - p.pad) & 3;
-        int rr = lane / p.WT, xo = lane - rr * p.WT;
-        for (int m = lane; m < ((p.debug & 64) ? 0 : npix); m += 32) {
-          const uint32_t src = patch + 4u * (uint32_t)(rr * p.S * p.BWp + xo * p.S + xshift);
-          const uint32_t dst = rows + 128u * (uint32_t)m;
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            if (j < nchunk) {
-              uint32_t w[4];
-#pragma unroll
-              for (int b = 0; b < 4; b++) w[b] = (4 * j + b < p.nw) ? lds_b32(src + 4u * (uint32_t)p.toff[4 * j + b]) : 0u;
-              sts_v4(dst + (uint32_t)((j ^ (m & 7)) << 4), w[0], w[1], w[2], w[3]);
-            }
-          }
-          xo += 32;
+        int rr = (32 * bw + lane) / p.WT, xo = (32 * bw + lane) - rr * p.WT;
+        for (int m = 32 * bw + lane; m < ((p.debug & 64) ? 0 : npix); m += 32 * NB) {
+          uint32_t src = patch + (uint32_t)rr * row_step + (uint32_t)xo * col_step;
+          asm volatile("" : "+r"(src));  // one register, not re-derived per load
+          const uint32_t dst = rows + 128u * (uint32_t)m, m7 = (uint32_t)m & 7u;
+          if (bias_word == 25) build_row<4, 25>(src, dst, m7, offs);     // 5x5 window
+          else if (bias_word == 9) build_row<2, 9>(src, dst, m7, offs);  // 3x3 window
+          else if (ksteps == 4) build_row<4, -1>(src, dst, m7, offs);
+          else if (ksteps == 2) build_row<2, -1>(src, dst, m7, offs);
+          else if (ksteps == 3) build_row<3, -1>(src, dst, m7, offs);
+          else build_row<1, -1>(src, dst, m7, offs);
+          xo += 32 * NB;
           while (xo >= p.WT) { xo -= p.WT; ++rr; }
         }
+        PROF_T(3);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&afull[set * p.nplanes]);
+        if (lane == 0) { mbar_arrive(&afull[set * p.nplanes]); mbar_arrive(&pempty[pb]); }
+        PROF_T(4);
       }
+      if (bw == 0 && lane == 0) PROF_FLUSH(0);
     } else if (lane == 0) {
       uint32_t tile_it = 0;
-      for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
-        const int img = (int)(t / tiles_per_img);
-        const int r = (int)(t % tiles_per_img);
-        const int x0 = (r % p.tiles_x) * p.WT, y0 = (r / p.tiles_x) * p.R;
-        const int set = tile_it % p.nsets;
-        const uint32_t par = ((tile_it / p.nsets) & 1) ^ 1;
+      for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next(), tile_it++) {
+        const int img = ti.img, x0 = ti.tx * p.WT, y0 = ti.ty * p.R;
+        const int set = (int)ring_idx(tile_it, p.nsets);
+        const uint32_t par = ring_par(tile_it, p.nsets) ^ 1u;
         for (int i = 0; i < p.nplanes; i++) {
           const Plane2& pl = p.planes[i];
           uint64_t* fb = &afull[set * p.nplanes + i];
@@ -266,26 +345,43 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint64_t desc0 = make_smem_desc(smem_u32(smem), 128);
     const uint32_t w_d0 = (uint32_t)p.w_off >> 4, w_dstep = (uint32_t)p.w_bytes >> 4;
     const int wstages = p.wstages, CB = p.CB, NPX = p.NPX, ksteps = p.ksteps, wstatic = p.wstatic;
+    PROF_START();
     for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
-      const int set = tile_it % p.nsets;
-      const uint32_t apar = (tile_it / p.nsets) & 1;
+      const int set = (int)ring_idx(tile_it, p.nsets);
+      const uint32_t apar = ring_par(tile_it, p.nsets);
       const uint64_t desc_set = desc0 + (uint32_t)((set * p.set_bytes) >> 4);
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
         const Phase2& P = p.phases[ph];
         const int nkb = P.nkb;
-        const int acc = acc_it % p.acc_stages;
-        mbar_wait(&tempty[acc], ((acc_it / p.acc_stages) & 1) ^ 1);
+        const int acc = (int)ring_idx(acc_it, p.acc_stages);
+        PROF_T(0);
+        WAITB(&tempty[acc], ring_par(acc_it, p.acc_stages) ^ 1u);
+        PROF_T(1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.acc_stride);
         for (int i = 0; i < nkb; i++) {
           const uint32_t flags = P.kb[i].flags, plane = set * p.nplanes + P.kb[i].plane;
           const uint64_t pdesc = desc_set + P.kb[i].d_off;
-          if (flags & KB_WAIT) mbar_wait(&afull[plane], apar);
-          mbar_wait(&wfull[s], wphase);
+          PROF_T(2);
+          if (flags & KB_WAIT) WAITB(&afull[plane], apar);
+          PROF_T(3);
+          WAITB(&wfull[s], wphase);
+          PROF_T(4);
           tc_fence_after();
           const uint64_t wdesc = desc0 + (w_d0 + (uint32_t)s * w_dstep);
           if (elect_one_sync()) {
-            if (!(p.debug & 128)) {
+            if (p.swap) {
+              // A = 128 im2col rows (pixels) per block, B = the CB*128 weight rows: D[pixel][channel]
+              if (!(p.debug & 128))
+                for (int blk = 0; blk < NPX / 128; blk++) {
+                  const uint32_t dt = d_tmem + (uint32_t)(blk * CB * 128);
+                  const uint64_t ad = pdesc + (uint64_t)(blk * 1024);  // 128 rows x 128 B = 16 KB (>> 4)
+                  umma_i8(dt, ad, wdesc, p.idesc_swap, 0u);
+                  if (ksteps > 1) umma_i8(dt, ad + 2, wdesc + 2, p.idesc_swap, 1u);
+                  if (ksteps > 2) umma_i8(dt, ad + 4, wdesc + 4, p.idesc_swap, 1u);
+                  if (ksteps > 3) umma_i8(dt, ad + 6, wdesc + 6, p.idesc_swap, 1u);
+                }
+            } else if (!(p.debug & 128)) {
             umma_i8(d_tmem, wdesc, pdesc, idesc, i ? 1u : 0u);
             if (ksteps > 1) umma_i8(d_tmem, wdesc + 2, pdesc + 2, idesc, 1u);
             if (ksteps > 2) umma_i8(d_tmem, wdesc + 4, pdesc + 4, idesc, 1u);
@@ -307,11 +403,16 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
     }
+    if (lane == 0) PROF_FLUSH(1);
   } else if (warp < 10) {
     // ===================== epilogue (warps 2..9): lane = output channel, TMEM column = pixel =====================
     // two warps per TMEM lane quarter; `half` splits the accumulator columns (pixels) between them
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const int col_lo = half * (p.NPX / 2), col_hi = col_lo + p.NPX / 2;
+    const bool alt = p.epi_alt != 0;
+    const int col_lo = alt ? 0 : half * (p.NPX / 2), col_hi = alt ? p.NPX : col_lo + p.NPX / 2;
+    const int ebar = alt ? 1 + half : 1, ecnt = alt ? 128 : 256;      // named barrier of this warp's epilogue group
+    const int erow0 = alt ? q : warp - 2, erows = alt ? 4 : 8;        // TMA-store rows dealt over the group's warps
+#define EPI_BAR() asm volatile("bar.sync %0, %1;" ::"r"(ebar), "r"(ecnt) : "memory")
     const int pk = p.epi.pool >= 2 ? p.epi.pool : 1;
     const bool fast = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && (p.OFM % 32) == 0 && p.P >= 4;
     // thresholds with comp::less / less_equal and a result that cannot wrap TR: monotone in the (wrapped, < 2^31) accumulator
@@ -322,32 +423,107 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (p.thr_off >= 0) for (int t = p.epi.thr_n + 1; (t >> (p.thr_top + gshift)) > 1;) gshift++;
     const bool thin = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
     uint32_t acc_it = 0;
-    for (long long t = cta0; t < total_tiles; t += ncta) {
-      const int img = (int)(t / tiles_per_img);
-      const int r = (int)(t % tiles_per_img);
+    PROF_START();
+    for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next()) {
+      const int img = ti.img;
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
-        const PixMap pm{p, (r % p.tiles_x) * p.WT, (r / p.tiles_x) * p.R, p.phases[ph].px, p.phases[ph].py,
-                        (unsigned long long)img * p.out_img_bytes};
-        const int acc = acc_it % p.acc_stages;
-        mbar_wait(&tfull[acc], (acc_it / p.acc_stages) & 1);
+        const PixMap pm{p, ti.tx * p.WT, ti.ty * p.R, p.phases[ph].px, p.phases[ph].py, (unsigned long long)img * p.out_img_bytes};
+        const int acc = (int)ring_idx(acc_it, p.acc_stages);
+        if (alt && acc != half) continue;  // the other group's accumulator
+        PROF_T(0);
+        WAITB(&tfull[acc], ring_par(acc_it, p.acc_stages));
+        PROF_T(1);
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
+        if (p.swap) {
+          // Swapped staged bias + ReLU epilogue: thread = pixel (TMEM lane), 32-column loads = 32 channels of that pixel ->
+          // 8 packed words -> two 16-byte stores into the SWIZZLE_128B staging row of the pixel; TMA stores un-swizzle.
+          const int sb = alt ? half : (int)ring_idx(acc_it, p.stg_bufs);
+          uint8_t* stg = smem + p.stg_off + sb * p.stg_bytes;
+          if (lane == 0) {
+            if (p.stg_bufs == 2 && !alt) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+          }
+          EPI_BAR();
+          PROF_T(2);
+          // items = (128-pixel block, 32-channel block), block-major; this warp takes every `its`-th item from `it0`
+          const int cpb = p.CB * 4, nitems = (p.debug & 8) ? 0 : (p.NPX / 128) * cpb;
+          const uint32_t bias_s = smem_u32(smem + p.stage_off);
+          const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+          const uint32_t stg_s = smem_u32(stg);
+          const bool fold = p.bias_word >= 0;
+          const int mlim = vrows * p.P;
+          auto process = [&](int blk, int cbk, const uint32_t (&v)[32]) {
+            const int m = blk * 128 + q * 32 + lane;
+            if (m >= mlim) return;  // rows of the tile that are never stored
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
+              uint32_t x = __byte_perm(lo, hi, 0x5410);  // low bytes of 4 channels = accumulators mod 256
+              if (!fold) x = __vadd4(x, lds_b32(bias_s + (uint32_t)(cbk * 32 + 4 * j)));
+              w[j] = x & ~prmt_sign_mask(x);             // ReLU on the wrapped value: bytes with bit 7 set -> 0
+            }
+            const uint32_t row = stg_s + (uint32_t)((cbk >> 2) * p.NPX * 128 + m * 128);
+            const uint32_t c0 = (uint32_t)((cbk & 3) * 2), m7 = (uint32_t)m & 7u;
+            sts_v4(row + ((c0 ^ m7) << 4), w[0], w[1], w[2], w[3]);
+            sts_v4(row + (((c0 + 1) ^ m7) << 4), w[4], w[5], w[6], w[7]);
+          };
+          const int it0 = alt ? 0 : half, its = alt ? 1 : 2;
+          if (it0 < nitems) {  // software pipeline: the next item's TMEM load is in flight while this one is packed
+            uint32_t va[32], vb[32];
+            int blk = 0, cbk = it0, left = (nitems - it0 + its - 1) / its;  // items this warp still has to load
+            int blk_n = blk, cbk_n = cbk;
+            auto advance = [&]() { cbk_n += its; if (cbk_n >= cpb) { cbk_n -= cpb; ++blk_n; } };
+            tmem_ld32(tacc + (uint32_t)(blk_n * p.CB * 128 + cbk_n * 32), va);
+            --left;
+            while (true) {
+              tmem_ld_wait();
+              blk = blk_n; cbk = cbk_n;
+              if (left > 0) { advance(); tmem_ld32(tacc + (uint32_t)(blk_n * p.CB * 128 + cbk_n * 32), vb); }
+              process(blk, cbk, va);
+              if (left-- <= 0) break;
+              tmem_ld_wait();
+              blk = blk_n; cbk = cbk_n;
+              if (left > 0) { advance(); tmem_ld32(tacc + (uint32_t)(blk_n * p.CB * 128 + cbk_n * 32), va); }
+              process(blk, cbk, vb);
+              if (left-- <= 0) break;
+            }
+          }
+          PROF_T(3);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          fence_proxy_async();
+          PROF_T(4);
+          EPI_BAR();
+          PROF_T(5);
+          if (lane == 0) {
+            for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++)
+              for (int rr = erow0; rr < vrows; rr += erows)
+                tma_store_4d(&tmO, stg + (cb * p.NPX + rr * p.P) * 128, cb * 128, pm.x0, pm.y0 + rr, img);
+            bulk_commit();
+          }
+          PROF_T(6);
+          continue;
+        }
         if (p.stg_bufs > 0) {
           // Staged bias + ReLU epilogue (conv_nonsquare_top.cpp:267-278): thread = channel turns its 32-column TMEM loads into
           // bytes of the tile's [pixel][channel] image in shared memory (a warp's 32 lanes write 32 consecutive bytes: one
           // wavefront, no shuffles, no predicates); one thread then issues a TMA store per tile row.  The register path below
           // (4-byte global stores after a quad transpose) is kept for plans whose planes leave no room for the staging tile.
-          const int sb = (int)(acc_it % (uint32_t)p.stg_bufs);
+          const int sb = alt ? half : (int)ring_idx(acc_it, p.stg_bufs);
           uint8_t* stg = smem + p.stg_off + sb * p.stg_bytes;
-          if (warp == 2 && lane == 0) {  // the buffer's previous stores must have finished reading it
-            if (p.stg_bufs == 2) bulk_wait_read<1>();
+          if (lane == 0) {  // this warp's previous stores from the buffer must have finished reading it
+            if (p.stg_bufs == 2 && !alt) bulk_wait_read<1>();
             else bulk_wait_read<0>();
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          EPI_BAR();
+          PROF_T(2);
           for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++) {
             const int ch = chbase + cb * 128 + q * 32 + lane;
-            const uint32_t bias4 = ((uint32_t)(int32_t)p.epi.bias[ch] & 0xFFu) * 0x01010101u;
+            const uint32_t bias4 = p.bias_word >= 0 ? 0u : ((uint32_t)(int32_t)p.epi.bias[ch] & 0xFFu) * 0x01010101u;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
             const uint32_t srow = smem_u32(stg) + (uint32_t)(cb * p.NPX * 128 + q * 32 + lane);
             for (int c0 = col_lo; c0 < col_hi && c0 < vrows * p.P; c0 += 32) {
@@ -367,19 +543,24 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               }
             }
           }
+          PROF_T(3);
           tc_fence_before();
-          mbar_arrive(&tempty[acc]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);  // one arrival per epilogue warp
           fence_proxy_async();  // generic-proxy writes -> visible to the TMA engine
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (warp == 2 && lane == 0) {
+          PROF_T(4);
+          EPI_BAR();
+          PROF_T(5);
+          if (lane == 0) {  // rows are dealt round-robin to the 8 epilogue warps: issuing a TMA store costs ~300 clocks of one thread
             for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++)
-              for (int rr = 0; rr < vrows; rr++) {
+              for (int rr = erow0; rr < vrows; rr += erows) {
                 const uint8_t* src = stg + (cb * p.NPX + rr * p.P) * 128;
                 if (p.deconv) tma_store_5d(&tmO, src, pm.px * p.OFM + chbase + cb * 128, pm.x0, pm.py, pm.y0 + rr, img);
                 else tma_store_4d(&tmO, src, chbase + cb * 128, pm.x0, pm.y0 + rr, img);
               }
             bulk_commit();
           }
+          PROF_T(6);
           continue;
         }
         if (thin) {
@@ -599,11 +780,13 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
         }
         tc_fence_before();
-        mbar_arrive(&tempty[acc]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
       }
     }
   }
-  if (warp == 2 && lane == 0 && p.stg_bufs > 0) bulk_wait<0>();  // staged stores still read shared memory
+  if (warp == 2 && lane == 0) PROF_FLUSH(2);
+  if (warp >= 2 && warp < 10 && lane == 0 && p.stg_bufs > 0) bulk_wait<0>();  // staged stores still read shared memory
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
@@ -738,7 +921,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   p.WT = bWT; p.R = bR; p.P = bWT + halo_x; p.PX = PX; p.PY = PY;
   p.tiles_x = (PX + bWT - 1) / bWT; p.tiles_y = (PY + bR - 1) / bR;
   p.out_x = g.out_x; p.out_y = g.out_y; p.out_word_bytes = (int)g.out_word_bytes; p.out_img_bytes = g.out_img_bytes;
-  p.wstages = bWS; p.w_bytes = w_bytes; p.ksteps = 4;
+  p.wstages = bWS; p.w_bytes = w_bytes; p.ksteps = 4; p.bias_word = -1;
   p.acc_stride = CBe * bNPX;
   p.acc_stages = (2 * p.acc_stride <= 512) ? 2 : 1;
   int tc = 32;
@@ -781,7 +964,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   p.w_off = off;
   off += bWS * w_bytes;
   p.bar_off = off;
-  off += (2 * bWS + 2 * np * p.nsets + 8) * 8;
+  off += (2 * bWS + 2 * np * p.nsets + 4 + 1 + 2 * (int)U2_NPB + 1) * 8;
   off = (off + 15) & ~15;
   p.stage_off = off;
   off += 8 * 256;
@@ -803,6 +986,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     p.stg_off = off;
     off += p.stg_bufs * p.stg_bytes;
   }
+  p.epi_alt = (p.stg_bufs == 2 && p.acc_stages == 2 && !getenv("FCB_U2_NO_ALT")) ? 1 : 0;
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
   // K-block lists: plane-major within each phase so planes are released progressively
@@ -843,13 +1027,13 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
 
 // Thin-input plan: d_w is [CB*128][128] s8 with k = (ky*KX + kx)*4 + lane (zero beyond the window / lanes >= C).
-int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, Umma2Plan** out) {
+int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, int bias_word, Umma2Plan** out) {
   *out = nullptr;
   const int s = g.SX, nw = g.KX * g.KY;
   if (g.kind != FCB_KIND_CONV || g.in_word_bytes != 4 || g.in_bits != 8 || nw > 32 || g.SX != g.SY || s < 1 || s > 2 || g.pool > 2 ||
@@ -872,12 +1056,16 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     }
   }
   const int w_bytes = CB * 128 * 128;
-  const int ksteps = (nw * 4 + 31) / 32;
+  const int ksteps = ((bias_word >= 0 ? nw + 1 : nw) * 4 + 31) / 32;
   int bWT = 0, bR = 0, bNPX = 0;
   double best = 1e30;
-  for (int NPX = 256; NPX >= 64; NPX /= 2) {
+  const bool fast_epi0 = epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && g.pool <= 1 && g.OFM % 128 == 0 &&
+                         g.out_word_bytes == (size_t)g.OFM && !getenv("FCB_U2_NO_STAGE");
+  const bool want_swap = fast_epi0 && PX >= 8 && !getenv("FCB_U2_NO_SWAP");
+  for (int NPX = 256; NPX >= (want_swap ? 128 : 64); NPX /= 2) {
     if (CB * NPX > 512) continue;
     for (int WT = step; WT <= std::min(PX + step - 1, 256); WT += step) {
+      if (want_swap && (WT % 8)) continue;  // swizzled staging rows: every tile row starts on a 1024-byte boundary
       const int BWp = (s * (WT - 1) + g.KX + 3 + 3) / 4 * 4;  // + up to 3 pixels of alignment slack on the left
       if (BWp > 256) continue;
       const int budget = (g.pool == 2 && (WT % 8)) ? NPX - 8 : NPX;  // pooled epilogue reads 8-column groups from row starts
@@ -886,7 +1074,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
       if (R < 1) continue;
       const int BHp = s * (R - 1) + g.KY;
       if (BHp > 256) continue;
-      const size_t need = (size_t)2 * NPX * 128 + w_bytes + 2 * (((size_t)BWp * BHp * 4 + 127) / 128 * 128) + 8192 + (thr_bytes ? thr_bytes + 128 : 0);
+      const size_t need = (size_t)2 * NPX * 128 + w_bytes + U2_NPB * (((size_t)BWp * BHp * 4 + 127) / 128 * 128) + 8192 + (thr_bytes ? thr_bytes + 128 : 0);
       if (need > (size_t)227 * 1024) continue;
       const double tiles = (double)((PX + WT - 1) / WT) * ((PY + R - 1) / R);
       // per tile: fixed cost ~ NPX columns of MMA/epilogue work + overheads; prefer full tiles and wide rows
@@ -912,6 +1100,9 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.tmem_cols = tc;
   p.idesc = make_idesc_i8(128, bNPX, 1, g.in_signed);
   p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
+  p.swap = want_swap ? 1 : 0;
+  p.bias_word = bias_word;
+  p.idesc_swap = make_idesc_i8(128, CB * 128, g.in_signed, 1);
   p.thin_in = 1; p.S = s; p.pad = g.PAD; p.nw = nw;
   p.BWp = (s * (bWT - 1) + g.KX + 3 + 3) / 4 * 4; p.BHp = s * (bR - 1) + g.KY;
   for (int i = 0; i < 32; i++) p.toff[i] = i < nw ? (i / g.KX) * p.BWp + (i % g.KX) : 0;
@@ -921,7 +1112,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.planes[0].smem_off = 0; p.planes[0].bytes = bNPX * 128;
   int off = 2 * p.set_bytes;
   p.w_off = off; off += w_bytes;
-  p.bar_off = off; off += (2 * 1 + 2 * 2 + 4 + 1 + 2) * 8 + 16;
+  p.bar_off = off; off += (2 * 1 + 2 * 2 + 4 + 1 + 2 * (int)U2_NPB + 1) * 8;
   off = (off + 15) & ~15;
   p.stage_off = off; off += 8 * 256;
   p.thr_off = -1; p.thr_top = thr_top;
@@ -929,13 +1120,15 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.stg_bytes = CB * bNPX * 128;
   const bool fast_epi = epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && g.pool <= 1 && g.OFM % 128 == 0 &&
                         g.out_word_bytes == (size_t)g.OFM;
-  off = (off + 127) & ~127;
+  off = (off + 1023) & ~1023;
   p.stg_off = off;
   if (fast_epi && !getenv("FCB_U2_NO_STAGE"))
     for (int nb = 2; nb >= 1; nb--)
-      if ((size_t)off + (size_t)nb * p.stg_bytes + 2 * p.patch_bytes + 1024 <= (size_t)227 * 1024) { p.stg_bufs = nb; break; }
+      if ((size_t)off + (size_t)nb * p.stg_bytes + U2_NPB * p.patch_bytes + 1024 <= (size_t)227 * 1024) { p.stg_bufs = nb; break; }
   off += p.stg_bufs * p.stg_bytes;
-  p.patch_off = off; off += 2 * p.patch_bytes;
+  if (p.swap && !p.stg_bufs) p.swap = 0;
+  p.epi_alt = (p.stg_bufs == 2 && p.acc_stages == 2 && !getenv("FCB_U2_NO_ALT")) ? 1 : 0;
+  p.patch_off = off; off += (int)U2_NPB * p.patch_bytes;
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
   Phase2& P = p.phases[0];
@@ -948,7 +1141,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -958,9 +1151,9 @@ void umma2_plan_destroy(Umma2Plan* U) { delete U; }
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   const Params2& p = U->p;
   if (p.thin_in) {
-    snprintf(buf, n, "smem-im2col (thin input, K=%d B, %d MMA/tile, weights resident) WT=%d R=%d NPX=%d CB=%d%s patch=%dx%d smem=%zu tiles=%dx%d",
-             p.nw * 4, p.ksteps * p.CB, p.WT, p.R, p.NPX, p.CB,
-             p.thr_off >= 0 ? " thr@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.BWp, p.BHp, U->smem,
+    snprintf(buf, n, "smem-im2col (thin input, K=%d B%s, %d MMA/tile, weights resident) WT=%d R=%d NPX=%d CB=%d%s patch=%dx%d smem=%zu tiles=%dx%d",
+             p.nw * 4, p.bias_word >= 0 ? " + bias row" : "", p.swap ? p.ksteps * (p.NPX / 128) : p.ksteps * p.CB, p.WT, p.R, p.NPX, p.CB,
+             p.thr_off >= 0 ? " thr@smem" : (p.swap ? " pixel-major tma-store" : p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.BWp, p.BHp, U->smem,
              p.tiles_x, p.tiles_y);
     return buf;
   }
@@ -1019,7 +1212,7 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
       const uint64_t dims[4] = {F, OX, OY, (uint64_t)n_images};
       const uint64_t strides[3] = {F, OX * F, OX * OY * F};
       const uint32_t box[4] = {128, (uint32_t)p.WT, 1, 1};
-      rc = umma_encode_map_ex(&tmO, d_out, 1, 0, 4, dims, strides, box);
+      rc = umma_encode_map_ex(&tmO, d_out, 1, p.swap ? 128 : 0, 4, dims, strides, box);
     }
     if (rc) return rc;
   }
@@ -1027,8 +1220,33 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   if (g.out_word_bytes * 8 != (size_t)g.OFM * g.out_bits) FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, g.out_img_bytes * n_images, st));
   const long long total = (long long)p.tiles_x * p.tiles_y * n_images;
   const int grid = (int)std::min<long long>(total, U->num_sms / p.chb) * p.chb;
-  umma2_conv_kernel<<<grid, U2_THREADS, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  unsigned long long* d_prof = nullptr;
+  if (getenv("FCB_U2_PROF")) {
+    FCB_CUDA_OK(cudaMalloc(&d_prof, (size_t)grid * 24 * 8));
+    FCB_CUDA_OK(cudaMemsetAsync(d_prof, 0, (size_t)grid * 24 * 8, st));
+    p.prof = d_prof;
+  }
+  p.spin = getenv("FCB_U2_SPIN") ? atoi(getenv("FCB_U2_SPIN")) : p.spin;
+  if (p.thin_in) umma2_conv_kernel<4><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else umma2_conv_kernel<1><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   FCB_CUDA_OK(cudaGetLastError());
+  if (d_prof) {  // debugging aid: average clocks per tile and segment over the CTAs
+    FCB_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> h((size_t)grid * 24);
+    FCB_CUDA_OK(cudaMemcpy(h.data(), d_prof, h.size() * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_prof);
+    const double tiles_per_cta = (double)total / grid;
+    const char* names[3] = {"builder", "mma", "epilogue"};
+    for (int role = 0; role < 3; role++) {
+      fprintf(stderr, "[u2 prof] %-8s clk/tile:", names[role]);
+      for (int sgm = 0; sgm < 8; sgm++) {
+        double sum = 0;
+        for (int c = 0; c < grid; c++) sum += (double)h[((size_t)c * 3 + role) * 8 + sgm];
+        fprintf(stderr, " %7.0f", sum / grid / tiles_per_cta);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
   return FCB_OK;
 }
 
