@@ -335,7 +335,13 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
       }
     }
   }
-  if (engine == ENG_UMMA && !L->lowered) {
+  if (engine == ENG_UMMA && !L->lowered && g.kind == FCB_KIND_DECONV522 && g.OFM <= 4) {
+    // thin-output transposed conv (the 3-channel last layer): dedicated plan, pixels on the MMA M axis
+    rc = umma_plan_create_dthin(g, W, L->epi, device, &L->umma);
+    if (rc == FCB_ERR_UNSUPPORTED) L->umma = nullptr;
+    else if (rc) { fcb_layer_destroy(L); return rc; }
+  }
+  if (engine == ENG_UMMA && !L->lowered && !L->umma) {
     rc = umma_plan_create(g, W, L->epi, device, &L->umma);
     if (rc == FCB_ERR_UNSUPPORTED) { engine = L->engine = ENG_IMAD; L->umma = nullptr; }  // shape the planner cannot tile
     else if (rc) { fcb_layer_destroy(L); return rc; }

@@ -66,6 +66,7 @@ int umma_eligible(const Geom& g);
 int umma_plan_create(const Geom& g, const std::vector<int32_t>& W /*[OFM][K]*/, const EpiParams& epi, int device, UmmaPlan** out);
 int umma_plan_create_thin(const Geom& g, const std::vector<int32_t>& W4 /*[OFM][128]*/, const EpiParams& epi, const int8_t* bias_host /*or NULL*/,
                           int device, UmmaPlan** out);
+int umma_plan_create_dthin(const Geom& g, const std::vector<int32_t>& W /*[OFM][K]*/, const EpiParams& epi, int device, UmmaPlan** out);
 void umma_plan_destroy(UmmaPlan* p);
 const char* umma_plan_describe(const UmmaPlan* p);
 int umma_run(UmmaPlan* p, const void* d_in, void* d_out, int n_images, cudaStream_t st, uint64_t* launches);

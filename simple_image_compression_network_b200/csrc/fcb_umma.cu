@@ -436,6 +436,38 @@ int umma_plan_create_thin(const Geom& g, const std::vector<int32_t>& W4, const E
   return FCB_OK;
 }
 
+// Thin-output transposed conv (deconv522, OFM 3..4): weights regrouped by input shift.  Output phase (py, px) uses tap
+// (ky, kx) = (2*offy + 2 - py, 2*offx + 2 - px) at shift (offy, offx) in {-1,0,1}^2 when that tap exists.
+int umma_plan_create_dthin(const Geom& g, const std::vector<int32_t>& W, const EpiParams& epi, int device, UmmaPlan** out) {
+  if (g.kind != FCB_KIND_DECONV522 || g.OFM < 3 || g.OFM > 4 || g.C % 128 || g.C > 256 || getenv("FCB_U2_NO_DTHIN")) return FCB_ERR_UNSUPPORTED;
+  UmmaPlan* P = new UmmaPlan();
+  P->g = g;
+  P->device = device;
+  cudaDeviceProp prop;
+  FCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  P->num_sms = prop.multiProcessorCount;
+  const int cch = g.C / 128;
+  std::vector<int8_t> w8((size_t)9 * cch * 16 * 128, 0);
+  for (int cc = 0; cc < cch; cc++)
+    for (int sft = 0; sft < 9; sft++) {
+      const int offy = sft / 3 - 1, offx = sft % 3 - 1;
+      for (int ph = 0; ph < 4; ph++) {
+        const int ky = 2 * offy + 2 - ph / 2, kx = 2 * offx + 2 - ph % 2;
+        if (ky < 0 || ky > 4 || kx < 0 || kx > 4) continue;
+        for (int o = 0; o < g.OFM; o++)
+          for (int c = 0; c < 128; c++)
+            w8[(((size_t)(cc * 9 + sft) * 16) + ph * 4 + o) * 128 + c] = (int8_t)W[(size_t)o * g.K + (ky * 5 + kx) * g.C + cc * 128 + c];
+      }
+    }
+  FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size()));
+  FCB_CUDA_OK(cudaMemcpy(P->d_w, w8.data(), w8.size(), cudaMemcpyHostToDevice));
+  int rc = umma2_plan_create_dthin(g, P->d_w, epi, P->num_sms, &P->v2);
+  if (rc) { umma_plan_destroy(P); return rc; }
+  umma2_describe(P->v2, P->desc, sizeof(P->desc));
+  *out = P;
+  return FCB_OK;
+}
+
 const char* umma_plan_describe(const UmmaPlan* P) { return P ? P->desc : ""; }
 
 void umma_plan_destroy(UmmaPlan* P) {

@@ -88,6 +88,11 @@ struct Params2 {
   // bias folded into the GEMM (thin-input mode): window word `bias_word` of every im2col row is the constant 1 and the weight
   // byte there is the channel's bias, so the accumulator already is acc + bias (all arithmetic is mod 2^8); -1 = not folded
   int bias_word;
+  // thin-output transposed conv (deconv522 with OFM <= 4, e.g. the 3-channel last layer): pixels on the MMA M axis, the 25 taps
+  // regrouped by their 9 input shifts so ONE N = 16 instruction serves the 4 output phases x 4 channel slots of a shift:
+  // D[pixel][phase*4 + ch]; the epilogue thread owns one input pixel = a 2x2 block of output words
+  int dthin;
+  uint32_t idesc_dthin;
   unsigned long long* prof;  // FCB_U2_PROF: per-CTA clock totals [role 0 builder | 1 mma | 2 epilogue][8 segments]
   int thin_in, S, pad, nw, BWp, BHp, patch_off, patch_bytes, ksteps, wstatic;
   int toff[32];  // patch word offset of window word i: ky*BWp + kx
@@ -242,7 +247,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             if (p.debug & 1) mbar_arrive(&wfull[s]);
             else {
               mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);
-              tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, chbase);
+              if (p.dthin) tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], 0, P.kb[i].w_k);  // 16-row block of shift w_k/16
+              else tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, chbase);
             }
             if (++s == p.wstages) { s = 0; wphase ^= 1; }
           }
@@ -365,12 +371,23 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           PROF_T(2);
           if (flags & KB_WAIT) WAITB(&afull[plane], apar);
           PROF_T(3);
-          WAITB(&wfull[s], wphase);
+          if (!wstatic || tile_it == 0) WAITB(&wfull[s], wphase);  // resident weights: loaded once, observed once
           PROF_T(4);
           tc_fence_after();
           const uint64_t wdesc = desc0 + (w_d0 + (uint32_t)s * w_dstep);
           if (elect_one_sync()) {
-            if (p.swap) {
+            if (p.dthin) {
+              // A = 128 plane rows (pixels) per block at this shift, B = 16 weight rows (4 phases x 4 channel slots)
+              if (!(p.debug & 128))
+                for (int blk = 0; blk < NPX / 128; blk++) {
+                  const uint32_t dt = d_tmem + (uint32_t)(blk * 16);
+                  const uint64_t ad = pdesc + (uint64_t)(blk * 1024);
+                  umma_i8(dt, ad, wdesc, p.idesc_dthin, i ? 1u : 0u);
+                  umma_i8(dt, ad + 2, wdesc + 2, p.idesc_dthin, 1u);
+                  umma_i8(dt, ad + 4, wdesc + 4, p.idesc_dthin, 1u);
+                  umma_i8(dt, ad + 6, wdesc + 6, p.idesc_dthin, 1u);
+                }
+            } else if (p.swap) {
               // A = 128 im2col rows (pixels) per block, B = the CB*128 weight rows: D[pixel][channel]
               if (!(p.debug & 128))
                 for (int blk = 0; blk < NPX / 128; blk++) {
@@ -436,6 +453,38 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
+        if (p.dthin) {
+          // thread = input pixel m of block `half`; its 16 columns are the 2x2 output words it produces (bias + ReLU on the
+          // wrapped 8-bit lane, conv_nonsquare_top.cpp:183-194); a warp writes two 256-byte runs of output row 2y and 2y+1
+          const int m = half * 128 + q * 32 + lane;
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + half * 16), v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          const int rr = m / p.P, xo = m - rr * p.P;
+          if (xo < vcols && rr < vrows && !(p.debug & 8)) {
+            uint32_t w[4];
+#pragma unroll
+            for (int ph = 0; ph < 4; ph++) {
+              uint32_t word = 0;
+#pragma unroll
+              for (int o = 0; o < 4; o++) {
+                if (o < p.OFM) {
+                  uint32_t r = (v[ph * 4 + o] + (uint32_t)(int32_t)p.epi.bias[o]) & 0xFFu;
+                  r = (r & 0x80u) ? 0u : r;
+                  word |= r << (8 * o);
+                }
+              }
+              w[ph] = word;
+            }
+            uint8_t* dst = p.out + pm.img_off + ((size_t)(2 * (pm.y0 + rr)) * p.out_x + 2 * (pm.x0 + xo)) * 4;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+            *reinterpret_cast<uint2*>(dst + (size_t)p.out_x * 4) = make_uint2(w[2], w[3]);
+          }
+          continue;
+        }
         if (p.swap) {
           // Swapped staged bias + ReLU epilogue: thread = pixel (TMEM lane), 32-column loads = 32 channels of that pixel ->
           // 8 packed words -> two 16-byte stores into the SWIZZLE_128B staging row of the pixel; TMA stores un-swizzle.
@@ -457,6 +506,10 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           auto process = [&](int blk, int cbk, const uint32_t (&v)[32]) {
             const int m = blk * 128 + q * 32 + lane;
             if (m >= mlim) return;  // rows of the tile that are never stored
+            if (p.debug & 512) {  // perf decomposition: TMEM loads only
+              if (v[0] == 0x12345678u && v[31] == 0x9abcdef0u) sts_v4(stg_s, v[1], v[2], v[3], v[4]);
+              return;
+            }
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -1146,10 +1199,91 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   return FCB_OK;
 }
 
+// Thin-output transposed conv plan: d_w is [9 shifts x cch chunks][16 rows][128] s8 (row = phase*4 + channel slot).
+int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, Umma2Plan** out) {
+  *out = nullptr;
+  if (g.kind != FCB_KIND_DECONV522 || g.OFM < 3 || g.OFM > 4 || g.out_word_bytes != 4 || g.C % 128 || g.C > 256 || g.pool > 1 ||
+      epi.act_kind != FCB_ACT_BIAS_RELU || epi.out_bits != 8 || epi.acc_bits != 8)
+    return FCB_ERR_UNSUPPORTED;
+  const int cch = g.C / 128, PX = g.IX, PY = g.IY, NPX = 256;
+  int bWT = 0, bR = 0;
+  double best = 1e30;
+  for (int WT = 1; WT <= std::min(PX, 252); WT++) {
+    const int P = WT + 2;
+    if (P > g.IX + 2) continue;
+    const int R = std::min(NPX / P, PY);
+    if (R < 1) continue;
+    const size_t plane = ((size_t)(2 * P + 2 + NPX) * 128 + 1023) / 1024 * 1024 * cch;
+    if (2 * plane + 9 * cch * 2048 + 8192 > (size_t)227 * 1024) continue;
+    const double tiles = (double)((PX + WT - 1) / WT) * ((PY + R - 1) / R);
+    const double cost = tiles * (1.0 + 0.0005 * R) / ((double)PX * PY);
+    if (cost < best * 0.999) { best = cost; bWT = WT; bR = R; }
+  }
+  if (!bWT) return FCB_ERR_UNSUPPORTED;
+  Umma2Plan* U = new Umma2Plan();
+  U->g = g; U->num_sms = num_sms;
+  Params2& p = U->p;
+  memset(&p, 0, sizeof(p));
+  p.epi = epi;
+  p.OFM = g.OFM; p.CB = 1; p.chb = 1; p.NPX = NPX; p.stride2 = 0; p.deconv = 1; p.nphases = 1; p.dthin = 1; p.bias_word = -1; p.ksteps = 4;
+  p.WT = bWT; p.R = bR; p.P = bWT + 2; p.PX = PX; p.PY = PY;
+  p.tiles_x = (PX + bWT - 1) / bWT; p.tiles_y = (PY + bR - 1) / bR;
+  p.out_x = g.out_x; p.out_y = g.out_y; p.out_word_bytes = 4; p.out_img_bytes = g.out_img_bytes;
+  p.wstages = 9 * cch; p.wstatic = 1; p.w_bytes = 2048;
+  p.acc_stride = 32; p.acc_stages = 2; p.tmem_cols = 64;
+  p.idesc = p.idesc_dthin = make_idesc_i8(128, 16, g.in_signed, 1);
+  p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
+  const int rows = bR + 2;
+  const size_t plane = ((size_t)(2 * p.P + 2 + NPX) * 128 + 1023) / 1024 * 1024;
+  int off = 0;
+  for (int cc = 0; cc < cch; cc++) {
+    Plane2& pl = p.planes[cc];
+    pl.smem_off = off; pl.bytes = rows * p.P * 128; pl.c0 = cc * 128; pl.dx = -1; pl.dy = -1; pl.par = 0; pl.map = 0;
+    off += (int)plane;
+  }
+  p.nplanes = cch; p.set_bytes = off; p.nsets = 2;
+  off *= 2;
+  U->box_rows[0] = U->box_rows[1] = rows;
+  p.w_off = off; off += p.wstages * p.w_bytes;
+  p.bar_off = off; off += (2 * p.wstages + 2 * cch * 2 + 4 + 1 + 2 * (int)U2_NPB + 1) * 8;
+  off = (off + 15) & ~15;
+  p.stage_off = off; off += 8 * 256;
+  p.thr_off = -1;
+  U->smem = (size_t)off + 1024;
+  if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
+  // K-blocks: (channel chunk, shift); shift s = (offy + 1) * 3 + (offx + 1)
+  Phase2& P = p.phases[0];
+  P.nkb = 0; P.px = P.py = 0;
+  for (int cc = 0; cc < cch; cc++)
+    for (int sft = 0; sft < 9; sft++) {
+      KB2& kb = P.kb[P.nkb++];
+      kb.plane = (uint16_t)cc;
+      kb.flags = (sft == 0 ? KB_WAIT : 0) | (sft == 8 ? KB_FREE : 0);
+      kb.a_off = (sft / 3) * p.P + (sft % 3);
+      kb.w_k = (cc * 9 + sft) * 16;  // first weight row of the block
+      kb.d_off = (uint32_t)(p.planes[cc].smem_off + kb.a_off * 128) >> 4;
+    }
+  {
+    const uint64_t dims[2] = {128, (uint64_t)(9 * cch * 16)};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {128, 16};
+    int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
+    if (rc) { delete U; return rc; }
+  }
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  *out = U;
+  return FCB_OK;
+}
+
 void umma2_plan_destroy(Umma2Plan* U) { delete U; }
 
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   const Params2& p = U->p;
+  if (p.dthin) {
+    snprintf(buf, n, "thin-output deconv: pixels on M, 9 shift blocks x N=16 (4 phases x 4 ch) WT=%d R=%d P=%d planes=%dx%d smem=%zu tiles=%dx%d",
+             p.WT, p.R, p.P, p.nplanes, p.nsets, U->smem, p.tiles_x, p.tiles_y);
+    return buf;
+  }
   if (p.thin_in) {
     snprintf(buf, n, "smem-im2col (thin input, K=%d B%s, %d MMA/tile, weights resident) WT=%d R=%d NPX=%d CB=%d%s patch=%dx%d smem=%zu tiles=%dx%d",
              p.nw * 4, p.bias_word >= 0 ? " + bias row" : "", p.swap ? p.ksteps * (p.NPX / 128) : p.ksteps * p.CB, p.WT, p.R, p.NPX, p.CB,
@@ -1217,7 +1351,8 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
     if (rc) return rc;
   }
   // sub-byte / padded output words are merged or partially written: start from zeroed words
-  if (g.out_word_bytes * 8 != (size_t)g.OFM * g.out_bits) FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, g.out_img_bytes * n_images, st));
+  if (g.out_word_bytes * 8 != (size_t)g.OFM * g.out_bits && !p.dthin)  // (the thin-output deconv epilogue writes whole words)
+    FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, g.out_img_bytes * n_images, st));
   const long long total = (long long)p.tiles_x * p.tiles_y * n_images;
   const int grid = (int)std::min<long long>(total, U->num_sms / p.chb) * p.chb;
   unsigned long long* d_prof = nullptr;

@@ -304,3 +304,20 @@ def test_thin_input_smem_im2col(name, fcb_lib, oracle_mod, monkeypatch):
     L2 = _layer(d, inp)
     assert not L2.plan.startswith("smem-im2col")
     assert np.array_equal(L2.run(inp["in_words"], reps), want), f"{name} [{L2.plan}]"
+
+
+@pytest.mark.parametrize("ix,iy,c,ofm,reps", [(24, 16, 128, 3, 1), (50, 7, 128, 4, 2), (100, 20, 256, 3, 2), (384, 8, 128, 3, 1)])
+def test_thin_output_deconv(ix, iy, c, ofm, reps, fcb_lib, oracle_mod, monkeypatch):
+    """deconv522 with OFM <= 4 (the 3-channel last layer of eight_layers_net): pixels on the MMA M axis, taps regrouped by input
+    shift, against the oracle and against the generic resident-planes plan."""
+    d = dataclasses.replace(cases.CASES["dc_d"], ifm_x=ix, ifm_y=iy, ifm_ch=c, ofm_ch=ofm, pe=ofm)
+    inp = cases.make_inputs(d, seed_shift=41, num_reps=reps, relu_range=True)
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], None, inp["bias"], num_reps=reps)
+    L = _layer(d, inp)
+    assert L.plan.startswith("thin-output deconv"), L.plan
+    got = L.run(inp["in_words"], reps)
+    assert np.array_equal(got, want), f"[{L.plan}]: {_diff(got, want)}"
+    monkeypatch.setenv("FCB_U2_NO_DTHIN", "1")
+    L2 = _layer(d, inp)
+    assert not L2.plan.startswith("thin-output deconv")
+    assert np.array_equal(L2.run(inp["in_words"], reps), want), f"[{L2.plan}]"

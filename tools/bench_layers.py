@@ -23,6 +23,9 @@ def timed(fn, steps=5, warm=2):
     return e0.elapsed_time(e1) / steps
 
 
+CHECK = False
+
+
 def bench_layer(name, d, n, mask=0x7F):
     prm = configs.synthetic_params(d)
     L = ConvLayer(d, prm["weights"], thresholds=prm["thresholds"], bias=prm["bias"])
@@ -30,11 +33,23 @@ def bench_layer(name, d, n, mask=0x7F):
     y = torch.empty(n * L.out_bytes, dtype=torch.uint8, device="cuda")
     synth_fill(x.data_ptr(), x.numel(), synth.SEED_INPUT, mask)
     ms = timed(lambda: L.run_device(x.data_ptr(), y.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+    if CHECK:  # first and last image against the independent IMAD engine (itself pinned to the oracle by tests/)
+        os.environ["FCB_FORCE_ENGINE"] = "imad"
+        xe = os.environ.pop("FCB_XNOR_ENGINE", None)
+        L2 = ConvLayer(d, prm["weights"], thresholds=prm["thresholds"], bias=prm["bias"])
+        del os.environ["FCB_FORCE_ENGINE"]
+        if xe: os.environ["FCB_XNOR_ENGINE"] = xe
+        assert L2.engine != L.engine or L.engine == "imad"
+        for i in sorted({0, n - 1}):
+            y2 = torch.empty(L.out_bytes, dtype=torch.uint8, device="cuda")
+            L2.run_device(x.data_ptr() + i * L.in_bytes, y2.data_ptr(), 1, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert torch.equal(y2, y[i * L.out_bytes:(i + 1) * L.out_bytes]), f"{name}: image {i} differs from the IMAD engine"
     macs = d.macs_per_image
     nz = macs / 4 if d.kind == KIND_DECONV522 else macs
     r = dict(layer=name, engine=L.engine, plan=L.plan, images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3),
              TOPs_dense=round(2 * macs * n / ms / 1e9, 1), TOPs_nonzero=round(2 * nz * n / ms / 1e9, 1),
-             GBs=round((L.in_bytes + L.out_bytes) * n / ms / 1e6, 1))
+             GBs=round((L.in_bytes + L.out_bytes) * n / ms / 1e6, 1), checked=bool(CHECK))
     print(json.dumps(r), flush=True)
     return L, r
 
@@ -43,7 +58,9 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=64)
     ap.add_argument("--only", default="", help="comma list of net layers to time alone, e.g. L0,L6 (skips the rest)")
+    ap.add_argument("--check", action="store_true", help="compare image 0 / n-1 of every timed layer with the IMAD engine")
     a = ap.parse_args()
+    CHECK = a.check
     c3 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=64, ofm_ch=64, ifm_x=128, ifm_y=96, stride_x=1, stride_y=1, pad=0,
                    simd=64, pe=16, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR, acc_bits=16, acc_signed=1,
                    act_kind=ACT_THRESHOLDS, out_bits=1, num_th=1)
