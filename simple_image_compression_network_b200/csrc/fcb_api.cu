@@ -261,6 +261,18 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     FCB_CUDA_OK(cudaMemcpy(L->d_bias, bias, g.OFM, cudaMemcpyHostToDevice));
     L->epi.bias = L->d_bias;
   }
+  // The TA wrap (mvau.hpp:112: every += wraps to TA) is the identity when no partial sum can leave TA's range: with
+  // |acc| <= max_ch sum_k |w| * max|a| < 2^(acc_bits-1) the device epilogue may treat the accumulator as a plain int32.
+  if (g.acc_signed && g.acc_bits < 32 && g.weight_kind == FCB_W_FIXED) {
+    const uint64_t amax = g.in_signed ? (1ull << (g.in_bits - 1)) : ((1ull << g.in_bits) - 1);
+    uint64_t worst = 0;
+    for (int ch = 0; ch < g.OFM; ch++) {
+      uint64_t sum = 0;
+      for (int k = 0; k < g.K; k++) sum += (uint64_t)std::abs(W[(size_t)ch * g.K + k]);
+      worst = std::max(worst, sum);
+    }
+    if (worst * amax < (1ull << (g.acc_bits - 1))) L->epi.acc_bits = 32;
+  }
   // thresholds: wrapped to TA and sorted per channel (the reference result is a count, activations.hpp:181-189)
   std::vector<std::vector<int32_t>> thr_rows;
   if (g.act_kind == FCB_ACT_THRESHOLDS) {

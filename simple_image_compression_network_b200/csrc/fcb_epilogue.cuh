@@ -89,25 +89,38 @@ template <int N>
 __device__ __forceinline__ void activate_thr_hybrid(const EpiParams& e, uint32_t top_saddr, int row_shift, int top_levels, int gshift,
                                                     const int32_t* __restrict__ row_cm /*global row of the channel*/,
                                                     const int32_t (&acc)[N], uint32_t (&out)[N]) {
+  // The running position is kept as a BYTE offset into the thread's column of the top table (posb = (pos >> gshift) << row_shift,
+  // plus the column's address), so a level is: one LDS at posb + (uniform step offset), one compare, one predicated add.
   int32_t a[N];
-  int pos[N];
+  uint32_t posb[N];
+  const uint32_t base = top_saddr - (1u << row_shift);  // row (j - 1) holds sorted index j * G - 1
 #pragma unroll
-  for (int i = 0; i < N; i++) { a[i] = wrap_ta(acc[i], e.acc_bits, e.acc_signed); pos[i] = 0; }
+  for (int i = 0; i < N; i++) { a[i] = wrap_ta(acc[i], e.acc_bits, e.acc_signed); posb[i] = base; }
   const bool strict = (e.cmp == FCB_CMP_LESS) || (e.cmp == FCB_CMP_GREATER_EQUAL);
-  int step = (e.thr_n + 1) >> 1;
-  const uint32_t base = top_saddr - (1u << row_shift);  // row (j - 1)
+  uint32_t stepb = (uint32_t)(((e.thr_n + 1) >> 1) >> gshift) << row_shift;  // warp-uniform
 #pragma unroll 1
-  for (int l = 0; l < top_levels; l++, step >>= 1) {
+  for (int l = 0; l < top_levels; l++, stepb >>= 1) {
     int32_t tv[N];
 #pragma unroll
-    for (int i = 0; i < N; i++) tv[i] = lds_s32(base + ((uint32_t)((pos[i] + step) >> gshift) << row_shift));
+    for (int i = 0; i < N; i++) tv[i] = lds_s32(posb[i] + stepb);
+    if (strict) {
 #pragma unroll
-    for (int i = 0; i < N; i++) pos[i] += (strict ? (tv[i] < a[i]) : (tv[i] <= a[i])) ? step : 0;
+      for (int i = 0; i < N; i++)
+        if (tv[i] < a[i]) posb[i] += stepb;
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        if (tv[i] <= a[i]) posb[i] += stepb;
+    }
   }
+  int pos[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) pos[i] = (int)(((posb[i] - base) >> row_shift) << gshift);
   if (gshift == 2) {  // G = 4: entries pos, pos+1, pos+2 of the sorted row decide the last two levels
     int4 qv[N];
+    const char* rowb = reinterpret_cast<const char*>(row_cm);
 #pragma unroll
-    for (int i = 0; i < N; i++) qv[i] = __ldg(reinterpret_cast<const int4*>(row_cm + pos[i]));
+    for (int i = 0; i < N; i++) qv[i] = __ldg(reinterpret_cast<const int4*>(rowb + (uint32_t)(((posb[i] - base) >> row_shift) << 4)));
 #pragma unroll
     for (int i = 0; i < N; i++) {
       pos[i] += strict ? ((qv[i].x < a[i]) + (qv[i].y < a[i]) + (qv[i].z < a[i])) : ((qv[i].x <= a[i]) + (qv[i].y <= a[i]) + (qv[i].z <= a[i]));

@@ -746,69 +746,82 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                       if (c0 + 8 * b < p.OFM) dst[b] = (uint8_t)(mine >> (8 * b));
                 }
               } else {
+                if (p.epi.out_bits == 8) {
+                  // byte lanes: one pointer per thread, advanced pixel by pixel (a warp store = 32 consecutive bytes of one word)
+                  uint8_t* dst = p.out + pm.word_off(rr, xo, 1) + ch;
+                  const int xstep = p.deconv ? 2 * p.out_word_bytes : p.out_word_bytes;  // a phase's pixels are every other output word
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                  if (xo < vcols && rr < vrows) store_lane(p.out + pm.word_off(rr, xo, 1), ch, chv, act[j], p.epi.out_bits);  // warp-uniform
-                  if (++xo == p.P) { xo = 0; ++rr; }
+                  for (int j = 0; j < 32; j++) {
+                    if (xo < vcols && rr < vrows && chv) *dst = (uint8_t)act[j];
+                    dst += xstep;
+                    if (++xo == p.P) { xo = 0; ++rr; dst = p.out + pm.word_off(rr, 0, 1) + ch; }
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; j++) {
+                    if (xo < vcols && rr < vrows) store_lane(p.out + pm.word_off(rr, xo, 1), ch, chv, act[j], p.epi.out_bits);  // warp-uniform
+                    if (++xo == p.P) { xo = 0; ++rr; }
+                  }
                 }
               }
             }
           } else {
             // 2x2 max pool: rows rr, rr+1 of the tile are columns m and m + P of the same thread
-            // work units = (row pair, 32-column block); the two warps of a lane quarter take alternate units
-            const int xblocks = (vcols + 31) >> 5, nunits = (vrows >> 1) * xblocks;
+            // work units = (row pair, 16-column block) = 8 pooled outputs; the two warps of a lane quarter take alternate units
+            const int xblocks = (vcols + 15) >> 4, nunits = (vrows >> 1) * xblocks;
 #pragma unroll 1
             for (int u = half; u < nunits; u += 2) {
               {
-                const int rr = 2 * (u / xblocks), xb = 32 * (u % xblocks);
+                const int rr = 2 * (u / xblocks), xb = 16 * (u % xblocks);
                 if (mono) {
                   // count-of-thresholds-below is non-decreasing in the TA-wrapped accumulator: pool first, then ONE search
-                  int32_t m16[16];
-                  uint32_t pooled[16];
+                  int32_t m8[8];
+                  uint32_t pooled[8];
+                  uint32_t va[2][8], vb[2][8];
+                  const bool second = xb + 8 < vcols;  // warp-uniform; 8-column groups keep reads inside the accumulator stage
+                  tmem_ld8(taddr + (uint32_t)(rr * p.P + xb), va[0]);
+                  tmem_ld8(taddr + (uint32_t)((rr + 1) * p.P + xb), vb[0]);
+                  if (second) {
+                    tmem_ld8(taddr + (uint32_t)(rr * p.P + xb + 8), va[1]);
+                    tmem_ld8(taddr + (uint32_t)((rr + 1) * p.P + xb + 8), vb[1]);
+                  }
+                  tmem_ld_wait();
 #pragma unroll
-                  for (int g4 = 0; g4 < 4; g4++) {
-                    uint32_t va[8], vb[8];
-                    if (xb + 8 * g4 < vcols) {  // warp-uniform; 8-column groups keep reads inside the accumulator stage
-                      tmem_ld8(taddr + (uint32_t)(rr * p.P + xb + 8 * g4), va);
-                      tmem_ld8(taddr + (uint32_t)((rr + 1) * p.P + xb + 8 * g4), vb);
-                      tmem_ld_wait();
-                    } else {
-#pragma unroll
-                      for (int j = 0; j < 8; j++) va[j] = vb[j] = 0;
-                    }
+                  for (int g2 = 0; g2 < 2; g2++) {
 #pragma unroll
                     for (int w = 0; w < 4; w++) {
-                      int32_t m0 = wrap_ta((int32_t)va[2 * w], p.epi.acc_bits, p.epi.acc_signed);
-                      m0 = max(m0, wrap_ta((int32_t)va[2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
-                      m0 = max(m0, wrap_ta((int32_t)vb[2 * w], p.epi.acc_bits, p.epi.acc_signed));
-                      m16[4 * g4 + w] = max(m0, wrap_ta((int32_t)vb[2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
+                      int32_t m0 = wrap_ta((int32_t)va[g2][2 * w], p.epi.acc_bits, p.epi.acc_signed);
+                      m0 = max(m0, wrap_ta((int32_t)va[g2][2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
+                      m0 = max(m0, wrap_ta((int32_t)vb[g2][2 * w], p.epi.acc_bits, p.epi.acc_signed));
+                      m0 = max(m0, wrap_ta((int32_t)vb[g2][2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
+                      m8[4 * g2 + w] = (g2 == 0 || second) ? m0 : 0;
                     }
                   }
                   if (p.debug & 16) {
 #pragma unroll
-                    for (int w = 0; w < 16; w++) pooled[w] = (uint32_t)m16[w] & 0xFFu;
+                    for (int w = 0; w < 8; w++) pooled[w] = (uint32_t)m8[w] & 0xFFu;
                   } else if (hybrid) {
+                    activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, m8, pooled);
+                  } else {
+                    activate_thrN<8>(p.epi, tbl, tstride, m8, pooled);
+                  }
+                  if (p.epi.out_bits == 8) {
+                    uint8_t* dst = p.out + pm.word_off(rr, xb, 2) + ch;  // x0 and xb are even: pooled pixel w sits w words further
 #pragma unroll
-                    for (int h8 = 0; h8 < 2; h8++) {
-                      int32_t a8[8];
-                      uint32_t o8[8];
-#pragma unroll
-                      for (int j = 0; j < 8; j++) a8[j] = m16[8 * h8 + j];
-                      activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, a8, o8);
-#pragma unroll
-                      for (int j = 0; j < 8; j++) pooled[8 * h8 + j] = o8[j];
+                    for (int w = 0; w < 8; w++) {
+                      if (xb + 2 * w < vcols && chv) *dst = (uint8_t)pooled[w];
+                      dst += p.out_word_bytes;
                     }
                   } else {
-                    activate_thrN<16>(p.epi, tbl, tstride, m16, pooled);
-                  }
 #pragma unroll
-                  for (int w = 0; w < 16; w++) {
-                    const int xo = xb + 2 * w;
-                    if (xo < vcols) store_lane(p.out + pm.word_off(rr, xo, 2), ch, chv, pooled[w], p.epi.out_bits);  // whole windows
+                    for (int w = 0; w < 8; w++) {
+                      const int xo = xb + 2 * w;
+                      if (xo < vcols) store_lane(p.out + pm.word_off(rr, xo, 2), ch, chv, pooled[w], p.epi.out_bits);  // whole windows
+                    }
                   }
                 } else {
 #pragma unroll 1
-                  for (int g4 = 0; g4 < 4; g4++) {
+                  for (int g4 = 0; g4 < 2; g4++) {
                     uint32_t va[8], vb[8];
                     if (xb + 8 * g4 >= vcols) break;
                     tmem_ld8(taddr + (uint32_t)(rr * p.P + xb + 8 * g4), va);
@@ -903,62 +916,71 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   // Threshold layers keep the top levels of the per-channel binary search in shared memory (activate_thr_hybrid):
   // all D levels if they fit ~66 KB, else D-2 (the rest is one 16-byte global load per output), else none.
   const int step = g.pool == 2 ? 2 : 1;
-  const int pool2 = g.pool == 2 ? 4 : 1;
   const bool thr = g.act_kind == FCB_ACT_THRESHOLDS;
-  int thr_top = 0, thr_bytes = 0;
+  // Candidates for where the per-channel threshold tables live (activate_thr_hybrid): the whole search in shared memory
+  // (D levels), the whole search with the channel blocks split over CTA groups (chb = CB: each CTA keeps 128 channels'
+  // tables and visits every tile), the top D-2 levels (+ one 16-byte global load per output), or global memory only.
+  struct Cand { int thr_top, chb; double epi_factor; };
+  std::vector<Cand> cands;
   if (thr && !getenv("FCB_U2_NO_SMEM_THR")) {
     int D = 0;
     while ((1 << D) < epi.thr_n + 1) D++;
-    const int cand[2] = {D, D - 2};
-    for (int c : cand) {
-      if (c < 1) continue;
-      const int bytes = ((1 << c) - 1) * CB * 128 * 4;
-      if (bytes <= 66 * 1024) { thr_top = c; thr_bytes = bytes; break; }
+    cands.push_back({D, 1, 40.0});
+    if (CB == 2 && !getenv("FCB_U2_NO_CHB")) cands.push_back({D, 2, 40.0});
+    if (D - 2 >= 1) cands.push_back({D - 2, 1, 60.0});
+  }
+  cands.push_back({0, 1, thr ? 120.0 : 0.0});
+  double best = 1e30;
+  int bWT = 0, bR = 0, bNPX = 0, bWS = 0, thr_top = 0, thr_bytes = 0, chb = 1, CBe = CB;
+  for (const Cand& cd : cands) {
+    const int cbe = CB / cd.chb;
+    const int tb = cd.thr_top ? ((1 << cd.thr_top) - 1) * cbe * 128 * 4 : 0;
+    if (tb > 136 * 1024) continue;
+    const int smem_limit = 227 * 1024 - 2048 - 2048 - (tb ? tb + 128 : 0);
+    const int w_bytes_c = cbe * 128 * 128;
+    for (int NPX = 256; NPX >= 64; NPX /= 2) {
+      if (cbe * NPX > 512) continue;
+      const int acc_st = (2 * cbe * NPX <= 512) ? 2 : 1;
+      for (int WS = 4; WS >= 2; WS--)
+        for (int WT = step; WT <= std::min(PX + step - 1, 254 - halo_x); WT += step) {
+          const int P = WT + halo_x;
+          if (P > xdim) continue;
+          const int budget = (g.pool == 2 && (P % 8)) ? NPX - 8 : NPX;  // pooled epilogue reads 8-column groups from row starts
+          int R = std::min(budget / P, PY);
+          if (g.pool == 2) R &= ~1;
+          if (R < 1) continue;
+          size_t plane_bytes = 0;
+          bool ok = true;
+          for (auto& h : ph4) {
+            if (!h.used) continue;
+            const int rows = R + (h.maxy - h.miny);
+            if (rows > 256 || rows > ydim) { ok = false; break; }
+            const int a_off_max = (h.maxy - h.miny) * P + (h.maxx - h.minx);
+            size_t b = std::max<size_t>((size_t)rows * P * 128, (size_t)(a_off_max + NPX) * 128);
+            plane_bytes += (b + 1023) / 1024 * 1024 * cch;
+          }
+          if (!ok || (long long)plane_bytes + (long long)WS * w_bytes_c > (long long)smem_limit) continue;
+          const double tiles = (double)((PX + WT - 1) / WT) * ((PY + R - 1) / R) * cd.chb;  // tile visits per CTA group
+          const double nkb = (double)taps.size() * cch;  // all phases
+          const double mma_clk = nkb * cbe * 4 * (NPX == 256 ? 146.0 : 102.0);  // measured clocks per instruction
+          const double fill_clk = ((double)plane_bytes + nkb * w_bytes_c) / 38.0;  // measured L2->SM fill, B/clk/SM
+          // epilogue: bias/ReLU ~7 clk per pixel and channel block.  Threshold search: instruction bound, epi_factor issue clocks
+          // per warp-level output (32 channels), counted with the padding of the 16-wide search batches
+          // (profiles/r01_cfg4_epilogue_profile.txt)
+          const double groups = g.pool == 2 ? (double)(R / 2) * ((WT + 15) / 16) * 8 : (double)((R * P + 31) / 32) * 32;
+          const double epi_clk = thr ? groups * nph * cbe * 4 * cd.epi_factor : (double)WT * R * nph * cbe * 7.0;
+          const double tile_clk = acc_st == 2 ? std::max(std::max(mma_clk, fill_clk), epi_clk) : std::max(mma_clk + epi_clk, fill_clk);
+          const double ws_pen = WS >= 3 ? 1.0 : 1.05;
+          // ties (e.g. 1x1 layers, where every WT is equally efficient) go to wide boxes: long contiguous TMA rows
+          const double cost = tiles * tile_clk * ws_pen * (1.0 + 0.0005 * R) / ((double)PX * PY);
+          if (cost < best * 0.999) {
+            best = cost; bWT = WT; bR = R; bNPX = NPX; bWS = WS;
+            thr_top = cd.thr_top; thr_bytes = tb; chb = cd.chb; CBe = cbe;
+          }
+        }
     }
   }
-  const int smem_limit = 227 * 1024 - 2048 - 2048 - (thr_bytes ? thr_bytes + 128 : 0);
-  const int w_bytes = CB * 128 * 128;
-  double best = 1e30;
-  int bWT = 0, bR = 0, bNPX = 0, bWS = 0;
-  for (int NPX = 256; NPX >= 64; NPX /= 2) {
-    if (CB * NPX > 512) continue;
-    const int acc_st = (2 * CB * NPX <= 512) ? 2 : 1;
-    for (int WS = 4; WS >= 2; WS--)
-      for (int WT = step; WT <= std::min(PX + step - 1, 254 - halo_x); WT += step) {
-        const int P = WT + halo_x;
-        if (P > xdim) continue;
-        const int budget = g.pool == 2 ? NPX - 8 : NPX;  // pooled epilogue reads 8-column groups from row starts
-        int R = std::min(budget / P, PY);
-        if (g.pool == 2) R &= ~1;
-        if (R < 1) continue;
-        size_t plane_bytes = 0;
-        bool ok = true;
-        for (auto& h : ph4) {
-          if (!h.used) continue;
-          const int rows = R + (h.maxy - h.miny);
-          if (rows > 256 || rows > ydim) { ok = false; break; }
-          const int a_off_max = (h.maxy - h.miny) * P + (h.maxx - h.minx);
-          size_t b = std::max<size_t>((size_t)rows * P * 128, (size_t)(a_off_max + NPX) * 128);
-          plane_bytes += (b + 1023) / 1024 * 1024 * cch;
-        }
-        if (!ok || (long long)plane_bytes + (long long)WS * w_bytes > (long long)smem_limit) continue;
-        const double tiles = (double)((PX + WT - 1) / WT) * ((PY + R - 1) / R);
-        const double nkb = (double)taps.size() * cch;  // all phases
-        const double mma_clk = nkb * CB * 4 * (NPX == 256 ? 146.0 : 102.0);  // measured clocks per instruction
-        const double fill_clk = ((double)plane_bytes + nkb * w_bytes) / 38.0;  // measured L2->SM fill, B/clk/SM
-        // epilogue: bias/ReLU ~7 clk per pixel and channel block.  Threshold search: instruction bound, ~60 issue clocks
-        // per warp-level output (32 channels), counted with the padding of the 16-wide search batches (measured on
-        // config 4: 37 k clk for a 22x10 pooled tile, profiles/r01_cfg4_epilogue_profile.txt)
-        const double groups = g.pool == 2 ? (double)(R / 2) * ((WT + 31) / 32) * 16 : (double)((R * P + 31) / 32) * 32;
-        const double epi_clk = thr ? groups * nph * CB * 4 * 60.0 : (double)WT * R * nph * CB * 7.0;
-        const double tile_clk = acc_st == 2 ? std::max(std::max(mma_clk, fill_clk), epi_clk) : std::max(mma_clk + epi_clk, fill_clk);
-        const double ws_pen = WS >= 3 ? 1.0 : 1.05;
-        // ties (e.g. 1x1 layers, where every WT is equally efficient) go to wide boxes: long contiguous TMA rows
-        const double cost = tiles * tile_clk * ws_pen * (1.0 + 0.0005 * R) / ((double)PX * PY);
-        if (cost < best * 0.999) { best = cost; bWT = WT; bR = R; bNPX = NPX; bWS = WS; }
-      }
-  }
-  const int chb = 1, CBe = CB, bMode = 0;
+  const int w_bytes = CBe * 128 * 128;
   if (getenv("FCB_U2_FORCE")) {  // "WT,R,NPX,WS" -- experiments only; the caller is responsible for it fitting
     int a, b, c, d;
     if (sscanf(getenv("FCB_U2_FORCE"), "%d,%d,%d,%d", &a, &b, &c, &d) == 4) { bWT = a; bR = b; bNPX = c; bWS = d; }

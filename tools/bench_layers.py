@@ -74,6 +74,8 @@ if __name__ == "__main__":
                 bench_layer("cfg3_xnor_tensor", c3, a.images, 0xFF)
             elif nm == "cfg3":
                 bench_layer("cfg3_xnor", c3, a.images, 0xFF)
+            elif nm == "cfg4n":
+                bench_layer("cfg4_thr_nopool", dataclasses.replace(c4, pool=0), a.images, 0xFF)
             elif nm == "cfg4":
                 bench_layer("cfg4_thr_pool", c4, a.images, 0xFF)
             else:
