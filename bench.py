@@ -50,7 +50,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -58,7 +58,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this call are reported."""
+        self.t0 = time.monotonic()
 
     def stop(self):
         if not self.proc:
@@ -69,7 +73,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        for ts, ln in self.lines:
+            if ts < t0:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -184,11 +191,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()  # nvidia-smi takes a while to produce its first line: start it before the warm-up, count from mark()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     l0 = layer.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)

@@ -190,14 +190,23 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* pempty = pfull + U2_NPB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool spin = p.spin != 0;  // short tiles: poll instead of suspending on the barriers of the tile pipeline
-#define WAITB(BAR_, PAR_) do { if (spin) mbar_wait_spin((BAR_), (PAR_)); else mbar_wait((BAR_), (PAR_)); } while (0)
-  // opt-in clock accounting: PROF_T(seg) adds the clocks since the previous PROF_T / PROF_START of this thread to segment `seg`
+  constexpr bool THIN = NB > 1;  // thin-input instantiations (im2col builder warps); NB == 1 serves resident planes and dthin
+#define WAITB(BAR_, PAR_) mbar_wait((BAR_), (PAR_))
+  // clock accounting and the perf-decomposition switches of the inner loops exist only in -DFCB_U2_PROF builds (tools/): even a
+  // predicted-not-taken branch per K-block shows in the MMA issue loop, which has ~580 clocks per K-block to stay ahead of the pipe
+#ifdef FCB_U2_PROF
   long long prof_c = 0;
   unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF_START() do { if (p.prof) prof_c = clock64(); } while (0)
 #define PROF_T(SEG_) do { if (p.prof) { const long long n_ = clock64(); prof_acc[SEG_] += (unsigned long long)(n_ - prof_c); prof_c = n_; } } while (0)
 #define PROF_FLUSH(ROLE_) do { if (p.prof) for (int i_ = 0; i_ < 8; i_++) p.prof[(blockIdx.x * 3 + (ROLE_)) * 8 + i_] = prof_acc[i_]; } while (0)
+#define DBG(MASK_) (p.debug & (MASK_))
+#else
+#define PROF_START() do { } while (0)
+#define PROF_T(SEG_) do { } while (0)
+#define PROF_FLUSH(ROLE_) do { } while (0)
+#define DBG(MASK_) false
+#endif
   const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
   const long long total_tiles = tiles_per_img * p.n_images;
   // CTA -> (channel block, tile sequence): with chb > 1 every tile is visited once per channel block
@@ -260,7 +269,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next(), it++) {
           const uint32_t b = it % U2_NPB;
           if (it >= U2_NPB) WAITB(&pempty[b], ((it / U2_NPB) & 1u) ^ 1u);
-          if (p.debug & 32) { mbar_arrive(&pfull[b]); continue; }
+          if (DBG(32)) { mbar_arrive(&pfull[b]); continue; }
           mbar_arrive_expect_tx(&pfull[b], (uint32_t)(p.BWp * p.BHp * 4));
           // the box starts at a multiple of 4 pixels: an un-swizzled TMA box must start 16-byte aligned in its innermost dimension
           // (anything else is an illegal instruction: tools/tma_probe.cu, profiles/r01_tma_inner_alignment_probe.log)
@@ -299,7 +308,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const uint32_t patch = smem_u32(smem + p.patch_off + pb * p.patch_bytes) + 4u * xshift;
         const uint32_t rows = smem_u32(smem + set * p.set_bytes + p.planes[0].smem_off);
         int rr = (32 * bw + lane) / p.WT, xo = (32 * bw + lane) - rr * p.WT;
-        for (int m = 32 * bw + lane; m < ((p.debug & 64) ? 0 : npix); m += 32 * NB) {
+        for (int m = 32 * bw + lane; m < (DBG(64) ? 0 : npix); m += 32 * NB) {
           uint32_t src = patch + (uint32_t)rr * row_step + (uint32_t)xo * col_step;
           asm volatile("" : "+r"(src));  // one register, not re-derived per load
           const uint32_t dst = rows + 128u * (uint32_t)m, m7 = (uint32_t)m & 7u;
@@ -371,25 +380,24 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           PROF_T(2);
           if (flags & KB_WAIT) WAITB(&afull[plane], apar);
           PROF_T(3);
-          if (!wstatic || tile_it == 0) WAITB(&wfull[s], wphase);  // resident weights: loaded once, observed once
+          if (!wstatic || tile_it == 0) mbar_wait(&wfull[s], wphase);  // resident weights: loaded once, observed once
           PROF_T(4);
           tc_fence_after();
           const uint64_t wdesc = desc0 + (w_d0 + (uint32_t)s * w_dstep);
           if (elect_one_sync()) {
-            if (p.dthin) {
+            if (!THIN && p.dthin) {
               // A = 128 plane rows (pixels) per block at this shift, B = 16 weight rows (4 phases x 4 channel slots)
-              if (!(p.debug & 128))
-                for (int blk = 0; blk < NPX / 128; blk++) {
-                  const uint32_t dt = d_tmem + (uint32_t)(blk * 16);
-                  const uint64_t ad = pdesc + (uint64_t)(blk * 1024);
-                  umma_i8(dt, ad, wdesc, p.idesc_dthin, i ? 1u : 0u);
-                  umma_i8(dt, ad + 2, wdesc + 2, p.idesc_dthin, 1u);
-                  umma_i8(dt, ad + 4, wdesc + 4, p.idesc_dthin, 1u);
-                  umma_i8(dt, ad + 6, wdesc + 6, p.idesc_dthin, 1u);
-                }
-            } else if (p.swap) {
+              for (int blk = 0; blk < NPX / 128; blk++) {
+                const uint32_t dt = d_tmem + (uint32_t)(blk * 16);
+                const uint64_t ad = pdesc + (uint64_t)(blk * 1024);
+                umma_i8(dt, ad, wdesc, p.idesc_dthin, i ? 1u : 0u);
+                umma_i8(dt, ad + 2, wdesc + 2, p.idesc_dthin, 1u);
+                umma_i8(dt, ad + 4, wdesc + 4, p.idesc_dthin, 1u);
+                umma_i8(dt, ad + 6, wdesc + 6, p.idesc_dthin, 1u);
+              }
+            } else if (THIN && p.swap) {
               // A = 128 im2col rows (pixels) per block, B = the CB*128 weight rows: D[pixel][channel]
-              if (!(p.debug & 128))
+              if (!DBG(128))
                 for (int blk = 0; blk < NPX / 128; blk++) {
                   const uint32_t dt = d_tmem + (uint32_t)(blk * CB * 128);
                   const uint64_t ad = pdesc + (uint64_t)(blk * 1024);  // 128 rows x 128 B = 16 KB (>> 4)
@@ -398,18 +406,18 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   if (ksteps > 2) umma_i8(dt, ad + 4, wdesc + 4, p.idesc_swap, 1u);
                   if (ksteps > 3) umma_i8(dt, ad + 6, wdesc + 6, p.idesc_swap, 1u);
                 }
-            } else if (!(p.debug & 128)) {
-            umma_i8(d_tmem, wdesc, pdesc, idesc, i ? 1u : 0u);
-            if (ksteps > 1) umma_i8(d_tmem, wdesc + 2, pdesc + 2, idesc, 1u);
-            if (ksteps > 2) umma_i8(d_tmem, wdesc + 4, pdesc + 4, idesc, 1u);
-            if (ksteps > 3) umma_i8(d_tmem, wdesc + 6, pdesc + 6, idesc, 1u);
-            if (CB == 2) {
-              const uint32_t dt = d_tmem + (uint32_t)NPX;
-              umma_i8(dt, wdesc + 1024, pdesc, idesc, i ? 1u : 0u);  // next 128 weight rows = +16 KB (>> 4)
-              if (ksteps > 1) umma_i8(dt, wdesc + 1026, pdesc + 2, idesc, 1u);
-              if (ksteps > 2) umma_i8(dt, wdesc + 1028, pdesc + 4, idesc, 1u);
-              if (ksteps > 3) umma_i8(dt, wdesc + 1030, pdesc + 6, idesc, 1u);
-            }
+            } else if (!DBG(128)) {
+              umma_i8(d_tmem, wdesc, pdesc, idesc, i ? 1u : 0u);
+              if (!THIN || ksteps > 1) umma_i8(d_tmem, wdesc + 2, pdesc + 2, idesc, 1u);
+              if (!THIN || ksteps > 2) umma_i8(d_tmem, wdesc + 4, pdesc + 4, idesc, 1u);
+              if (!THIN || ksteps > 3) umma_i8(d_tmem, wdesc + 6, pdesc + 6, idesc, 1u);
+              if (CB == 2) {
+                const uint32_t dt = d_tmem + (uint32_t)NPX;
+                umma_i8(dt, wdesc + 1024, pdesc, idesc, i ? 1u : 0u);  // next 128 weight rows = +16 KB (>> 4)
+                if (!THIN || ksteps > 1) umma_i8(dt, wdesc + 1026, pdesc + 2, idesc, 1u);
+                if (!THIN || ksteps > 2) umma_i8(dt, wdesc + 1028, pdesc + 4, idesc, 1u);
+                if (!THIN || ksteps > 3) umma_i8(dt, wdesc + 1030, pdesc + 6, idesc, 1u);
+              }
             }
             if (!wstatic) umma_commit(&wempty[s]);
             if (flags & KB_FREE) umma_commit(&aempty[plane]);
@@ -506,7 +514,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           auto process = [&](int blk, int cbk, const uint32_t (&v)[32]) {
             const int m = blk * 128 + q * 32 + lane;
             if (m >= mlim) return;  // rows of the tile that are never stored
-            if (p.debug & 512) {  // perf decomposition: TMEM loads only
+            if (DBG(512)) {  // perf decomposition: TMEM loads only
               if (v[0] == 0x12345678u && v[31] == 0x9abcdef0u) sts_v4(stg_s, v[1], v[2], v[3], v[4]);
               return;
             }
@@ -1217,6 +1225,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     if (rc) { delete U; return rc; }
   }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1378,13 +1387,17 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   const long long total = (long long)p.tiles_x * p.tiles_y * n_images;
   const int grid = (int)std::min<long long>(total, U->num_sms / p.chb) * p.chb;
   unsigned long long* d_prof = nullptr;
+#ifdef FCB_U2_PROF
   if (getenv("FCB_U2_PROF")) {
     FCB_CUDA_OK(cudaMalloc(&d_prof, (size_t)grid * 24 * 8));
     FCB_CUDA_OK(cudaMemsetAsync(d_prof, 0, (size_t)grid * 24 * 8, st));
     p.prof = d_prof;
   }
-  p.spin = getenv("FCB_U2_SPIN") ? atoi(getenv("FCB_U2_SPIN")) : p.spin;
-  if (p.thin_in) umma2_conv_kernel<4><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+#endif
+  // thin-input: 4 builder warps beside the light bias/ReLU epilogue (128 registers per thread suffice); 2 beside the threshold
+  // epilogue, whose lock-step searches need ~170 registers to stay out of local memory
+  if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.thin_in) umma2_conv_kernel<4><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else umma2_conv_kernel<1><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   FCB_CUDA_OK(cudaGetLastError());
   if (d_prof) {  // debugging aid: average clocks per tile and segment over the CTAs

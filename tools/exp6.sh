@@ -1,2 +1,7 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for E in X=1 FCB_U2_NO_CHB=1; do for L in cfg4 cfg4n; do echo -n "$E $L: "; env $E python tools/bench_layers.py --images 512 --only $L 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms'],'ms',d['img_s'],'img/s',d['plan'][:110])"; done; done
+python tools/bench_layers.py --images 64 --only L0,L1,L2,L5,L6,L7,cfg4 2>&1 | python -c "
+import sys,json
+for l in sys.stdin.read().strip().splitlines():
+    try: d=json.loads(l)
+    except Exception: print(l[:300]); continue
+    print(d['layer'], d.get('ms'), 'ms', d.get('img_s'), 'img/s', d.get('TOPs_nonzero', d.get('TOPs')), 'TOPs')"
