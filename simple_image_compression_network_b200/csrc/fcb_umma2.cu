@@ -85,6 +85,9 @@ struct Params2 {
   // warps 6..9 stage 1, so one group's barriers, fences and store issue overlap the other group's TMEM reads (64 B/clk/SM:
   // ~2048 clocks for a 256 x 128 int32 tile -- the floor of a store-bound layer)
   int epi_alt;
+  // MMA-bound layers on the register epilogue: only warps 2..5 work (one per TMEM lane quarter); the second epilogue warp of each
+  // SM sub-partition would only compete with the MMA issue warp for issue slots
+  int epi4;
   // bias folded into the GEMM (thin-input mode): window word `bias_word` of every im2col row is the constant 1 and the weight
   // byte there is the channel's bias, so the accumulator already is acc + bias (all arithmetic is mod 2^8); -1 = not folded
   int bias_word;
@@ -232,7 +235,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int i = 0; i < p.nsets * p.nplanes; i++) { mbar_init(&afull[i], p.thin_in ? NB : 1); mbar_init(&aempty[i], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], p.epi_alt ? 4 : 8); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (p.epi_alt || p.epi4) ? 4 : 8); }
     for (int a = 0; a < U2_NPB; a++) { mbar_init(&pfull[a], 1); mbar_init(&pempty[a], NB); }
     fence_barrier_init();
   }
@@ -434,7 +437,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // two warps per TMEM lane quarter; `half` splits the accumulator columns (pixels) between them
     const int q = warp & 3, half = (warp - 2) >> 2;
     const bool alt = p.epi_alt != 0;
-    const int col_lo = alt ? 0 : half * (p.NPX / 2), col_hi = alt ? p.NPX : col_lo + p.NPX / 2;
+    const bool whole = alt || p.epi4;  // this warp covers every column of the accumulators it serves
+    const int col_lo = whole ? 0 : half * (p.NPX / 2), col_hi = whole ? p.NPX : col_lo + p.NPX / 2;
     const int ebar = alt ? 1 + half : 1, ecnt = alt ? 128 : 256;      // named barrier of this warp's epilogue group
     const int erow0 = alt ? q : warp - 2, erows = alt ? 4 : 8;        // TMA-store rows dealt over the group's warps
 #define EPI_BAR() asm volatile("bar.sync %0, %1;" ::"r"(ebar), "r"(ecnt) : "memory")
@@ -449,7 +453,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const bool thin = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
     uint32_t acc_it = 0;
     PROF_START();
-    for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next()) {
+    for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid() && !(p.epi4 && half); ti.next()) {
       const int img = ti.img;
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
         const PixMap pm{p, ti.tx * p.WT, ti.ty * p.R, p.phases[ph].px, p.phases[ph].py, (unsigned long long)img * p.out_img_bytes};
@@ -1070,6 +1074,18 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     off += p.stg_bufs * p.stg_bytes;
   }
   p.epi_alt = (p.stg_bufs == 2 && p.acc_stages == 2 && !getenv("FCB_U2_NO_ALT")) ? 1 : 0;
+  {
+    // register bias/ReLU epilogue, ~30 clocks per pixel with 4 warps (measured on the deconv layers before they were staged):
+    // if that hides under the tile's MMA time with margin, run it on 4 warps
+    const bool reg_fast = epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && g.pool <= 1 && g.OFM % 32 == 0 &&
+                          p.P >= 4 && p.stg_bufs == 0 && g.OFM > 8;
+    const double mma_tile = (double)taps.size() * cch * CBe * 4 * (bNPX == 256 ? 146.0 : 102.0) / nph;
+    const double epi_tile = (double)bWT * bR * CBe * 30.0;
+    // measured on CONV_1: 147.3 k img/s with 4 warps vs 150.5 k with 8 -- issue-slot competition is not what holds the tensor
+    // pipe at ~85 %, so this stays an experiment switch (FCB_U2_EPI4=1)
+    (void)mma_tile; (void)epi_tile;
+    p.epi4 = (reg_fast && p.acc_stages == 2 && getenv("FCB_U2_EPI4") && atoi(getenv("FCB_U2_EPI4"))) ? 1 : 0;
+  }
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
   // K-block lists: plane-major within each phase so planes are released progressively
@@ -1323,7 +1339,7 @@ const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
     return buf;
   }
   snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d chb=%d%s planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT,
-           p.R, p.P, p.NPX, p.CB, p.chb, p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
+           p.R, p.P, p.NPX, p.CB, p.chb, p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : p.epi4 ? " epi-warps=4" : ""), p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
            p.tiles_x, p.tiles_y);
   return buf;
 }
