@@ -175,7 +175,9 @@ __device__ __forceinline__ void build_row(uint32_t src, uint32_t dst, uint32_t m
 }
 
 // NB = warps from index 10 on: 1 = plane TMA producer (resident-planes mode); 4 = im2col builders (thin-input mode)
-template <int NB>
+// DTHIN: the thin-output transposed-conv instantiation.  Mode flags are template parameters because the MMA issue loop has no
+// slack for per-K-block loads of kernel parameters (each LDCU + dependent branch costs ~50 clocks of its ~580-clock budget).
+template <int NB, bool DTHIN>
 __global__ void __launch_bounds__(320 + 32 * NB, 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params2 p) {
@@ -193,7 +195,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* pempty = pfull + U2_NPB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool THIN = NB > 1;  // thin-input instantiations (im2col builder warps); NB == 1 serves resident planes and dthin
+  constexpr bool THIN = NB > 1;         // thin-input instantiations (im2col builder warps)
+  constexpr bool WSTATIC = THIN || DTHIN;  // every weight K-block has its own stage: loaded once, never released
 #define WAITB(BAR_, PAR_) mbar_wait((BAR_), (PAR_))
   // clock accounting and the perf-decomposition switches of the inner loops exist only in -DFCB_U2_PROF builds (tools/): even a
   // predicted-not-taken branch per K-block shows in the MMA issue loop, which has ~580 clocks per K-block to stay ahead of the pipe
@@ -251,7 +254,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       int s = 0;
       uint32_t wphase = 1;
       for (long long t = cta0; t < total_tiles; t += ncta) {
-        if (p.wstatic && t != cta0) break;  // every K-block of the layer has its own stage: loaded once, never released
+        if (WSTATIC && t != cta0) break;
         for (int ph = 0; ph < p.nphases; ph++) {
           const Phase2& P = p.phases[ph];
           for (int i = 0; i < P.nkb; i++) {
@@ -259,7 +262,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             if (p.debug & 1) mbar_arrive(&wfull[s]);
             else {
               mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);
-              if (p.dthin) tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], 0, P.kb[i].w_k);  // 16-row block of shift w_k/16
+              if (DTHIN) tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], 0, P.kb[i].w_k);  // 16-row block of shift w_k/16
               else tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, chbase);
             }
             if (++s == p.wstages) { s = 0; wphase ^= 1; }
@@ -362,7 +365,9 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint32_t idesc = p.idesc;
     const uint64_t desc0 = make_smem_desc(smem_u32(smem), 128);
     const uint32_t w_d0 = (uint32_t)p.w_off >> 4, w_dstep = (uint32_t)p.w_bytes >> 4;
-    const int wstages = p.wstages, CB = p.CB, NPX = p.NPX, ksteps = p.ksteps, wstatic = p.wstatic;
+    int wstages = p.wstages, CB = p.CB;
+    asm volatile("" : "+r"(wstages), "+r"(CB));  // held in registers: not re-read from the parameter bank per K-block
+    const int NPX = p.NPX, ksteps = p.ksteps;
     PROF_START();
     for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
       const int set = (int)ring_idx(tile_it, p.nsets);
@@ -383,12 +388,12 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           PROF_T(2);
           if (flags & KB_WAIT) WAITB(&afull[plane], apar);
           PROF_T(3);
-          if (!wstatic || tile_it == 0) mbar_wait(&wfull[s], wphase);  // resident weights: loaded once, observed once
+          if (!WSTATIC || tile_it == 0) mbar_wait(&wfull[s], wphase);  // resident weights: loaded once, observed once
           PROF_T(4);
           tc_fence_after();
           const uint64_t wdesc = desc0 + (w_d0 + (uint32_t)s * w_dstep);
           if (elect_one_sync()) {
-            if (!THIN && p.dthin) {
+            if (DTHIN) {
               // A = 128 plane rows (pixels) per block at this shift, B = 16 weight rows (4 phases x 4 channel slots)
               for (int blk = 0; blk < NPX / 128; blk++) {
                 const uint32_t dt = d_tmem + (uint32_t)(blk * 16);
@@ -422,12 +427,12 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 if (!THIN || ksteps > 3) umma_i8(dt, wdesc + 1030, pdesc + 6, idesc, 1u);
               }
             }
-            if (!wstatic) umma_commit(&wempty[s]);
+            if (!WSTATIC) umma_commit(&wempty[s]);
             if (flags & KB_FREE) umma_commit(&aempty[plane]);
             if (i == nkb - 1) umma_commit(&tfull[acc]);
           }
           __syncwarp();
-          if (++s == wstages) { s = 0; wphase ^= wstatic ? 0u : 1u; }
+          if (++s == wstages) { s = 0; wphase ^= WSTATIC ? 0u : 1u; }
         }
       }
     }
@@ -465,7 +470,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
-        if (p.dthin) {
+        if (DTHIN) {
           // thread = input pixel m of block `half`; its 16 columns are the 2x2 output words it produces (bias + ReLU on the
           // wrapped 8-bit lane, conv_nonsquare_top.cpp:183-194); a warp writes two 256-byte runs of output row 2y and 2y+1
           const int m = half * 128 + q * 32 + lane;
@@ -1126,7 +1131,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1240,8 +1245,8 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1317,7 +1322,7 @@ int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& e
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1412,9 +1417,10 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
 #endif
   // thin-input: 4 builder warps beside the light bias/ReLU epilogue (128 registers per thread suffice); 2 beside the threshold
   // epilogue, whose lock-step searches need ~170 registers to stay out of local memory
-  if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (p.thin_in) umma2_conv_kernel<4><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else umma2_conv_kernel<1><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2, false><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.thin_in) umma2_conv_kernel<4, false><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.dthin) umma2_conv_kernel<1, true><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else umma2_conv_kernel<1, false><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   FCB_CUDA_OK(cudaGetLastError());
   if (d_prof) {  // debugging aid: average clocks per tile and segment over the CTAs
     FCB_CUDA_OK(cudaStreamSynchronize(st));
