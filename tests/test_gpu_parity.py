@@ -321,3 +321,75 @@ def test_thin_output_deconv(ix, iy, c, ofm, reps, fcb_lib, oracle_mod, monkeypat
     L2 = _layer(d, inp)
     assert not L2.plan.startswith("thin-output deconv")
     assert np.array_equal(L2.run(inp["in_words"], reps), want), f"[{L2.plan}]"
+
+
+def _random_descs(seed, count):
+    """Random small layer shapes across every plan family (resident planes, thin input, thin-output deconv, thresholds with and
+    without pool, xnor, IMAD fall-backs), seeded: the same cases on every run."""
+    from simple_image_compression_network_b200.desc import (ACT_BIAS_RELU, ACT_PASSTHROUGH, ACT_THRESHOLDS, KIND_CONV, KIND_DECONV522, W_BINARY_XNOR,
+                                          LayerDesc)
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        fam = rng.integers(0, 6)
+        if fam == 0:  # channel-heavy conv, bias+ReLU
+            c = int(rng.choice([16, 32, 64, 128, 256])); ofm = int(rng.choice([32, 64, 128, 192, 256]))
+            k = int(rng.choice([1, 3, 5])); s = int(rng.choice([1, 2])) if c % 128 == 0 else 1
+            pad = int(rng.integers(0, k // 2 + 1))
+            x = int(rng.integers(k, 40)) * s; y = int(rng.integers(k, 12)) * s
+            d = LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=s, stride_y=s, pad=pad,
+                          simd=16, pe=16, in_bits=8, w_bits=int(rng.choice([2, 4, 8])), acc_bits=8, acc_signed=0, act_kind=ACT_BIAS_RELU, out_bits=8)
+        elif fam == 1:  # thin input
+            c = int(rng.choice([3, 4])); ofm = int(rng.choice([16, 64, 128, 256])); k = int(rng.choice([3, 5])); s = int(rng.choice([1, 2]))
+            x = 4 * int(rng.integers(3, 40)); y = int(rng.integers(k, 14)) * 2
+            thr = bool(rng.integers(0, 2))
+            kw = dict(act_kind=ACT_THRESHOLDS, acc_bits=24, acc_signed=1, out_bits=8, num_th=int(rng.choice([15, 255])),
+                      pool=int(rng.choice([0, 2])) if s == 1 else 0) if thr else dict(act_kind=ACT_BIAS_RELU, acc_bits=8, acc_signed=0, out_bits=8)
+            d = LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=s, stride_y=s, pad=k // 2,
+                          simd=c, pe=16, in_bits=8, w_bits=4, **kw)
+        elif fam == 2:  # deconv522, thin and wide outputs
+            c = int(rng.choice([16, 128, 256])); ofm = int(rng.choice([3, 4, 32, 128]))
+            d = LayerDesc(kind=KIND_DECONV522, kernel_x=5, kernel_y=5, ifm_ch=c, ofm_ch=ofm, ifm_x=int(rng.integers(2, 60)), ifm_y=int(rng.integers(2, 12)),
+                          stride_x=2, stride_y=2, pad=2, simd=16, pe=ofm if ofm < 16 else 16, in_bits=8, w_bits=4, acc_bits=8, acc_signed=0,
+                          act_kind=ACT_BIAS_RELU, out_bits=8)
+        elif fam == 3:  # thresholds on channel-heavy layers
+            c = int(rng.choice([32, 128, 256])); ofm = int(rng.choice([32, 128, 256])); pool = int(rng.choice([0, 2]))
+            x = 2 * int(rng.integers(2, 30)); y = 2 * int(rng.integers(2, 8))
+            d = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=1, stride_y=1, pad=1, simd=32, pe=32,
+                          in_bits=8, w_bits=4, acc_bits=int(rng.choice([16, 24, 32])), acc_signed=1, act_kind=ACT_THRESHOLDS,
+                          out_bits=int(rng.choice([2, 4, 8])), num_th=0, pool=pool, cmp=int(rng.integers(0, 4)))
+            d = dataclasses.replace(d, num_th=(1 << d.out_bits) - 1)
+        elif fam == 4:  # xnor
+            c = int(rng.choice([32, 64, 128])); ofm = int(rng.choice([16, 64]))
+            d = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=int(rng.integers(3, 40)), ifm_y=int(rng.integers(3, 12)),
+                          stride_x=1, stride_y=1, pad=int(rng.integers(0, 2)), simd=32, pe=16, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR,
+                          acc_bits=16, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=1, num_th=1)
+        else:  # odd widths on the universal engine
+            d = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=int(rng.choice([1, 3])), ifm_ch=int(rng.choice([2, 6, 10])), ofm_ch=int(rng.choice([3, 5, 12])),
+                          ifm_x=int(rng.integers(3, 20)), ifm_y=int(rng.integers(3, 9)), stride_x=1, stride_y=1, pad=0, simd=2, pe=1,
+                          in_bits=int(rng.choice([2, 4, 8])), w_bits=int(rng.choice([3, 5, 8])), acc_bits=16, acc_signed=1, act_kind=ACT_PASSTHROUGH,
+                          out_bits=16, in_signed=int(rng.integers(0, 2)))
+        out.append(d)
+    return out
+
+
+@pytest.mark.parametrize("seed", [101, 202, 303])
+def test_random_shapes_match_oracle(seed, fcb_lib, oracle_mod):
+    """Seeded fuzz over the plan families: every layer the library accepts must equal the oracle bit for bit; shapes it
+    rejects must be rejected with FCB_ERR_SHAPE / UNSUPPORTED (never a wrong answer)."""
+    from simple_image_compression_network_b200._lib import FcbError
+    ran, plans = 0, set()
+    for i, d in enumerate(_random_descs(seed, 40)):
+        reps = 1 + (i % 3)
+        try:
+            inp = cases.make_inputs(d, seed_shift=seed + i, num_reps=reps, relu_range=bool(i % 2))
+            L = _layer(d, inp)
+        except (FcbError, ValueError, AssertionError):
+            continue
+        got = L.run(inp["in_words"], reps)
+        want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=reps)
+        assert np.array_equal(got, want), f"seed {seed} case {i} {d} [{L.engine}: {L.plan}]: {_diff(got, want)}"
+        ran += 1
+        plans.add(L.plan.split(" ")[0] + ":" + L.engine)
+    assert ran >= 25, f"only {ran} of 40 random layers were accepted"
+    assert len(plans) >= 4, plans
