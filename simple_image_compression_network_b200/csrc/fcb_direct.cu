@@ -87,6 +87,36 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const DirectParams p) 
     }
     __syncthreads();
     // ---- multiply-accumulate ----------------------------------------------------------
+    if (ENGINE == ENG_XNOR && (cc & 1) == 0) {
+      // channel words in pairs: one 8-byte patch load feeds two popcounts per output, the two counts and the accumulator meet
+      // in one 3-input add, and the weights of the next (tap, pair) are fetched while this one is counted
+      const uint32_t* wt = reinterpret_cast<const uint32_t*>(p.wt);
+      const uint2* patch2 = reinterpret_cast<const uint2*>(smem_raw);
+      const int cc2 = cc >> 1, nit = p.KY * p.KX * cc2;
+      int ky = 0, kx = 0, c2 = 0;
+      auto wrow_of = [&](int ky_, int kx_, int c2_) { return (size_t)((ky_ * p.KX + kx_) * CU + c0 + 2 * c2_) * p.OFMp + ch0; };
+      uint32_t wn[4];
+      {
+        const size_t r = wrow_of(0, 0, 0);
+        wn[0] = __ldg(wt + r); wn[1] = __ldg(wt + r + 32); wn[2] = __ldg(wt + r + p.OFMp); wn[3] = __ldg(wt + r + p.OFMp + 32);
+      }
+      for (int it = 0; it < nit; it++) {
+        const uint32_t w00 = wn[0], w01 = wn[1], w10 = wn[2], w11 = wn[3];
+        const int poff = (ky * p.patch_w + kx) * cc2 + c2;
+        if (++c2 == cc2) { c2 = 0; if (++kx == p.KX) { kx = 0; ++ky; } }
+        if (it + 1 < nit) {
+          const size_t r = wrow_of(ky, kx, c2);
+          wn[0] = __ldg(wt + r); wn[1] = __ldg(wt + r + 32); wn[2] = __ldg(wt + r + p.OFMp); wn[3] = __ldg(wt + r + p.OFMp + 32);
+        }
+#pragma unroll
+        for (int i = 0; i < PXB * PXB; i++) {
+          const int ly = wy + (i >> 2), lx = wx + (i & 3);
+          const uint2 a = patch2[(ly * p.SYe * p.patch_w + lx * p.SXe) * cc2 + poff];
+          acc[i][0] += __popc(~(a.x ^ w00)) + __popc(~(a.y ^ w10));
+          acc[i][1] += __popc(~(a.x ^ w01)) + __popc(~(a.y ^ w11));
+        }
+      }
+    } else
     for (int ky = 0; ky < p.KY; ky++)
       for (int kx = 0; kx < p.KX; kx++) {
         const int kbase = (ky * p.KX + kx) * CU + c0;
