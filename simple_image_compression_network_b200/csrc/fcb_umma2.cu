@@ -96,6 +96,9 @@ struct Params2 {
   // D[pixel][phase*4 + ch]; the epilogue thread owns one input pixel = a 2x2 block of output words
   int dthin;
   uint32_t idesc_dthin;
+  // dthin == 2 (col2im form): D[(tap*OFM + ch)][pixel] over the tile's (R+2) x (WT+2) pixels; the epilogue writes the rows as bytes
+  // to shared memory (pitch `s_pitch`) and each thread then sums the taps of its input pixel's 2x2 output words
+  int s_pitch;
   unsigned long long* prof;  // FCB_U2_PROF: per-CTA clock totals [role 0 builder | 1 mma | 2 epilogue][8 segments]
   int thin_in, S, pad, nw, BWp, BHp, patch_off, patch_bytes, ksteps, wstatic;
   int toff[32];  // patch word offset of window word i: ky*BWp + kx
@@ -174,10 +177,37 @@ __device__ __forceinline__ void build_row(uint32_t src, uint32_t dst, uint32_t m
   for (int j = 0; j < 2 * KS; j++) sts_v4(dst + (((uint32_t)j ^ m7) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
 
+// col2im of the thin-output transposed conv: the 25 x OFM partial bytes of one input pixel's 2x2 output block, read from the
+// byte tile S[row = tap*OFM + ch][pixel] (pitch DCOL_PITCH).  b[0..2] = shared addresses of the pixel shifted by offy = -1, 0, +1
+// rows; every other offset is an immediate.  Tap (ky, kx) belongs to phase (ky & 1, kx & 1) at shift ((ky + (ky&1) - 2) / 2, ...).
+constexpr int DCOL_PITCH = 272;
+template <int IMM>
+__device__ __forceinline__ uint32_t lds_u8_imm(uint32_t base) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1 + %2];" : "=r"(v) : "r"(base), "n"(IMM));
+  return v;
+}
+template <int OFM, int T>
+struct DcolGather {
+  static __device__ __forceinline__ void run(const uint32_t (&b)[3], uint32_t (&sum)[4][4]) {
+    constexpr int ky = T / 5, kx = T % 5;
+    constexpr int offy = (ky + (ky & 1) - 2) / 2, offx = (kx + (kx & 1) - 2) / 2, ph = (ky & 1) * 2 + (kx & 1);
+    sum[ph][0] += lds_u8_imm<(T * OFM + 0) * DCOL_PITCH + offx>(b[offy + 1]);
+    sum[ph][1] += lds_u8_imm<(T * OFM + 1) * DCOL_PITCH + offx>(b[offy + 1]);
+    sum[ph][2] += lds_u8_imm<(T * OFM + 2) * DCOL_PITCH + offx>(b[offy + 1]);
+    if (OFM == 4) sum[ph][3] += lds_u8_imm<(T * OFM + (OFM == 4 ? 3 : 0)) * DCOL_PITCH + offx>(b[offy + 1]);
+    DcolGather<OFM, T + 1>::run(b, sum);
+  }
+};
+template <int OFM>
+struct DcolGather<OFM, 25> {
+  static __device__ __forceinline__ void run(const uint32_t (&)[3], uint32_t (&)[4][4]) {}
+};
+
 // NB = warps from index 10 on: 1 = plane TMA producer (resident-planes mode); 4 = im2col builders (thin-input mode)
 // DTHIN: the thin-output transposed-conv instantiation.  Mode flags are template parameters because the MMA issue loop has no
 // slack for per-K-block loads of kernel parameters (each LDCU + dependent branch costs ~50 clocks of its ~580-clock budget).
-template <int NB, bool DTHIN>
+template <int NB, int DT>
 __global__ void __launch_bounds__(320 + 32 * NB, 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params2 p) {
@@ -196,7 +226,9 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool THIN = NB > 1;         // thin-input instantiations (im2col builder warps)
-  constexpr bool WSTATIC = THIN || DTHIN;  // every weight K-block has its own stage: loaded once, never released
+  constexpr bool DTHIN = DT == 1;   // thin-output deconv, 9 shift blocks x N=16 (pixels on M)
+  constexpr bool DCOL = DT == 2;    // thin-output deconv, GEMM over (tap, channel) rows + col2im in shared memory
+  constexpr bool WSTATIC = THIN || DT != 0;  // every weight K-block has its own stage: loaded once, never released
 #define WAITB(BAR_, PAR_) mbar_wait((BAR_), (PAR_))
   // clock accounting and the perf-decomposition switches of the inner loops exist only in -DFCB_U2_PROF builds (tools/): even a
   // predicted-not-taken branch per K-block shows in the MMA issue loop, which has ~580 clocks per K-block to stay ahead of the pipe
@@ -262,7 +294,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             if (p.debug & 1) mbar_arrive(&wfull[s]);
             else {
               mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);
-              if (DTHIN) tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], 0, P.kb[i].w_k);  // 16-row block of shift w_k/16
+              if (DTHIN || DCOL) tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], 0, P.kb[i].w_k);  // row block w_k
               else tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, chbase);
             }
             if (++s == p.wstages) { s = 0; wphase ^= 1; }
@@ -470,6 +502,74 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
+        if (DCOL) {
+          // (always two accumulator stages: warps 2..5 serve stage 0, warps 6..9 stage 1, each group with its own byte tile)
+          const int nrows = 25 * p.OFM;
+          uint8_t* S = smem + p.stg_off + half * p.stg_bytes;
+          const uint32_t S_s = smem_u32(S);
+          EPI_BAR();  // the group's previous col2im pass has finished reading S
+          // ---- phase 1: accumulator rows -> bytes (all arithmetic is mod 2^8, so the partial sums may be truncated now)
+          if (q * 32 < nrows && !(p.debug & 8)) {
+            const int row = q * 32 + lane;
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+            const uint32_t srow = S_s + (uint32_t)(row * p.s_pitch);
+            const int ncols = (vrows + 2) * p.P;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32(tacc + (uint32_t)c0, v);
+              tmem_ld_wait();
+              if (row < nrows) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                  const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
+                  w[j] = __byte_perm(lo, hi, 0x5410);
+                }
+                sts_v4(srow + (uint32_t)c0, w[0], w[1], w[2], w[3]);
+                sts_v4(srow + (uint32_t)c0 + 16u, w[4], w[5], w[6], w[7]);
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          EPI_BAR();
+          // ---- phase 2: col2im.  Thread = one interior input pixel (r, xo); tap (ky, kx) of phase (ky & 1, kx & 1) reads the
+          // partial of pixel (r + offy, xo + offx), offy = (ky + (ky & 1) - 2) / 2
+          const int npx = vrows * p.WT;
+          for (int idx = (warp & 3) * 32 + lane; idx < ((p.debug & 8) ? 0 : npx); idx += 128) {
+            const int rr = idx / p.WT, xo = idx - rr * p.WT;
+            if (xo >= vcols) continue;
+            uint32_t b[3];
+            b[1] = S_s + (uint32_t)((rr + 1) * p.P + (xo + 1));
+            b[0] = b[1] - (uint32_t)p.P;
+            b[2] = b[1] + (uint32_t)p.P;
+            uint32_t sum[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+              for (int o = 0; o < 4; o++) sum[a][o] = 0;
+            if (p.OFM == 3) DcolGather<3, 0>::run(b, sum);
+            else DcolGather<4, 0>::run(b, sum);
+            uint32_t w[4];
+#pragma unroll
+            for (int ph = 0; ph < 4; ph++) {
+              uint32_t word = 0;
+#pragma unroll
+              for (int o = 0; o < 4; o++)
+                if (o < p.OFM) {
+                  uint32_t r = (sum[ph][o] + (uint32_t)(int32_t)p.epi.bias[o]) & 0xFFu;
+                  r = (r & 0x80u) ? 0u : r;
+                  word |= r << (8 * o);
+                }
+              w[ph] = word;
+            }
+            uint8_t* dst = p.out + pm.img_off + ((size_t)(2 * (pm.y0 + rr)) * p.out_x + 2 * (pm.x0 + xo)) * 4;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+            *reinterpret_cast<uint2*>(dst + (size_t)p.out_x * 4) = make_uint2(w[2], w[3]);
+          }
+          continue;
+        }
         if (DTHIN) {
           // thread = input pixel m of block `half`; its 16 columns are the 2x2 output words it produces (bias + ReLU on the
           // wrapped 8-bit lane, conv_nonsquare_top.cpp:183-194); a warp writes two 256-byte runs of output row 2y and 2y+1
@@ -1131,7 +1231,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1245,8 +1345,8 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1322,7 +1422,79 @@ int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& e
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  *out = U;
+  return FCB_OK;
+}
+
+// Thin-output transposed conv, col2im form: d_w is [cch][128 rows (tap*OFM + ch, zero beyond 25*OFM)][128] s8.
+int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, Umma2Plan** out) {
+  *out = nullptr;
+  if (g.kind != FCB_KIND_DECONV522 || g.OFM < 3 || g.OFM > 4 || g.out_word_bytes != 4 || g.C % 128 || g.C > 256 || g.pool > 1 ||
+      epi.act_kind != FCB_ACT_BIAS_RELU || epi.out_bits != 8 || epi.acc_bits != 8)
+    return FCB_ERR_UNSUPPORTED;
+  const int cch = g.C / 128, PX = g.IX, PY = g.IY, NPX = 256;
+  int bWT = 0, bR = 0;
+  double best = 1e30;
+  for (int WT = 1; WT <= std::min(PX, 254); WT++) {
+    const int P = WT + 2;
+    const int R = std::min(NPX / P - 2, PY);
+    if (R < 1) continue;
+    const double tiles = (double)((PX + WT - 1) / WT) * ((PY + R - 1) / R);
+    const double cost = tiles / ((double)PX * PY);  // every tile costs the same (256 columns of MMA, TMEM read and col2im)
+    if (cost < best * 0.999) { best = cost; bWT = WT; bR = R; }
+  }
+  if (!bWT) return FCB_ERR_UNSUPPORTED;
+  Umma2Plan* U = new Umma2Plan();
+  U->g = g; U->num_sms = num_sms;
+  Params2& p = U->p;
+  memset(&p, 0, sizeof(p));
+  p.epi = epi;
+  p.OFM = g.OFM; p.CB = 1; p.chb = 1; p.NPX = NPX; p.stride2 = 0; p.deconv = 1; p.nphases = 1; p.dthin = 2; p.bias_word = -1; p.ksteps = 4;
+  p.WT = bWT; p.R = bR; p.P = bWT + 2; p.PX = PX; p.PY = PY;
+  p.tiles_x = (PX + bWT - 1) / bWT; p.tiles_y = (PY + bR - 1) / bR;
+  p.out_x = g.out_x; p.out_y = g.out_y; p.out_word_bytes = 4; p.out_img_bytes = g.out_img_bytes;
+  p.wstages = cch; p.wstatic = 1; p.w_bytes = 128 * 128;
+  p.acc_stride = NPX; p.acc_stages = 2; p.tmem_cols = 512;
+  p.idesc = make_idesc_i8(128, NPX, 1, g.in_signed);
+  p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
+  p.epi_alt = 1;  // one epilogue group per accumulator stage
+  p.s_pitch = DCOL_PITCH;  // 272: lanes (rows) 272 bytes apart -> 16-byte stores of 8 consecutive rows hit 8 distinct bank groups
+  const int rows = bR + 2;
+  int off = 0;
+  for (int cc = 0; cc < cch; cc++) {
+    Plane2& pl = p.planes[cc];
+    pl.smem_off = off; pl.bytes = rows * p.P * 128; pl.c0 = cc * 128; pl.dx = -1; pl.dy = -1; pl.par = 0; pl.map = 0;
+    off += NPX * 128;
+  }
+  p.nplanes = cch; p.set_bytes = off; p.nsets = 2;
+  off *= 2;
+  U->box_rows[0] = U->box_rows[1] = rows;
+  p.w_off = off; off += p.wstages * p.w_bytes;
+  p.bar_off = off; off += (2 * p.wstages + 2 * cch * 2 + 4 + 1 + 2 * (int)U2_NPB + 1) * 8;
+  off = (off + 15) & ~15;
+  p.stage_off = off; off += 8 * 256;
+  p.thr_off = -1;
+  off = (off + 127) & ~127;
+  p.stg_off = off; p.stg_bytes = (25 * g.OFM * p.s_pitch + 127) / 128 * 128; p.stg_bufs = 0;  // (stg_bufs stays 0: not the TMA-store path)
+  off += 2 * p.stg_bytes;
+  U->smem = (size_t)off + 1024;
+  if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
+  Phase2& P = p.phases[0];
+  P.nkb = 0; P.px = P.py = 0;
+  for (int cc = 0; cc < cch; cc++) {
+    KB2& kb = P.kb[P.nkb++];
+    kb.plane = (uint16_t)cc; kb.flags = KB_WAIT | KB_FREE; kb.a_off = 0; kb.w_k = cc * 128;  // weight rows cc*128 .. +127
+    kb.d_off = (uint32_t)p.planes[cc].smem_off >> 4;
+  }
+  {
+    const uint64_t dims[2] = {128, (uint64_t)(cch * 128)};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {128, 128};
+    int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
+    if (rc) { delete U; return rc; }
+  }
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1331,6 +1503,11 @@ void umma2_plan_destroy(Umma2Plan* U) { delete U; }
 
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   const Params2& p = U->p;
+  if (p.dthin == 2) {
+    snprintf(buf, n, "thin-output deconv: GEMM over (tap, channel) rows + shared-memory col2im, WT=%d R=%d (+1 halo ring, %d of 256 columns) planes=%dx%d smem=%zu tiles=%dx%d",
+             p.WT, p.R, (p.WT + 2) * (p.R + 2), p.nplanes, p.nsets, U->smem, p.tiles_x, p.tiles_y);
+    return buf;
+  }
   if (p.dthin) {
     snprintf(buf, n, "thin-output deconv: pixels on M, 9 shift blocks x N=16 (4 phases x 4 ch) WT=%d R=%d P=%d planes=%dx%d smem=%zu tiles=%dx%d",
              p.WT, p.R, p.P, p.nplanes, p.nsets, U->smem, p.tiles_x, p.tiles_y);
@@ -1417,10 +1594,11 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
 #endif
   // thin-input: 4 builder warps beside the light bias/ReLU epilogue (128 registers per thread suffice); 2 beside the threshold
   // epilogue, whose lock-step searches need ~170 registers to stay out of local memory
-  if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2, false><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (p.thin_in) umma2_conv_kernel<4, false><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (p.dthin) umma2_conv_kernel<1, true><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else umma2_conv_kernel<1, false><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2, 0><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.thin_in) umma2_conv_kernel<4, 0><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.dthin == 2) umma2_conv_kernel<1, 2><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.dthin) umma2_conv_kernel<1, 1><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else umma2_conv_kernel<1, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   FCB_CUDA_OK(cudaGetLastError());
   if (d_prof) {  // debugging aid: average clocks per tile and segment over the CTAs
     FCB_CUDA_OK(cudaStreamSynchronize(st));

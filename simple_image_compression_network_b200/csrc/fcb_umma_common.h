@@ -14,6 +14,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
 // bias_word >= 0: d_w carries the bias in byte 4*bias_word of every row and the producer writes a constant 1 there
 int umma2_plan_create_thin(const Geom& g, const int8_t* d_w /*[CB*128][128]*/, const EpiParams& epi, int num_sms, int bias_word, Umma2Plan** out);
 int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w /*[9*cch*16][128]*/, const EpiParams& epi, int num_sms, Umma2Plan** out);
+int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w /*[cch*128][128]*/, const EpiParams& epi, int num_sms, Umma2Plan** out);
 void umma2_plan_destroy(Umma2Plan* U);
 int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStream_t st);
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n);

@@ -317,6 +317,11 @@ def test_thin_output_deconv(ix, iy, c, ofm, reps, fcb_lib, oracle_mod, monkeypat
     assert L.plan.startswith("thin-output deconv"), L.plan
     got = L.run(inp["in_words"], reps)
     assert np.array_equal(got, want), f"[{L.plan}]: {_diff(got, want)}"
+    assert "col2im" in L.plan, L.plan
+    monkeypatch.setenv("FCB_U2_NO_DCOL", "1")  # the shift-block form (pixels on the MMA M axis)
+    L1 = _layer(d, inp)
+    assert L1.plan.startswith("thin-output deconv: pixels on M"), L1.plan
+    assert np.array_equal(L1.run(inp["in_words"], reps), want), f"[{L1.plan}]"
     monkeypatch.setenv("FCB_U2_NO_DTHIN", "1")
     L2 = _layer(d, inp)
     assert not L2.plan.startswith("thin-output deconv")

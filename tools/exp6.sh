@@ -1,2 +1,3 @@
-python -m pytest tests -m gpu -x -q -k "xn or xnor or random" 2>&1 | tail -3
-python tools/bench_layers.py --images 1024 --only cfg3 --check 2>&1 | cut -c1-260
+python -m pytest tests -m gpu -x -q -k "thin_output or dc_ or random or net" 2>&1 | tail -12 | cut -c1-400
+python tools/bench_layers.py --images 64 --only L7 --check 2>&1 | cut -c1-400
+FCB_U2_NO_DCOL=1 python tools/bench_layers.py --images 64 --only L7 2>&1 | cut -c1-100,250-400
