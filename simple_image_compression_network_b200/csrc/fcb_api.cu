@@ -140,9 +140,13 @@ struct fcb_net {
   std::vector<fcb_layer*> layers;
   std::vector<void*> bufs;  // intermediate activations, one per layer boundary, sized for cap_imgs
   size_t cap_imgs = 0;
-  void* s_in = nullptr;
-  void* s_out = nullptr;
+  // host-buffer entry point: two staging slots and three streams (H2D | layers | D2H) so the copies of chunk k+1 / k-1 run
+  // under the kernels of chunk k
+  void* s_in[2] = {nullptr, nullptr};
+  void* s_out[2] = {nullptr, nullptr};
   size_t s_imgs = 0;
+  cudaStream_t st_in = nullptr, st_run = nullptr, st_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int device = 0;
 };
 
@@ -544,7 +548,15 @@ void fcb_net_destroy(fcb_net* N) {
   if (!N) return;
   cudaSetDevice(N->device);
   for (void* b : N->bufs) cudaFree(b);
-  cudaFree(N->s_in); cudaFree(N->s_out);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(N->s_in[i]); cudaFree(N->s_out[i]);
+    if (N->ev_in[i]) cudaEventDestroy(N->ev_in[i]);
+    if (N->ev_run[i]) cudaEventDestroy(N->ev_run[i]);
+    if (N->ev_out[i]) cudaEventDestroy(N->ev_out[i]);
+  }
+  if (N->st_in) cudaStreamDestroy(N->st_in);
+  if (N->st_run) cudaStreamDestroy(N->st_run);
+  if (N->st_out) cudaStreamDestroy(N->st_out);
   delete N;
 }
 
@@ -589,23 +601,50 @@ int fcb_net_run(fcb_net* N, const void* in_words, void* out_words, uint32_t numR
   if (!numReps) return FCB_OK;
   FCB_CUDA_OK(cudaSetDevice(N->device));
   const size_t in_b = N->layers.front()->g.in_img_bytes, out_b = N->layers.back()->g.out_img_bytes;
-  size_t chunk = std::max<size_t>(1, ((size_t)256 << 20) / std::max(in_b, out_b));
+  // chunks of <= 64 MiB of input or output: small enough that the pipeline fills quickly, large enough to hide launch overheads
+  size_t chunk = std::max<size_t>(1, ((size_t)64 << 20) / std::max(in_b, out_b));
+  if (getenv("FCB_NET_CHUNK")) chunk = std::max(1, atoi(getenv("FCB_NET_CHUNK")));  // tests: force many small chunks
   chunk = std::min<size_t>(chunk, numReps);
   if (N->s_imgs < chunk) {
-    cudaFree(N->s_in); cudaFree(N->s_out);
-    N->s_in = N->s_out = nullptr;
-    FCB_CUDA_OK(cudaMalloc(&N->s_in, in_b * chunk));
-    FCB_CUDA_OK(cudaMalloc(&N->s_out, out_b * chunk));
+    for (int i = 0; i < 2; i++) {
+      cudaFree(N->s_in[i]); cudaFree(N->s_out[i]);
+      N->s_in[i] = N->s_out[i] = nullptr;
+      FCB_CUDA_OK(cudaMalloc(&N->s_in[i], in_b * chunk));
+      FCB_CUDA_OK(cudaMalloc(&N->s_out[i], out_b * chunk));
+      if (!N->ev_in[i]) {
+        FCB_CUDA_OK(cudaEventCreateWithFlags(&N->ev_in[i], cudaEventDisableTiming));
+        FCB_CUDA_OK(cudaEventCreateWithFlags(&N->ev_run[i], cudaEventDisableTiming));
+        FCB_CUDA_OK(cudaEventCreateWithFlags(&N->ev_out[i], cudaEventDisableTiming));
+      }
+    }
+    if (!N->st_in) {
+      FCB_CUDA_OK(cudaStreamCreateWithFlags(&N->st_in, cudaStreamNonBlocking));
+      FCB_CUDA_OK(cudaStreamCreateWithFlags(&N->st_run, cudaStreamNonBlocking));
+      FCB_CUDA_OK(cudaStreamCreateWithFlags(&N->st_out, cudaStreamNonBlocking));
+    }
     N->s_imgs = chunk;
   }
-  for (size_t n0 = 0; n0 < numReps; n0 += chunk) {
-    const size_t nb = std::min<size_t>(chunk, numReps - n0);
-    FCB_CUDA_OK(cudaMemcpyAsync(N->s_in, (const uint8_t*)in_words + n0 * in_b, nb * in_b, cudaMemcpyHostToDevice, 0));
-    int rc = fcb_net_run_device(N, N->s_in, N->s_out, (uint32_t)nb, nullptr);
+  size_t k = 0;
+  for (size_t n0 = 0; n0 < numReps; n0 += chunk, k++) {
+    const size_t nb = std::min(chunk, (size_t)numReps - n0);
+    const int slot = (int)(k & 1);
+    // H2D of chunk k: its input slot was last read by the layers of chunk k-2
+    if (k >= 2) FCB_CUDA_OK(cudaStreamWaitEvent(N->st_in, N->ev_run[slot], 0));
+    FCB_CUDA_OK(cudaMemcpyAsync(N->s_in[slot], (const uint8_t*)in_words + n0 * in_b, nb * in_b, cudaMemcpyHostToDevice, N->st_in));
+    FCB_CUDA_OK(cudaEventRecord(N->ev_in[slot], N->st_in));
+    // layers of chunk k: need its input, and its output slot drained by the D2H of chunk k-2
+    FCB_CUDA_OK(cudaStreamWaitEvent(N->st_run, N->ev_in[slot], 0));
+    if (k >= 2) FCB_CUDA_OK(cudaStreamWaitEvent(N->st_run, N->ev_out[slot], 0));
+    int rc = fcb_net_run_device(N, N->s_in[slot], N->s_out[slot], (uint32_t)nb, N->st_run);
     if (rc) return rc;
-    FCB_CUDA_OK(cudaMemcpyAsync((uint8_t*)out_words + n0 * out_b, N->s_out, nb * out_b, cudaMemcpyDeviceToHost, 0));
+    FCB_CUDA_OK(cudaEventRecord(N->ev_run[slot], N->st_run));
+    // D2H of chunk k
+    FCB_CUDA_OK(cudaStreamWaitEvent(N->st_out, N->ev_run[slot], 0));
+    FCB_CUDA_OK(cudaMemcpyAsync((uint8_t*)out_words + n0 * out_b, N->s_out[slot], nb * out_b, cudaMemcpyDeviceToHost, N->st_out));
+    FCB_CUDA_OK(cudaEventRecord(N->ev_out[slot], N->st_out));
   }
-  FCB_CUDA_OK(cudaStreamSynchronize(0));
+  FCB_CUDA_OK(cudaStreamSynchronize(N->st_out));
+  FCB_CUDA_OK(cudaStreamSynchronize(N->st_run));
   return FCB_OK;
 }
 

@@ -109,6 +109,10 @@ class Net:
         _lib.check(_lib.lib().fcb_net_run(self._h, _ptr(x), _ptr(out), num_reps))
         return out
 
+    def run_raw(self, in_ptr: int, out_ptr: int, num_reps: int) -> None:
+        """Host pointers (e.g. pinned memory): H2D, the layers and D2H of consecutive chunks overlap on three streams."""
+        _lib.check(_lib.lib().fcb_net_run(self._h, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), num_reps))
+
     def run_device(self, d_in: int, d_out: int, num_reps: int, stream: int = 0) -> None:
         _lib.check(_lib.lib().fcb_net_run_device(self._h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), num_reps,
                                                  ctypes.c_void_p(stream)))

@@ -398,3 +398,20 @@ def test_random_shapes_match_oracle(seed, fcb_lib, oracle_mod):
         plans.add(L.plan.split(" ")[0] + ":" + L.engine)
     assert ran >= 25, f"only {ran} of 40 random layers were accepted"
     assert len(plans) >= 4, plans
+
+
+def test_net_host_pipeline_many_chunks(fcb_lib, oracle_mod, monkeypatch):
+    """fcb_net_run with the batch cut into many chunks (H2D / layers / D2H of neighbouring chunks overlap on three streams and two
+    staging slots): every image must still come out in place and bit-exact."""
+    from simple_image_compression_network_b200.layer import Net
+    monkeypatch.setenv("FCB_NET_CHUNK", "2")
+    d1 = cases.CASES["c2d_e"]
+    d2 = dataclasses.replace(cases.CASES["dc_c"], ifm_x=24, ifm_y=16)
+    reps = 11  # 6 chunks, the last one short
+    i1, i2 = cases.make_inputs(d1, num_reps=reps, relu_range=True), cases.make_inputs(d2, seed_shift=9)
+    net = Net([_layer(d1, i1), _layer(d2, i2)])
+    got = net.run(i1["in_words"], reps)
+    mid = oracle_mod.run_layer(d1, i1["in_words"], i1["weights"], None, i1["bias"], num_reps=reps)
+    want = oracle_mod.run_layer(d2, mid, i2["weights"], None, i2["bias"], num_reps=reps)
+    assert np.array_equal(got, want)
+    assert np.array_equal(net.run(i1["in_words"], reps), want)  # slots and events are reusable

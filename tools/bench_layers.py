@@ -95,6 +95,19 @@ if __name__ == "__main__":
     ms = timed(lambda: net.run_device(x.data_ptr(), y.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
     print(json.dumps(dict(layer="eight_layers_net", images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3, 1),
                           TOPs_nonzero=round(2 * 28.94e9 * n / ms / 1e9, 1))), flush=True)
+    # the same network through the host-buffer entry point (pinned memory; H2D + 8 layers + D2H, chunks pipelined on 3 streams)
+    n = a.images * 8
+    hx = torch.empty(n * net.in_bytes, dtype=torch.uint8, pin_memory=True)
+    hy = torch.empty(n * net.out_bytes, dtype=torch.uint8, pin_memory=True)
+    hx.random_(0, 256)
+    import time
+    net.run_raw(hx.data_ptr(), hy.data_ptr(), n)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        net.run_raw(hx.data_ptr(), hy.data_ptr(), n)
+    dt = (time.perf_counter() - t0) / 3
+    print(json.dumps(dict(layer="eight_layers_net_e2e_host_buffers", images=n, ms=round(dt * 1e3, 3), img_s=round(n / dt, 1),
+                          pcie_GBs=round(n * (net.in_bytes + net.out_bytes) / dt / 1e9, 1))), flush=True)
     # BASELINE.json config 5b: analysis-transform-shaped stack [K3 S1 P1 conv -> 255 thresholds (u8) -> 2x2 max pool] x 4,
     # channels 3 -> 128 -> 128 -> 128 -> 192 on 768x512; 5a = layers 0-3 of the reference net
     def stage(c, ofm, x, y, simd, pe):
