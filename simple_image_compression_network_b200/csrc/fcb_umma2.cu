@@ -76,7 +76,6 @@ struct Params2 {
   // thin-input mode (input word = one 4-byte pixel of <= 4 lanes, e.g. the C = 3 first layer): warp 10 builds the tile's
   // im2col rows in shared memory (one 128-byte SWIZZLE_128B row per output pixel, word (ky*KX + kx) = input pixel of that tap)
   // from a raw patch fetched by TMA; the layer is then ONE K-block of `ksteps` MMAs per tile with resident weights.
-  int cscale, spin;
   // swapped orientation (thin-input + bias/ReLU): pixels on the MMA M axis (D[pixel][channel]) so an epilogue thread owns ONE
   // pixel and assembles its 128-byte output word with 16-byte shared-memory stores (the tile is store-bound: K is tiny)
   int swap;
@@ -311,7 +310,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           mbar_arrive_expect_tx(&pfull[b], (uint32_t)(p.BWp * p.BHp * 4));
           // the box starts at a multiple of 4 pixels: an un-swizzled TMA box must start 16-byte aligned in its innermost dimension
           // (anything else is an illegal instruction: tools/tma_probe.cu, profiles/r01_tma_inner_alignment_probe.log)
-          tma_load_3d(smem + p.patch_off + b * p.patch_bytes, &tmA0, &pfull[b], ((p.S * ti.tx * p.WT - p.pad) & ~3) * p.cscale,
+          tma_load_3d(smem + p.patch_off + b * p.patch_bytes, &tmA0, &pfull[b], (p.S * ti.tx * p.WT - p.pad) & ~3,
                       p.S * ti.ty * p.R - p.pad, ti.img);
         }
       }
@@ -1536,19 +1535,10 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   for (int m = 0; m < 2; m++) {
     int rc;
     if (p.thin_in) {  // raw image of 4-byte pixels; the patch of a tile is one box, borders zero-filled
-      if (getenv("FCB_THIN_U8")) {
-        const uint64_t dims[3] = {X * 4, Y, (uint64_t)n_images};
-        const uint64_t strides[2] = {X * 4, X * Y * 4};
-        const uint32_t box[3] = {(uint32_t)p.BWp * 4, (uint32_t)p.BHp, 1};
-        p.cscale = 4;
-        rc = umma_encode_map_ex(&tmA[m], const_cast<void*>(d_in), 1, 0, 3, dims, strides, box);
-      } else {
       const uint64_t dims[3] = {X, Y, (uint64_t)n_images};
       const uint64_t strides[2] = {X * 4, X * Y * 4};
       const uint32_t box[3] = {(uint32_t)p.BWp, (uint32_t)p.BHp, 1};
-      p.cscale = 1;
       rc = umma_encode_map_ex(&tmA[m], const_cast<void*>(d_in), 4, 0, 3, dims, strides, box);
-      }
     } else if (p.stride2) {
       const uint64_t dims[5] = {2 * C, X / 2, 2, Y / 2, (uint64_t)n_images};
       const uint64_t strides[4] = {2 * C, X * C, 2 * X * C, X * Y * C};

@@ -1,9 +1,13 @@
+"""Run ONE parity case on the GPU and print where it differs from the oracle (pixels / channels of the mismatches).
+    python tools/check_case.py <name>      name = a key of oracle/cases.py CASES or of tests/test_gpu_parity.py::_thin_cases()"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from oracle import cases, oracle
 from simple_image_compression_network_b200.layer import ConvLayer
+
 name = sys.argv[1] if len(sys.argv) > 1 else "c2d_a"
 reps = 1
 if name in cases.CASES:
@@ -21,9 +25,9 @@ try:
     bad = np.flatnonzero(got != want)
     print("mismatches", bad.size, "of", got.size, bad[:12], got[bad[:12]], want[bad[:12]])
     if bad.size:
-        wb = d.ofm_ch
+        wb = max(1, got.size // (d.ofm_x * d.ofm_y * reps))
         px = bad // wb
-        print("bad pixels: count", np.unique(px).size, "of", got.size // wb, "first", np.unique(px)[:20], "last", np.unique(px)[-5:])
-        print("bad channels:", np.unique(bad % wb)[:40])
+        print("bad pixels: count", np.unique(px).size, "first", np.unique(px)[:20], "last", np.unique(px)[-5:])
+        print("bad byte-in-word:", np.unique(bad % wb)[:40])
 except Exception as e:
     print("FAILED after", time.time() - t0, str(e)[:300], flush=True)
