@@ -80,6 +80,9 @@ struct Params2 {
   // pixel and assembles its 128-byte output word with 16-byte shared-memory stores (the tile is store-bound: K is tiny)
   int swap;
   uint32_t idesc_swap;
+  // warp-local stores (swap + alternating groups + WT % 32 == 0): a warp owns whole 128-byte rows of 32 consecutive pixels of one
+  // tile row, so it issues its own TMA store per 128-pixel block and the epilogue needs no block-wide barrier at all
+  int wl;
   // alternating epilogue groups (staged paths with two accumulator stages): warps 2..5 own accumulator stage / staging buffer 0,
   // warps 6..9 stage 1, so one group's barriers, fences and store issue overlap the other group's TMEM reads (64 B/clk/SM:
   // ~2048 clocks for a 256 x 128 int32 tile -- the floor of a store-bound layer)
@@ -610,7 +613,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             if (p.stg_bufs == 2 && !alt) bulk_wait_read<1>();
             else bulk_wait_read<0>();
           }
-          EPI_BAR();
+          if (p.wl) __syncwarp();
+          else EPI_BAR();
           PROF_T(2);
           // items = (128-pixel block, 32-channel block), block-major; this warp takes every `its`-th item from `it0`
           const int cpb = p.CB * 4, nitems = (p.debug & 8) ? 0 : (p.NPX / 128) * cpb;
@@ -639,6 +643,14 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             sts_v4(row + ((c0 ^ m7) << 4), w[0], w[1], w[2], w[3]);
             sts_v4(row + (((c0 + 1) ^ m7) << 4), w[4], w[5], w[6], w[7]);
           };
+          // warp-local mode: after the last channel block of a 128-pixel block this warp's 32 rows are complete
+          auto store_block = [&](int blk) {
+            fence_proxy_async();
+            __syncwarp();
+            const int m0 = blk * 128 + q * 32, rr = m0 / p.WT, xo = m0 - rr * p.WT;
+            if (lane == 0 && rr < vrows)
+              for (int cb = 0; cb < p.CB; cb++) tma_store_4d(&tmO, stg + (cb * p.NPX + m0) * 128, cb * 128, pm.x0 + xo, pm.y0 + rr, img);
+          };
           const int it0 = alt ? 0 : half, its = alt ? 1 : 2;
           if (it0 < nitems) {  // software pipeline: the next item's TMEM load is in flight while this one is packed
             uint32_t va[32], vb[32];
@@ -652,11 +664,13 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               blk = blk_n; cbk = cbk_n;
               if (left > 0) { advance(); tmem_ld32(tacc + (uint32_t)(blk_n * p.CB * 128 + cbk_n * 32), vb); }
               process(blk, cbk, va);
+              if (p.wl && cbk == cpb - 1) store_block(blk);
               if (left-- <= 0) break;
               tmem_ld_wait();
               blk = blk_n; cbk = cbk_n;
               if (left > 0) { advance(); tmem_ld32(tacc + (uint32_t)(blk_n * p.CB * 128 + cbk_n * 32), va); }
               process(blk, cbk, vb);
+              if (p.wl && cbk == cpb - 1) store_block(blk);
               if (left-- <= 0) break;
             }
           }
@@ -664,6 +678,11 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (p.wl) {
+            if (lane == 0) bulk_commit();
+            PROF_T(6);
+            continue;
+          }
           fence_proxy_async();
           PROF_T(4);
           EPI_BAR();
@@ -1268,7 +1287,8 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   for (int NPX = 256; NPX >= (want_swap ? 128 : 64); NPX /= 2) {
     if (CB * NPX > 512) continue;
     for (int WT = step; WT <= std::min(PX + step - 1, 256); WT += step) {
-      if (want_swap && (WT % 8)) continue;  // swizzled staging rows: every tile row starts on a 1024-byte boundary
+      // swizzled staging rows: every tile row starts on a 1024-byte boundary; rows of whole 32-pixel segments allow warp-local stores
+      if (want_swap && (WT % (PX >= 32 ? 32 : 8))) continue;
       const int BWp = (s * (WT - 1) + g.KX + 3 + 3) / 4 * 4;  // + up to 3 pixels of alignment slack on the left
       if (BWp > 256) continue;
       const int budget = (g.pool == 2 && (WT % 8)) ? NPX - 8 : NPX;  // pooled epilogue reads 8-column groups from row starts
@@ -1331,6 +1351,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   off += p.stg_bufs * p.stg_bytes;
   if (p.swap && !p.stg_bufs) p.swap = 0;
   p.epi_alt = (p.stg_bufs == 2 && p.acc_stages == 2 && !getenv("FCB_U2_NO_ALT")) ? 1 : 0;
+  p.wl = (p.swap && p.epi_alt && bWT % 32 == 0 && !getenv("FCB_U2_NO_WL")) ? 1 : 0;
   p.patch_off = off; off += (int)U2_NPB * p.patch_bytes;
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
@@ -1515,7 +1536,7 @@ const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   if (p.thin_in) {
     snprintf(buf, n, "smem-im2col (thin input, K=%d B%s, %d MMA/tile, weights resident) WT=%d R=%d NPX=%d CB=%d%s patch=%dx%d smem=%zu tiles=%dx%d",
              p.nw * 4, p.bias_word >= 0 ? " + bias row" : "", p.swap ? p.ksteps * (p.NPX / 128) : p.ksteps * p.CB, p.WT, p.R, p.NPX, p.CB,
-             p.thr_off >= 0 ? " thr@smem" : (p.swap ? " pixel-major tma-store" : p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.BWp, p.BHp, U->smem,
+             p.thr_off >= 0 ? " thr@smem" : (p.wl ? " pixel-major warp-local tma-store" : p.swap ? " pixel-major tma-store" : p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.BWp, p.BHp, U->smem,
              p.tiles_x, p.tiles_y);
     return buf;
   }
@@ -1564,7 +1585,7 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
     } else {
       const uint64_t dims[4] = {F, OX, OY, (uint64_t)n_images};
       const uint64_t strides[3] = {F, OX * F, OX * OY * F};
-      const uint32_t box[4] = {128, (uint32_t)p.WT, 1, 1};
+      const uint32_t box[4] = {128, (uint32_t)(p.wl ? 32 : p.WT), 1, 1};
       rc = umma_encode_map_ex(&tmO, d_out, 1, p.swap ? 128 : 0, 4, dims, strides, box);
     }
     if (rc) return rc;
