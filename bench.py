@@ -244,8 +244,8 @@ def run_ours(args):
     achieved = ops / (kernel_ms / 1000.0) / 1e12
     peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     # DRAM traffic of this kernel from the committed `ncu --set full` capture (profiles/r01_conv1_ncu_full_summary_latest.txt:
-    # 3.235 GB read + 0.788 GB written for a 256-image launch = 15.72 MB per image), scaled to this launch's image count
-    traffic = (3.235386e9 + 0.788159e9) / 256.0 * n_img if layer.plan.startswith("resident-planes") else None
+    # 3.229 GB read + 0.786 GB written for a 256-image launch = 15.68 MB per image), scaled to this launch's image count
+    traffic = (3.228541e9 + 0.785940e9) / 256.0 * n_img if layer.plan.startswith("resident-planes") else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write of a 256-image launch, per image x images of this launch",
                 "kernel": layer.plan, "kernel_ms": kernel_ms,
