@@ -117,6 +117,8 @@ struct fcb_layer {
   int8_t* d_bias = nullptr;
   int32_t* d_thr = nullptr;
   int32_t* d_thr_cm = nullptr;
+  uint8_t* d_thr_lut = nullptr;
+  int32_t* d_thr_lo = nullptr;  // [2][OFMpad]: lo, then sh
   EpiParams epi{};
   DirectParams dp{};
   size_t smem = 0;
@@ -183,7 +185,7 @@ void fcb_layer_destroy(fcb_layer* L) {
   if (!L) return;
   cudaSetDevice(L->device);
   if (L->umma) umma_plan_destroy(L->umma);
-  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_thr_cm); cudaFree(L->d_scratch);
+  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_thr_cm); cudaFree(L->d_thr_lut); cudaFree(L->d_thr_lo); cudaFree(L->d_scratch);
   for (int i = 0; i < 2; i++) {
     cudaFree(L->s_in[i]); cudaFree(L->s_out[i]);
     if (L->s_stream[i]) cudaStreamDestroy(L->s_stream[i]);
@@ -212,6 +214,43 @@ static int upload_thresholds(fcb_layer* L, const std::vector<std::vector<int32_t
   FCB_CUDA_OK(cudaMalloc(&L->d_thr_cm, TC.size() * sizeof(int32_t)));
   FCB_CUDA_OK(cudaMemcpy(L->d_thr_cm, TC.data(), TC.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   L->epi.thr = L->d_thr; L->epi.thr_cm = L->d_thr_cm; L->epi.thr_n = tn; L->epi.thr_stride = tstride;
+  // bucket LUT for the 255-threshold class of tables (see EpiParams): 256 buckets of width 2^sh from the smallest threshold
+  cudaFree(L->d_thr_lut); cudaFree(L->d_thr_lo);
+  L->d_thr_lut = nullptr; L->d_thr_lo = nullptr;
+  L->epi.thr_lut = nullptr; L->epi.thr_lo = L->epi.thr_sh = nullptr;
+  if (nth >= 64 && nth <= 255) {
+    std::vector<uint8_t> lut((size_t)tstride * 256, 0);
+    std::vector<int32_t> losh((size_t)2 * tstride, 0);
+    bool ok = true;
+    int worst = 0;
+    for (int ch = 0; ch < ofm && ok; ch++) {
+      const std::vector<int32_t>& r = rows[ch];
+      const int64_t lo = r.front(), span = (int64_t)r.back() - lo;
+      if (lo < -(1ll << 30) || r.back() > (1ll << 30)) { ok = false; break; }
+      int sh = 0;
+      while ((span >> sh) > 255) sh++;
+      losh[ch] = (int32_t)lo; losh[tstride + ch] = sh;
+      int idx = 0;
+      for (int b = 0; b < 256; b++) {
+        const int64_t start = lo + ((int64_t)b << sh);
+        while (idx < nth && r[idx] < start) idx++;
+        lut[(size_t)ch * 256 + b] = (uint8_t)idx;
+        int64_t end = lo + ((int64_t)(b + 1) << sh);
+        int inside = 0;
+        for (int j = idx; j < nth && (b == 255 || r[j] < end); j++) inside++;
+        worst = std::max(worst, inside);
+        if (inside > 15) { ok = false; break; }
+      }
+    }
+    if (ok) {
+      FCB_CUDA_OK(cudaMalloc(&L->d_thr_lut, lut.size()));
+      FCB_CUDA_OK(cudaMemcpy(L->d_thr_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
+      FCB_CUDA_OK(cudaMalloc(&L->d_thr_lo, losh.size() * sizeof(int32_t)));
+      FCB_CUDA_OK(cudaMemcpy(L->d_thr_lo, losh.data(), losh.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      L->epi.thr_lut_levels = worst <= 7 ? 3 : 4;
+      L->epi.thr_lut = L->d_thr_lut; L->epi.thr_lo = L->d_thr_lo; L->epi.thr_sh = L->d_thr_lo + tstride;
+    }
+  }
   return FCB_OK;
 }
 

@@ -130,6 +130,40 @@ __device__ __forceinline__ void activate_thr_hybrid(const EpiParams& e, uint32_t
   for (int i = 0; i < N; i++) out[i] = thr_finish(e, pos[i]);
 }
 
+// Bucket-LUT search over a FULL-depth shared-memory table (threshold-major, row i = sorted index i): the LUT byte gives the sorted
+// index the accumulator's bucket starts at (clamped so that the 2^levels-wide window stays inside the 2^D - 1 rows); `levels`
+// binary levels resolve the <= 2^levels - 1 thresholds inside the bucket.  Thresholds of later buckets are larger than every value of this bucket, so
+// probing past the bucket's end can only compare false: exact for all four comp:: functors.
+template <int N>
+__device__ __forceinline__ void activate_thr_lut(const EpiParams& e, uint32_t top_saddr, int row_shift, uint32_t lut_saddr /*this channel's 256 bytes*/,
+                                                 int32_t lo, int sh, const int32_t (&acc)[N], uint32_t (&out)[N]) {
+  int32_t a[N];
+  uint32_t posb[N];
+  const uint32_t base = top_saddr - (1u << row_shift);
+  const int levels = e.thr_lut_levels, pmax = e.thr_n + 1 - (1 << levels);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    a[i] = wrap_ta(acc[i], e.acc_bits, e.acc_signed);
+    const int b = min(max((a[i] - lo) >> sh, 0), 255);
+    uint32_t p0;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(p0) : "r"(lut_saddr + (uint32_t)b));
+    posb[i] = base + ((uint32_t)min((int)p0, pmax) << row_shift);
+  }
+  const bool strict = (e.cmp == FCB_CMP_LESS) || (e.cmp == FCB_CMP_GREATER_EQUAL);
+#pragma unroll 1
+  for (int l = 0; l < levels; l++) {
+    const uint32_t stepb = ((1u << (levels - 1)) >> l) << row_shift;
+    int32_t tv[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) tv[i] = lds_s32(posb[i] + stepb);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (strict ? (tv[i] < a[i]) : (tv[i] <= a[i])) posb[i] += stepb;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) out[i] = thr_finish(e, (int)((posb[i] - base) >> row_shift));
+}
+
 // Store one output lane per thread of a warp: lane `l` holds channel ch0 + l of one pixel.
 // `word` points at that pixel's output word; sub-byte lanes are merged across the warp.
 // Must be called by all 32 lanes (uses shuffles); `valid` masks channels >= OFM.

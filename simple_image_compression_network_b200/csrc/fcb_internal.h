@@ -40,6 +40,13 @@ struct EpiParams {
   const int32_t* thr;    // [thr_n][thr_stride]: threshold i of channel ch at thr[i*thr_stride + ch]; per channel sorted
                          // ascending, wrapped to TA, padded with INT32_MAX up to thr_n = 2^k - 1 entries (FCB_ACT_THRESHOLDS)
   int thr_n, thr_stride;
+  // bucket LUT (optional, NULL if a bucket would hold more than 15 thresholds): for channel ch, bucket b = clamp((a - lo[ch]) >> sh[ch], 0, 255)
+  // starts at sorted index lut[ch*256 + b] = #thresholds below the bucket's first value; at most 2^levels - 1 thresholds lie inside it, so
+  // `thr_lut_levels` binary levels finish the search
+  const uint8_t* thr_lut;
+  int thr_lut_levels;  // 3 (<= 7 thresholds per bucket) or 4 (<= 15)
+  const int32_t* thr_lo;
+  const int32_t* thr_sh;
   const int32_t* thr_cm; // [thr_stride][thr_n + 1] channel-major copy (same values, INT32_MAX padded): the bottom levels of a
                          // search are one aligned 16-byte group of it
 };

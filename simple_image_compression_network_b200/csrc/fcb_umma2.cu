@@ -68,6 +68,7 @@ struct Params2 {
   int chb;      // channel blocks the grid is split into (CTA c serves channel block c % chb); > 1 only with smem thresholds
   int thr_off;  // smem offset of the top `thr_top` search levels of this CTA's channels, [2^thr_top - 1][CB*128] (-1: none)
   int thr_top;
+  int lut_off;  // smem offset of the bucket LUT of this CTA's channels, [CB*128][256] bytes (-1: none; needs thr_top == all levels)
   int nsets, set_bytes;  // plane sets (double buffering of the input patch across tiles when shared memory allows)
   int w_off, bar_off, stage_off;  // stage_off: 8 x 256 B staging rows of the thin-output epilogue (OFM <= 8)
   // staged epilogue: the tile's output words are assembled in shared memory ([CB][NPX] rows of 128 B, stg_bufs buffers) and
@@ -264,6 +265,11 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   }
 
+  if (p.lut_off >= 0) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.epi.thr_lut + (size_t)chbase * 256);
+    uint4* dst = reinterpret_cast<uint4*>(smem + p.lut_off);
+    for (int idx = threadIdx.x; idx < p.CB * 128 * 16; idx += blockDim.x) dst[idx] = __ldg(src + idx);
+  }
   if (p.swap)  // bias bytes of this CTA's channels (read as packed words by every epilogue thread)
     for (int idx = threadIdx.x; idx < p.CB * 128; idx += blockDim.x) smem[p.stage_off + idx] = idx < p.OFM ? (uint8_t)p.epi.bias[idx] : 0;
   if (warp == 0 && lane == 0) {
@@ -797,6 +803,10 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const uint32_t top_s = smem_u32(smem + (p.thr_off >= 0 ? p.thr_off : 0)) + 4u * (uint32_t)(cb * 128 + q * 32 + lane);
           const int32_t* row_cm = p.epi.thr_cm + (size_t)chs * (p.epi.thr_n + 1);
           const bool hybrid = p.thr_off >= 0;
+          const bool use_lut = p.lut_off >= 0;
+          const uint32_t lut_s = smem_u32(smem + (use_lut ? p.lut_off : 0)) + 256u * (uint32_t)(cb * 128 + q * 32 + lane);
+          const int32_t lut_lo = use_lut ? p.epi.thr_lo[chs] : 0;
+          const int lut_sh = use_lut ? p.epi.thr_sh[chs] : 0;
           const int row_shift = p.CB == 2 ? 10 : 9;  // log2(CB * 128 channels * 4 bytes)
           const bool chv = ch < p.OFM;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
@@ -846,7 +856,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                       uint32_t o8[8];
 #pragma unroll
                       for (int j = 0; j < 8; j++) a8[j] = a16[8 * h8 + j];
-                      activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, a8, o8);
+                      if (use_lut) activate_thr_lut<8>(p.epi, top_s, row_shift, lut_s, lut_lo, lut_sh, a8, o8);
+                      else activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, a8, o8);
 #pragma unroll
                       for (int j = 0; j < 8; j++) o16[8 * h8 + j] = o8[j];
                     }
@@ -935,6 +946,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   if (p.debug & 16) {
 #pragma unroll
                     for (int w = 0; w < 8; w++) pooled[w] = (uint32_t)m8[w] & 0xFFu;
+                  } else if (use_lut) {
+                    activate_thr_lut<8>(p.epi, top_s, row_shift, lut_s, lut_lo, lut_sh, m8, pooled);
                   } else if (hybrid) {
                     activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, m8, pooled);
                   } else {
@@ -1185,6 +1198,17 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     p.thr_off = off;
     off += thr_bytes;
   }
+  p.lut_off = -1;
+  {
+    int D = 0;
+    while ((1 << D) < epi.thr_n + 1) D++;
+    const int lut_bytes = CBe * 128 * 256;
+    if (thr_bytes && thr_top == D && epi.thr_lut && !getenv("FCB_U2_NO_LUT") && (size_t)off + lut_bytes + 2048 <= (size_t)227 * 1024) {
+      off = (off + 127) & ~127;
+      p.lut_off = off;
+      off += lut_bytes;
+    }
+  }
   // staged epilogue (bias + ReLU on whole 128-channel blocks): two buffers if they fit, else one, else the register path
   p.stg_off = 0; p.stg_bufs = 0; p.stg_bytes = CBe * bNPX * 128;
   const bool fast_epi = epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && g.pool <= 1 && g.OFM % 128 == 0 &&
@@ -1340,6 +1364,29 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.stage_off = off; off += 8 * 256;
   p.thr_off = -1; p.thr_top = thr_top;
   if (thr_bytes) { off = (off + 127) & ~127; p.thr_off = off; off += thr_bytes; }
+  p.lut_off = -1;
+  {
+    int D = 0;
+    while ((1 << D) < epi.thr_n + 1) D++;
+    const int lut_bytes = CB * 128 * 256;
+    if (thr_bytes && thr_top == D && epi.thr_lut && !getenv("FCB_U2_NO_LUT")) {
+      const size_t rest = (size_t)U2_NPB * p.patch_bytes + 2048;
+      if ((size_t)off + lut_bytes + rest > (size_t)227 * 1024 && p.nsets == 2) {
+        // single-buffer the im2col rows to make room: the layer is bound by its threshold epilogue, not by the builders
+        const int saved = p.set_bytes;
+        if ((size_t)off - saved + lut_bytes + rest <= (size_t)227 * 1024) {
+          p.nsets = 1;
+          p.w_off -= saved; p.bar_off -= saved; p.stage_off -= saved; p.thr_off -= saved;
+          off -= saved;
+        }
+      }
+      if ((size_t)off + lut_bytes + rest <= (size_t)227 * 1024) {
+        off = (off + 127) & ~127;
+        p.lut_off = off;
+        off += lut_bytes;
+      }
+    }
+  }
   p.stg_bytes = CB * bNPX * 128;
   const bool fast_epi = epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && g.pool <= 1 && g.OFM % 128 == 0 &&
                         g.out_word_bytes == (size_t)g.OFM;
@@ -1420,7 +1467,7 @@ int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& e
   p.bar_off = off; off += (2 * p.wstages + 2 * cch * 2 + 4 + 1 + 2 * (int)U2_NPB + 1) * 8;
   off = (off + 15) & ~15;
   p.stage_off = off; off += 8 * 256;
-  p.thr_off = -1;
+  p.thr_off = -1; p.lut_off = -1;
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
   // K-blocks: (channel chunk, shift); shift s = (offy + 1) * 3 + (offx + 1)
@@ -1494,7 +1541,7 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.bar_off = off; off += (2 * p.wstages + 2 * cch * 2 + 4 + 1 + 2 * (int)U2_NPB + 1) * 8;
   off = (off + 15) & ~15;
   p.stage_off = off; off += 8 * 256;
-  p.thr_off = -1;
+  p.thr_off = -1; p.lut_off = -1;
   off = (off + 127) & ~127;
   p.stg_off = off; p.stg_bytes = (25 * g.OFM * p.s_pitch + 127) / 128 * 128; p.stg_bufs = 0;  // (stg_bufs stays 0: not the TMA-store path)
   off += 2 * p.stg_bytes;
@@ -1536,12 +1583,12 @@ const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
   if (p.thin_in) {
     snprintf(buf, n, "smem-im2col (thin input, K=%d B%s, %d MMA/tile, weights resident) WT=%d R=%d NPX=%d CB=%d%s patch=%dx%d smem=%zu tiles=%dx%d",
              p.nw * 4, p.bias_word >= 0 ? " + bias row" : "", p.swap ? p.ksteps * (p.NPX / 128) : p.ksteps * p.CB, p.WT, p.R, p.NPX, p.CB,
-             p.thr_off >= 0 ? " thr@smem" : (p.wl ? " pixel-major warp-local tma-store" : p.swap ? " pixel-major tma-store" : p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.BWp, p.BHp, U->smem,
+             p.lut_off >= 0 ? " thr@smem + bucket LUT" : p.thr_off >= 0 ? " thr@smem" : (p.wl ? " pixel-major warp-local tma-store" : p.swap ? " pixel-major tma-store" : p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : ""), p.BWp, p.BHp, U->smem,
              p.tiles_x, p.tiles_y);
     return buf;
   }
   snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d chb=%d%s planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT,
-           p.R, p.P, p.NPX, p.CB, p.chb, p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : p.epi4 ? " epi-warps=4" : ""), p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
+           p.R, p.P, p.NPX, p.CB, p.chb, p.lut_off >= 0 ? " thr@smem + bucket LUT" : p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : p.epi4 ? " epi-warps=4" : ""), p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
            p.tiles_x, p.tiles_y);
   return buf;
 }
