@@ -128,6 +128,10 @@ FCB_API int fcb_layer_query(const fcb_layer_desc* desc, size_t* in_bytes_per_ima
 FCB_API int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void* thresholds, const void* bias,
                              int device, fcb_layer** out);
 FCB_API void fcb_layer_destroy(fcb_layer* layer);
+/* Replace the layer's parameters in place (same descriptor, same handle): the run-time-writable weight memories of the
+ * reference -- GenParamStream feeding Matrix_Vector_Activate_Stream_Batch (dma.h:214-236, mvau.hpp:209-307) -- as one call.
+ * Images as for fcb_layer_create; on error the layer keeps its previous parameters. Not concurrent with runs of the layer. */
+FCB_API int fcb_layer_set_params(fcb_layer* layer, const void* weights, const void* thresholds, const void* bias);
 /* Host-buffer call: in_words -> H2D -> kernels -> D2H -> out_words, numReps images, synchronous.
  * Mirrors `top(in_stream, out_stream, numReps)`. */
 FCB_API int fcb_layer_run(fcb_layer* layer, const void* in_words, void* out_words, uint32_t numReps);

@@ -111,6 +111,7 @@ using namespace fcb;
 
 struct fcb_layer {
   Geom g;
+  fcb_layer_desc desc{};  // as given to fcb_layer_create (fcb_layer_set_params rebuilds from it)
   int device = 0;
   int engine = ENG_IMAD;
   void* d_wt = nullptr;
@@ -276,6 +277,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
 
   fcb_layer* L = new fcb_layer();
   L->g = g;
+  L->desc = *desc;
   L->device = device;
 
   // ---- weights: m_weights[pe][nf*SF+sf] lanes -> W[ch][k] (mvau.hpp:117,148; weights.hpp:134-140)
@@ -474,6 +476,26 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     p.wt = L->d_wt;
   }
   *out = L;
+  return FCB_OK;
+}
+
+int fcb_layer_set_params(fcb_layer* L, const void* weights, const void* thresholds, const void* bias) {
+  if (!L) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  // parameters are re-laid-out per plan (K-major tiles, sorted threshold tables, folded bias rows ...): build a fresh layer from the
+  // stored descriptor and adopt its device state; the caller's handle, launch counter and staging slots stay
+  fcb_layer* fresh = nullptr;
+  int rc = fcb_layer_create(&L->desc, weights, thresholds, bias, L->device, &fresh);
+  if (rc) return rc;
+  std::swap(L->engine, fresh->engine);
+  std::swap(L->d_wt, fresh->d_wt); std::swap(L->d_bias, fresh->d_bias);
+  std::swap(L->d_thr, fresh->d_thr); std::swap(L->d_thr_cm, fresh->d_thr_cm);
+  std::swap(L->d_thr_lut, fresh->d_thr_lut); std::swap(L->d_thr_lo, fresh->d_thr_lo);
+  std::swap(L->epi, fresh->epi); std::swap(L->dp, fresh->dp); std::swap(L->smem, fresh->smem);
+  std::swap(L->umma, fresh->umma);
+  std::swap(L->lowered, fresh->lowered); std::swap(L->lower_bits, fresh->lower_bits); std::swap(L->ip, fresh->ip);
+  std::swap(L->d_scratch, fresh->d_scratch); std::swap(L->scratch_imgs, fresh->scratch_imgs); std::swap(L->scratch_img_bytes, fresh->scratch_img_bytes);
+  memcpy(L->plan_desc, fresh->plan_desc, sizeof(L->plan_desc));
+  fcb_layer_destroy(fresh);
   return FCB_OK;
 }
 

@@ -43,6 +43,16 @@ class ConvLayer:
         _lib.check(L.fcb_layer_create(ctypes.byref(c), _ptr(w), _ptr(t), _ptr(b), device, ctypes.byref(h)))
         self._h = h
 
+    def set_params(self, weights, thresholds=None, bias=None) -> None:
+        """Swap the layer's weights / thresholds / bias in place (the reference's run-time-writable weight memories,
+        dma.h:214-236 + mvau.hpp:209-307); the handle, and any Net built on it, stay valid."""
+        w = np.ascontiguousarray(weights, dtype=np.uint8)
+        t = None if thresholds is None else np.ascontiguousarray(thresholds, dtype=np.uint8)
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.uint8)
+        if w.size != self.weight_bytes or (t is not None and t.size != self.threshold_bytes) or (b is not None and b.size != self.bias_bytes):
+            raise ValueError("parameter image size does not match the layer")
+        _lib.check(_lib.lib().fcb_layer_set_params(self._h, _ptr(w), _ptr(t), _ptr(b)))
+
     @property
     def engine(self) -> str:
         return _lib.lib().fcb_layer_engine(self._h).decode()

@@ -415,3 +415,23 @@ def test_net_host_pipeline_many_chunks(fcb_lib, oracle_mod, monkeypatch):
     want = oracle_mod.run_layer(d2, mid, i2["weights"], None, i2["bias"], num_reps=reps)
     assert np.array_equal(got, want)
     assert np.array_equal(net.run(i1["in_words"], reps), want)  # slots and events are reusable
+
+
+@pytest.mark.parametrize("name", ["c2d_e", "c2d_c", "th_cfg4", "dc_d", "xn_c"])
+def test_set_params_swaps_weights_in_place(name, fcb_lib, oracle_mod):
+    """fcb_layer_set_params (run-time-writable weight memories, dma.h:214-236 + mvau.hpp:209-307): same handle, new weights /
+    thresholds / bias, results follow the oracle with the new parameters -- also through a Net built before the swap."""
+    from simple_image_compression_network_b200.layer import Net
+    d = cases.CASES[name]
+    a, b = cases.make_inputs(d, seed_shift=0), cases.make_inputs(d, seed_shift=77)
+    L = _layer(d, a)
+    net = Net([L])
+    x = a["in_words"]
+    assert np.array_equal(L.run(x), oracle_mod.run_layer(d, x, a["weights"], a["thresholds"], a["bias"]))
+    L.set_params(b["weights"], thresholds=b["thresholds"], bias=b["bias"])
+    want = oracle_mod.run_layer(d, x, b["weights"], b["thresholds"], b["bias"])
+    assert not np.array_equal(want, oracle_mod.run_layer(d, x, a["weights"], a["thresholds"], a["bias"]))
+    assert np.array_equal(L.run(x), want)
+    assert np.array_equal(net.run(x), want)
+    with pytest.raises(ValueError):
+        L.set_params(b["weights"][:-1])
