@@ -85,8 +85,7 @@ struct Params2 {
   // tile row, so it issues its own TMA store per 128-pixel block and the epilogue needs no block-wide barrier at all
   int wl;
   // alternating epilogue groups (staged paths with two accumulator stages): warps 2..5 own accumulator stage / staging buffer 0,
-  // warps 6..9 stage 1, so one group's barriers, fences and store issue overlap the other group's TMEM reads (64 B/clk/SM:
-  // ~2048 clocks for a 256 x 128 int32 tile -- the floor of a store-bound layer)
+  // warps 6..9 stage 1, so one group's barriers, fences and store issue overlap the other group's TMEM reads and packing
   int epi_alt;
   // MMA-bound layers on the register epilogue: only warps 2..5 work (one per TMEM lane quarter); the second epilogue warp of each
   // SM sub-partition would only compete with the MMA issue warp for issue slots
