@@ -639,10 +639,16 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 8; j++) {
               const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
-              uint32_t x = __byte_perm(lo, hi, 0x5410);  // low bytes of 4 channels = accumulators mod 256
-              if (!fold) x = __vadd4(x, lds_b32(bias_s + (uint32_t)(cbk * 32 + 4 * j)));
-              w[j] = x & ~prmt_sign_mask(x);             // ReLU on the wrapped value: bytes with bit 7 set -> 0
+              w[j] = __byte_perm(lo, hi, 0x5410);  // low bytes of 4 channels = accumulators mod 256
             }
+            if (!fold) {  // a real (warp-uniform) branch: predicated-off byte adds would still cost ~45 issue slots per item
+              asm volatile("" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < 8; j++) w[j] = __vadd4(w[j], lds_b32(bias_s + (uint32_t)(cbk * 32 + 4 * j)));
+              asm volatile("" ::: "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) w[j] &= ~prmt_sign_mask(w[j]);  // ReLU on the wrapped value: bytes with bit 7 set -> 0
             const uint32_t row = stg_s + (uint32_t)((cbk >> 2) * p.NPX * 128 + m * 128);
             const uint32_t c0 = (uint32_t)((cbk & 3) * 2), m7 = (uint32_t)m & 7u;
             sts_v4(row + ((c0 ^ m7) << 4), w[0], w[1], w[2], w[3]);
