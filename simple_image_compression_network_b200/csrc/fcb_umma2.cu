@@ -160,6 +160,13 @@ struct TileIter {
     if (ty >= tiles_y) { ty -= tiles_y; ++img; }
   }
 };
+// ring of n plane sets walked tile by tile (n is small but not a power of two in general: no division per tile)
+struct SetRing {
+  int idx = 0, n;
+  uint32_t par = 0;
+  __device__ __forceinline__ explicit SetRing(int n_) : n(n_) {}
+  __device__ __forceinline__ void next() { if (++idx == n) { idx = 0; par ^= 1u; } }
+};
 // rings of 1 or 2 slots: slot and phase parity of iteration `it`
 __device__ __forceinline__ uint32_t ring_idx(uint32_t it, int n) { return n == 2 ? (it & 1u) : 0u; }
 __device__ __forceinline__ uint32_t ring_par(uint32_t it, int n) { return n == 2 ? ((it >> 1) & 1u) : (it & 1u); }
@@ -342,12 +349,13 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const uint32_t row_step = 4u * (uint32_t)(p.S * p.BWp), col_step = 4u * (uint32_t)p.S;
       uint32_t tile_it = 0;
       PROF_START();
-      for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next(), tile_it++) {
-        const uint32_t set = ring_idx(tile_it, p.nsets), pb = tile_it % U2_NPB;
+      SetRing sr(p.nsets);
+      for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next(), tile_it++, sr.next()) {
+        const uint32_t set = (uint32_t)sr.idx, pb = tile_it % U2_NPB;
         PROF_T(0);
         WAITB(&pfull[pb], (tile_it / U2_NPB) & 1u);
         PROF_T(1);
-        WAITB(&aempty[set * p.nplanes], ring_par(tile_it, p.nsets) ^ 1u);
+        WAITB(&aempty[set * p.nplanes], sr.par ^ 1u);
         PROF_T(2);
         const uint32_t xshift = (uint32_t)((p.S * ti.tx * p.WT - p.pad) & 3);
         const uint32_t patch = smem_u32(smem + p.patch_off + pb * p.patch_bytes) + 4u * xshift;
@@ -375,10 +383,11 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (bw == 0 && lane == 0) PROF_FLUSH(0);
     } else if (lane == 0) {
       uint32_t tile_it = 0;
-      for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next(), tile_it++) {
+      SetRing sr(p.nsets);
+      for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid(); ti.next(), tile_it++, sr.next()) {
         const int img = ti.img, x0 = ti.tx * p.WT, y0 = ti.ty * p.R;
-        const int set = (int)ring_idx(tile_it, p.nsets);
-        const uint32_t par = ring_par(tile_it, p.nsets) ^ 1u;
+        const int set = sr.idx;
+        const uint32_t par = sr.par ^ 1u;
         for (int i = 0; i < p.nplanes; i++) {
           const Plane2& pl = p.planes[i];
           uint64_t* fb = &afull[set * p.nplanes + i];
@@ -408,9 +417,10 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     asm volatile("" : "+r"(wstages), "+r"(CB));  // held in registers: not re-read from the parameter bank per K-block
     const int NPX = p.NPX, ksteps = p.ksteps;
     PROF_START();
-    for (long long t = cta0; t < total_tiles; t += ncta, tile_it++) {
-      const int set = (int)ring_idx(tile_it, p.nsets);
-      const uint32_t apar = ring_par(tile_it, p.nsets);
+    SetRing sr(p.nsets);
+    for (long long t = cta0; t < total_tiles; t += ncta, tile_it++, sr.next()) {
+      const int set = sr.idx;
+      const uint32_t apar = sr.par;
       const uint64_t desc_set = desc0 + (uint32_t)((set * p.set_bytes) >> 4);
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
         const Phase2& P = p.phases[ph];
@@ -1539,11 +1549,16 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
     pl.smem_off = off; pl.bytes = rows * p.P * 128; pl.c0 = cc * 128; pl.dx = -1; pl.dy = -1; pl.par = 0; pl.map = 0;
     off += NPX * 128;
   }
-  p.nplanes = cch; p.set_bytes = off; p.nsets = 2;
-  off *= 2;
+  // the whole tile is one K-block, so nothing inside a tile hides the ~2.5 k clocks a 32 KB plane takes to arrive from HBM:
+  // the planes are prefetched three tiles ahead
+  p.nplanes = cch; p.set_bytes = off;
+  p.nsets = 4;  // measured on L7: 2 sets 201.5 k, 3 sets 209 k, 4 sets 218 k, 5 sets 212 k img/s
+  if (getenv("FCB_U2_NSETS")) p.nsets = std::max(1, std::min(5, atoi(getenv("FCB_U2_NSETS"))));
+  while (p.nsets > 1 && (size_t)p.nsets * off + (size_t)cch * 16384 + 2 * ((25 * g.OFM * DCOL_PITCH + 127) / 128 * 128) + 8192 > (size_t)227 * 1024) p.nsets--;
+  off *= p.nsets;
   U->box_rows[0] = U->box_rows[1] = rows;
   p.w_off = off; off += p.wstages * p.w_bytes;
-  p.bar_off = off; off += (2 * p.wstages + 2 * cch * 2 + 4 + 1 + 2 * (int)U2_NPB + 1) * 8;
+  p.bar_off = off; off += (2 * p.wstages + 2 * cch * p.nsets + 4 + 1 + 2 * (int)U2_NPB + 1) * 8;
   off = (off + 15) & ~15;
   p.stage_off = off; off += 8 * 256;
   p.thr_off = -1; p.lut_off = -1;
