@@ -833,6 +833,12 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const int li = lane & 3, cgrp = chbase + cb * 128 + q * 32 + (lane & ~3);  // pixel-in-quad, first of this lane's 4 channels
             const uint32_t selA = (lane & 1) ? 0x3715u : 0x6240u, selB = (lane & 2) ? 0x3276u : 0x5410u;
             int rr = (col_lo + li) / p.P, xo = (col_lo + li) - rr * p.P;  // this lane's pixel after the transpose: m = c0 + 4*j + li
+            // one running pointer per lane (4 pixels further per word, re-derived at a tile-row wrap) and predicated stores: the
+            // epilogue is ~2/3 of this kernel's instructions on MMA-bound layers, and under the power cap instructions are clocks
+            const long long xstep = p.deconv ? 2 * p.out_word_bytes : p.out_word_bytes, xstep4 = 4 * xstep;
+            const long long wrap_delta = (long long)(p.deconv ? 2 : 1) * p.out_x * p.out_word_bytes - (long long)p.P * xstep;  // next tile row, P pixels back
+            uint8_t* dst = p.out + pm.word_off(rr, xo, 1) + cgrp;
+            const bool chq = cgrp < p.OFM;
             for (int c0 = col_lo; c0 < col_hi && c0 < vrows * p.P; c0 += 32) {
               uint32_t v[32];
               tmem_ld32(taddr + (uint32_t)c0, v);
@@ -841,12 +847,15 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               for (int j = 0; j < 8; j++) {
                 const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
                 uint32_t w = __vadd4(__byte_perm(lo, hi, 0x5410), bias4);      // (acc + bias) mod 256, 4 pixels at once
-                w &= ~(((w >> 7) & 0x01010101u) * 0xFFu);                      // bit 7 set -> 0
+                w &= ~prmt_sign_mask(w);                                       // bit 7 set -> 0
                 const uint32_t a = __byte_perm(w, __shfl_xor_sync(0xffffffffu, w, 1), selA);
                 const uint32_t y = __byte_perm(a, __shfl_xor_sync(0xffffffffu, a, 2), selB);
-                if (xo < vcols && rr < vrows && cgrp < p.OFM) *reinterpret_cast<uint32_t*>(p.out + pm.word_off(rr, xo, 1) + cgrp) = y;
+                if (chq && xo < vcols && rr < vrows) *reinterpret_cast<uint32_t*>(dst) = y;
                 xo += 4;
-                if (xo >= p.P) { xo -= p.P; ++rr; }
+                const bool wrapped = xo >= p.P;  // branch-free: a select and two adds
+                xo -= wrapped ? p.P : 0;
+                rr += wrapped ? 1 : 0;
+                dst += xstep4 + (wrapped ? wrap_delta : 0ll);
               }
             }
           } else if (pk == 1) {
