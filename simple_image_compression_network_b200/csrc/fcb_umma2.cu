@@ -744,7 +744,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               for (int j = 0; j < 8; j++) {
                 const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
                 uint32_t w = __vadd4(__byte_perm(lo, hi, 0x5410), bias4);  // (acc + bias) mod 256, 4 pixels at once
-                w &= ~(((w >> 7) & 0x01010101u) * 0xFFu);                  // bit 7 set -> 0
+                w &= ~prmt_sign_mask(w);  // bit 7 set -> 0
                 sts_u8(sa + (4 * j + 0) * 128, w);
                 sts_u8(sa + (4 * j + 1) * 128, w >> 8);
                 sts_u8(sa + (4 * j + 2) * 128, w >> 16);
@@ -788,7 +788,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               for (int j = 0; j < 8; j++) {
                 const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
                 uint32_t w = __vadd4(__byte_perm(lo, hi, 0x5410), bias4);
-                w &= ~(((w >> 7) & 0x01010101u) * 0xFFu);
+                w &= ~prmt_sign_mask(w);
                 if (lane < p.OFM) *reinterpret_cast<uint32_t*>(stage + lane * 256 + c0 + 4 * j) = w;
               }
             }
