@@ -219,7 +219,8 @@ static int upload_thresholds(fcb_layer* L, const std::vector<std::vector<int32_t
   cudaFree(L->d_thr_lut); cudaFree(L->d_thr_lo);
   L->d_thr_lut = nullptr; L->d_thr_lo = nullptr;
   L->epi.thr_lut = nullptr; L->epi.thr_lo = L->epi.thr_sh = nullptr;
-  if (nth >= 64 && nth <= 255) {
+  // (a - lo) is formed in 32 bits on the device: accumulators and thresholds must stay within +-2^30 (TA of at most 31 bits)
+  if (nth >= 64 && nth <= 255 && L->g.acc_bits <= 30) {
     std::vector<uint8_t> lut((size_t)tstride * 256, 0);
     std::vector<int32_t> losh((size_t)2 * tstride, 0);
     bool ok = true;
