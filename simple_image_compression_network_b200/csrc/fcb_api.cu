@@ -277,6 +277,13 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   FCB_CUDA_OK(cudaSetDevice(device));
 
   fcb_layer* L = new fcb_layer();
+  // every early return below (FCB_CUDA_OK, explicit error returns) releases the half-built layer; `armed` is cleared on success.
+  // (paths that call fcb_layer_destroy(L) themselves disarm first)
+  struct Guard {
+    fcb_layer*& L;
+    bool armed = true;
+    ~Guard() { if (armed && L) fcb_layer_destroy(L); }
+  } guard{L};
   L->g = g;
   L->desc = *desc;
   L->device = device;
@@ -337,7 +344,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         std::sort(row.begin(), row.end());
       }
     rc = upload_thresholds(L, thr_rows);
-    if (rc) { fcb_layer_destroy(L); return rc; }
+    if (rc) { guard.armed = false; fcb_layer_destroy(L); return rc; }
   }
 
   // ---- engine selection
@@ -371,7 +378,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
       for (auto& t : r) t = 2 * t - g.K;
     if (umma_eligible(g2)) {
       rc = upload_thresholds(L, rows2);
-      if (rc) { fcb_layer_destroy(L); return rc; }
+      if (rc) { guard.armed = false; fcb_layer_destroy(L); return rc; }
       EpiParams e2 = L->epi;
       e2.acc_bits = 32; e2.acc_signed = 1;
       rc = umma_plan_create(g2, W2, e2, device, &L->umma);
@@ -388,8 +395,8 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
       } else {
         L->umma = nullptr;
         int rc3 = upload_thresholds(L, thr_rows);  // back to the popcount engine's tables
-        if (rc3) { fcb_layer_destroy(L); return rc3; }
-        if (rc != FCB_ERR_UNSUPPORTED) { fcb_layer_destroy(L); return rc; }
+        if (rc3) { guard.armed = false; fcb_layer_destroy(L); return rc3; }
+        if (rc != FCB_ERR_UNSUPPORTED) { guard.armed = false; fcb_layer_destroy(L); return rc; }
       }
     }
   }
@@ -397,12 +404,12 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     // thin-output transposed conv (the 3-channel last layer): dedicated plan, pixels on the MMA M axis
     rc = umma_plan_create_dthin(g, W, L->epi, device, &L->umma);
     if (rc == FCB_ERR_UNSUPPORTED) L->umma = nullptr;
-    else if (rc) { fcb_layer_destroy(L); return rc; }
+    else if (rc) { guard.armed = false; fcb_layer_destroy(L); return rc; }
   }
   if (engine == ENG_UMMA && !L->lowered && !L->umma) {
     rc = umma_plan_create(g, W, L->epi, device, &L->umma);
     if (rc == FCB_ERR_UNSUPPORTED) { engine = L->engine = ENG_IMAD; L->umma = nullptr; }  // shape the planner cannot tile
-    else if (rc) { fcb_layer_destroy(L); return rc; }
+    else if (rc) { guard.armed = false; fcb_layer_destroy(L); return rc; }
   }
   // thin-input layers (one 4-byte word per pixel, e.g. the ap_uint<24> C = 3 first layer): the sliding window is built in
   // shared memory inside the tensor-core kernel (fcb_umma2.cu, thin-input mode); FCB_THIN=im2col keeps the two-kernel lowering
@@ -416,7 +423,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         for (int c = 0; c < g.C; c++) W4[(size_t)ch * 128 + tap * 4 + c] = W[(size_t)ch * g.K + tap * g.C + c];
     rc = umma_plan_create_thin(g, W4, L->epi, g.act_kind == FCB_ACT_BIAS_RELU ? (const int8_t*)bias : nullptr, device, &L->umma);
     if (rc == FCB_OK) engine = L->engine = ENG_UMMA;
-    else if (rc != FCB_ERR_UNSUPPORTED) { fcb_layer_destroy(L); return rc; }
+    else if (rc != FCB_ERR_UNSUPPORTED) { guard.armed = false; fcb_layer_destroy(L); return rc; }
     else L->umma = nullptr;
   }
   // older two-kernel lowering: conv2d with Kx*Ky*C <= 128 bytes of window as im2col rows + a 1x1 layer
@@ -438,7 +445,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         ip.IX = g.IX; ip.IY = g.IY; ip.OX = g.OX; ip.OY = g.OY; ip.S = g.SX; ip.PAD = g.PAD; ip.K = g.K; ip.C = g.C; ip.KX = g.KX;
         ip.in_word_bytes = (int)g.in_word_bytes; ip.in_img_bytes = g.in_img_bytes;
         snprintf(L->plan_desc, sizeof(L->plan_desc), "im2col rows (K=%d -> 128 B) + 1x1 %s", g.K, umma_plan_describe(L->umma));
-      } else if (rc != FCB_ERR_UNSUPPORTED) { fcb_layer_destroy(L); return rc; }
+      } else if (rc != FCB_ERR_UNSUPPORTED) { guard.armed = false; fcb_layer_destroy(L); return rc; }
       else L->umma = nullptr;
     }
   }
@@ -454,7 +461,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     const int cu = engine == ENG_XNOR ? g.C / 32 : g.C;
     const size_t budget = 96 * 1024;
     int cc = (int)(budget / ((size_t)p.patch_w * p.patch_h * 4));
-    if (cc < 1) { set_error("kernel %dx%d stride %d: patch does not fit shared memory", g.KX, g.KY, g.SX); fcb_layer_destroy(L); return FCB_ERR_UNSUPPORTED; }
+    if (cc < 1) { set_error("kernel %dx%d stride %d: patch does not fit shared memory", g.KX, g.KY, g.SX); guard.armed = false; fcb_layer_destroy(L); return FCB_ERR_UNSUPPORTED; }
     p.CC = std::min(cc, cu);
     L->smem = direct_smem_bytes(engine, p.patch_w, p.patch_h, p.CC);
     if (engine == ENG_XNOR) {
@@ -476,6 +483,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     }
     p.wt = L->d_wt;
   }
+  guard.armed = false;
   *out = L;
   return FCB_OK;
 }
