@@ -63,3 +63,23 @@ def test_gpu_net_batch_of_two(params, fcb_lib):
     ga = np.load(os.path.join(GOLD, "net8_ones.npz"))["out"]
     gb = np.load(os.path.join(GOLD, "net8_rand.npz"))["out"]
     assert np.array_equal(both, np.concatenate([ga, gb]))
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_layers_random_weights(fcb_lib, oracle_mod):
+    """Every layer of config_nonsquare.h at FULL size (768x512 image) with seeded random weights and biases -- the fixture
+    weights of memdata_nonsquare.h repeat one row per PE -- chained on the GPU, checked layer by layer against
+    the oracle fed with the GPU's own previous output (so a wrong layer is named, not just the end of the chain)."""
+    from simple_image_compression_network_b200.layer import ConvLayer
+    s = None
+    for i in range(8):
+        d = configs.net_layer(i)
+        prm = configs.synthetic_params(d, seed_shift=50 + i)
+        if s is None:
+            _, s = configs.synthetic_input(d, 50, 1, False)
+        L = ConvLayer(d, prm["weights"], bias=prm["bias"])
+        got = L.run(s, 1)
+        want = oracle_mod.run_layer(d, s, prm["weights"], None, prm["bias"])
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, f"layer {i} [{L.engine}: {L.plan}]: {bad.size}/{got.size} bytes differ, first at {bad[:8].tolist()}"
+        s = got
