@@ -435,3 +435,23 @@ def test_set_params_swaps_weights_in_place(name, fcb_lib, oracle_mod):
     assert np.array_equal(net.run(x), want)
     with pytest.raises(ValueError):
         L.set_params(b["weights"][:-1])
+
+
+def test_judged_configs_at_full_size(fcb_lib, oracle_mod):
+    """BASELINE.json configs 3 and 5b (first and last stage) at their full sizes against the oracle (config 4 at full size is
+    `th_cfg4` above; config 2 is `c2d_L1`; config 5a / the full network are tests/test_net8.py)."""
+    from simple_image_compression_network_b200.desc import ACT_THRESHOLDS, KIND_CONV, W_BINARY_XNOR, LayerDesc
+    c3 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=64, ofm_ch=64, ifm_x=128, ifm_y=96, stride_x=1, stride_y=1, pad=0,
+                   simd=64, pe=16, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR, acc_bits=16, acc_signed=1, act_kind=ACT_THRESHOLDS,
+                   out_bits=1, num_th=1)
+
+    def stage(c, ofm, x, y, simd, pe):
+        return LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=1, stride_y=1, pad=1,
+                         simd=simd, pe=pe, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8,
+                         num_th=255, pool=2)
+    for name, d in (("config 3", c3), ("config 5b stage 1", stage(3, 128, 768, 512, 3, 16)), ("config 5b stage 4", stage(128, 192, 96, 64, 32, 24))):
+        inp = cases.make_inputs(d, seed_shift=61)
+        L = _layer(d, inp)
+        got = L.run(inp["in_words"])
+        want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"])
+        assert np.array_equal(got, want), f"{name} [{L.engine}: {L.plan}]: {_diff(got, want)}"
