@@ -1104,7 +1104,10 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   cands.push_back({0, 1, thr ? 120.0 : 0.0});
   double best = 1e30;
   int bWT = 0, bR = 0, bNPX = 0, bWS = 0, thr_top = 0, thr_bytes = 0, chb = 1, CBe = CB;
-  for (const Cand& cd : cands) {
+  const int only_cand = getenv("FCB_U2_CAND") ? atoi(getenv("FCB_U2_CAND")) : -1;  // experiments: evaluate one candidate only
+  for (size_t ci = 0; ci < cands.size(); ci++) {
+    const Cand& cd = cands[ci];
+    if (only_cand >= 0 && (int)ci != only_cand) continue;
     const int cbe = CB / cd.chb;
     const int tb = cd.thr_top ? ((1 << cd.thr_top) - 1) * cbe * 128 * 4 : 0;
     if (tb > 136 * 1024) continue;
