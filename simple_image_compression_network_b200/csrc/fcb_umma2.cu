@@ -510,9 +510,9 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid() && !(p.epi4 && half); ti.next()) {
       const int img = ti.img;
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
-        const PixMap pm{p, ti.tx * p.WT, ti.ty * p.R, p.phases[ph].px, p.phases[ph].py, (unsigned long long)img * p.out_img_bytes};
         const int acc = (int)ring_idx(acc_it, p.acc_stages);
         if (alt && acc != half) continue;  // the other group's accumulator
+        const PixMap pm{p, ti.tx * p.WT, ti.ty * p.R, p.phases[ph].px, p.phases[ph].py, (unsigned long long)img * p.out_img_bytes};
         PROF_T(0);
         WAITB(&tfull[acc], ring_par(acc_it, p.acc_stages));
         PROF_T(1);
