@@ -148,6 +148,22 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def _bind_to_gpu_numa_node(index: int):
+    """Run this rank on the CPUs next to its GPU (NVML's affinity mask), so the pinned host buffers of the e2e leg are
+    first-touched on the NUMA node its PCIe link hangs off; with every rank on node 0 the host-buffer path stops scaling."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -161,6 +177,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    _bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
