@@ -939,10 +939,13 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             // 2x2 max pool: rows rr, rr+1 of the tile are columns m and m + P of the same thread
             // work units = (row pair, 16-column block) = 8 pooled outputs; the two warps of a lane quarter take alternate units
             const int xblocks = (vcols + 15) >> 4, nunits = (vrows >> 1) * xblocks;
+            int urow = 2 * (half / xblocks), ublk = half % xblocks;  // unit -> (row pair, x block), advanced without divisions
 #pragma unroll 1
             for (int u = half; u < nunits; u += 2) {
               {
-                const int rr = 2 * (u / xblocks), xb = 16 * (u % xblocks);
+                const int rr = urow, xb = 16 * ublk;
+                ublk += 2;
+                while (ublk >= xblocks) { ublk -= xblocks; urow += 2; }
                 if (mono) {
                   // count-of-thresholds-below is non-decreasing in the TA-wrapped accumulator: pool first, then ONE search
                   int32_t m8[8];
