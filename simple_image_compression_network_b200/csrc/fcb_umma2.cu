@@ -216,7 +216,9 @@ struct DcolGather<OFM, 25> {
 // NB = warps from index 10 on: 1 = plane TMA producer (resident-planes mode); 4 = im2col builders (thin-input mode)
 // DTHIN: the thin-output transposed-conv instantiation.  Mode flags are template parameters because the MMA issue loop has no
 // slack for per-K-block loads of kernel parameters (each LDCU + dependent branch costs ~50 clocks of its ~580-clock budget).
-template <int NB, int DT>
+// EPI = 1: the instantiation for pooled 8-bit threshold layers (monotone compare, shared-memory tables): every other epilogue is
+// compiled out, which frees registers and instruction cache for the lock-step search.
+template <int NB, int DT, int EPI>
 __global__ void __launch_bounds__(320 + 32 * NB, 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params2 p) {
@@ -235,6 +237,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool THIN = NB > 1;         // thin-input instantiations (im2col builder warps)
+  constexpr bool THRP = EPI == 1;   // pooled 8-bit thresholds only
   constexpr bool DTHIN = DT == 1;   // thin-output deconv, 9 shift blocks x N=16 (pixels on M)
   constexpr bool DCOL = DT == 2;    // thin-output deconv, GEMM over (tap, channel) rows + col2im in shared memory
   constexpr bool WSTATIC = THIN || DT != 0;  // every weight K-block has its own stage: loaded once, never released
@@ -496,15 +499,15 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int ebar = alt ? 1 + half : 1, ecnt = alt ? 128 : 256;      // named barrier of this warp's epilogue group
     const int erow0 = alt ? q : warp - 2, erows = alt ? 4 : 8;        // TMA-store rows dealt over the group's warps
 #define EPI_BAR() asm volatile("bar.sync %0, %1;" ::"r"(ebar), "r"(ecnt) : "memory")
-    const int pk = p.epi.pool >= 2 ? p.epi.pool : 1;
-    const bool fast = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && (p.OFM % 32) == 0 && p.P >= 4;
+    const int pk = THRP ? 2 : (p.epi.pool >= 2 ? p.epi.pool : 1);
+    const bool fast = !THRP && p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && (p.OFM % 32) == 0 && p.P >= 4;
     // thresholds with comp::less / less_equal and a result that cannot wrap TR: monotone in the (wrapped, < 2^31) accumulator
-    const bool mono = p.epi.act_kind == FCB_ACT_THRESHOLDS && (p.epi.cmp == FCB_CMP_LESS || p.epi.cmp == FCB_CMP_LESS_EQUAL) &&
+    const bool mono = THRP || p.epi.act_kind == FCB_ACT_THRESHOLDS && (p.epi.cmp == FCB_CMP_LESS || p.epi.cmp == FCB_CMP_LESS_EQUAL) &&
                       p.epi.act_val >= 0 && (p.epi.out_bits >= 31 || p.epi.act_val + p.epi.num_th < (1 << p.epi.out_bits)) &&
                       (p.epi.acc_signed || p.epi.acc_bits < 32);
     int gshift = 0;  // log2 of the group the shared-memory levels of the threshold search narrow down to
     if (p.thr_off >= 0) for (int t = p.epi.thr_n + 1; (t >> (p.thr_top + gshift)) > 1;) gshift++;
-    const bool thin = p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
+    const bool thin = !THRP && p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
     uint32_t acc_it = 0;
     PROF_START();
     for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid() && !(p.epi4 && half); ti.next()) {
@@ -519,7 +522,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
-        if (DCOL) {
+        if (!THRP && DCOL) {
           // (always two accumulator stages: warps 2..5 serve stage 0, warps 6..9 stage 1, each group with its own byte tile)
           const int nrows = 25 * p.OFM;
           uint8_t* S = smem + p.stg_off + half * p.stg_bytes;
@@ -587,7 +590,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           continue;
         }
-        if (DTHIN) {
+        if (!THRP && DTHIN) {
           // thread = input pixel m of block `half`; its 16 columns are the 2x2 output words it produces (bias + ReLU on the
           // wrapped 8-bit lane, conv_nonsquare_top.cpp:183-194); a warp writes two 256-byte runs of output row 2y and 2y+1
           const int m = half * 128 + q * 32 + lane;
@@ -619,7 +622,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           continue;
         }
-        if (p.swap) {
+        if (!THRP && p.swap) {
           // Swapped staged bias + ReLU epilogue: thread = pixel (TMEM lane), 32-column loads = 32 channels of that pixel ->
           // 8 packed words -> two 16-byte stores into the SWIZZLE_128B staging row of the pixel; TMA stores un-swizzle.
           const int sb = alt ? half : (int)ring_idx(acc_it, p.stg_bufs);
@@ -717,7 +720,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           PROF_T(6);
           continue;
         }
-        if (p.stg_bufs > 0) {
+        if (!THRP && p.stg_bufs > 0) {
           // Staged bias + ReLU epilogue (conv_nonsquare_top.cpp:267-278): thread = channel turns its 32-column TMEM loads into
           // bytes of the tile's [pixel][channel] image in shared memory (a warp's 32 lanes write 32 consecutive bytes: one
           // wavefront, no shuffles, no predicates); one thread then issues a TMA store per tile row.  The register path below
@@ -772,7 +775,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           PROF_T(6);
           continue;
         }
-        if (thin) {
+        if (!THRP && thin) {
           // Thin output (OFM <= 8, e.g. the 3-channel last layer): only lanes < OFM of the first lane quarter hold data.
           // They turn their 256 columns into bytes in a shared staging row per channel; then all 128 epilogue threads
           // assemble and store whole output words, one pixel per thread (coalesced), instead of 3 lanes doing everything.
@@ -825,7 +828,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const int row_shift = p.CB == 2 ? 10 : 9;  // log2(CB * 128 channels * 4 bytes)
           const bool chv = ch < p.OFM;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
-          if (fast) {
+          if (!THRP && fast) {
             // bias + ReLU on the wrapped 8-bit value (conv_nonsquare_top.cpp:267-278).  The thread owns one channel and
             // 32 pixels; a 4x4 byte transpose across each lane quad (2 shuffles + 2 PRMT per word) turns that into
             // 4 consecutive channel bytes of one pixel per lane, so a warp store writes 4 pixels x 32 B.
@@ -858,7 +861,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 dst += xstep4 + (wrapped ? wrap_delta : 0ll);
               }
             }
-          } else if (pk == 1) {
+          } else if (!THRP && pk == 1) {
             int rr = col_lo / p.P, xo = col_lo - rr * p.P;
 #pragma unroll 1
             for (int c0 = col_lo; c0 < col_hi && rr < vrows; c0 += 32) {
@@ -975,12 +978,12 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     for (int w = 0; w < 8; w++) pooled[w] = (uint32_t)m8[w] & 0xFFu;
                   } else if (use_lut) {
                     activate_thr_lut<8>(p.epi, top_s, row_shift, lut_s, lut_lo, lut_sh, m8, pooled);
-                  } else if (hybrid) {
+                  } else if (THRP || hybrid) {
                     activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, m8, pooled);
                   } else {
                     activate_thrN<8>(p.epi, tbl, tstride, m8, pooled);
                   }
-                  if (p.epi.out_bits == 8) {
+                  if (THRP || p.epi.out_bits == 8) {
                     uint8_t* dst = p.out + pm.word_off(rr, xb, 2) + ch;  // x0 and xb are even: pooled pixel w sits w words further
 #pragma unroll
                     for (int w = 0; w < 8; w++) {
@@ -1303,7 +1306,8 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1442,8 +1446,9 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1519,7 +1524,7 @@ int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& e
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1596,7 +1601,7 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1687,11 +1692,18 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
 #endif
   // thin-input: 4 builder warps beside the light bias/ReLU epilogue (128 registers per thread suffice); 2 beside the threshold
   // epilogue, whose lock-step searches need ~170 registers to stay out of local memory
-  if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2, 0><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (p.thin_in) umma2_conv_kernel<4, 0><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (p.dthin == 2) umma2_conv_kernel<1, 2><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (p.dthin) umma2_conv_kernel<1, 1><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else umma2_conv_kernel<1, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  // pooled 8-bit threshold layers with a monotone compare and shared-memory tables get the instantiation that contains nothing else
+  const EpiParams& e = p.epi;
+  const bool thrp = e.act_kind == FCB_ACT_THRESHOLDS && e.pool == 2 && e.out_bits == 8 && p.thr_off >= 0 && !p.deconv &&
+                    (e.cmp == FCB_CMP_LESS || e.cmp == FCB_CMP_LESS_EQUAL) && e.act_val >= 0 && e.act_val + e.num_th < 256 &&
+                    (e.acc_signed || e.acc_bits < 32) && !getenv("FCB_U2_NO_THRP");
+  if (p.thin_in && thrp) umma2_conv_kernel<2, 0, 1><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2, 0, 0><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.thin_in) umma2_conv_kernel<4, 0, 0><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.dthin == 2) umma2_conv_kernel<1, 2, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.dthin) umma2_conv_kernel<1, 1, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (thrp) umma2_conv_kernel<1, 0, 1><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else umma2_conv_kernel<1, 0, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   FCB_CUDA_OK(cudaGetLastError());
   if (d_prof) {  // debugging aid: average clocks per tile and segment over the CTAs
     FCB_CUDA_OK(cudaStreamSynchronize(st));
