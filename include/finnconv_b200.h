@@ -132,6 +132,10 @@ FCB_API void fcb_layer_destroy(fcb_layer* layer);
  * reference -- GenParamStream feeding Matrix_Vector_Activate_Stream_Batch (dma.h:214-236, mvau.hpp:209-307) -- as one call.
  * Images as for fcb_layer_create; on error the layer keeps its previous parameters. Not concurrent with runs of the layer. */
 FCB_API int fcb_layer_set_params(fcb_layer* layer, const void* weights, const void* thresholds, const void* bias);
+/* The same, with the weights in the reference's parameter-STREAM format: one period (TILES words) of what GenParamStream
+ * (dma.h:214-236) writes and Matrix_Vector_Activate_Stream_Batch (mvau.hpp:209-307) reads -- word `tile` is an
+ * ap_uint<SIMD*PE*WP> container holding m_weights[pe][tile] at bits [pe*SIMD*WP, (pe+1)*SIMD*WP). thresholds / bias as above. */
+FCB_API int fcb_layer_set_param_stream(fcb_layer* layer, const void* param_words, const void* thresholds, const void* bias);
 /* Host-buffer call: in_words -> H2D -> kernels -> D2H -> out_words, numReps images, synchronous.
  * Mirrors `top(in_stream, out_stream, numReps)`. */
 FCB_API int fcb_layer_run(fcb_layer* layer, const void* in_words, void* out_words, uint32_t numReps);

@@ -7,6 +7,7 @@ the fixture-weight dumps + eight_layers_net outputs from oracle/_ref/libref_net.
 
     python -m oracle.gen_golden            # all layer cases
     python -m oracle.gen_golden --net      # also the 8-layer net fixtures (minutes)
+    python -m oracle.gen_golden --streams-only   # only the parameter-stream fixtures
 """
 from __future__ import annotations
 
@@ -48,6 +49,28 @@ def gen_layers(names):
             raise SystemExit(f"restatement differs from the reference on {name}")
 
 
+STREAM_CASES = ("th_a", "th_b", "th_c")  # STREAM_CASES of ref_layers.cpp
+
+
+def gen_param_streams():
+    """Streamed-weights form (GenParamStream -> Matrix_Vector_Activate_Stream_Batch): the parameter-stream image of each case's
+    weights as the reference emits it, and proof that the streamed MVAU gives the stored layer output."""
+    for name in STREAM_CASES:
+        d = cases.CASES[name]
+        inp = cases.make_inputs(d)
+        s = oracle.query(d)
+        pbytes = s.sf * s.nf * oracle.lib().fo_word_bytes(d.simd * d.pe * d.w_bits)
+        out, pw = oracle.ref_stream_run(name, inp["in_words"], inp["weights"], inp["thresholds"], s.out_bytes_per_image, pbytes)
+        gold = np.load(os.path.join(GOLD, f"layer_{name}.npz"))
+        same_out = sha(out) == str(gold["out_sha"])
+        mine = oracle.gen_param_stream(d, inp["weights"])
+        ok = np.array_equal(mine, pw)
+        np.savez_compressed(os.path.join(GOLD, f"param_stream_{name}.npz"), param_words=pw, w_sha=sha(inp["weights"]), out_sha=sha(out))
+        print(f"param_stream_{name}: {pw.size} bytes, streamed MVAU == static MVAU: {same_out}, restatement_matches={ok}", flush=True)
+        if not (ok and same_out):
+            raise SystemExit(f"parameter-stream mismatch on {name}")
+
+
 def gen_net():
     lib = ctypes.CDLL(os.path.join(oracle.HERE, "_ref", "libref_net.so"))
     lib.ref_dump_weights.restype = ctypes.c_long
@@ -79,6 +102,8 @@ def gen_net():
 
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    gen_layers(args or list(cases.CASES))
+    if "--streams-only" not in sys.argv:
+        gen_layers(args or list(cases.CASES))
+    gen_param_streams()
     if "--net" in sys.argv:
         gen_net()

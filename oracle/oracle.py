@@ -137,3 +137,32 @@ def ref_pool(name: str, in_words, out_bytes: int) -> np.ndarray:
     if rc:
         raise RuntimeError(f"ref_{name} rc={rc}")
     return out
+
+
+def gen_param_stream(desc, weights) -> np.ndarray:
+    """Restatement of GenParamStream (dma.h:214-236) for one repetition: image of m_weights[PE][TILES] -> TILES stream words
+    of SIMD*PE*WP bits, strMem((SIMD*WP)*(pe+1)-1, (SIMD*WP)*pe) = m_weights[pe][tile] (dma.h:229)."""
+    s = query(desc)
+    tiles, pe, lane_bits = s.sf * s.nf, desc.pe, desc.simd * desc.w_bits
+    wb, sw = int(s.weight_word_bytes), int(lib().fo_word_bytes(lane_bits * pe))
+    img = np.ascontiguousarray(weights, dtype=np.uint8).reshape(pe, tiles, wb)
+    bits = np.unpackbits(img, axis=2, bitorder="little")[:, :, :lane_bits]          # [pe][tile][bit]
+    word = np.zeros((tiles, sw * 8), dtype=np.uint8)
+    word[:, : pe * lane_bits] = bits.transpose(1, 0, 2).reshape(tiles, pe * lane_bits)  # PE little-endian
+    return np.packbits(word, axis=1, bitorder="little").reshape(-1)
+
+
+def ref_stream_run(case: str, in_words, weights, thresholds, out_bytes: int, param_bytes: int):
+    """Reference case with streamed weights (GenParamStream -> Matrix_Vector_Activate_Stream_Batch, ref_layers.cpp).
+    Returns (packed output, first period of the parameter stream)."""
+    fn = getattr(ref_lib(), "ref_stream_" + case)
+    fn.argtypes = [ctypes.c_void_p] * 5
+    in_words = np.ascontiguousarray(in_words, dtype=np.uint8)
+    weights = np.ascontiguousarray(weights, dtype=np.uint8)
+    thresholds = np.ascontiguousarray(thresholds, dtype=np.uint8)
+    out = np.zeros(out_bytes, dtype=np.uint8)
+    pw = np.zeros(param_bytes, dtype=np.uint8)
+    rc = fn(_ptr(in_words), _ptr(weights), _ptr(thresholds), _ptr(out), _ptr(pw))
+    if rc:
+        raise RuntimeError(f"ref_stream_{case} rc={rc}")
+    return out, pw

@@ -174,6 +174,36 @@ int run_thresh(const uint8_t* in, const uint8_t* wts, const uint8_t* thr, uint8_
   return drain_stream<OFM * TRB>(s_out, out, (size_t)OX * OY);
 }
 
+// ---- the same library path with the weights arriving as a STREAM: GenParamStream (dma.h:214-236) feeding
+//      Matrix_Vector_Activate_Stream_Batch (mvau.hpp:209-307).  Also hands back the first period (TILES words) of the
+//      parameter stream, the image fcb_layer_set_param_stream takes.
+template <unsigned K, unsigned SIMD, unsigned PE, unsigned WB, unsigned C, unsigned OFM, unsigned IX, unsigned IY, unsigned PAD,
+          unsigned INB, unsigned NTH, int TAB, unsigned TRB, int AV>
+int run_thresh_stream(const uint8_t* in, const uint8_t* wts, const uint8_t* thr, uint8_t* out, uint8_t* param_words) {
+  constexpr unsigned PX = IX + 2 * PAD, PY = IY + 2 * PAD, OX = PX - K + 1, OY = PY - K + 1;
+  constexpr unsigned MW = K * K * C, MH = OFM, SF = MW / SIMD, NF = MH / PE;
+  static FixedPointWeights<SIMD, ap_int<WB>, PE, SF * NF> w;
+  static ThresholdsActivation<NF, PE, NTH, ap_int<TAB>, ap_uint<TRB>, AV> act;
+  load_weights(w, wts);
+  load_thresholds(act, thr);
+  hls::stream<ap_uint<C * INB> > s_in("in"), s_pad("pad");
+  hls::stream<ap_uint<SIMD * INB> > s_wa("wa"), s_win("win");
+  hls::stream<ap_uint<SIMD * PE * WB> > s_par("par"), s_one("one");
+  hls::stream<ap_uint<PE * TRB> > s_mv("mv");
+  hls::stream<ap_uint<OFM * TRB> > s_out("out");
+  GenParamStream<SF * NF, SIMD, PE, WB>(w, s_one, 1);
+  if (drain_stream<SIMD * PE * WB>(s_one, param_words, (size_t)SF * NF)) return -3;
+  fill_stream<C * INB>(s_in, in, (size_t)IX * IY);
+  FMPadding_nonsquare<PX, PY, 2 * PAD, 2 * PAD, C, C, ap_uint<INB> >(s_in, s_pad);
+  StreamingDataWidthConverter_Batch<C * INB, SIMD * INB, PX * PY>(s_pad, s_wa, 1);
+  ConvolutionInputGenerator_NonSquare<K, K, C, INB, PX, PY, OX, OY, SIMD, 1, 1>(s_wa, s_win, 1, ap_resource_dflt());
+  GenParamStream<SF * NF, SIMD, PE, WB>(w, s_par, OX * OY);
+  Matrix_Vector_Activate_Stream_Batch<MW, MH, SIMD, PE, Slice<ap_uint<INB> >, Slice<ap_uint<TRB> >, Identity, ap_int<WB> >(
+      s_win, s_mv, s_par, act, OX * OY, ap_resource_dsp());
+  StreamingDataWidthConverter_Batch<PE * TRB, OFM * TRB, OX * OY * NF>(s_mv, s_out, 1);
+  return drain_stream<OFM * TRB>(s_out, out, (size_t)OX * OY);
+}
+
 // ---- 1-bit path: BinaryWeights + Recast<XnorMul> + ThresholdsActivation (NumTH=1, TR=ap_uint<1>)
 //      weights.hpp:66-98, interpret.hpp:57-73,126-175, activations.hpp:168-190; no padding (ConvLayer_Batch semantics)
 template <unsigned K, unsigned SIMD, unsigned PE, unsigned C, unsigned OFM, unsigned IX, unsigned IY, int TAB>
@@ -268,6 +298,18 @@ DECONV_CASES(X)
     return run_thresh<K, SIMD, PE, WB, C, OFM, IX, IY, PAD, INB, NTH, TAB, TRB, AV>(in, w, t, out, secs);       \
   }
 THRESH_CASES(X)
+#undef X
+
+// streamed-weights form of the small threshold cases: ref_stream_<name>(in, weights, thresholds, out, param_words_out)
+#define STREAM_CASES(X)                                            \
+  X(th_a, 3, 4, 2, 4, 8, 8, 10, 6, 1, 8, 15, 24, 4, 0)             \
+  X(th_b, 3, 16, 8, 4, 32, 32, 16, 12, 1, 8, 255, 24, 8, 0)        \
+  X(th_c, 3, 8, 4, 4, 16, 16, 9, 7, 0, 8, 3, 16, 2, 0)
+#define X(name, K, SIMD, PE, WB, C, OFM, IX, IY, PAD, INB, NTH, TAB, TRB, AV)                                         \
+  REF_API int ref_stream_##name(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, uint8_t* pw) { \
+    return run_thresh_stream<K, SIMD, PE, WB, C, OFM, IX, IY, PAD, INB, NTH, TAB, TRB, AV>(in, w, t, out, pw);        \
+  }
+STREAM_CASES(X)
 #undef X
 
 // xnor path.  Name, K, SIMD,PE, C,OFM, IX,IY, TAB

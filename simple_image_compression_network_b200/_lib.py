@@ -36,6 +36,7 @@ def lib() -> ctypes.CDLL:
     L.fcb_layer_query.argtypes = [ctypes.POINTER(CLayerDesc)] + [ctypes.POINTER(sz)] * 5
     L.fcb_layer_create.argtypes = [ctypes.POINTER(CLayerDesc), vp, vp, vp, ctypes.c_int, ctypes.POINTER(vp)]
     L.fcb_layer_set_params.argtypes = [vp, vp, vp, vp]
+    L.fcb_layer_set_param_stream.argtypes = [vp, vp, vp, vp]
     L.fcb_layer_destroy.argtypes = [vp]
     L.fcb_layer_destroy.restype = None
     L.fcb_layer_run.argtypes = [vp, vp, vp, u32]

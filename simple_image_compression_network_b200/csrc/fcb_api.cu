@@ -508,6 +508,27 @@ int fcb_layer_set_params(fcb_layer* L, const void* weights, const void* threshol
   return FCB_OK;
 }
 
+int fcb_layer_set_param_stream(fcb_layer* L, const void* param_words, const void* thresholds, const void* bias) {
+  if (!L || !param_words) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  // one period of the GenParamStream sequence (dma.h:214-236): word `tile` carries m_weights[pe][tile] in bits
+  // [pe*SIMD*WP, (pe+1)*SIMD*WP) -- "Little Endian PE order" -- which Matrix_Vector_Activate_Stream_Batch slices back apart
+  // (mvau.hpp:262-266).  Re-assemble the m_weights[PE][TILES] image and take the ordinary path.
+  const auto& g = L->g;
+  const uint32_t tiles = g.SF * g.NF, lane_bits = g.simd * g.w_bits;
+  const size_t sw = word_bytes(lane_bits * g.pe);
+  std::vector<uint8_t> img(g.weight_bytes, 0);
+  const uint8_t* src = (const uint8_t*)param_words;
+  for (uint32_t t = 0; t < tiles; t++)
+    for (uint32_t pe = 0; pe < g.pe; pe++) {
+      uint8_t* dst = img.data() + ((size_t)pe * tiles + t) * g.w_word_bytes;
+      for (uint32_t b = 0; b < lane_bits; b += 8) {
+        const uint32_t n = std::min<uint32_t>(8, lane_bits - b);
+        dst[b >> 3] = (uint8_t)get_bits(src + (size_t)t * sw, (uint64_t)pe * lane_bits + b, n);
+      }
+    }
+  return fcb_layer_set_params(L, img.data(), thresholds, bias);
+}
+
 const char* fcb_layer_engine(const fcb_layer* L) {
   if (!L) return "";
   return L->engine == ENG_UMMA ? "umma_i8" : L->engine == ENG_XNOR ? "xnor_popc" : "imad";

@@ -219,7 +219,7 @@ struct DcolGather<OFM, 25> {
 // EPI = 1: the instantiation for pooled 8-bit threshold layers (monotone compare, shared-memory tables): every other epilogue is
 // compiled out, which frees registers and instruction cache for the lock-step search.
 template <int NB, int DT, int EPI>
-__global__ void __launch_bounds__(320 + 32 * NB, 1)
+__global__ void __launch_bounds__(320 + 32 * NB + (EPI >= 2 ? 128 * (EPI - 1) : 0), 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params2 p) {
   extern __shared__ uint8_t smem_raw[];
@@ -237,7 +237,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool THIN = NB > 1;         // thin-input instantiations (im2col builder warps)
-  constexpr bool THRP = EPI == 1;   // pooled 8-bit thresholds only
+  constexpr bool THRP = EPI >= 1;   // pooled 8-bit thresholds only
+  constexpr int XEPI = EPI >= 2 ? 4 * (EPI - 1) : 0;  // EPI = 2, 3: 4 / 8 more epilogue warps behind the producer warps (the search is latency-bound)
   constexpr bool DTHIN = DT == 1;   // thin-output deconv, 9 shift blocks x N=16 (pixels on M)
   constexpr bool DCOL = DT == 2;    // thin-output deconv, GEMM over (tap, channel) rows + col2im in shared memory
   constexpr bool WSTATIC = THIN || DT != 0;  // every weight K-block has its own stage: loaded once, never released
@@ -287,7 +288,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int i = 0; i < p.nsets * p.nplanes; i++) { mbar_init(&afull[i], p.thin_in ? NB : 1); mbar_init(&aempty[i], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (p.epi_alt || p.epi4) ? 4 : 8); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], THRP ? 8 + XEPI : (p.epi_alt || p.epi4) ? 4 : 8); }
     for (int a = 0; a < U2_NPB; a++) { mbar_init(&pfull[a], 1); mbar_init(&pempty[a], NB); }
     fence_barrier_init();
   }
@@ -333,7 +334,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
     }
-  } else if (warp >= 10) {
+  } else if (warp >= 10 && warp < 10 + NB) {
     // ===================== TMA producer: input planes =====================
     // Independent of the weight ring: plane i of the next tile is fetched the moment the MMAs that read plane i of
     // the current tile have retired (aempty), i.e. while the remaining taps of the current tile execute.
@@ -489,12 +490,14 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
     if (lane == 0) PROF_FLUSH(1);
-  } else if (warp < 10) {
+  } else if (warp < 10 || XEPI > 0) {
     // ===================== epilogue (warps 2..9): lane = output channel, TMEM column = pixel =====================
     // two warps per TMEM lane quarter; `half` splits the accumulator columns (pixels) between them
-    const int q = warp & 3, half = (warp - 2) >> 2;
-    const bool alt = p.epi_alt != 0;
-    const bool whole = alt || p.epi4;  // this warp covers every column of the accumulators it serves
+    // (EPI >= 2: further groups of four warps behind the producers, `half` = 2, 3)
+    const int q = warp & 3, half = warp < 10 ? (warp - 2) >> 2 : 2 + ((warp - 10 - NB) >> 2);
+    constexpr int NHALF = 2 + XEPI / 4;
+    const bool alt = !THRP && p.epi_alt != 0;
+    const bool whole = alt || (!THRP && p.epi4);  // this warp covers every column of the accumulators it serves
     const int col_lo = whole ? 0 : half * (p.NPX / 2), col_hi = whole ? p.NPX : col_lo + p.NPX / 2;
     const int ebar = alt ? 1 + half : 1, ecnt = alt ? 128 : 256;      // named barrier of this warp's epilogue group
     const int erow0 = alt ? q : warp - 2, erows = alt ? 4 : 8;        // TMA-store rows dealt over the group's warps
@@ -510,7 +513,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const bool thin = !THRP && p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
     uint32_t acc_it = 0;
     PROF_START();
-    for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid() && !(p.epi4 && half); ti.next()) {
+    for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid() && !(!THRP && p.epi4 && half); ti.next()) {
       const int img = ti.img;
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
         const int acc = (int)ring_idx(acc_it, p.acc_stages);
@@ -944,10 +947,10 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const int xblocks = (vcols + 15) >> 4, nunits = (vrows >> 1) * xblocks;
             int urow = 2 * (half / xblocks), ublk = half % xblocks;  // unit -> (row pair, x block), advanced without divisions
 #pragma unroll 1
-            for (int u = half; u < nunits; u += 2) {
+            for (int u = half; u < nunits; u += NHALF) {
               {
                 const int rr = urow, xb = 16 * ublk;
-                ublk += 2;
+                ublk += NHALF;
                 while (ublk >= xblocks) { ublk -= xblocks; urow += 2; }
                 if (mono) {
                   // count-of-thresholds-below is non-decreasing in the TA-wrapped accumulator: pool first, then ONE search
@@ -1308,6 +1311,8 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1449,6 +1454,8 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1608,7 +1615,32 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
 
 void umma2_plan_destroy(Umma2Plan* U) { delete U; }
 
+static const char* umma2_describe_base(const Umma2Plan* U, char* buf, size_t n);
+// Pooled 8-bit threshold layers with a monotone compare and shared-memory tables run the instantiation that contains nothing else
+// (EPI >= 1).  Returns -1 for other layers, else the number of EXTRA epilogue warps (0, 4, 8).
+// The lock-step search is latency-bound (issue slots ~40 % busy with 8 epilogue warps): tiles with enough (row pair, 16-column)
+// units get the group count that minimises units per group.  Measured (img/s with 8 / 12 / 16 epilogue warps): config 5b stage 1
+// (8 units) 21.5 k / 24.2 k / 25.8 k, stage 2 (6 units) 60.1 k / 69.3 k / 67.5 k, config 4 (4 units) 583 k / 532 k / 560 k.
+static int thrp_extra_warps(const Params2& p) {
+  const EpiParams& e = p.epi;
+  const bool thrp = e.act_kind == FCB_ACT_THRESHOLDS && e.pool == 2 && e.out_bits == 8 && p.thr_off >= 0 && !p.deconv &&
+                    (e.cmp == FCB_CMP_LESS || e.cmp == FCB_CMP_LESS_EQUAL) && e.act_val >= 0 && e.act_val + e.num_th < 256 &&
+                    (e.acc_signed || e.acc_bits < 32) && !getenv("FCB_U2_NO_THRP");
+  if (!thrp) return -1;
+  if (const char* xe = getenv("FCB_U2_XEPI")) return atoi(xe) >= 8 ? 8 : atoi(xe) >= 4 ? 4 : 0;  // experiment switch
+  const int nunits = (p.R >> 1) * ((p.WT + 15) >> 4);
+  return nunits < 6 ? 0 : (nunits + 3) / 4 < (nunits + 2) / 3 ? 8 : 4;
+}
+
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n) {
+  const char* d = umma2_describe_base(U, buf, n);
+  const int xw = thrp_extra_warps(U->p);
+  const size_t len = strlen(buf);
+  if (xw >= 0 && len + 24 < n) snprintf(buf + len, n - len, " epi-warps=%d", 8 + xw);
+  return d;
+}
+
+static const char* umma2_describe_base(const Umma2Plan* U, char* buf, size_t n) {
   const Params2& p = U->p;
   if (p.dthin == 2) {
     snprintf(buf, n, "thin-output deconv: GEMM over (tap, channel) rows + shared-memory col2im, WT=%d R=%d (+1 halo ring, %d of 256 columns) planes=%dx%d smem=%zu tiles=%dx%d",
@@ -1692,16 +1724,17 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
 #endif
   // thin-input: 4 builder warps beside the light bias/ReLU epilogue (128 registers per thread suffice); 2 beside the threshold
   // epilogue, whose lock-step searches need ~170 registers to stay out of local memory
-  // pooled 8-bit threshold layers with a monotone compare and shared-memory tables get the instantiation that contains nothing else
-  const EpiParams& e = p.epi;
-  const bool thrp = e.act_kind == FCB_ACT_THRESHOLDS && e.pool == 2 && e.out_bits == 8 && p.thr_off >= 0 && !p.deconv &&
-                    (e.cmp == FCB_CMP_LESS || e.cmp == FCB_CMP_LESS_EQUAL) && e.act_val >= 0 && e.act_val + e.num_th < 256 &&
-                    (e.acc_signed || e.acc_bits < 32) && !getenv("FCB_U2_NO_THRP");
-  if (p.thin_in && thrp) umma2_conv_kernel<2, 0, 1><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  const int xepi = thrp_extra_warps(p);
+  const bool thrp = xepi >= 0;
+  if (p.thin_in && thrp && xepi == 8) umma2_conv_kernel<2, 0, 3><<<grid, 320 + 32 * 2 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.thin_in && thrp && xepi == 4) umma2_conv_kernel<2, 0, 2><<<grid, 320 + 32 * 2 + 128, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.thin_in && thrp) umma2_conv_kernel<2, 0, 1><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2, 0, 0><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.thin_in) umma2_conv_kernel<4, 0, 0><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.dthin == 2) umma2_conv_kernel<1, 2, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.dthin) umma2_conv_kernel<1, 1, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (thrp && xepi == 8) umma2_conv_kernel<1, 0, 3><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (thrp && xepi == 4) umma2_conv_kernel<1, 0, 2><<<grid, 320 + 32 + 128, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (thrp) umma2_conv_kernel<1, 0, 1><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else umma2_conv_kernel<1, 0, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   FCB_CUDA_OK(cudaGetLastError());

@@ -13,7 +13,7 @@ import ctypes
 
 import numpy as np
 
-from . import _lib
+from . import _lib, pack
 from .desc import LayerDesc
 
 
@@ -52,6 +52,19 @@ class ConvLayer:
         if w.size != self.weight_bytes or (t is not None and t.size != self.threshold_bytes) or (b is not None and b.size != self.bias_bytes):
             raise ValueError("parameter image size does not match the layer")
         _lib.check(_lib.lib().fcb_layer_set_params(self._h, _ptr(w), _ptr(t), _ptr(b)))
+
+    def set_param_stream(self, param_words, thresholds=None, bias=None) -> None:
+        """set_params with the weights as one period of the reference's parameter stream (GenParamStream, dma.h:214-236:
+        TILES words of SIMD*PE*WP bits, as Matrix_Vector_Activate_Stream_Batch consumes them, mvau.hpp:262-266)."""
+        d = self.desc
+        tiles = (d.kernel_x * d.kernel_y * d.ifm_ch // d.simd) * (d.ofm_ch // d.pe)
+        w = np.ascontiguousarray(param_words, dtype=np.uint8)
+        t = None if thresholds is None else np.ascontiguousarray(thresholds, dtype=np.uint8)
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.uint8)
+        if w.size != tiles * pack.word_bytes(d.simd * d.pe * d.w_bits) or (t is not None and t.size != self.threshold_bytes) or \
+                (b is not None and b.size != self.bias_bytes):
+            raise ValueError("parameter image size does not match the layer")
+        _lib.check(_lib.lib().fcb_layer_set_param_stream(self._h, _ptr(w), _ptr(t), _ptr(b)))
 
     @property
     def engine(self) -> str:

@@ -78,6 +78,17 @@ def pack_weights(w: np.ndarray, simd: int, pe: int, w_bits: int) -> np.ndarray:
     return pack_words(t, w_bits).reshape(-1)
 
 
+def pack_param_stream(w: np.ndarray, simd: int, pe: int, w_bits: int) -> np.ndarray:
+    """W[OFM, K] -> one period (TILES words) of the parameter stream GenParamStream writes (dma.h:214-236): word `tile`
+    = ap_uint<SIMD*PE*WP>, PE-row pe at bits [pe*SIMD*WP, (pe+1)*SIMD*WP), SIMD lane l of it at l*WP."""
+    ofm, k = w.shape
+    assert ofm % pe == 0 and k % simd == 0
+    nf, sf = ofm // pe, k // simd
+    # [nf, pe, sf, simd] -> [nf, sf, pe*simd]
+    t = np.asarray(w).reshape(nf, pe, sf, simd).transpose(0, 2, 1, 3).reshape(nf * sf, pe * simd)
+    return pack_words(t, w_bits).reshape(-1)
+
+
 def unpack_weights(buf: np.ndarray, ofm: int, k: int, simd: int, pe: int, w_bits: int, signed: bool = True) -> np.ndarray:
     nf, sf = ofm // pe, k // simd
     wb = word_bytes(simd * w_bits)

@@ -437,6 +437,23 @@ def test_set_params_swaps_weights_in_place(name, fcb_lib, oracle_mod):
         L.set_params(b["weights"][:-1])
 
 
+@pytest.mark.parametrize("name", ["th_a", "th_b", "th_c", "c2d_e", "dc_d", "xn_c"])
+def test_set_param_stream(name, fcb_lib, oracle_mod):
+    """fcb_layer_set_param_stream: weights handed over as one period of the reference's parameter stream (GenParamStream,
+    dma.h:214-236; golden image recorded from the reference for the th_* cases) -- results follow the oracle."""
+    d = cases.CASES[name]
+    a, b = cases.make_inputs(d, seed_shift=0), cases.make_inputs(d, seed_shift=31)
+    L = _layer(d, b)
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"param_stream_{name}.npz")
+    pw = np.load(gold)["param_words"] if os.path.exists(gold) else oracle_mod.gen_param_stream(d, a["weights"])
+    assert np.array_equal(pw, oracle_mod.gen_param_stream(d, a["weights"]))
+    L.set_param_stream(pw, thresholds=a["thresholds"], bias=a["bias"])
+    x = a["in_words"]
+    assert np.array_equal(L.run(x), oracle_mod.run_layer(d, x, a["weights"], a["thresholds"], a["bias"]))
+    with pytest.raises(ValueError):
+        L.set_param_stream(pw[:-1])
+
+
 def test_judged_configs_at_full_size(fcb_lib, oracle_mod):
     """BASELINE.json configs 3 and 5b (first and last stage) at their full sizes against the oracle (config 4 at full size is
     `th_cfg4` above; config 2 is `c2d_L1`; config 5a / the full network are tests/test_net8.py)."""

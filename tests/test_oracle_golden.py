@@ -38,6 +38,28 @@ def test_restatement_matches_golden(name, oracle_mod):
         assert np.array_equal(out, g["out"])
 
 
+@pytest.mark.parametrize("name", ["th_a", "th_b", "th_c"])
+def test_param_stream_matches_golden(name, oracle_mod):
+    """The weight stream GenParamStream writes (dma.h:214-236), as recorded from the reference (param_stream_*.npz, whose
+    out_sha is the output of Matrix_Vector_Activate_Stream_Batch fed by it == the static-weights layer output): the oracle's
+    restatement and the host packer must produce the same bytes."""
+    from simple_image_compression_network_b200 import pack
+    g = np.load(os.path.join(GOLD, f"param_stream_{name}.npz"))
+    d = cases.CASES[name]
+    inp = cases.make_inputs(d)
+    assert _sha(inp["weights"]) == str(g["w_sha"])
+    assert str(g["out_sha"]) == str(np.load(os.path.join(GOLD, f"layer_{name}.npz"))["out_sha"])
+    assert np.array_equal(oracle_mod.gen_param_stream(d, inp["weights"]), g["param_words"])
+    assert np.array_equal(pack.pack_param_stream(inp["w"], d.simd, d.pe, d.w_bits), g["param_words"])
+    if oracle_mod.ref_available():
+        s = oracle_mod.query(d)
+        inp2 = cases.make_inputs(d, seed_shift=5)
+        out, pw = oracle_mod.ref_stream_run(name, inp2["in_words"], inp2["weights"], inp2["thresholds"], s.out_bytes_per_image,
+                                            g["param_words"].size)
+        assert np.array_equal(pw, oracle_mod.gen_param_stream(d, inp2["weights"]))
+        assert np.array_equal(out, oracle_mod.run_layer(d, inp2["in_words"], inp2["weights"], inp2["thresholds"], None))
+
+
 @pytest.mark.parametrize("name", [n for n in cases.CASES if n not in cases.SLOW])
 def test_restatement_matches_live_reference(name, oracle_mod):
     if not oracle_mod.ref_available():

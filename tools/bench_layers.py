@@ -67,8 +67,19 @@ if __name__ == "__main__":
     c4 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=256, ofm_ch=256, ifm_x=64, ifm_y=48, stride_x=1, stride_y=1, pad=1,
                    simd=32, pe=32, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8, num_th=255,
                    pool=2)
+    # BASELINE.json config 5b: analysis-transform-shaped stack [K3 S1 P1 conv -> 255 thresholds (u8) -> 2x2 max pool] x 4,
+    # channels 3 -> 128 -> 128 -> 128 -> 192 on 768x512 (SURVEY.md 8(d)); 5a = layers 0-3 of the reference net
+    def stage(c, ofm, x, y, simd, pe):
+        return LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=1, stride_y=1, pad=1,
+                         simd=simd, pe=pe, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8,
+                         num_th=255, pool=2)
+    st = [stage(3, 128, 768, 512, 3, 16), stage(128, 128, 384, 256, 32, 16), stage(128, 128, 192, 128, 32, 16), stage(128, 192, 96, 64, 32, 24)]
     if a.only:
         for nm in a.only.split(","):
+            if nm.startswith("s5b"):
+                i = int(nm[3:]) - 1
+                bench_layer(f"stack5b_stage{i + 1}", st[i], a.images if i == 0 else a.images * 4, 0xFF)
+                continue
             if nm == "cfg3t":
                 os.environ["FCB_XNOR_ENGINE"] = "tensor"
                 bench_layer("cfg3_xnor_tensor", c3, a.images, 0xFF)
@@ -108,13 +119,6 @@ if __name__ == "__main__":
     dt = (time.perf_counter() - t0) / 3
     print(json.dumps(dict(layer="eight_layers_net_e2e_host_buffers", images=n, ms=round(dt * 1e3, 3), img_s=round(n / dt, 1),
                           pcie_GBs=round(n * (net.in_bytes + net.out_bytes) / dt / 1e9, 1))), flush=True)
-    # BASELINE.json config 5b: analysis-transform-shaped stack [K3 S1 P1 conv -> 255 thresholds (u8) -> 2x2 max pool] x 4,
-    # channels 3 -> 128 -> 128 -> 128 -> 192 on 768x512 (SURVEY.md 8(d)); 5a = layers 0-3 of the reference net
-    def stage(c, ofm, x, y, simd, pe):
-        return LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=1, stride_y=1, pad=1,
-                         simd=simd, pe=pe, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8,
-                         num_th=255, pool=2)
-    st = [stage(3, 128, 768, 512, 3, 16), stage(128, 128, 384, 256, 32, 16), stage(128, 128, 192, 128, 32, 16), stage(128, 192, 96, 64, 32, 24)]
     sl = []
     for i, d in enumerate(st):
         L, _ = bench_layer(f"stack5b_stage{i + 1}", d, a.images if i == 0 else a.images * 4, 0xFF)
