@@ -219,7 +219,7 @@ struct DcolGather<OFM, 25> {
 // EPI = 1: the instantiation for pooled 8-bit threshold layers (monotone compare, shared-memory tables): every other epilogue is
 // compiled out, which frees registers and instruction cache for the lock-step search.
 template <int NB, int DT, int EPI>
-__global__ void __launch_bounds__(320 + 32 * NB + (EPI >= 2 ? 128 * (EPI - 1) : 0), 1)
+__global__ void __launch_bounds__(320 + 32 * NB + (EPI == 4 ? 256 : EPI >= 2 ? 128 * (EPI - 1) : 0), 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params2 p) {
   extern __shared__ uint8_t smem_raw[];
@@ -237,8 +237,13 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool THIN = NB > 1;         // thin-input instantiations (im2col builder warps)
-  constexpr bool THRP = EPI >= 1;   // pooled 8-bit thresholds only
-  constexpr int XEPI = EPI >= 2 ? 4 * (EPI - 1) : 0;  // EPI = 2, 3: 4 / 8 more epilogue warps behind the producer warps (the search is latency-bound)
+  constexpr bool THRP = EPI >= 1 && EPI <= 3;   // pooled 8-bit thresholds only
+  // EPI = 4: pixel-major bias+ReLU with warp-local TMA stores only (thin-input layers), FOUR epilogue groups: group g serves
+  // accumulator stage g & 1 and the 128-pixel block g >> 1 of its tiles (a warp issues one instruction per ~5 clocks on this
+  // path -- fixed-latency dependency stalls -- so the issue slots are filled with more warps instead)
+  constexpr bool SWPX = EPI == 4;
+  constexpr bool GEN = EPI == 0;  // the general instantiation: every epilogue family behind run-time flags
+  constexpr int XEPI = SWPX ? 8 : EPI >= 2 ? 4 * (EPI - 1) : 0;  // EPI = 2, 3: 4 / 8 more epilogue warps behind the producer warps (the search is latency-bound)
   constexpr bool DTHIN = DT == 1;   // thin-output deconv, 9 shift blocks x N=16 (pixels on M)
   constexpr bool DCOL = DT == 2;    // thin-output deconv, GEMM over (tap, channel) rows + col2im in shared memory
   constexpr bool WSTATIC = THIN || DT != 0;  // every weight K-block has its own stage: loaded once, never released
@@ -288,7 +293,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int i = 0; i < p.nsets * p.nplanes; i++) { mbar_init(&afull[i], p.thin_in ? NB : 1); mbar_init(&aempty[i], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], THRP ? 8 + XEPI : (p.epi_alt || p.epi4) ? 4 : 8); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], THRP ? 8 + XEPI : SWPX ? 8 : (p.epi_alt || p.epi4) ? 4 : 8); }
     for (int a = 0; a < U2_NPB; a++) { mbar_init(&pfull[a], 1); mbar_init(&pempty[a], NB); }
     fence_barrier_init();
   }
@@ -496,28 +501,28 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // (EPI >= 2: further groups of four warps behind the producers, `half` = 2, 3)
     const int q = warp & 3, half = warp < 10 ? (warp - 2) >> 2 : 2 + ((warp - 10 - NB) >> 2);
     constexpr int NHALF = 2 + XEPI / 4;
-    const bool alt = !THRP && p.epi_alt != 0;
-    const bool whole = alt || (!THRP && p.epi4);  // this warp covers every column of the accumulators it serves
+    const bool alt = SWPX || (GEN && p.epi_alt != 0);
+    const bool whole = alt || (GEN && p.epi4);  // this warp covers every column of the accumulators it serves
     const int col_lo = whole ? 0 : half * (p.NPX / 2), col_hi = whole ? p.NPX : col_lo + p.NPX / 2;
     const int ebar = alt ? 1 + half : 1, ecnt = alt ? 128 : 256;      // named barrier of this warp's epilogue group
     const int erow0 = alt ? q : warp - 2, erows = alt ? 4 : 8;        // TMA-store rows dealt over the group's warps
 #define EPI_BAR() asm volatile("bar.sync %0, %1;" ::"r"(ebar), "r"(ecnt) : "memory")
     const int pk = THRP ? 2 : (p.epi.pool >= 2 ? p.epi.pool : 1);
-    const bool fast = !THRP && p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && (p.OFM % 32) == 0 && p.P >= 4;
+    const bool fast = GEN && p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && (p.OFM % 32) == 0 && p.P >= 4;
     // thresholds with comp::less / less_equal and a result that cannot wrap TR: monotone in the (wrapped, < 2^31) accumulator
     const bool mono = THRP || p.epi.act_kind == FCB_ACT_THRESHOLDS && (p.epi.cmp == FCB_CMP_LESS || p.epi.cmp == FCB_CMP_LESS_EQUAL) &&
                       p.epi.act_val >= 0 && (p.epi.out_bits >= 31 || p.epi.act_val + p.epi.num_th < (1 << p.epi.out_bits)) &&
                       (p.epi.acc_signed || p.epi.acc_bits < 32);
     int gshift = 0;  // log2 of the group the shared-memory levels of the threshold search narrow down to
     if (p.thr_off >= 0) for (int t = p.epi.thr_n + 1; (t >> (p.thr_top + gshift)) > 1;) gshift++;
-    const bool thin = !THRP && p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
+    const bool thin = GEN && p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
     uint32_t acc_it = 0;
     PROF_START();
-    for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid() && !(!THRP && p.epi4 && half); ti.next()) {
+    for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid() && !(GEN && p.epi4 && half); ti.next()) {
       const int img = ti.img;
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
         const int acc = (int)ring_idx(acc_it, p.acc_stages);
-        if (alt && acc != half) continue;  // the other group's accumulator
+        if (alt && acc != (SWPX ? (half & 1) : half)) continue;  // the other group's accumulator
         const PixMap pm{p, ti.tx * p.WT, ti.ty * p.R, p.phases[ph].px, p.phases[ph].py, (unsigned long long)img * p.out_img_bytes};
         PROF_T(0);
         WAITB(&tfull[acc], ring_par(acc_it, p.acc_stages));
@@ -525,7 +530,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
-        if (!THRP && DCOL) {
+        if (GEN && DCOL) {
           // (always two accumulator stages: warps 2..5 serve stage 0, warps 6..9 stage 1, each group with its own byte tile)
           const int nrows = 25 * p.OFM;
           uint8_t* S = smem + p.stg_off + half * p.stg_bytes;
@@ -593,7 +598,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           continue;
         }
-        if (!THRP && DTHIN) {
+        if (GEN && DTHIN) {
           // thread = input pixel m of block `half`; its 16 columns are the 2x2 output words it produces (bias + ReLU on the
           // wrapped 8-bit lane, conv_nonsquare_top.cpp:183-194); a warp writes two 256-byte runs of output row 2y and 2y+1
           const int m = half * 128 + q * 32 + lane;
@@ -625,16 +630,16 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           continue;
         }
-        if (!THRP && p.swap) {
+        if (SWPX || (GEN && p.swap)) {
           // Swapped staged bias + ReLU epilogue: thread = pixel (TMEM lane), 32-column loads = 32 channels of that pixel ->
           // 8 packed words -> two 16-byte stores into the SWIZZLE_128B staging row of the pixel; TMA stores un-swizzle.
-          const int sb = alt ? half : (int)ring_idx(acc_it, p.stg_bufs);
+          const int sb = SWPX ? (half & 1) : alt ? half : (int)ring_idx(acc_it, p.stg_bufs);
           uint8_t* stg = smem + p.stg_off + sb * p.stg_bytes;
           if (lane == 0) {
             if (p.stg_bufs == 2 && !alt) bulk_wait_read<1>();
             else bulk_wait_read<0>();
           }
-          if (p.wl) __syncwarp();
+          if (SWPX || p.wl) __syncwarp();
           else EPI_BAR();
           PROF_T(2);
           // items = (128-pixel block, 32-channel block), block-major; this warp takes every `its`-th item from `it0`
@@ -679,7 +684,19 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               for (int cb = 0; cb < p.CB; cb++) tma_store_4d(&tmO, stg + (cb * p.NPX + m0) * 128, cb * 128, pm.x0 + xo, pm.y0 + rr, img);
           };
           const int it0 = alt ? 0 : half, its = alt ? 1 : 2;
-          if (it0 < nitems) {  // software pipeline: the next item's TMEM load is in flight while this one is packed
+          if (SWPX) {
+            // four groups: this group's items are the channel blocks of pixel block half >> 1; one load in flight per warp --
+            // 88 registers per thread leave no room for a second buffer, the other three warps of the scheduler cover the latency
+            uint32_t va[32];
+            const int blk = half >> 1;
+#pragma unroll 1
+            for (int cbk = 0; cbk < cpb; cbk++) {
+              tmem_ld32(tacc + (uint32_t)(blk * p.CB * 128 + cbk * 32), va);
+              tmem_ld_wait();
+              process(blk, cbk, va);
+            }
+            store_block(blk);
+          } else if (it0 < nitems) {  // software pipeline: the next item's TMEM load is in flight while this one is packed
             uint32_t va[32], vb[32];
             int blk = 0, cbk = it0, left = (nitems - it0 + its - 1) / its;  // items this warp still has to load
             int blk_n = blk, cbk_n = cbk;
@@ -688,24 +705,28 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             --left;
             while (true) {
               tmem_ld_wait();
+              PROF_T(3);
               blk = blk_n; cbk = cbk_n;
               if (left > 0) { advance(); tmem_ld32(tacc + (uint32_t)(blk_n * p.CB * 128 + cbk_n * 32), vb); }
               process(blk, cbk, va);
-              if (p.wl && cbk == cpb - 1) store_block(blk);
+              PROF_T(4);
+              if (p.wl && cbk == cpb - 1) { store_block(blk); PROF_T(5); }
               if (left-- <= 0) break;
               tmem_ld_wait();
+              PROF_T(3);
               blk = blk_n; cbk = cbk_n;
               if (left > 0) { advance(); tmem_ld32(tacc + (uint32_t)(blk_n * p.CB * 128 + cbk_n * 32), va); }
               process(blk, cbk, vb);
-              if (p.wl && cbk == cpb - 1) store_block(blk);
+              PROF_T(4);
+              if (p.wl && cbk == cpb - 1) { store_block(blk); PROF_T(5); }
               if (left-- <= 0) break;
             }
           }
-          PROF_T(3);
+          PROF_T(7);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
-          if (p.wl) {
+          if (SWPX || p.wl) {
             if (lane == 0) bulk_commit();
             PROF_T(6);
             continue;
@@ -723,7 +744,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           PROF_T(6);
           continue;
         }
-        if (!THRP && p.stg_bufs > 0) {
+        if (SWPX) continue;
+        if (GEN && p.stg_bufs > 0) {
           // Staged bias + ReLU epilogue (conv_nonsquare_top.cpp:267-278): thread = channel turns its 32-column TMEM loads into
           // bytes of the tile's [pixel][channel] image in shared memory (a warp's 32 lanes write 32 consecutive bytes: one
           // wavefront, no shuffles, no predicates); one thread then issues a TMA store per tile row.  The register path below
@@ -778,7 +800,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           PROF_T(6);
           continue;
         }
-        if (!THRP && thin) {
+        if (GEN && thin) {
           // Thin output (OFM <= 8, e.g. the 3-channel last layer): only lanes < OFM of the first lane quarter hold data.
           // They turn their 256 columns into bytes in a shared staging row per channel; then all 128 epilogue threads
           // assemble and store whole output words, one pixel per thread (coalesced), instead of 3 lanes doing everything.
@@ -831,7 +853,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const int row_shift = p.CB == 2 ? 10 : 9;  // log2(CB * 128 channels * 4 bytes)
           const bool chv = ch < p.OFM;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
-          if (!THRP && fast) {
+          if (GEN && fast) {
             // bias + ReLU on the wrapped 8-bit value (conv_nonsquare_top.cpp:267-278).  The thread owns one channel and
             // 32 pixels; a 4x4 byte transpose across each lane quad (2 shuffles + 2 PRMT per word) turns that into
             // 4 consecutive channel bytes of one pixel per lane, so a warp store writes 4 pixels x 32 B.
@@ -864,7 +886,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 dst += xstep4 + (wrapped ? wrap_delta : 0ll);
               }
             }
-          } else if (!THRP && pk == 1) {
+          } else if (GEN && pk == 1) {
             int rr = col_lo / p.P, xo = col_lo - rr * p.P;
 #pragma unroll 1
             for (int c0 = col_lo; c0 < col_hi && rr < vrows; c0 += 32) {
@@ -1033,7 +1055,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   }
   if (warp == 2 && lane == 0) PROF_FLUSH(2);
-  if (warp >= 2 && warp < 10 && lane == 0 && p.stg_bufs > 0) bulk_wait<0>();  // staged stores still read shared memory
+  if (warp >= 2 && (warp < 10 || warp >= 10 + NB) && lane == 0 && p.stg_bufs > 0) bulk_wait<0>();  // staged stores still read shared memory
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
@@ -1452,6 +1474,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     if (rc) { delete U; return rc; }
   }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1730,6 +1753,8 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   else if (p.thin_in && thrp && xepi == 4) umma2_conv_kernel<2, 0, 2><<<grid, 320 + 32 * 2 + 128, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.thin_in && thrp) umma2_conv_kernel<2, 0, 1><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2, 0, 0><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.thin_in && p.swap && p.wl && p.epi_alt && p.NPX == 256 && !getenv("FCB_U2_NO_SWPX"))  // pixel-major bias+ReLU, warp-local stores: 16 epilogue warps
+    umma2_conv_kernel<4, 0, 4><<<grid, 320 + 32 * 4 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.thin_in) umma2_conv_kernel<4, 0, 0><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.dthin == 2) umma2_conv_kernel<1, 2, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.dthin) umma2_conv_kernel<1, 1, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
