@@ -219,7 +219,7 @@ struct DcolGather<OFM, 25> {
 // EPI = 1: the instantiation for pooled 8-bit threshold layers (monotone compare, shared-memory tables): every other epilogue is
 // compiled out, which frees registers and instruction cache for the lock-step search.
 template <int NB, int DT, int EPI>
-__global__ void __launch_bounds__(320 + 32 * NB + (EPI == 4 ? 256 : EPI >= 2 ? 128 * (EPI - 1) : 0), 1)
+__global__ void __launch_bounds__(320 + 32 * NB + (EPI >= 4 ? 256 : EPI >= 2 ? 128 * (EPI - 1) : 0), 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params2 p) {
   extern __shared__ uint8_t smem_raw[];
@@ -243,7 +243,13 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   // path -- fixed-latency dependency stalls -- so the issue slots are filled with more warps instead)
   constexpr bool SWPX = EPI == 4;
   constexpr bool GEN = EPI == 0;  // the general instantiation: every epilogue family behind run-time flags
-  constexpr int XEPI = SWPX ? 8 : EPI >= 2 ? 4 * (EPI - 1) : 0;  // EPI = 2, 3: 4 / 8 more epilogue warps behind the producer warps (the search is latency-bound)
+  // EPI = 5 (with DT = 2): the col2im epilogue alone, four groups: groups g and g + 2 share accumulator stage g & 1 and its byte
+  // tile, splitting the columns of phase 1 and the pixels of phase 2
+  constexpr bool DCX = EPI == 5;
+  // EPI = 6: the staged channel-major bias+ReLU epilogue alone (two staging tiles, one per accumulator stage), four groups:
+  // groups g and g + 2 share stage g & 1, taking alternate 32-column blocks and alternate rows of the TMA stores
+  constexpr bool STX = EPI == 6;
+  constexpr int XEPI = (SWPX || DCX || STX) ? 8 : EPI >= 2 ? 4 * (EPI - 1) : 0;  // EPI = 2, 3: 4 / 8 more epilogue warps behind the producer warps (the search is latency-bound)
   constexpr bool DTHIN = DT == 1;   // thin-output deconv, 9 shift blocks x N=16 (pixels on M)
   constexpr bool DCOL = DT == 2;    // thin-output deconv, GEMM over (tap, channel) rows + col2im in shared memory
   constexpr bool WSTATIC = THIN || DT != 0;  // every weight K-block has its own stage: loaded once, never released
@@ -293,7 +299,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int i = 0; i < p.nsets * p.nplanes; i++) { mbar_init(&afull[i], p.thin_in ? NB : 1); mbar_init(&aempty[i], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], THRP ? 8 + XEPI : SWPX ? 8 : (p.epi_alt || p.epi4) ? 4 : 8); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], THRP ? 8 + XEPI : (SWPX || DCX || STX) ? 8 : (p.epi_alt || p.epi4) ? 4 : 8); }
     for (int a = 0; a < U2_NPB; a++) { mbar_init(&pfull[a], 1); mbar_init(&pempty[a], NB); }
     fence_barrier_init();
   }
@@ -501,11 +507,12 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // (EPI >= 2: further groups of four warps behind the producers, `half` = 2, 3)
     const int q = warp & 3, half = warp < 10 ? (warp - 2) >> 2 : 2 + ((warp - 10 - NB) >> 2);
     constexpr int NHALF = 2 + XEPI / 4;
-    const bool alt = SWPX || (GEN && p.epi_alt != 0);
+    const bool alt = SWPX || DCX || STX || (GEN && p.epi_alt != 0);
     const bool whole = alt || (GEN && p.epi4);  // this warp covers every column of the accumulators it serves
-    const int col_lo = whole ? 0 : half * (p.NPX / 2), col_hi = whole ? p.NPX : col_lo + p.NPX / 2;
-    const int ebar = alt ? 1 + half : 1, ecnt = alt ? 128 : 256;      // named barrier of this warp's epilogue group
-    const int erow0 = alt ? q : warp - 2, erows = alt ? 4 : 8;        // TMA-store rows dealt over the group's warps
+    const int col_lo = STX ? 32 * (half >> 1) : whole ? 0 : half * (p.NPX / 2), col_hi = whole ? p.NPX : col_lo + p.NPX / 2;
+    constexpr int col_step = STX ? 64 : 32;
+    const int ebar = alt ? 1 + (half & 1) : 1, ecnt = (DCX || STX) ? 256 : alt ? 128 : 256;      // named barrier of this warp's epilogue group
+    const int erow0 = STX ? 4 * (half >> 1) + q : alt ? q : warp - 2, erows = (alt && !STX) ? 4 : 8;        // TMA-store rows dealt over the group's warps
 #define EPI_BAR() asm volatile("bar.sync %0, %1;" ::"r"(ebar), "r"(ecnt) : "memory")
     const int pk = THRP ? 2 : (p.epi.pool >= 2 ? p.epi.pool : 1);
     const bool fast = GEN && p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && (p.OFM % 32) == 0 && p.P >= 4;
@@ -522,7 +529,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int img = ti.img;
       for (int ph = 0; ph < p.nphases; ph++, acc_it++) {
         const int acc = (int)ring_idx(acc_it, p.acc_stages);
-        if (alt && acc != (SWPX ? (half & 1) : half)) continue;  // the other group's accumulator
+        if (alt && acc != (half & 1)) continue;  // the other group's accumulator
         const PixMap pm{p, ti.tx * p.WT, ti.ty * p.R, p.phases[ph].px, p.phases[ph].py, (unsigned long long)img * p.out_img_bytes};
         PROF_T(0);
         WAITB(&tfull[acc], ring_par(acc_it, p.acc_stages));
@@ -530,11 +537,13 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
-        if (GEN && DCOL) {
+        if ((GEN || DCX) && DCOL) {
           // (always two accumulator stages: warps 2..5 serve stage 0, warps 6..9 stage 1, each group with its own byte tile)
           const int nrows = 25 * p.OFM;
-          uint8_t* S = smem + p.stg_off + half * p.stg_bytes;
+          uint8_t* S = smem + p.stg_off + (half & 1) * p.stg_bytes;
           const uint32_t S_s = smem_u32(S);
+          const int sub = DCX ? half >> 1 : 0;  // which of the stage's two groups this warp belongs to
+          constexpr int NSUB = DCX ? 2 : 1;
           EPI_BAR();  // the group's previous col2im pass has finished reading S
           // ---- phase 1: accumulator rows -> bytes (all arithmetic is mod 2^8, so the partial sums may be truncated now)
           if (q * 32 < nrows && !(p.debug & 8)) {
@@ -542,7 +551,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
             const uint32_t srow = S_s + (uint32_t)(row * p.s_pitch);
             const int ncols = (vrows + 2) * p.P;
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
+            for (int c0 = 32 * sub; c0 < ncols; c0 += 32 * NSUB) {
               uint32_t v[32];
               tmem_ld32(tacc + (uint32_t)c0, v);
               tmem_ld_wait();
@@ -565,7 +574,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           // ---- phase 2: col2im.  Thread = one interior input pixel (r, xo); tap (ky, kx) of phase (ky & 1, kx & 1) reads the
           // partial of pixel (r + offy, xo + offx), offy = (ky + (ky & 1) - 2) / 2
           const int npx = vrows * p.WT;
-          for (int idx = (warp & 3) * 32 + lane; idx < ((p.debug & 8) ? 0 : npx); idx += 128) {
+          for (int idx = sub * 128 + (warp & 3) * 32 + lane; idx < ((p.debug & 8) ? 0 : npx); idx += 128 * NSUB) {
             const int rr = idx / p.WT, xo = idx - rr * p.WT;
             if (xo >= vcols) continue;
             uint32_t b[3];
@@ -598,6 +607,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           continue;
         }
+        if (DCX) continue;
         if (GEN && DTHIN) {
           // thread = input pixel m of block `half`; its 16 columns are the 2x2 output words it produces (bias + ReLU on the
           // wrapped 8-bit lane, conv_nonsquare_top.cpp:183-194); a warp writes two 256-byte runs of output row 2y and 2y+1
@@ -745,12 +755,12 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           continue;
         }
         if (SWPX) continue;
-        if (GEN && p.stg_bufs > 0) {
+        if (STX || (GEN && p.stg_bufs > 0)) {
           // Staged bias + ReLU epilogue (conv_nonsquare_top.cpp:267-278): thread = channel turns its 32-column TMEM loads into
           // bytes of the tile's [pixel][channel] image in shared memory (a warp's 32 lanes write 32 consecutive bytes: one
           // wavefront, no shuffles, no predicates); one thread then issues a TMA store per tile row.  The register path below
           // (4-byte global stores after a quad transpose) is kept for plans whose planes leave no room for the staging tile.
-          const int sb = alt ? half : (int)ring_idx(acc_it, p.stg_bufs);
+          const int sb = alt ? (half & 1) : (int)ring_idx(acc_it, p.stg_bufs);
           uint8_t* stg = smem + p.stg_off + sb * p.stg_bytes;
           if (lane == 0) {  // this warp's previous stores from the buffer must have finished reading it
             if (p.stg_bufs == 2 && !alt) bulk_wait_read<1>();
@@ -763,7 +773,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const uint32_t bias4 = p.bias_word >= 0 ? 0u : ((uint32_t)(int32_t)p.epi.bias[ch] & 0xFFu) * 0x01010101u;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
             const uint32_t srow = smem_u32(stg) + (uint32_t)(cb * p.NPX * 128 + q * 32 + lane);
-            for (int c0 = col_lo; c0 < col_hi && c0 < vrows * p.P; c0 += 32) {
+            for (int c0 = col_lo; c0 < col_hi && c0 < vrows * p.P; c0 += col_step) {
               uint32_t v[32];
               tmem_ld32(taddr + (uint32_t)c0, v);
               tmem_ld_wait();
@@ -800,6 +810,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           PROF_T(6);
           continue;
         }
+        if (STX) continue;
         if (GEN && thin) {
           // Thin output (OFM <= 8, e.g. the 3-channel last layer): only lanes < OFM of the first lane quarter hold data.
           // They turn their 256 columns into bytes in a shared staging row per channel; then all 128 epilogue threads
@@ -1333,6 +1344,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
@@ -1632,6 +1644,7 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
     if (rc) { delete U; return rc; }
   }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
 }
@@ -1756,8 +1769,11 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   else if (p.thin_in && p.swap && p.wl && p.epi_alt && p.NPX == 256 && !getenv("FCB_U2_NO_SWPX"))  // pixel-major bias+ReLU, warp-local stores: 16 epilogue warps
     umma2_conv_kernel<4, 0, 4><<<grid, 320 + 32 * 4 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.thin_in) umma2_conv_kernel<4, 0, 0><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.dthin == 2 && !getenv("FCB_U2_NO_DCX")) umma2_conv_kernel<1, 2, 5><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.dthin == 2) umma2_conv_kernel<1, 2, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.dthin) umma2_conv_kernel<1, 1, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (!thrp && p.stg_bufs == 2 && p.epi_alt && !p.swap && !getenv("FCB_U2_NO_STX"))  // staged bias+ReLU, two tiles: 16 epilogue warps
+    umma2_conv_kernel<1, 0, 6><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (thrp && xepi == 8) umma2_conv_kernel<1, 0, 3><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (thrp && xepi == 4) umma2_conv_kernel<1, 0, 2><<<grid, 320 + 32 + 128, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (thrp) umma2_conv_kernel<1, 0, 1><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
