@@ -92,4 +92,19 @@ int launch_expand_bits(const Im2colParams& p, int n_images, cudaStream_t st);
 // synthetic data (fcb_synth.cu)
 int synth_fill(void* d_ptr, size_t n_bytes, uint64_t seed, uint32_t mask, uint64_t offset, cudaStream_t st);
 
+// Thin-output deconv522, col2im form: index (0..24) of tap t = ky*5 + kx in a pixel's record of 25 four-byte words.  Taps are grouped
+// by input shift (offy, offx) = ((k + (k & 1) - 2) / 2): the four 4-tap shifts first (16-byte aligned, words in output-phase order
+// ph = 2*(ky&1) + (kx&1)), then the four 2-tap shifts, then tap (0,0).  Weight rows (fcb_umma.cu) and the epilogue (fcb_umma2.cu) share it.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr int dcol_word(int t) {
+  const int ky = t / 5, kx = t % 5;
+  const int oy = (ky + (ky & 1) - 2) / 2, ox = (kx + (kx & 1) - 2) / 2;
+  return (oy >= 0 && ox >= 0) ? (oy * 2 + ox) * 4 + (ky & 1) * 2 + (kx & 1)
+         : (oy < 0 && ox >= 0) ? 16 + ox * 2 + (kx & 1)
+         : (oy >= 0 && ox < 0) ? 20 + oy * 2 + (ky & 1)
+                               : 24;
+}
+
 }  // namespace fcb

@@ -448,13 +448,13 @@ int umma_plan_create_dthin(const Geom& g, const std::vector<int32_t>& W, const E
   P->num_sms = prop.multiProcessorCount;
   const int cch = g.C / 128;
   if (!getenv("FCB_U2_NO_DCOL")) {
-    // col2im form: one GEMM over rows (tap * OFM + channel), K = the input channels; the taps are summed after the GEMM
+    // col2im form: one GEMM over rows (tap word * 4 + channel, dcol_word()), K = the input channels; the taps are summed after the GEMM
     std::vector<int8_t> wc((size_t)cch * 128 * 128, 0);
     for (int cc = 0; cc < cch; cc++)
       for (int t = 0; t < 25; t++)
         for (int o = 0; o < g.OFM; o++)
           for (int c = 0; c < 128; c++)
-            wc[((size_t)cc * 128 + t * g.OFM + o) * 128 + c] = (int8_t)W[(size_t)o * g.K + t * g.C + cc * 128 + c];
+            wc[((size_t)cc * 128 + dcol_word(t) * 4 + o) * 128 + c] = (int8_t)W[(size_t)o * g.K + t * g.C + cc * 128 + c];
     FCB_CUDA_OK(cudaMalloc(&P->d_w, wc.size()));
     FCB_CUDA_OK(cudaMemcpy(P->d_w, wc.data(), wc.size(), cudaMemcpyHostToDevice));
     int rc = umma2_plan_create_dcol(g, P->d_w, epi, P->num_sms, &P->v2);

@@ -186,32 +186,49 @@ __device__ __forceinline__ void build_row(uint32_t src, uint32_t dst, uint32_t m
   for (int j = 0; j < 2 * KS; j++) sts_v4(dst + (((uint32_t)j ^ m7) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
 
-// col2im of the thin-output transposed conv: the 25 x OFM partial bytes of one input pixel's 2x2 output block, read from the
-// byte tile S[row = tap*OFM + ch][pixel] (pitch DCOL_PITCH).  b[0..2] = shared addresses of the pixel shifted by offy = -1, 0, +1
-// rows; every other offset is an immediate.  Tap (ky, kx) belongs to phase (ky & 1, kx & 1) at shift ((ky + (ky&1) - 2) / 2, ...).
-constexpr int DCOL_PITCH = 272;
+// col2im of the thin-output transposed conv.  The byte tile is PIXEL-major: S[pixel][word][ch], one 4-byte word per tap
+// (word order dcol_word(), fcb_internal.h: taps grouped by input shift, sorted by output phase inside a group), pitch DCOL_PIX bytes
+// per pixel.  An input pixel's 2x2 output block is then 9 vector loads (one per shift: 4 x 16 B, 4 x 8 B, 1 x 4 B) and 21 packed
+// byte adds instead of 75 byte loads and adds.  pitch 112 B = 28 words: the 16-byte loads of 8 consecutive pixels hit 8 bank groups.
+constexpr int DCOL_PIX = 112;
 template <int IMM>
-__device__ __forceinline__ uint32_t lds_u8_imm(uint32_t base) {
+__device__ __forceinline__ void lds_v4_imm(uint32_t base, uint32_t (&v)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4 + %5];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(base), "n"(IMM));
+}
+template <int IMM>
+__device__ __forceinline__ void lds_v2_imm(uint32_t base, uint32_t (&v)[2]) {
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2 + %3];" : "=r"(v[0]), "=r"(v[1]) : "r"(base), "n"(IMM));
+}
+template <int IMM>
+__device__ __forceinline__ uint32_t lds_b32_imm(uint32_t base) {
   uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1 + %2];" : "=r"(v) : "r"(base), "n"(IMM));
+  asm volatile("ld.shared.b32 %0, [%1 + %2];" : "=r"(v) : "r"(base), "n"(IMM));
   return v;
 }
-template <int OFM, int T>
-struct DcolGather {
-  static __device__ __forceinline__ void run(const uint32_t (&b)[3], uint32_t (&sum)[4][4]) {
-    constexpr int ky = T / 5, kx = T % 5;
-    constexpr int offy = (ky + (ky & 1) - 2) / 2, offx = (kx + (kx & 1) - 2) / 2, ph = (ky & 1) * 2 + (kx & 1);
-    sum[ph][0] += lds_u8_imm<(T * OFM + 0) * DCOL_PITCH + offx>(b[offy + 1]);
-    sum[ph][1] += lds_u8_imm<(T * OFM + 1) * DCOL_PITCH + offx>(b[offy + 1]);
-    sum[ph][2] += lds_u8_imm<(T * OFM + 2) * DCOL_PITCH + offx>(b[offy + 1]);
-    if (OFM == 4) sum[ph][3] += lds_u8_imm<(T * OFM + (OFM == 4 ? 3 : 0)) * DCOL_PITCH + offx>(b[offy + 1]);
-    DcolGather<OFM, T + 1>::run(b, sum);
-  }
-};
-template <int OFM>
-struct DcolGather<OFM, 25> {
-  static __device__ __forceinline__ void run(const uint32_t (&)[3], uint32_t (&)[4][4]) {}
-};
+// bm[i] = shared address of pixel (r + i - 1, x - 1): shift (oy, ox) is bm[oy + 1] + (ox + 1) * DCOL_PIX.  s[ph] = packed byte
+// sums of output phase ph = 2 * py + px (all arithmetic mod 2^8 per byte lane).
+__device__ __forceinline__ void dcol_gather(const uint32_t (&bm)[3], uint32_t (&s)[4]) {
+  uint32_t g[4], h[2];
+  lds_v4_imm<1 * DCOL_PIX + 0>(bm[1], s);                      // shift ( 0,  0): ky in {1,2}, kx in {1,2}
+  lds_v4_imm<2 * DCOL_PIX + 16>(bm[1], g);                     // shift ( 0, +1)
+#pragma unroll
+  for (int i = 0; i < 4; i++) s[i] = __vadd4(s[i], g[i]);
+  lds_v4_imm<1 * DCOL_PIX + 32>(bm[2], g);                     // shift (+1,  0)
+#pragma unroll
+  for (int i = 0; i < 4; i++) s[i] = __vadd4(s[i], g[i]);
+  lds_v4_imm<2 * DCOL_PIX + 48>(bm[2], g);                     // shift (+1, +1)
+#pragma unroll
+  for (int i = 0; i < 4; i++) s[i] = __vadd4(s[i], g[i]);
+  lds_v2_imm<1 * DCOL_PIX + 64>(bm[0], h);                     // shift (-1,  0): ky = 0 -> py = 0; words = px 0, 1
+  s[0] = __vadd4(s[0], h[0]); s[1] = __vadd4(s[1], h[1]);
+  lds_v2_imm<2 * DCOL_PIX + 72>(bm[0], h);                     // shift (-1, +1)
+  s[0] = __vadd4(s[0], h[0]); s[1] = __vadd4(s[1], h[1]);
+  lds_v2_imm<0 * DCOL_PIX + 80>(bm[1], h);                     // shift ( 0, -1): kx = 0 -> px = 0; words = py 0, 1
+  s[0] = __vadd4(s[0], h[0]); s[2] = __vadd4(s[2], h[1]);
+  lds_v2_imm<0 * DCOL_PIX + 88>(bm[2], h);                     // shift (+1, -1)
+  s[0] = __vadd4(s[0], h[0]); s[2] = __vadd4(s[2], h[1]);
+  s[0] = __vadd4(s[0], lds_b32_imm<0 * DCOL_PIX + 96>(bm[0])); // shift (-1, -1): tap (0, 0)
+}
 
 // NB = warps from index 10 on: 1 = plane TMA producer (resident-planes mode); 4 = im2col builders (thin-input mode)
 // DTHIN: the thin-output transposed-conv instantiation.  Mode flags are template parameters because the MMA issue loop has no
@@ -457,10 +474,12 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           tc_fence_after();
           const uint64_t wdesc = desc0 + (w_d0 + (uint32_t)s * w_dstep);
           if (elect_one_sync()) {
-            if (DTHIN) {
-              // A = 128 plane rows (pixels) per block at this shift, B = 16 weight rows (4 phases x 4 channel slots)
+            if (DTHIN || DCOL) {
+              // A = 128 plane rows (pixels) per block at this shift, B = 16 weight rows (4 phases x 4 channel slots);
+              // col2im form: B = the 112 (tap word, channel) weight rows, D[pixel][tap word * 4 + channel]
+              constexpr int DSTEP = DCOL ? 112 : 16;
               for (int blk = 0; blk < NPX / 128; blk++) {
-                const uint32_t dt = d_tmem + (uint32_t)(blk * 16);
+                const uint32_t dt = d_tmem + (uint32_t)(blk * DSTEP);
                 const uint64_t ad = pdesc + (uint64_t)(blk * 1024);
                 umma_i8(dt, ad, wdesc, p.idesc_dthin, i ? 1u : 0u);
                 umma_i8(dt, ad + 2, wdesc + 2, p.idesc_dthin, 1u);
@@ -524,6 +543,9 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (p.thr_off >= 0) for (int t = p.epi.thr_n + 1; (t >> (p.thr_top + gshift)) > 1;) gshift++;
     const bool thin = GEN && p.epi.act_kind == FCB_ACT_BIAS_RELU && p.epi.out_bits == 8 && p.epi.acc_bits == 8 && pk == 1 && p.OFM <= 8;
     uint32_t acc_it = 0;
+    uint32_t dcol_bias = 0;  // col2im epilogue: the output word's bias bytes
+    if (DCOL)
+      for (int o = 0; o < p.OFM && o < 4; o++) dcol_bias |= ((uint32_t)(int32_t)p.epi.bias[o] & 0xFFu) << (8 * o);
     PROF_START();
     for (TileIter ti(cta0, ncta, p.tiles_x, p.tiles_y, p.n_images); ti.valid() && !(GEN && p.epi4 && half); ti.next()) {
       const int img = ti.img;
@@ -539,72 +561,73 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
         if ((GEN || DCX) && DCOL) {
           // (always two accumulator stages: warps 2..5 serve stage 0, warps 6..9 stage 1, each group with its own byte tile)
-          const int nrows = 25 * p.OFM;
+          // (25 taps x 4 byte lanes = 100 accumulator columns; lanes >= OFM have zero weights: they give the zero pad byte)
           uint8_t* S = smem + p.stg_off + (half & 1) * p.stg_bytes;
           const uint32_t S_s = smem_u32(S);
           const int sub = DCX ? half >> 1 : 0;  // which of the stage's two groups this warp belongs to
           constexpr int NSUB = DCX ? 2 : 1;
           EPI_BAR();  // the group's previous col2im pass has finished reading S
+          PROF_T(2);
           // ---- phase 1: accumulator rows -> bytes (all arithmetic is mod 2^8, so the partial sums may be truncated now)
-          if (q * 32 < nrows && !(p.debug & 8)) {
-            const int row = q * 32 + lane;
-            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-            const uint32_t srow = S_s + (uint32_t)(row * p.s_pitch);
-            const int ncols = (vrows + 2) * p.P;
-            for (int c0 = 32 * sub; c0 < ncols; c0 += 32 * NSUB) {
-              uint32_t v[32];
-              tmem_ld32(tacc + (uint32_t)c0, v);
-              tmem_ld_wait();
-              if (row < nrows) {
+          if (!(p.debug & 8)) {
+            // thread = pixel (TMEM lane), columns = the bytes of its record: 3 x 32 columns -> 2 x 16-byte stores each, + the
+            // last word (tap (0,0)); the stage's groups (two with 16 epilogue warps) take one 128-pixel block each
+            const int ncols = (vrows + 2) * p.P;  // pixels of the tile, halo ring included
+            for (int blk = sub; blk < 2; blk += NSUB) {
+              if (blk * 128 + q * 32 >= ncols) continue;  // warp-uniform
+              const int m = blk * 128 + q * 32 + lane;
+              const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + blk * 112);
+              const uint32_t srec = S_s + (uint32_t)(m * DCOL_PIX);
+#pragma unroll 1
+              for (int cbk = 0; cbk < 3; cbk++) {
+                uint32_t v[32];
+                tmem_ld32(tacc + (uint32_t)(cbk * 32), v);
+                tmem_ld_wait();
                 uint32_t w[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                   const uint32_t lo = __byte_perm(v[4 * j], v[4 * j + 1], 0x4040), hi = __byte_perm(v[4 * j + 2], v[4 * j + 3], 0x4040);
-                  w[j] = __byte_perm(lo, hi, 0x5410);
+                  w[j] = __byte_perm(lo, hi, 0x5410);  // low bytes = accumulators mod 2^8
                 }
-                sts_v4(srow + (uint32_t)c0, w[0], w[1], w[2], w[3]);
-                sts_v4(srow + (uint32_t)c0 + 16u, w[4], w[5], w[6], w[7]);
+                if (m < ncols) {
+                  sts_v4(srec + (uint32_t)(cbk * 32), w[0], w[1], w[2], w[3]);
+                  sts_v4(srec + (uint32_t)(cbk * 32) + 16u, w[4], w[5], w[6], w[7]);
+                }
               }
+              uint32_t t[8];
+              tmem_ld8(tacc + 96u, t);
+              tmem_ld_wait();
+              if (m < ncols) sts_b32(srec + 96u, __byte_perm(__byte_perm(t[0], t[1], 0x4040), __byte_perm(t[2], t[3], 0x4040), 0x5410));
             }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
+          PROF_T(3);
           EPI_BAR();
+          PROF_T(4);
           // ---- phase 2: col2im.  Thread = one interior input pixel (r, xo); tap (ky, kx) of phase (ky & 1, kx & 1) reads the
           // partial of pixel (r + offy, xo + offx), offy = (ky + (ky & 1) - 2) / 2
           const int npx = vrows * p.WT;
           for (int idx = sub * 128 + (warp & 3) * 32 + lane; idx < ((p.debug & 8) ? 0 : npx); idx += 128 * NSUB) {
             const int rr = idx / p.WT, xo = idx - rr * p.WT;
             if (xo >= vcols) continue;
-            uint32_t b[3];
-            b[1] = S_s + (uint32_t)((rr + 1) * p.P + (xo + 1));
-            b[0] = b[1] - (uint32_t)p.P;
-            b[2] = b[1] + (uint32_t)p.P;
-            uint32_t sum[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-              for (int o = 0; o < 4; o++) sum[a][o] = 0;
-            if (p.OFM == 3) DcolGather<3, 0>::run(b, sum);
-            else DcolGather<4, 0>::run(b, sum);
+            uint32_t bm[3];
+            bm[1] = S_s + (uint32_t)(((rr + 1) * p.P + xo) * DCOL_PIX);
+            bm[0] = bm[1] - (uint32_t)(p.P * DCOL_PIX);
+            bm[2] = bm[1] + (uint32_t)(p.P * DCOL_PIX);
             uint32_t w[4];
+            dcol_gather(bm, w);
 #pragma unroll
             for (int ph = 0; ph < 4; ph++) {
-              uint32_t word = 0;
-#pragma unroll
-              for (int o = 0; o < 4; o++)
-                if (o < p.OFM) {
-                  uint32_t r = (sum[ph][o] + (uint32_t)(int32_t)p.epi.bias[o]) & 0xFFu;
-                  r = (r & 0x80u) ? 0u : r;
-                  word |= r << (8 * o);
-                }
-              w[ph] = word;
+              w[ph] = __vadd4(w[ph], dcol_bias);
+              w[ph] &= ~prmt_sign_mask(w[ph]);  // ReLU on the wrapped bytes; the pad lane stays 0
             }
             uint8_t* dst = p.out + pm.img_off + ((size_t)(2 * (pm.y0 + rr)) * p.out_x + 2 * (pm.x0 + xo)) * 4;
             *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
             *reinterpret_cast<uint2*>(dst + (size_t)p.out_x * 4) = make_uint2(w[2], w[3]);
           }
+          PROF_T(5);
           continue;
         }
         if (DCX) continue;
@@ -1599,11 +1622,11 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.tiles_x = (PX + bWT - 1) / bWT; p.tiles_y = (PY + bR - 1) / bR;
   p.out_x = g.out_x; p.out_y = g.out_y; p.out_word_bytes = 4; p.out_img_bytes = g.out_img_bytes;
   p.wstages = cch; p.wstatic = 1; p.w_bytes = 128 * 128;
-  p.acc_stride = NPX; p.acc_stages = 2; p.tmem_cols = 512;
-  p.idesc = make_idesc_i8(128, NPX, 1, g.in_signed);
+  p.acc_stride = 2 * 112; p.acc_stages = 2; p.tmem_cols = 512;  // per stage: two 128-pixel blocks x 112 columns
+  p.idesc = p.idesc_dthin = make_idesc_i8(128, 112, g.in_signed, 1);  // A = plane rows (pixels), B = the (tap word, channel) weight rows
   p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
   p.epi_alt = 1;  // one epilogue group per accumulator stage
-  p.s_pitch = DCOL_PITCH;  // 272: lanes (rows) 272 bytes apart -> 16-byte stores of 8 consecutive rows hit 8 distinct bank groups
+  p.s_pitch = DCOL_PIX;  // pixel-major byte tile: 112 bytes per pixel (25 tap words + pad)
   const int rows = bR + 2;
   int off = 0;
   for (int cc = 0; cc < cch; cc++) {
@@ -1616,7 +1639,7 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.nplanes = cch; p.set_bytes = off;
   p.nsets = 4;  // measured on L7: 2 sets 201.5 k, 3 sets 209 k, 4 sets 218 k, 5 sets 212 k img/s
   if (getenv("FCB_U2_NSETS")) p.nsets = std::max(1, std::min(5, atoi(getenv("FCB_U2_NSETS"))));
-  while (p.nsets > 1 && (size_t)p.nsets * off + (size_t)cch * 16384 + 2 * ((25 * g.OFM * DCOL_PITCH + 127) / 128 * 128) + 8192 > (size_t)227 * 1024) p.nsets--;
+  while (p.nsets > 1 && (size_t)p.nsets * off + (size_t)cch * 16384 + 2 * (NPX * DCOL_PIX) + 8192 > (size_t)227 * 1024) p.nsets--;
   off *= p.nsets;
   U->box_rows[0] = U->box_rows[1] = rows;
   p.w_off = off; off += p.wstages * p.w_bytes;
@@ -1625,7 +1648,7 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.stage_off = off; off += 8 * 256;
   p.thr_off = -1; p.lut_off = -1;
   off = (off + 127) & ~127;
-  p.stg_off = off; p.stg_bytes = (25 * g.OFM * p.s_pitch + 127) / 128 * 128; p.stg_bufs = 0;  // (stg_bufs stays 0: not the TMA-store path)
+  p.stg_off = off; p.stg_bytes = NPX * DCOL_PIX; p.stg_bufs = 0;  // (stg_bufs stays 0: not the TMA-store path)
   off += 2 * p.stg_bytes;
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
