@@ -328,6 +328,50 @@ def test_thin_output_deconv(ix, iy, c, ofm, reps, fcb_lib, oracle_mod, monkeypat
     assert np.array_equal(L2.run(inp["in_words"], reps), want), f"[{L2.plan}]"
 
 
+def _family_cases():
+    """Shapes that select the single-family instantiations (16 / 12 epilogue warps), ragged on purpose; value = the switch that
+    sends the same plan to the general kernel instead."""
+    from simple_image_compression_network_b200.desc import ACT_BIAS_RELU, ACT_THRESHOLDS, KIND_CONV, LayerDesc
+
+    def conv(k, s, p, c, ofm, x, y, simd, pe, thr=0, pool=0):
+        kw = dict(act_kind=ACT_THRESHOLDS, acc_bits=24, acc_signed=1, out_bits=8, num_th=thr, pool=pool) if thr else \
+            dict(act_kind=ACT_BIAS_RELU, acc_bits=8, acc_signed=0, out_bits=8)
+        return LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=s, stride_y=s, pad=p,
+                         simd=simd, pe=pe, in_bits=8, w_bits=4, **kw)
+    dc = cases.CASES["dc_c"]
+    return {
+        "pixel_major_16w": (conv(5, 2, 2, 3, 128, 300, 70, 3, 16), "FCB_U2_NO_SWPX", 2),                    # L0 family, ragged both ways
+        "pixel_major_16w_k3s1": (conv(3, 1, 1, 3, 128, 150, 11, 3, 16), "FCB_U2_NO_SWPX", 1),
+        "col2im_16w": (dataclasses.replace(cases.CASES["dc_d"], ifm_x=77, ifm_y=37), "FCB_U2_NO_DCX", 2),          # L7 family
+        "col2im_16w_c256_ofm4": (dataclasses.replace(cases.CASES["dc_d"], ifm_x=29, ifm_y=50, ifm_ch=256, ofm_ch=4, pe=4), "FCB_U2_NO_DCX", 1),
+        "staged_deconv_16w": (dataclasses.replace(dc, ifm_x=70, ifm_y=23), "FCB_U2_NO_STX", 2),                    # L5 / L6 family
+        "thr_pool_stage1": (conv(3, 1, 1, 3, 128, 300, 22, 3, 16, thr=255, pool=2), "FCB_U2_XEPI", 1),              # 16 epilogue warps
+        "thr_pool_stage2": (conv(3, 1, 1, 128, 128, 100, 18, 32, 16, thr=255, pool=2), "FCB_U2_XEPI", 1),           # 12 epilogue warps
+    }
+
+
+@pytest.mark.parametrize("name", list(_family_cases()))
+def test_single_family_instantiations(name, fcb_lib, oracle_mod, monkeypatch):
+    """The single-epilogue-family kernels with 12 / 16 epilogue warps (EPI = 2..6 of umma2_conv_kernel) against the oracle and
+    against the general kernel (EPI = 0 / 8 epilogue warps) on the same plan."""
+    d, switch, reps = _family_cases()[name]
+    inp = cases.make_inputs(d, seed_shift=53, num_reps=reps, relu_range=d.kind != 0)
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=reps)
+    L = _layer(d, inp)
+    assert L.engine == "umma_i8", L.plan
+    got = L.run(inp["in_words"], reps)
+    assert np.array_equal(got, want), f"{name} [{L.plan}]: {_diff(got, want)}"
+    monkeypatch.setenv(switch, "0" if switch == "FCB_U2_XEPI" else "1")
+    L0 = _layer(d, inp)
+    got0 = L0.run(inp["in_words"], reps)
+    assert np.array_equal(got0, want), f"{name} general kernel [{L0.plan}]: {_diff(got0, want)}"
+    if switch == "FCB_U2_XEPI":  # and every epilogue-warp count of the pooled threshold family
+        for n in ("4", "8"):
+            monkeypatch.setenv(switch, n)
+            Ln = _layer(d, inp)
+            assert np.array_equal(Ln.run(inp["in_words"], reps), want), f"{name} [{Ln.plan}]"
+
+
 def _random_descs(seed, count):
     """Random small layer shapes across every plan family (resident planes, thin input, thin-output deconv, thresholds with and
     without pool, xnor, IMAD fall-backs), seeded: the same cases on every run."""
