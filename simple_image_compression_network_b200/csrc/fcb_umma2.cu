@@ -549,6 +549,13 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     PROF_START();
     // alternating groups on single-phase layers own every other tile outright: they walk their own tile sequence (stride 2 CTAs'
     // worth) instead of stepping through -- and skipping -- the other group's tiles (~40 instructions at 6-8 clocks each per tile)
+    // tile-invariant pixel coordinates of this warp's TMA-store block (EPI = 4) / this thread's col2im pixel: divided once here
+    int pre_rr = 0, pre_xo = 0;
+    if (SWPX || DCOL) {
+      const int i0 = SWPX ? (half >> 1) * 128 + q * 32 : (DCX ? (half >> 1) * 128 : 0) + (warp & 3) * 32 + lane;
+      pre_rr = i0 / p.WT;
+      pre_xo = i0 - pre_rr * p.WT;
+    }
     const bool alt1 = alt && p.nphases == 1;
     const uint32_t acc_step = alt1 ? 2u : 1u;
     if (alt1) acc_it = (uint32_t)(half & 1);
@@ -615,8 +622,9 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           // ---- phase 2: col2im.  Thread = one interior input pixel (r, xo); tap (ky, kx) of phase (ky & 1, kx & 1) reads the
           // partial of pixel (r + offy, xo + offx), offy = (ky + (ky & 1) - 2) / 2
           const int npx = vrows * p.WT;
-          for (int idx = sub * 128 + (warp & 3) * 32 + lane; idx < ((p.debug & 8) ? 0 : npx); idx += 128 * NSUB) {
-            const int rr = idx / p.WT, xo = idx - rr * p.WT;
+          const int idx0 = sub * 128 + (warp & 3) * 32 + lane;
+          for (int idx = idx0; idx < ((p.debug & 8) ? 0 : npx); idx += 128 * NSUB) {
+            const int rr = idx == idx0 ? pre_rr : idx / p.WT, xo = idx == idx0 ? pre_xo : idx - rr * p.WT;
             if (xo >= vcols) continue;
             uint32_t bm[3];
             bm[1] = S_s + (uint32_t)(((rr + 1) * p.P + xo) * DCOL_PIX);
@@ -718,7 +726,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           auto store_block = [&](int blk) {
             fence_proxy_async();
             __syncwarp();
-            const int m0 = blk * 128 + q * 32, rr = m0 / p.WT, xo = m0 - rr * p.WT;
+            const int m0 = blk * 128 + q * 32, rr = SWPX ? pre_rr : m0 / p.WT, xo = SWPX ? pre_xo : m0 - rr * p.WT;
             if (lane == 0 && rr < vrows)
               for (int cb = 0; cb < p.CB; cb++) tma_store_4d(&tmO, stg + (cb * p.NPX + m0) * 128, cb * 128, pm.x0 + xo, pm.y0 + rr, img);
           };
