@@ -1,5 +1,5 @@
 """Run ONE parity case on the GPU and print where it differs from the oracle (pixels / channels of the mismatches).
-    python tools/check_case.py <name>      name = a key of oracle/cases.py CASES or of tests/test_gpu_parity.py::_thin_cases()"""
+    python tests/check_case.py <name>      name = a key of oracle/cases.py CASES or of tests/test_gpu_parity.py::_thin_cases()"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

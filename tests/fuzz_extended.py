@@ -1,10 +1,10 @@
 """Extended seeded fuzz of the CUDA library against the oracle: the shape generator of tests/test_gpu_parity.py with more seeds
 (and larger batches) than the test suite runs.  Test infrastructure (uses oracle/).
-    python tools/fuzz.py [first_seed] [n_seeds] [cases_per_seed]"""
+    python tests/fuzz_extended.py [first_seed] [n_seeds] [cases_per_seed]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # (this directory)
 import numpy as np
 import test_gpu_parity as T
 from oracle import cases, oracle
