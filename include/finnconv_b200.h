@@ -75,6 +75,14 @@ typedef enum fcb_act_kind { FCB_ACT_PASSTHROUGH = 0, FCB_ACT_BIAS_RELU = 1, FCB_
  * evaluated as Compare()(threshold, accu) (activations.hpp:185) */
 typedef enum fcb_cmp { FCB_CMP_LESS = 0, FCB_CMP_GREATER = 1, FCB_CMP_LESS_EQUAL = 2, FCB_CMP_GREATER_EQUAL = 3 } fcb_cmp;
 
+/* Which arithmetic unit multiplies: the counterpart of the reference's resource argument `R` of
+ * Matrix_Vector_Activate_Batch (ap_resource_dsp / ap_resource_lut / ap_resource_dflt, mvau.hpp:87-98, mac.hpp:87-144), which
+ * like here changes the implementation and never the result.  AUTO picks the fastest engine that covers the layer;
+ * IMAD = CUDA-core integer MACs (covers everything); XNOR_POPC = XNOR + __popc on packed 1-bit lanes (FCB_W_BINARY_XNOR only);
+ * TENSOR = tcgen05 kind::i8 (for FCB_W_BINARY_XNOR: lanes expanded to +-1 int8, thresholds remapped 2t-K).  A hint the layer
+ * cannot honour fails fcb_layer_create with FCB_ERR_UNSUPPORTED. */
+typedef enum fcb_engine_hint { FCB_ENGINE_AUTO = 0, FCB_ENGINE_IMAD = 1, FCB_ENGINE_XNOR_POPC = 2, FCB_ENGINE_TENSOR = 3 } fcb_engine_hint;
+
 /* Run-time mirror of the reference's compile-time parameter set. */
 typedef struct fcb_layer_desc {
   uint32_t struct_size; /* = sizeof(fcb_layer_desc) */
@@ -102,7 +110,15 @@ typedef struct fcb_layer_desc {
   uint32_t cmp;         /* fcb_cmp */
   uint32_t pool;        /* 0 or 1: none; k>=2: k x k, stride k max pool on the out_bits lanes
                            (StreamingMaxPool_Precision, maxpool.h:137-185; OR for out_bits==1, :66-96) */
-  uint32_t reserved[6]; /* must be zero */
+  uint32_t engine_hint; /* fcb_engine_hint; 0 = automatic */
+  /* FMPadding_nonsquare's own parameter set (streamtools.h:361-379) for paddings `pad` cannot express: used when
+   * pad_style != 0 (then `pad` must be 0).  Padding_x = pad_x_total zeros are split left = P/2 + (pad_style == 2 ? P % 2 : 0),
+   * right = P - left; likewise up / down with pad_y_total.  pad_style 2 is the reference's default PaddingStyle. */
+  uint32_t pad_x_total, pad_y_total, pad_style;
+  /* StreamingMaxPool_Precision's ActType signedness and min_value (maxpool.h:137-170): lanes are compared as signed
+   * out_bits-wide integers when pool_signed != 0; every window's maximum starts from pool_min_value. */
+  uint32_t pool_signed;
+  int32_t pool_min_value;
 } fcb_layer_desc;
 
 typedef struct fcb_layer fcb_layer; /* opaque: one layer resident on one device */
@@ -142,6 +158,10 @@ FCB_API int fcb_layer_run(fcb_layer* layer, const void* in_words, void* out_word
 /* Device-buffer call on `stream` (a cudaStream_t, or NULL for the default stream); asynchronous.
  * d_in/d_out hold the same word images in device memory of layer's device. */
 FCB_API int fcb_layer_run_device(fcb_layer* layer, const void* d_in, void* d_out, uint32_t numReps, void* stream);
+/* Every entry point runs on the handle's device and restores the caller's current CUDA device before it returns. */
+/* Images per staging slot of fcb_layer_run (two slots double-buffer H2D / kernels / D2H); 0 restores the default
+ * (<= 256 MiB per slot).  The burst length of the reference's Mem2Stream_Batch / Stream2Mem_Batch (16 images, dma.h:166-176). */
+FCB_API int fcb_layer_set_host_chunk(fcb_layer* layer, uint32_t images);
 /* Which kernel family serves this layer: "umma_i8", "imad", "xnor_popc" (diagnostics / tests). */
 FCB_API const char* fcb_layer_engine(const fcb_layer* layer);
 /* Human-readable tiling plan of the layer (tile shape, shared-memory planes, pipeline depth). */
@@ -156,6 +176,10 @@ FCB_API void fcb_net_destroy(fcb_net* net);
 FCB_API int fcb_net_run(fcb_net* net, const void* in_words, void* out_words, uint32_t numReps);
 FCB_API int fcb_net_run_device(fcb_net* net, const void* d_in, void* d_out, uint32_t numReps, void* stream);
 FCB_API uint64_t fcb_net_launches(const fcb_net* net);
+/* Images per staging slot of fcb_net_run (0 = default, <= 64 MiB per slot), and images per pass of the layer chain inside
+ * fcb_net_run_device (0 = default: the largest intermediate stream stays <= 1 GiB; small values keep the intermediates in L2). */
+FCB_API int fcb_net_set_host_chunk(fcb_net* net, uint32_t images);
+FCB_API int fcb_net_set_device_chunk(fcb_net* net, uint32_t images);
 
 /* --- synthetic data (bench / tests): byte i of the buffer = splitmix64(seed ^ (offset + i)) & mask,
  * the rule of SURVEY.md 8(d); d_ptr is device memory, 16-byte aligned; asynchronous on `stream`. */

@@ -10,6 +10,8 @@ from .desc import CLayerDesc
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libfinnconv_b200.so")
 
+EXP_LIB_PATH = os.path.join(os.path.dirname(PKG), "tools", "libfinnconv_exp.so")
+
 _lib = None
 
 
@@ -19,14 +21,12 @@ class FcbError(RuntimeError):
         self.code = code
 
 
-def lib() -> ctypes.CDLL:
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m simple_image_compression_network_b200.build` "
+def load(path: str) -> ctypes.CDLL:
+    """dlopen one build of the library and declare its ABI (include/finnconv_b200.h)."""
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -m simple_image_compression_network_b200.build` "
                           "(nvcc, sm_100a). There is no CPU fallback.")
-    L = ctypes.CDLL(LIB_PATH)
+    L = ctypes.CDLL(path)
     vp, u32, u64, sz = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_size_t
     L.fcb_version.restype = ctypes.c_char_p
     L.fcb_last_error.restype = ctypes.c_char_p
@@ -41,6 +41,7 @@ def lib() -> ctypes.CDLL:
     L.fcb_layer_destroy.restype = None
     L.fcb_layer_run.argtypes = [vp, vp, vp, u32]
     L.fcb_layer_run_device.argtypes = [vp, vp, vp, u32, vp]
+    L.fcb_layer_set_host_chunk.argtypes = [vp, u32]
     L.fcb_layer_engine.argtypes = [vp]
     L.fcb_layer_engine.restype = ctypes.c_char_p
     L.fcb_layer_plan.argtypes = [vp]
@@ -52,13 +53,29 @@ def lib() -> ctypes.CDLL:
     L.fcb_net_destroy.restype = None
     L.fcb_net_run.argtypes = [vp, vp, vp, u32]
     L.fcb_net_run_device.argtypes = [vp, vp, vp, u32, vp]
+    L.fcb_net_set_host_chunk.argtypes = [vp, u32]
+    L.fcb_net_set_device_chunk.argtypes = [vp, u32]
     L.fcb_net_launches.argtypes = [vp]
     L.fcb_net_launches.restype = u64
     L.fcb_synth_fill.argtypes = [vp, sz, u64, u32, u64, vp]
-    _lib = L
     return L
 
 
-def check(rc: int) -> None:
+def lib() -> ctypes.CDLL:
+    """The library new handles are created from: the product build unless set_default() installed another one."""
+    global _lib
+    if _lib is None:
+        _lib = load(LIB_PATH)
+    return _lib
+
+
+def set_default(L) -> None:
+    """Tests / tools: make `L` (e.g. load(EXP_LIB_PATH), the experiment build) the library of handles created from now on;
+    None restores the product build.  Existing handles keep the library they were created from."""
+    global _lib
+    _lib = L
+
+
+def check(rc: int, L=None) -> None:
     if rc != 0:
-        raise FcbError(rc, lib().fcb_last_error().decode())
+        raise FcbError(rc, (L or lib()).fcb_last_error().decode())

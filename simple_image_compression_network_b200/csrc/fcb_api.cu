@@ -35,7 +35,9 @@ static size_t word_bytes(uint32_t bits) {
 int derive_geom(const fcb_layer_desc* d, Geom* g) {
   if (!d) { set_error("descriptor is NULL"); return FCB_ERR_INVALID_ARG; }
   if (d->struct_size != sizeof(fcb_layer_desc)) { set_error("struct_size %u != %zu", d->struct_size, sizeof(fcb_layer_desc)); return FCB_ERR_INVALID_ARG; }
-  for (int i = 0; i < 6; i++) if (d->reserved[i]) { set_error("reserved fields must be zero"); return FCB_ERR_INVALID_ARG; }
+  if (d->engine_hint > FCB_ENGINE_TENSOR || d->pad_style > 2) { set_error("bad enum value"); return FCB_ERR_INVALID_ARG; }
+  if (d->pad_style && d->pad) { set_error("pad must be 0 when pad_style selects pad_x_total / pad_y_total"); return FCB_ERR_INVALID_ARG; }
+  if (!d->pad_style && (d->pad_x_total || d->pad_y_total)) { set_error("pad_x_total / pad_y_total need pad_style 1 or 2"); return FCB_ERR_INVALID_ARG; }
   if (!d->simd || !d->pe || !d->ifm_ch || !d->ofm_ch || !d->kernel_x || !d->kernel_y || !d->stride_x || !d->stride_y || !d->ifm_x || !d->ifm_y) {
     set_error("zero-sized parameter"); return FCB_ERR_INVALID_ARG;
   }
@@ -44,6 +46,12 @@ int derive_geom(const fcb_layer_desc* d, Geom* g) {
   }
   if (d->ifm_ch % d->simd) { set_error("IFM_CH %% SIMD != 0 (%u %% %u)", d->ifm_ch, d->simd); return FCB_ERR_SHAPE; }
   if (d->ofm_ch % d->pe) { set_error("OFM_CH %% PE != 0 (%u %% %u)", d->ofm_ch, d->pe); return FCB_ERR_SHAPE; }
+  // FMPadding_nonsquare (streamtools.h:374-379): left/up = P/2 (+ P%2 with PaddingStyle 2), right/down = the rest
+  uint32_t pl = d->pad, pr = d->pad, pu = d->pad, pd = d->pad;
+  if (d->pad_style) {
+    pl = d->pad_x_total / 2 + (d->pad_style == 2 ? d->pad_x_total % 2 : 0); pr = d->pad_x_total - pl;
+    pu = d->pad_y_total / 2 + (d->pad_style == 2 ? d->pad_y_total % 2 : 0); pd = d->pad_y_total - pu;
+  }
   uint32_t ox, oy;
   if (d->kind == FCB_KIND_DECONV522) {
     if (d->kernel_x != 5 || d->kernel_y != 5 || d->stride_x != 2 || d->stride_y != 2 || d->pad != 2) {
@@ -51,9 +59,9 @@ int derive_geom(const fcb_layer_desc* d, Geom* g) {
     }
     ox = 2 * d->ifm_x; oy = 2 * d->ifm_y;
   } else {
-    if (d->ifm_x + 2 * d->pad < d->kernel_x || d->ifm_y + 2 * d->pad < d->kernel_y) { set_error("kernel larger than padded input"); return FCB_ERR_SHAPE; }
-    ox = (d->ifm_x + 2 * d->pad - d->kernel_x) / d->stride_x + 1;
-    oy = (d->ifm_y + 2 * d->pad - d->kernel_y) / d->stride_y + 1;
+    if (d->ifm_x + pl + pr < d->kernel_x || d->ifm_y + pu + pd < d->kernel_y) { set_error("kernel larger than padded input"); return FCB_ERR_SHAPE; }
+    ox = (d->ifm_x + pl + pr - d->kernel_x) / d->stride_x + 1;
+    oy = (d->ifm_y + pu + pd - d->kernel_y) / d->stride_y + 1;
   }
   if (ox != d->ofm_x || oy != d->ofm_y) { set_error("ofm %ux%u does not match geometry %ux%u", d->ofm_x, d->ofm_y, ox, oy); return FCB_ERR_SHAPE; }
   if (d->weight_kind == FCB_W_BINARY_XNOR && (d->w_bits != 1 || d->in_bits != 1)) { set_error("xnor needs 1-bit weights and activations"); return FCB_ERR_SHAPE; }
@@ -74,7 +82,9 @@ int derive_geom(const fcb_layer_desc* d, Geom* g) {
   if (d->act_kind == FCB_ACT_BIAS_RELU && d->out_bits < 2) { set_error("bias+ReLU needs out_bits >= 2"); return FCB_ERR_UNSUPPORTED; }
 
   g->kind = d->kind; g->C = d->ifm_ch; g->OFM = d->ofm_ch; g->KX = d->kernel_x; g->KY = d->kernel_y;
-  g->IX = d->ifm_x; g->IY = d->ifm_y; g->OX = ox; g->OY = oy; g->SX = d->stride_x; g->SY = d->stride_y; g->PAD = d->pad;
+  g->IX = d->ifm_x; g->IY = d->ifm_y; g->OX = ox; g->OY = oy; g->SX = d->stride_x; g->SY = d->stride_y; g->PAD = (int)pl;
+  g->pad_l = (int)pl; g->pad_r = (int)pr; g->pad_u = (int)pu; g->pad_d = (int)pd;
+  g->engine_hint = (int)d->engine_hint; g->pool_signed = d->pool_signed ? 1 : 0; g->pool_min = d->pool_min_value;
   g->simd = d->simd; g->pe = d->pe; g->K = g->KX * g->KY * g->C; g->SF = g->K / g->simd; g->NF = g->OFM / g->pe;
   g->in_bits = d->in_bits; g->in_signed = d->in_signed ? 1 : 0; g->w_bits = d->w_bits; g->weight_kind = d->weight_kind;
   g->acc_bits = d->acc_bits; g->acc_signed = d->acc_signed ? 1 : 0; g->act_kind = d->act_kind; g->out_bits = d->out_bits;
@@ -109,6 +119,28 @@ static inline int32_t wrap_host(int64_t v, int bits, int sgn) {
 
 using namespace fcb;
 
+namespace {
+// Every entry point works on the handle's device and leaves the caller's current device as it found it.
+struct DeviceScope {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceScope(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    err = (prev == dev) ? cudaSuccess : cudaSetDevice(dev);
+  }
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define FCB_ON_DEVICE(dev)          \
+  DeviceScope dev_scope__(dev);     \
+  FCB_CUDA_OK(dev_scope__.err)
+// images per chunk such that every chunk's byte offset into both streams stays 16-byte aligned (TMA / vector accesses)
+size_t align_chunk(size_t chunk, size_t in_img, size_t out_img) {
+  size_t m = 1;
+  while (((m * in_img) & 15) || ((m * out_img) & 15)) m *= 2;  // m <= 16
+  return std::max(m, chunk / m * m);
+}
+}  // namespace
+
 struct fcb_layer {
   Geom g;
   fcb_layer_desc desc{};  // as given to fcb_layer_create (fcb_layer_set_params rebuilds from it)
@@ -128,8 +160,9 @@ struct fcb_layer {
   bool lowered = false;
   bool lower_bits = false;  // lowering = 1-bit -> +-1 int8 expansion (instead of im2col rows)
   Im2colParams ip{};
-  void* d_scratch = nullptr;
+  void* d_scratch[2] = {nullptr, nullptr};  // one per staging slot / stream of the host-buffer call (slot 0 serves device calls)
   size_t scratch_imgs = 0, scratch_img_bytes = 0;
+  size_t host_chunk = 0;  // fcb_layer_set_host_chunk (0 = default)
   char plan_desc[256] = "";
   // staging for the host-buffer entry point (two slots, double buffered)
   void* s_in[2] = {nullptr, nullptr};
@@ -151,7 +184,12 @@ struct fcb_net {
   cudaStream_t st_in = nullptr, st_run = nullptr, st_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int device = 0;
+  size_t host_chunk = 0;    // fcb_net_set_host_chunk (0 = default)
+  size_t device_chunk = 0;  // fcb_net_set_device_chunk (0 = default)
 };
+
+static int layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, cudaStream_t st, int slot);
+static int lowered_reserve(fcb_layer* L);
 
 extern "C" {
 
@@ -184,9 +222,10 @@ int fcb_layer_query(const fcb_layer_desc* desc, size_t* in_b, size_t* out_b, siz
 
 void fcb_layer_destroy(fcb_layer* L) {
   if (!L) return;
-  cudaSetDevice(L->device);
+  DeviceScope ds(L->device);
   if (L->umma) umma_plan_destroy(L->umma);
-  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_thr_cm); cudaFree(L->d_thr_lut); cudaFree(L->d_thr_lo); cudaFree(L->d_scratch);
+  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_thr_cm); cudaFree(L->d_thr_lut); cudaFree(L->d_thr_lo);
+  cudaFree(L->d_scratch[0]); cudaFree(L->d_scratch[1]);
   for (int i = 0; i < 2; i++) {
     cudaFree(L->s_in[i]); cudaFree(L->s_out[i]);
     if (L->s_stream[i]) cudaStreamDestroy(L->s_stream[i]);
@@ -274,7 +313,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   cudaDeviceProp prop;
   FCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return FCB_ERR_CUDA; }
-  FCB_CUDA_OK(cudaSetDevice(device));
+  FCB_ON_DEVICE(device);
 
   fcb_layer* L = new fcb_layer();
   // every early return below (FCB_CUDA_OK, explicit error returns) releases the half-built layer; `armed` is cleared on success.
@@ -344,41 +383,56 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         std::sort(row.begin(), row.end());
       }
     rc = upload_thresholds(L, thr_rows);
-    if (rc) { guard.armed = false; fcb_layer_destroy(L); return rc; }
+    if (rc) return rc;
   }
 
-  // ---- engine selection
-  const char* force = getenv("FCB_FORCE_ENGINE");
+  // ---- engine selection (fcb_engine_hint: the reference's resource argument R, mvau.hpp:87-98 -- never changes the result)
+  const int hint = g.engine_hint;
+  auto env_is = [](const char* name, const char* want) { const char* v = exp_env(name); return v && !strcmp(v, want); };
+  const bool force_imad = hint == FCB_ENGINE_IMAD || env_is("FCB_FORCE_ENGINE", "imad");
   int engine = ENG_IMAD;
   const bool dense_bits = (g.in_word_bytes * 8 == (size_t)g.C * g.in_bits);
-  if (g.weight_kind == FCB_W_BINARY_XNOR && g.C % 32 == 0 && dense_bits) engine = ENG_XNOR;
+  const bool xnor_ok = g.weight_kind == FCB_W_BINARY_XNOR && g.C % 32 == 0 && dense_bits;
+  if (xnor_ok) engine = ENG_XNOR;
   if (umma_eligible(g)) engine = ENG_UMMA;
-  if (force && !strcmp(force, "imad")) engine = ENG_IMAD;
-  if (force && !strcmp(force, "xnor") && g.weight_kind == FCB_W_BINARY_XNOR && g.C % 32 == 0 && dense_bits) engine = ENG_XNOR;
+  if (force_imad) engine = ENG_IMAD;
+  if (hint == FCB_ENGINE_XNOR_POPC) {
+    if (!xnor_ok) { set_error("engine_hint XNOR_POPC needs FCB_W_BINARY_XNOR with IFM_CH %% 32 == 0"); return FCB_ERR_UNSUPPORTED; }
+    engine = ENG_XNOR;
+  }
   L->engine = engine;
 
-  // opt-in (FCB_XNOR_ENGINE=tensor): the 1-bit layer on the tensor cores.  With a^ = 2a-1, w^ = 2w-1 in {-1,+1}:
+  // FCB_ENGINE_TENSOR on a 1-bit xnor layer: the layer on the tensor cores.  With a^ = 2a-1, w^ = 2w-1 in {-1,+1}:
   // sum_k [w_k == a_k] = (K + sum_k a^_k w^_k) / 2 (interpret.hpp:57-73), so thr < matches  <=>  2*thr - K < sum a^w^ :
   // bits are expanded to s8 (a zero-padded border bit is an ordinary 0 activation = -1), thresholds are remapped once,
   // and the layer runs on umma_i8.  north_star names XNOR/popc as the implementation of this path, so that stays the default.
-  const char* xeng = getenv("FCB_XNOR_ENGINE");
-  if (xeng && !strcmp(xeng, "tensor") && g.weight_kind == FCB_W_BINARY_XNOR && g.act_kind == FCB_ACT_THRESHOLDS && g.kind == FCB_KIND_CONV &&
-      dense_bits && g.SX == g.SY && g.SX == 1 && g.OFM <= 256 && g.pool <= 2 && (g.acc_bits >= 31 || g.K < (1 << (g.acc_bits - (g.acc_signed ? 1 : 0))))) {
+  const bool want_xnor_tensor = g.weight_kind == FCB_W_BINARY_XNOR && (hint == FCB_ENGINE_TENSOR || env_is("FCB_XNOR_ENGINE", "tensor"));
+  bool xnor_tensor_done = false;
+  if (want_xnor_tensor && g.act_kind == FCB_ACT_THRESHOLDS && g.kind == FCB_KIND_CONV && dense_bits && g.SX == g.SY && g.SX == 1 && g.OFM <= 256 &&
+      g.pool <= 2 && g.pad_l == g.pad_r && g.pad_u == g.pad_d && g.pad_l == g.pad_u &&
+      (g.acc_bits >= 31 || g.K < (1 << (g.acc_bits - (g.acc_signed ? 1 : 0))))) {
     const int Cp = (g.C + 15) / 16 * 16;
     Geom g2 = g;
     g2.C = Cp; g2.K = g.KX * g.KY * Cp; g2.IX = g.IX + 2 * g.PAD; g2.IY = g.IY + 2 * g.PAD; g2.PAD = 0;
+    g2.pad_l = g2.pad_r = g2.pad_u = g2.pad_d = 0;
     g2.in_bits = 8; g2.in_signed = 1; g2.w_bits = 8; g2.weight_kind = FCB_W_FIXED; g2.acc_bits = 32; g2.acc_signed = 1;
     g2.in_word_bytes = Cp; g2.in_img_bytes = (size_t)Cp * g2.IX * g2.IY;
     std::vector<int32_t> W2((size_t)g.OFM * g2.K, 0);
     for (int ch = 0; ch < g.OFM; ch++)
       for (int tap = 0; tap < g.KX * g.KY; tap++)
         for (int c = 0; c < g.C; c++) W2[(size_t)ch * g2.K + tap * Cp + c] = W[(size_t)ch * g.K + tap * g.C + c] ? 1 : -1;
+    // t' = 2t - K in 64 bits: the remapped table must stay inside int32 (and below the INT32_MAX padding value)
     std::vector<std::vector<int32_t>> rows2 = thr_rows;
+    bool remap_ok = true;
     for (auto& r : rows2)
-      for (auto& t : r) t = 2 * t - g.K;
-    if (umma_eligible(g2)) {
+      for (auto& t : r) {
+        const int64_t t2 = 2 * (int64_t)t - g.K;
+        if (t2 <= INT32_MIN || t2 >= INT32_MAX) remap_ok = false;
+        t = (int32_t)t2;
+      }
+    if (remap_ok && umma_eligible(g2)) {
       rc = upload_thresholds(L, rows2);
-      if (rc) { guard.armed = false; fcb_layer_destroy(L); return rc; }
+      if (rc) return rc;
       EpiParams e2 = L->epi;
       e2.acc_bits = 32; e2.acc_signed = 1;
       rc = umma_plan_create(g2, W2, e2, device, &L->umma);
@@ -392,29 +446,34 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         ip.IX = g.IX; ip.IY = g.IY; ip.OX = g2.IX; ip.OY = g2.IY; ip.S = 1; ip.PAD = g.PAD; ip.K = Cp; ip.C = g.C; ip.KX = g.KX;
         ip.in_word_bytes = (int)g.in_word_bytes; ip.in_img_bytes = g.in_img_bytes;
         snprintf(L->plan_desc, sizeof(L->plan_desc), "xnor as +-1 int8: bit expansion (C=%d -> %d B) + %s", g.C, Cp, umma_plan_describe(L->umma));
+        xnor_tensor_done = true;
       } else {
         L->umma = nullptr;
         int rc3 = upload_thresholds(L, thr_rows);  // back to the popcount engine's tables
-        if (rc3) { guard.armed = false; fcb_layer_destroy(L); return rc3; }
-        if (rc != FCB_ERR_UNSUPPORTED) { guard.armed = false; fcb_layer_destroy(L); return rc; }
+        if (rc3) return rc3;
+        if (rc != FCB_ERR_UNSUPPORTED) return rc;
       }
     }
+  }
+  if (hint == FCB_ENGINE_TENSOR && g.weight_kind == FCB_W_BINARY_XNOR && !xnor_tensor_done) {
+    set_error("engine_hint TENSOR: this xnor layer has no tensor-core form (needs thresholds, stride 1, OFM <= 256, symmetric padding)");
+    return FCB_ERR_UNSUPPORTED;
   }
   if (engine == ENG_UMMA && !L->lowered && g.kind == FCB_KIND_DECONV522 && g.OFM <= 4) {
     // thin-output transposed conv (the 3-channel last layer): dedicated plan, pixels on the MMA M axis
     rc = umma_plan_create_dthin(g, W, L->epi, device, &L->umma);
     if (rc == FCB_ERR_UNSUPPORTED) L->umma = nullptr;
-    else if (rc) { guard.armed = false; fcb_layer_destroy(L); return rc; }
+    else if (rc) return rc;
   }
   if (engine == ENG_UMMA && !L->lowered && !L->umma) {
     rc = umma_plan_create(g, W, L->epi, device, &L->umma);
     if (rc == FCB_ERR_UNSUPPORTED) { engine = L->engine = ENG_IMAD; L->umma = nullptr; }  // shape the planner cannot tile
-    else if (rc) { guard.armed = false; fcb_layer_destroy(L); return rc; }
+    else if (rc) return rc;
   }
   // thin-input layers (one 4-byte word per pixel, e.g. the ap_uint<24> C = 3 first layer): the sliding window is built in
   // shared memory inside the tensor-core kernel (fcb_umma2.cu, thin-input mode); FCB_THIN=im2col keeps the two-kernel lowering
-  const char* thin_env = getenv("FCB_THIN");
-  if (engine == ENG_IMAD && !(force && !strcmp(force, "imad")) && !(thin_env && !strcmp(thin_env, "im2col")) && g.kind == FCB_KIND_CONV &&
+  const bool sym_pad = g.pad_l == g.pad_r && g.pad_u == g.pad_d && g.pad_l == g.pad_u;
+  if (engine == ENG_IMAD && !force_imad && !env_is("FCB_THIN", "im2col") && g.kind == FCB_KIND_CONV && sym_pad &&
       g.weight_kind == FCB_W_FIXED && g.w_bits <= 8 && g.in_bits == 8 && g.in_word_bytes == 4 && g.KX * g.KY <= 32 && g.OFM <= 256 &&
       g.pool <= 2 && g.SX == g.SY && g.SX <= 2 && g.IX % 4 == 0 && (uint64_t)g.K * 255ull * 128ull < (1ull << 31)) {
     std::vector<int32_t> W4((size_t)g.OFM * 128, 0);
@@ -423,11 +482,11 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         for (int c = 0; c < g.C; c++) W4[(size_t)ch * 128 + tap * 4 + c] = W[(size_t)ch * g.K + tap * g.C + c];
     rc = umma_plan_create_thin(g, W4, L->epi, g.act_kind == FCB_ACT_BIAS_RELU ? (const int8_t*)bias : nullptr, device, &L->umma);
     if (rc == FCB_OK) engine = L->engine = ENG_UMMA;
-    else if (rc != FCB_ERR_UNSUPPORTED) { guard.armed = false; fcb_layer_destroy(L); return rc; }
+    else if (rc != FCB_ERR_UNSUPPORTED) return rc;
     else L->umma = nullptr;
   }
   // older two-kernel lowering: conv2d with Kx*Ky*C <= 128 bytes of window as im2col rows + a 1x1 layer
-  if (engine == ENG_IMAD && !(force && !strcmp(force, "imad")) && g.kind == FCB_KIND_CONV && g.weight_kind == FCB_W_FIXED &&
+  if (engine == ENG_IMAD && !force_imad && g.kind == FCB_KIND_CONV && g.weight_kind == FCB_W_FIXED && sym_pad &&
       g.w_bits <= 8 && g.in_bits == 8 && g.K <= 128 && g.OFM <= 256 && g.pool <= 2 && g.SX == g.SY) {
     Geom g2 = g;
     g2.C = 128; g2.KX = g2.KY = 1; g2.K = 128; g2.IX = g.OX; g2.IY = g.OY; g2.SX = g2.SY = 1; g2.PAD = 0;
@@ -445,10 +504,11 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         ip.IX = g.IX; ip.IY = g.IY; ip.OX = g.OX; ip.OY = g.OY; ip.S = g.SX; ip.PAD = g.PAD; ip.K = g.K; ip.C = g.C; ip.KX = g.KX;
         ip.in_word_bytes = (int)g.in_word_bytes; ip.in_img_bytes = g.in_img_bytes;
         snprintf(L->plan_desc, sizeof(L->plan_desc), "im2col rows (K=%d -> 128 B) + 1x1 %s", g.K, umma_plan_describe(L->umma));
-      } else if (rc != FCB_ERR_UNSUPPORTED) { guard.armed = false; fcb_layer_destroy(L); return rc; }
+      } else if (rc != FCB_ERR_UNSUPPORTED) return rc;
       else L->umma = nullptr;
     }
   }
+  if (hint == FCB_ENGINE_TENSOR && engine != ENG_UMMA) { set_error("engine_hint TENSOR: no tensor-core plan covers this layer"); return FCB_ERR_UNSUPPORTED; }
   if (engine != ENG_UMMA) {
     DirectParams& p = L->dp;
     const int deconv = g.kind == FCB_KIND_DECONV522;
@@ -461,7 +521,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     const int cu = engine == ENG_XNOR ? g.C / 32 : g.C;
     const size_t budget = 96 * 1024;
     int cc = (int)(budget / ((size_t)p.patch_w * p.patch_h * 4));
-    if (cc < 1) { set_error("kernel %dx%d stride %d: patch does not fit shared memory", g.KX, g.KY, g.SX); guard.armed = false; fcb_layer_destroy(L); return FCB_ERR_UNSUPPORTED; }
+    if (cc < 1) { set_error("kernel %dx%d stride %d: patch does not fit shared memory", g.KX, g.KY, g.SX); return FCB_ERR_UNSUPPORTED; }
     p.CC = std::min(cc, cu);
     L->smem = direct_smem_bytes(engine, p.patch_w, p.patch_h, p.CC);
     if (engine == ENG_XNOR) {
@@ -483,6 +543,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     }
     p.wt = L->d_wt;
   }
+  if (L->lowered && (rc = lowered_reserve(L))) return rc;  // the lowering scratch is allocated here, never inside a run call
   guard.armed = false;
   *out = L;
   return FCB_OK;
@@ -502,7 +563,7 @@ int fcb_layer_set_params(fcb_layer* L, const void* weights, const void* threshol
   std::swap(L->epi, fresh->epi); std::swap(L->dp, fresh->dp); std::swap(L->smem, fresh->smem);
   std::swap(L->umma, fresh->umma);
   std::swap(L->lowered, fresh->lowered); std::swap(L->lower_bits, fresh->lower_bits); std::swap(L->ip, fresh->ip);
-  std::swap(L->d_scratch, fresh->d_scratch); std::swap(L->scratch_imgs, fresh->scratch_imgs); std::swap(L->scratch_img_bytes, fresh->scratch_img_bytes);
+  std::swap(L->d_scratch[0], fresh->d_scratch[0]); std::swap(L->d_scratch[1], fresh->d_scratch[1]); std::swap(L->scratch_imgs, fresh->scratch_imgs); std::swap(L->scratch_img_bytes, fresh->scratch_img_bytes);
   memcpy(L->plan_desc, fresh->plan_desc, sizeof(L->plan_desc));
   fcb_layer_destroy(fresh);
   return FCB_OK;
@@ -540,30 +601,29 @@ const char* fcb_layer_plan(const fcb_layer* L) {
 }
 uint64_t fcb_layer_launches(const fcb_layer* L) { return L ? L->launches : 0; }
 
-int fcb_layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, void* stream) {
-  if (!L || !d_in || !d_out) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
-  if (numReps == 0) return FCB_OK;
-  FCB_CUDA_OK(cudaSetDevice(L->device));
-  cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+
+// Scratch of a lowered layer (im2col rows / expanded bits): two slots of <= 64 MiB (at least 16 images' worth of alignment), one per
+// staging slot of the host-buffer call, so the lowering kernel of chunk k+1 never overwrites rows the GEMM of chunk k still reads.
+static int lowered_reserve(fcb_layer* L) {
+  size_t cap = std::max<size_t>(1, ((size_t)64 << 20) / L->scratch_img_bytes);
+  cap = align_chunk(cap, L->g.in_img_bytes, L->g.out_img_bytes);
+  for (int i = 0; i < 2; i++) FCB_CUDA_OK(cudaMalloc(&L->d_scratch[i], L->scratch_img_bytes * cap));
+  L->scratch_imgs = cap;
+  return FCB_OK;
+}
+
+static int layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, cudaStream_t st, int slot) {
   if (L->lowered) {
-    size_t cap = std::max<size_t>(1, ((size_t)1 << 30) / L->scratch_img_bytes);
-    cap = std::min<size_t>(cap, numReps);
-    if (L->scratch_imgs < cap) {
-      cudaFree(L->d_scratch);
-      L->d_scratch = nullptr;
-      L->scratch_imgs = 0;
-      FCB_CUDA_OK(cudaMalloc(&L->d_scratch, L->scratch_img_bytes * cap));
-      L->scratch_imgs = cap;
-    }
     for (size_t n0 = 0; n0 < numReps; n0 += L->scratch_imgs) {
       const int nb = (int)std::min<size_t>(L->scratch_imgs, numReps - n0);
       Im2colParams ip = L->ip;
       ip.in = (const uint8_t*)d_in + n0 * L->g.in_img_bytes;
-      ip.out = (uint8_t*)L->d_scratch;
+      ip.out = (uint8_t*)L->d_scratch[slot];
       int rc = L->lower_bits ? launch_expand_bits(ip, nb, st) : launch_im2col(ip, nb, st);
       if (rc) return rc;
       L->launches++;
-      rc = umma_run(L->umma, L->d_scratch, (uint8_t*)d_out + n0 * L->g.out_img_bytes, nb, st, &L->launches);
+      rc = umma_run(L->umma, L->d_scratch[slot], (uint8_t*)d_out + n0 * L->g.out_img_bytes, nb, st, &L->launches);
       if (rc) return rc;
     }
     return FCB_OK;
@@ -581,17 +641,35 @@ int fcb_layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t n
   return rc;
 }
 
+extern "C" {
+
+int fcb_layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, void* stream) {
+  if (!L || !d_in || !d_out) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  if (numReps == 0) return FCB_OK;
+  FCB_ON_DEVICE(L->device);
+  return layer_run_device(L, d_in, d_out, numReps, (cudaStream_t)stream, 0);
+}
+
+int fcb_layer_set_host_chunk(fcb_layer* L, uint32_t images) {
+  if (!L) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  L->host_chunk = images;
+  return FCB_OK;
+}
+
 int fcb_layer_run(fcb_layer* L, const void* in_words, void* out_words, uint32_t numReps) {
   if (!L || !in_words || !out_words) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
   if (numReps == 0) return FCB_OK;
-  FCB_CUDA_OK(cudaSetDevice(L->device));
-  // chunk so that one slot stays <= 256 MiB of input; two slots overlap copy and compute
-  size_t chunk = std::max<size_t>(1, ((size_t)256 << 20) / std::max(L->g.in_img_bytes, L->g.out_img_bytes));
-  chunk = std::min<size_t>(chunk, numReps);
+  FCB_ON_DEVICE(L->device);
+  // chunk so that one slot stays <= 256 MiB of input or output; two slots overlap copy and compute
+  size_t chunk = L->host_chunk ? L->host_chunk : std::max<size_t>(1, ((size_t)256 << 20) / std::max(L->g.in_img_bytes, L->g.out_img_bytes));
+  chunk = align_chunk(std::min<size_t>(chunk, numReps), L->g.in_img_bytes, L->g.out_img_bytes);
   if (L->s_imgs < chunk) {
+    L->s_imgs = 0;  // a failed reallocation must not leave a stale capacity behind
     for (int i = 0; i < 2; i++) {
       cudaFree(L->s_in[i]); cudaFree(L->s_out[i]);
       L->s_in[i] = L->s_out[i] = nullptr;
+    }
+    for (int i = 0; i < 2; i++) {
       FCB_CUDA_OK(cudaMalloc(&L->s_in[i], L->g.in_img_bytes * chunk));
       FCB_CUDA_OK(cudaMalloc(&L->s_out[i], L->g.out_img_bytes * chunk));
       if (!L->s_stream[i]) FCB_CUDA_OK(cudaStreamCreateWithFlags(&L->s_stream[i], cudaStreamNonBlocking));
@@ -603,7 +681,7 @@ int fcb_layer_run(fcb_layer* L, const void* in_words, void* out_words, uint32_t 
     const size_t nb = std::min<size_t>(chunk, numReps - n0);
     cudaStream_t st = L->s_stream[slot];
     FCB_CUDA_OK(cudaMemcpyAsync(L->s_in[slot], (const uint8_t*)in_words + n0 * L->g.in_img_bytes, nb * L->g.in_img_bytes, cudaMemcpyHostToDevice, st));
-    int rc = fcb_layer_run_device(L, L->s_in[slot], L->s_out[slot], (uint32_t)nb, st);
+    int rc = layer_run_device(L, L->s_in[slot], L->s_out[slot], (uint32_t)nb, st, slot);
     if (rc) return rc;
     FCB_CUDA_OK(cudaMemcpyAsync((uint8_t*)out_words + n0 * L->g.out_img_bytes, L->s_out[slot], nb * L->g.out_img_bytes, cudaMemcpyDeviceToHost, st));
   }
@@ -637,7 +715,7 @@ int fcb_net_create(fcb_layer* const* layers, uint32_t n, fcb_net** out) {
 
 void fcb_net_destroy(fcb_net* N) {
   if (!N) return;
-  cudaSetDevice(N->device);
+  DeviceScope ds(N->device);
   for (void* b : N->bufs) cudaFree(b);
   for (int i = 0; i < 2; i++) {
     cudaFree(N->s_in[i]); cudaFree(N->s_out[i]);
@@ -653,33 +731,33 @@ void fcb_net_destroy(fcb_net* N) {
 
 static int net_reserve(fcb_net* N, size_t imgs) {
   if (N->cap_imgs >= imgs) return FCB_OK;
+  N->cap_imgs = 0;  // a failed reallocation must not leave a stale capacity behind
   for (size_t i = 0; i < N->bufs.size(); i++) {
     cudaFree(N->bufs[i]);
     N->bufs[i] = nullptr;
-    FCB_CUDA_OK(cudaMalloc(&N->bufs[i], N->layers[i]->g.out_img_bytes * imgs));
   }
+  for (size_t i = 0; i < N->bufs.size(); i++) FCB_CUDA_OK(cudaMalloc(&N->bufs[i], N->layers[i]->g.out_img_bytes * imgs));
   N->cap_imgs = imgs;
   return FCB_OK;
 }
 
-int fcb_net_run_device(fcb_net* N, const void* d_in, void* d_out, uint32_t numReps, void* stream) {
-  if (!N || !d_in || !d_out) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
-  if (!numReps) return FCB_OK;
-  FCB_CUDA_OK(cudaSetDevice(N->device));
-  // bound the intermediates: process in chunks of images
+}  // extern "C"
+
+static int net_run_device(fcb_net* N, const void* d_in, void* d_out, uint32_t numReps, cudaStream_t st, int slot) {
+  // bound the intermediates: process in chunks of images (default: the largest intermediate stays <= 1 GiB)
   size_t biggest = 1;
   for (size_t i = 0; i + 1 < N->layers.size(); i++) biggest = std::max(biggest, N->layers[i]->g.out_img_bytes);
-  size_t chunk = std::max<size_t>(1, ((size_t)1 << 30) / biggest);
-  chunk = std::min<size_t>(chunk, numReps);
+  size_t chunk = N->device_chunk ? N->device_chunk : std::max<size_t>(1, ((size_t)1 << 30) / biggest);
+  const size_t in_b = N->layers.front()->g.in_img_bytes, out_b = N->layers.back()->g.out_img_bytes;
+  chunk = align_chunk(std::min<size_t>(chunk, numReps), in_b, out_b);
   int rc = net_reserve(N, chunk);
   if (rc) return rc;
-  const size_t in_b = N->layers.front()->g.in_img_bytes, out_b = N->layers.back()->g.out_img_bytes;
   for (size_t n0 = 0; n0 < numReps; n0 += chunk) {
     const uint32_t nb = (uint32_t)std::min<size_t>(chunk, numReps - n0);
     const void* src = (const uint8_t*)d_in + n0 * in_b;
     for (size_t i = 0; i < N->layers.size(); i++) {
       void* dst = (i + 1 == N->layers.size()) ? (void*)((uint8_t*)d_out + n0 * out_b) : N->bufs[i];
-      rc = fcb_layer_run_device(N->layers[i], src, dst, nb, stream);
+      rc = layer_run_device(N->layers[i], src, dst, nb, st, slot);
       if (rc) return rc;
       src = dst;
     }
@@ -687,32 +765,51 @@ int fcb_net_run_device(fcb_net* N, const void* d_in, void* d_out, uint32_t numRe
   return FCB_OK;
 }
 
+extern "C" {
+
+int fcb_net_run_device(fcb_net* N, const void* d_in, void* d_out, uint32_t numReps, void* stream) {
+  if (!N || !d_in || !d_out) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  if (!numReps) return FCB_OK;
+  FCB_ON_DEVICE(N->device);
+  return net_run_device(N, d_in, d_out, numReps, (cudaStream_t)stream, 0);
+}
+
+int fcb_net_set_host_chunk(fcb_net* N, uint32_t images) {
+  if (!N) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  N->host_chunk = images;
+  return FCB_OK;
+}
+
+int fcb_net_set_device_chunk(fcb_net* N, uint32_t images) {
+  if (!N) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  N->device_chunk = images;
+  return FCB_OK;
+}
+
 int fcb_net_run(fcb_net* N, const void* in_words, void* out_words, uint32_t numReps) {
   if (!N || !in_words || !out_words) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
   if (!numReps) return FCB_OK;
-  FCB_CUDA_OK(cudaSetDevice(N->device));
+  FCB_ON_DEVICE(N->device);
   const size_t in_b = N->layers.front()->g.in_img_bytes, out_b = N->layers.back()->g.out_img_bytes;
   // chunks of <= 64 MiB of input or output: small enough that the pipeline fills quickly, large enough to hide launch overheads
-  size_t chunk = std::max<size_t>(1, ((size_t)64 << 20) / std::max(in_b, out_b));
-  if (getenv("FCB_NET_CHUNK")) chunk = std::max(1, atoi(getenv("FCB_NET_CHUNK")));  // tests: force many small chunks
-  chunk = std::min<size_t>(chunk, numReps);
+  size_t chunk = N->host_chunk ? N->host_chunk : std::max<size_t>(1, ((size_t)64 << 20) / std::max(in_b, out_b));
+  chunk = align_chunk(std::min<size_t>(chunk, numReps), in_b, out_b);
   if (N->s_imgs < chunk) {
+    N->s_imgs = 0;  // a failed reallocation must not leave a stale capacity behind
     for (int i = 0; i < 2; i++) {
       cudaFree(N->s_in[i]); cudaFree(N->s_out[i]);
       N->s_in[i] = N->s_out[i] = nullptr;
+    }
+    for (int i = 0; i < 2; i++) {
       FCB_CUDA_OK(cudaMalloc(&N->s_in[i], in_b * chunk));
       FCB_CUDA_OK(cudaMalloc(&N->s_out[i], out_b * chunk));
-      if (!N->ev_in[i]) {
-        FCB_CUDA_OK(cudaEventCreateWithFlags(&N->ev_in[i], cudaEventDisableTiming));
-        FCB_CUDA_OK(cudaEventCreateWithFlags(&N->ev_run[i], cudaEventDisableTiming));
-        FCB_CUDA_OK(cudaEventCreateWithFlags(&N->ev_out[i], cudaEventDisableTiming));
-      }
+      if (!N->ev_in[i]) FCB_CUDA_OK(cudaEventCreateWithFlags(&N->ev_in[i], cudaEventDisableTiming));
+      if (!N->ev_run[i]) FCB_CUDA_OK(cudaEventCreateWithFlags(&N->ev_run[i], cudaEventDisableTiming));
+      if (!N->ev_out[i]) FCB_CUDA_OK(cudaEventCreateWithFlags(&N->ev_out[i], cudaEventDisableTiming));
     }
-    if (!N->st_in) {
-      FCB_CUDA_OK(cudaStreamCreateWithFlags(&N->st_in, cudaStreamNonBlocking));
-      FCB_CUDA_OK(cudaStreamCreateWithFlags(&N->st_run, cudaStreamNonBlocking));
-      FCB_CUDA_OK(cudaStreamCreateWithFlags(&N->st_out, cudaStreamNonBlocking));
-    }
+    if (!N->st_in) FCB_CUDA_OK(cudaStreamCreateWithFlags(&N->st_in, cudaStreamNonBlocking));
+    if (!N->st_run) FCB_CUDA_OK(cudaStreamCreateWithFlags(&N->st_run, cudaStreamNonBlocking));
+    if (!N->st_out) FCB_CUDA_OK(cudaStreamCreateWithFlags(&N->st_out, cudaStreamNonBlocking));
     N->s_imgs = chunk;
   }
   size_t k = 0;
@@ -723,10 +820,11 @@ int fcb_net_run(fcb_net* N, const void* in_words, void* out_words, uint32_t numR
     if (k >= 2) FCB_CUDA_OK(cudaStreamWaitEvent(N->st_in, N->ev_run[slot], 0));
     FCB_CUDA_OK(cudaMemcpyAsync(N->s_in[slot], (const uint8_t*)in_words + n0 * in_b, nb * in_b, cudaMemcpyHostToDevice, N->st_in));
     FCB_CUDA_OK(cudaEventRecord(N->ev_in[slot], N->st_in));
-    // layers of chunk k: need its input, and its output slot drained by the D2H of chunk k-2
+    // layers of chunk k: need its input, and its output slot drained by the D2H of chunk k-2.  All chunks run on ONE stream, so the
+    // intermediates and lowering scratch (slot 0) are never shared between chunks in flight.
     FCB_CUDA_OK(cudaStreamWaitEvent(N->st_run, N->ev_in[slot], 0));
     if (k >= 2) FCB_CUDA_OK(cudaStreamWaitEvent(N->st_run, N->ev_out[slot], 0));
-    int rc = fcb_net_run_device(N, N->s_in[slot], N->s_out[slot], (uint32_t)nb, N->st_run);
+    int rc = net_run_device(N, N->s_in[slot], N->s_out[slot], (uint32_t)nb, N->st_run, 0);
     if (rc) return rc;
     FCB_CUDA_OK(cudaEventRecord(N->ev_run[slot], N->st_run));
     // D2H of chunk k

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -21,9 +22,24 @@ void set_error(const char* fmt, ...);
     }                                                                                          \
   } while (0)
 
+// Experiment switches (environment variables that bend plans for measurements and cross-checks) exist only in experiment builds
+// (-DFCB_EXPERIMENT -> tools/libfinnconv_exp.so).  In the product library exp_env() is the constant nullptr: no environment
+// variable can change the kernel a caller gets.
+#ifdef FCB_EXPERIMENT
+inline const char* exp_env(const char* name) { return getenv(name); }
+#else
+constexpr const char* exp_env(const char*) { return nullptr; }
+#endif
+inline int exp_int(const char* name, int dflt) {
+  const char* v = exp_env(name);
+  return v ? atoi(v) : dflt;
+}
+
 // ---- derived geometry -------------------------------------------------------------
 struct Geom {
   int kind, C, OFM, KX, KY, IX, IY, OX, OY, SX, SY, PAD;
+  int pad_l, pad_r, pad_u, pad_d;  // FMPadding_nonsquare split (streamtools.h:374-379); PAD = pad_l when all four are equal
+  int engine_hint, pool_signed, pool_min;
   int simd, pe, SF, NF, K;
   int in_bits, in_signed, w_bits, weight_kind;
   int acc_bits, acc_signed, act_kind, out_bits, num_th, act_val, cmp, pool;
@@ -67,7 +83,7 @@ struct DirectParams {  // imad / xnor_popc direct convolution
 int launch_direct(const DirectParams& p, int engine, int n_images, size_t smem_bytes, cudaStream_t st);
 size_t direct_smem_bytes(int engine, int patch_w, int patch_h, int cc);
 
-// tcgen05 implicit GEMM (fcb_umma.cu)
+// tcgen05 implicit GEMM (fcb_plan.cu: host glue; fcb_umma2.cu: kernels)
 struct UmmaPlan;  // opaque to the API file
 int umma_eligible(const Geom& g);
 int umma_plan_create(const Geom& g, const std::vector<int32_t>& W /*[OFM][K]*/, const EpiParams& epi, int device, UmmaPlan** out);

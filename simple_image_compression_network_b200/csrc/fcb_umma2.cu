@@ -113,6 +113,14 @@ struct Params2 {
 
 __device__ __forceinline__ bool chv_of(int ch, int ofm) { return ch < ofm; }
 
+// tensor maps of one (input, output, batch) triple: encoding three maps costs ~2 us of host time, and steady-state callers (the
+// layer chain's intermediates, the staging slots of the host-buffer calls, benchmarks) present the same few triples again and again
+struct MapSet {
+  const void* d_in = nullptr;
+  void* d_out = nullptr;
+  int n_images = 0;
+  CUtensorMap tmA[2], tmO;
+};
 struct Umma2Plan {
   Geom g;
   Params2 p;
@@ -120,6 +128,8 @@ struct Umma2Plan {
   size_t smem;
   int num_sms;
   uint32_t box_rows[2];
+  MapSet maps[4];
+  int map_next = 0;
 };
 
 // pixel bookkeeping of the epilogue: column m of the accumulator -> output word
@@ -273,7 +283,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #define WAITB(BAR_, PAR_) mbar_wait((BAR_), (PAR_))
   // clock accounting and the perf-decomposition switches of the inner loops exist only in -DFCB_U2_PROF builds (tools/): even a
   // predicted-not-taken branch per K-block shows in the MMA issue loop, which has ~580 clocks per K-block to stay ahead of the pipe
-#ifdef FCB_U2_PROF
+#if defined(FCB_U2_PROF)
   long long prof_c = 0;
   unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF_START() do { if (p.prof) prof_c = clock64(); } while (0)
@@ -284,7 +294,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #define PROF_START() do { } while (0)
 #define PROF_T(SEG_) do { } while (0)
 #define PROF_FLUSH(ROLE_) do { } while (0)
-#define DBG(MASK_) false
+#define DBG(MASK_) (false)
 #endif
   const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
   const long long total_tiles = tiles_per_img * p.n_images;
@@ -337,7 +347,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const Phase2& P = p.phases[ph];
           for (int i = 0; i < P.nkb; i++) {
             mbar_wait(&wempty[s], wphase);
-            if (p.debug & 1) mbar_arrive(&wfull[s]);
+            if (DBG(1)) mbar_arrive(&wfull[s]);
             else {
               mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);
               if (DTHIN || DCOL) tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], 0, P.kb[i].w_k);  // row block w_k
@@ -424,7 +434,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const Plane2& pl = p.planes[i];
           uint64_t* fb = &afull[set * p.nplanes + i];
           mbar_wait(&aempty[set * p.nplanes + i], par);
-          if (p.debug & 2) { mbar_arrive(fb); continue; }
+          if (DBG(2)) { mbar_arrive(fb); continue; }
           mbar_arrive_expect_tx(fb, (uint32_t)pl.bytes);
           const CUtensorMap* m = pl.map ? &tmA1 : &tmA0;
           uint8_t* dst = smem + set * p.set_bytes + pl.smem_off;
@@ -571,7 +581,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         PROF_T(1);
         tc_fence_after();
         // valid extent of this tile (rows/columns past it are halo, padding or beyond the image)
-        const int vrows = (p.debug & 4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
+        const int vrows = DBG(4) ? 0 : min(p.R, p.PY - pm.y0), vcols = min(p.WT, p.PX - pm.x0);
         if ((GEN || DCX) && DCOL) {
           // (always two accumulator stages: warps 2..5 serve stage 0, warps 6..9 stage 1, each group with its own byte tile)
           // (25 taps x 4 byte lanes = 100 accumulator columns; lanes >= OFM have zero weights: they give the zero pad byte)
@@ -582,7 +592,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           EPI_BAR();  // the group's previous col2im pass has finished reading S
           PROF_T(2);
           // ---- phase 1: accumulator rows -> bytes (all arithmetic is mod 2^8, so the partial sums may be truncated now)
-          if (!(p.debug & 8)) {
+          if (!DBG(8)) {
             // thread = pixel (TMEM lane), columns = the bytes of its record: 3 x 32 columns -> 2 x 16-byte stores each, + the
             // last word (tap (0,0)); the stage's groups (two with 16 epilogue warps) take one 128-pixel block each
             const int ncols = (vrows + 2) * p.P;  // pixels of the tile, halo ring included
@@ -623,7 +633,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           // partial of pixel (r + offy, xo + offx), offy = (ky + (ky & 1) - 2) / 2
           const int npx = vrows * p.WT;
           const int idx0 = sub * 128 + (warp & 3) * 32 + lane;
-          for (int idx = idx0; idx < ((p.debug & 8) ? 0 : npx); idx += 128 * NSUB) {
+          for (int idx = idx0; idx < (DBG(8) ? 0 : npx); idx += 128 * NSUB) {
             const int rr = idx == idx0 ? pre_rr : idx / p.WT, xo = idx == idx0 ? pre_xo : idx - rr * p.WT;
             if (xo >= vcols) continue;
             uint32_t bm[3];
@@ -656,7 +666,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
           const int rr = m / p.P, xo = m - rr * p.P;
-          if (xo < vcols && rr < vrows && !(p.debug & 8)) {
+          if (xo < vcols && rr < vrows && !DBG(8)) {
             uint32_t w[4];
 #pragma unroll
             for (int ph = 0; ph < 4; ph++) {
@@ -690,7 +700,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           else EPI_BAR();
           PROF_T(2);
           // items = (128-pixel block, 32-channel block), block-major; this warp takes every `its`-th item from `it0`
-          const int cpb = p.CB * 4, nitems = (p.debug & 8) ? 0 : (p.NPX / 128) * cpb;
+          const int cpb = p.CB * 4, nitems = DBG(8) ? 0 : (p.NPX / 128) * cpb;
           const uint32_t bias_s = smem_u32(smem + p.stage_off);
           const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
           const uint32_t stg_s = smem_u32(stg);
@@ -783,7 +793,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           EPI_BAR();
           PROF_T(5);
           if (lane == 0) {
-            for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++)
+            for (int cb = 0; cb < (DBG(8) ? 0 : p.CB); cb++)
               for (int rr = erow0; rr < vrows; rr += erows)
                 tma_store_4d(&tmO, stg + (cb * p.NPX + rr * p.P) * 128, cb * 128, pm.x0, pm.y0 + rr, img);
             bulk_commit();
@@ -805,7 +815,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           EPI_BAR();
           PROF_T(2);
-          for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++) {
+          for (int cb = 0; cb < (DBG(8) ? 0 : p.CB); cb++) {
             const int ch = chbase + cb * 128 + q * 32 + lane;
             const uint32_t bias4 = p.bias_word >= 0 ? 0u : ((uint32_t)(int32_t)p.epi.bias[ch] & 0xFFu) * 0x01010101u;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
@@ -836,7 +846,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           EPI_BAR();
           PROF_T(5);
           if (lane == 0) {  // rows are dealt round-robin to the 8 epilogue warps: issuing a TMA store costs ~300 clocks of one thread
-            for (int cb = 0; cb < ((p.debug & 8) ? 0 : p.CB); cb++)
+            for (int cb = 0; cb < (DBG(8) ? 0 : p.CB); cb++)
               for (int rr = erow0; rr < vrows; rr += erows) {
                 const uint8_t* src = stg + (cb * p.NPX + rr * p.P) * 128;
                 if (p.deconv) tma_store_5d(&tmO, src, pm.px * p.OFM + chbase + cb * 128, pm.x0, pm.py, pm.y0 + rr, img);
@@ -884,7 +894,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");  // staging rows are reused by the next accumulator
         }
-        for (int cb = 0; cb < ((p.debug & 8) || thin ? 0 : p.CB); cb++) {
+        for (int cb = 0; cb < (DBG(8) || thin ? 0 : p.CB); cb++) {
           if (chbase + cb * 128 + q * 32 >= p.OFM) continue;  // this warp's 32 channels do not exist (warp-uniform)
           const int ch = chbase + cb * 128 + q * 32 + lane;
           // threshold tables of this thread's channel: top levels in shared memory + channel-major global row, or all global
@@ -1046,7 +1056,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                       m8[4 * g2 + w] = (g2 == 0 || second) ? m0 : 0;
                     }
                   }
-                  if (p.debug & 16) {
+                  if (DBG(16)) {
 #pragma unroll
                     for (int w = 0; w < 8; w++) pooled[w] = (uint32_t)m8[w] & 0xFFu;
                   } else if (use_lut) {
@@ -1173,17 +1183,17 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   // tables and visits every tile), the top D-2 levels (+ one 16-byte global load per output), or global memory only.
   struct Cand { int thr_top, chb; double epi_factor; };
   std::vector<Cand> cands;
-  if (thr && !getenv("FCB_U2_NO_SMEM_THR")) {
+  if (thr && !exp_env("FCB_U2_NO_SMEM_THR")) {
     int D = 0;
     while ((1 << D) < epi.thr_n + 1) D++;
     cands.push_back({D, 1, 40.0});
-    if (CB == 2 && !getenv("FCB_U2_NO_CHB")) cands.push_back({D, 2, 40.0});
+    if (CB == 2 && !exp_env("FCB_U2_NO_CHB")) cands.push_back({D, 2, 40.0});
     if (D - 2 >= 1) cands.push_back({D - 2, 1, 60.0});
   }
   cands.push_back({0, 1, thr ? 120.0 : 0.0});
   double best = 1e30;
   int bWT = 0, bR = 0, bNPX = 0, bWS = 0, thr_top = 0, thr_bytes = 0, chb = 1, CBe = CB;
-  const int only_cand = getenv("FCB_U2_CAND") ? atoi(getenv("FCB_U2_CAND")) : -1;  // experiments: evaluate one candidate only
+  const int only_cand = exp_int("FCB_U2_CAND", -1);  // experiments: evaluate one candidate only
   for (size_t ci = 0; ci < cands.size(); ci++) {
     const Cand& cd = cands[ci];
     if (only_cand >= 0 && (int)ci != only_cand) continue;
@@ -1235,9 +1245,9 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     }
   }
   const int w_bytes = CBe * 128 * 128;
-  if (getenv("FCB_U2_FORCE")) {  // "WT,R,NPX,WS" -- experiments only; the caller is responsible for it fitting
+  if (const char* force = exp_env("FCB_U2_FORCE")) {  // "WT,R,NPX,WS" -- experiments only; the caller is responsible for it fitting
     int a, b, c, d;
-    if (sscanf(getenv("FCB_U2_FORCE"), "%d,%d,%d,%d", &a, &b, &c, &d) == 4) { bWT = a; bR = b; bNPX = c; bWS = d; }
+    if (sscanf(force, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) { bWT = a; bR = b; bNPX = c; bWS = d; }
   }
   if (!bWT) return FCB_ERR_UNSUPPORTED;
 
@@ -1257,7 +1267,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   while (tc < p.acc_stages * p.acc_stride) tc *= 2;
   p.tmem_cols = tc;
   p.idesc = make_idesc_i8(128, bNPX, /*A = weights*/ 1, /*B = activations*/ g.in_signed);
-  p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
+  p.debug = exp_int("FCB_U2_DEBUG", 0);
   // planes
   int plane_of[4][4];
   int off = 0, np = 0, nmaps = 0;
@@ -1287,7 +1297,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   p.nplanes = np;
   p.set_bytes = off;
   p.nsets = ((size_t)2 * off + (size_t)bWS * w_bytes + 4096 + (thr_bytes ? thr_bytes + 128 : 0) <= (size_t)227 * 1024 - 1024) ? 2 : 1;
-  if (getenv("FCB_U2_NSETS")) p.nsets = std::max(1, std::min(p.nsets, atoi(getenv("FCB_U2_NSETS"))));
+  p.nsets = std::max(1, std::min(p.nsets, exp_int("FCB_U2_NSETS", p.nsets)));
   off *= p.nsets;
   U->box_rows[0] = map_rows[0]; U->box_rows[1] = nmaps > 1 ? map_rows[1] : map_rows[0];
   p.w_off = off;
@@ -1309,7 +1319,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     int D = 0;
     while ((1 << D) < epi.thr_n + 1) D++;
     const int lut_bytes = CBe * 128 * 256;
-    if (thr_bytes && thr_top == D && epi.thr_lut && !getenv("FCB_U2_NO_LUT") && (size_t)off + lut_bytes + 2048 <= (size_t)227 * 1024) {
+    if (thr_bytes && thr_top == D && epi.thr_lut && !exp_env("FCB_U2_NO_LUT") && (size_t)off + lut_bytes + 2048 <= (size_t)227 * 1024) {
       off = (off + 127) & ~127;
       p.lut_off = off;
       off += lut_bytes;
@@ -1319,14 +1329,14 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   p.stg_off = 0; p.stg_bufs = 0; p.stg_bytes = CBe * bNPX * 128;
   const bool fast_epi = epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && g.pool <= 1 && g.OFM % 128 == 0 &&
                         g.out_word_bytes == (size_t)g.OFM;
-  if (fast_epi && !getenv("FCB_U2_NO_STAGE")) {
+  if (fast_epi && !exp_env("FCB_U2_NO_STAGE")) {
     off = (off + 127) & ~127;
     for (int nb = 2; nb >= 1; nb--)
       if ((size_t)off + (size_t)nb * p.stg_bytes + 1024 <= (size_t)227 * 1024) { p.stg_bufs = nb; break; }
     p.stg_off = off;
     off += p.stg_bufs * p.stg_bytes;
   }
-  p.epi_alt = (p.stg_bufs == 2 && p.acc_stages == 2 && !getenv("FCB_U2_NO_ALT")) ? 1 : 0;
+  p.epi_alt = (p.stg_bufs == 2 && p.acc_stages == 2 && !exp_env("FCB_U2_NO_ALT")) ? 1 : 0;
   {
     // register bias/ReLU epilogue, ~30 clocks per pixel with 4 warps (measured on the deconv layers before they were staged):
     // if that hides under the tile's MMA time with margin, run it on 4 warps
@@ -1337,7 +1347,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     // measured on CONV_1: 147.3 k img/s with 4 warps vs 150.5 k with 8 -- issue-slot competition is not what holds the tensor
     // pipe at ~85 %, so this stays an experiment switch (FCB_U2_EPI4=1)
     (void)mma_tile; (void)epi_tile;
-    p.epi4 = (reg_fast && p.acc_stages == 2 && getenv("FCB_U2_EPI4") && atoi(getenv("FCB_U2_EPI4"))) ? 1 : 0;
+    p.epi4 = (reg_fast && p.acc_stages == 2 && exp_int("FCB_U2_EPI4", 0)) ? 1 : 0;
   }
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
@@ -1400,7 +1410,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   const int step = g.pool == 2 ? 2 : 1;
   const bool thr = g.act_kind == FCB_ACT_THRESHOLDS;
   int thr_top = 0, thr_bytes = 0;
-  if (thr && !getenv("FCB_U2_NO_SMEM_THR")) {
+  if (thr && !exp_env("FCB_U2_NO_SMEM_THR")) {
     int D = 0;
     while ((1 << D) < epi.thr_n + 1) D++;
     // the whole search in shared memory when it fits beside the small operands of this mode, else all but the last two levels
@@ -1416,8 +1426,8 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   int bWT = 0, bR = 0, bNPX = 0;
   double best = 1e30;
   const bool fast_epi0 = epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && g.pool <= 1 && g.OFM % 128 == 0 &&
-                         g.out_word_bytes == (size_t)g.OFM && !getenv("FCB_U2_NO_STAGE");
-  const bool want_swap = fast_epi0 && PX >= 8 && !getenv("FCB_U2_NO_SWAP");
+                         g.out_word_bytes == (size_t)g.OFM && !exp_env("FCB_U2_NO_STAGE");
+  const bool want_swap = fast_epi0 && PX >= 8 && !exp_env("FCB_U2_NO_SWAP");
   for (int NPX = 256; NPX >= (want_swap ? 128 : 64); NPX /= 2) {
     if (CB * NPX > 512) continue;
     for (int WT = step; WT <= std::min(PX + step - 1, 256); WT += step) {
@@ -1456,7 +1466,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   while (tc < p.acc_stages * p.acc_stride) tc *= 2;
   p.tmem_cols = tc;
   p.idesc = make_idesc_i8(128, bNPX, 1, g.in_signed);
-  p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
+  p.debug = exp_int("FCB_U2_DEBUG", 0);
   p.swap = want_swap ? 1 : 0;
   p.bias_word = bias_word;
   p.idesc_swap = make_idesc_i8(128, CB * 128, g.in_signed, 1);
@@ -1479,7 +1489,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     int D = 0;
     while ((1 << D) < epi.thr_n + 1) D++;
     const int lut_bytes = CB * 128 * 256;
-    if (thr_bytes && thr_top == D && epi.thr_lut && !getenv("FCB_U2_NO_LUT")) {
+    if (thr_bytes && thr_top == D && epi.thr_lut && !exp_env("FCB_U2_NO_LUT")) {
       const size_t rest = (size_t)U2_NPB * p.patch_bytes + 2048;
       if ((size_t)off + lut_bytes + rest > (size_t)227 * 1024 && p.nsets == 2) {
         // single-buffer the im2col rows to make room: the layer is bound by its threshold epilogue, not by the builders
@@ -1502,13 +1512,13 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
                         g.out_word_bytes == (size_t)g.OFM;
   off = (off + 1023) & ~1023;
   p.stg_off = off;
-  if (fast_epi && !getenv("FCB_U2_NO_STAGE"))
+  if (fast_epi && !exp_env("FCB_U2_NO_STAGE"))
     for (int nb = 2; nb >= 1; nb--)
       if ((size_t)off + (size_t)nb * p.stg_bytes + U2_NPB * p.patch_bytes + 1024 <= (size_t)227 * 1024) { p.stg_bufs = nb; break; }
   off += p.stg_bufs * p.stg_bytes;
   if (p.swap && !p.stg_bufs) p.swap = 0;
-  p.epi_alt = (p.stg_bufs == 2 && p.acc_stages == 2 && !getenv("FCB_U2_NO_ALT")) ? 1 : 0;
-  p.wl = (p.swap && p.epi_alt && bWT % 32 == 0 && !getenv("FCB_U2_NO_WL")) ? 1 : 0;
+  p.epi_alt = (p.stg_bufs == 2 && p.acc_stages == 2 && !exp_env("FCB_U2_NO_ALT")) ? 1 : 0;
+  p.wl = (p.swap && p.epi_alt && bWT % 32 == 0 && !exp_env("FCB_U2_NO_WL")) ? 1 : 0;
   p.patch_off = off; off += (int)U2_NPB * p.patch_bytes;
   U->smem = (size_t)off + 1024;
   if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
@@ -1535,6 +1545,10 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
 // Thin-output transposed conv plan: d_w is [9 shifts x cch chunks][16 rows][128] s8 (row = phase*4 + channel slot).
 int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, Umma2Plan** out) {
   *out = nullptr;
+#ifndef FCB_EXPERIMENT
+  (void)g; (void)d_w; (void)epi; (void)num_sms;
+  return FCB_ERR_UNSUPPORTED;  // cross-check form: experiment builds only
+#else
   if (g.kind != FCB_KIND_DECONV522 || g.OFM < 3 || g.OFM > 4 || g.out_word_bytes != 4 || g.C % 128 || g.C > 256 || g.pool > 1 ||
       epi.act_kind != FCB_ACT_BIAS_RELU || epi.out_bits != 8 || epi.acc_bits != 8)
     return FCB_ERR_UNSUPPORTED;
@@ -1565,7 +1579,7 @@ int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& e
   p.wstages = 9 * cch; p.wstatic = 1; p.w_bytes = 2048;
   p.acc_stride = 32; p.acc_stages = 2; p.tmem_cols = 64;
   p.idesc = p.idesc_dthin = make_idesc_i8(128, 16, g.in_signed, 1);
-  p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
+  p.debug = exp_int("FCB_U2_DEBUG", 0);
   const int rows = bR + 2;
   const size_t plane = ((size_t)(2 * p.P + 2 + NPX) * 128 + 1023) / 1024 * 1024;
   int off = 0;
@@ -1606,6 +1620,7 @@ int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& e
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
+#endif
 }
 
 // Thin-output transposed conv, col2im form: d_w is [cch][128 rows (tap*OFM + ch, zero beyond 25*OFM)][128] s8.
@@ -1638,7 +1653,7 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.wstages = cch; p.wstatic = 1; p.w_bytes = 128 * 128;
   p.acc_stride = 2 * 112; p.acc_stages = 2; p.tmem_cols = 512;  // per stage: two 128-pixel blocks x 112 columns
   p.idesc = p.idesc_dthin = make_idesc_i8(128, 112, g.in_signed, 1);  // A = plane rows (pixels), B = the (tap word, channel) weight rows
-  p.debug = getenv("FCB_U2_DEBUG") ? atoi(getenv("FCB_U2_DEBUG")) : 0;
+  p.debug = exp_int("FCB_U2_DEBUG", 0);
   p.epi_alt = 1;  // one epilogue group per accumulator stage
   p.s_pitch = DCOL_PIX;  // pixel-major byte tile: 112 bytes per pixel (25 tap words + pad)
   const int rows = bR + 2;
@@ -1652,7 +1667,7 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
   // the planes are prefetched three tiles ahead
   p.nplanes = cch; p.set_bytes = off;
   p.nsets = 4;  // measured on L7: 2 sets 201.5 k, 3 sets 209 k, 4 sets 218 k, 5 sets 212 k img/s
-  if (getenv("FCB_U2_NSETS")) p.nsets = std::max(1, std::min(5, atoi(getenv("FCB_U2_NSETS"))));
+  p.nsets = std::max(1, std::min(5, exp_int("FCB_U2_NSETS", p.nsets)));
   while (p.nsets > 1 && (size_t)p.nsets * off + (size_t)cch * 16384 + 2 * (NPX * DCOL_PIX) + 8192 > (size_t)227 * 1024) p.nsets--;
   off *= p.nsets;
   U->box_rows[0] = U->box_rows[1] = rows;
@@ -1680,7 +1695,9 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
   }
+#ifdef FCB_EXPERIMENT
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#endif
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = U;
   return FCB_OK;
@@ -1698,9 +1715,9 @@ static int thrp_extra_warps(const Params2& p) {
   const EpiParams& e = p.epi;
   const bool thrp = e.act_kind == FCB_ACT_THRESHOLDS && e.pool == 2 && e.out_bits == 8 && p.thr_off >= 0 && !p.deconv &&
                     (e.cmp == FCB_CMP_LESS || e.cmp == FCB_CMP_LESS_EQUAL) && e.act_val >= 0 && e.act_val + e.num_th < 256 &&
-                    (e.acc_signed || e.acc_bits < 32) && !getenv("FCB_U2_NO_THRP");
+                    (e.acc_signed || e.acc_bits < 32) && !exp_env("FCB_U2_NO_THRP");
   if (!thrp) return -1;
-  if (const char* xe = getenv("FCB_U2_XEPI")) return atoi(xe) >= 8 ? 8 : atoi(xe) >= 4 ? 4 : 0;  // experiment switch
+  if (exp_env("FCB_U2_XEPI")) { const int xe = exp_int("FCB_U2_XEPI", 0); return xe >= 8 ? 8 : xe >= 4 ? 4 : 0; }  // experiment switch
   const int nunits = (p.R >> 1) * ((p.WT + 15) >> 4);
   return nunits < 6 ? 0 : (nunits + 3) / 4 < (nunits + 2) / 3 ? 8 : 4;
 }
@@ -1738,12 +1755,9 @@ static const char* umma2_describe_base(const Umma2Plan* U, char* buf, size_t n) 
   return buf;
 }
 
-int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStream_t st) {
+static int umma2_encode_maps(const Umma2Plan* U, MapSet* ms, const void* d_in, void* d_out, int n_images) {
   const Geom& g = U->g;
-  Params2 p = U->p;
-  p.out = (uint8_t*)d_out;
-  p.n_images = n_images;
-  CUtensorMap tmA[2];
+  const Params2& p = U->p;
   const uint64_t C = g.C, X = g.IX, Y = g.IY;
   for (int m = 0; m < 2; m++) {
     int rc;
@@ -1751,21 +1765,21 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
       const uint64_t dims[3] = {X, Y, (uint64_t)n_images};
       const uint64_t strides[2] = {X * 4, X * Y * 4};
       const uint32_t box[3] = {(uint32_t)p.BWp, (uint32_t)p.BHp, 1};
-      rc = umma_encode_map_ex(&tmA[m], const_cast<void*>(d_in), 4, 0, 3, dims, strides, box);
+      rc = umma_encode_map_ex(&ms->tmA[m], const_cast<void*>(d_in), 4, 0, 3, dims, strides, box);
     } else if (p.stride2) {
       const uint64_t dims[5] = {2 * C, X / 2, 2, Y / 2, (uint64_t)n_images};
       const uint64_t strides[4] = {2 * C, X * C, 2 * X * C, X * Y * C};
       const uint32_t box[5] = {128, (uint32_t)p.P, 1, U->box_rows[m], 1};
-      rc = umma_encode_map(&tmA[m], const_cast<void*>(d_in), 5, dims, strides, box);
+      rc = umma_encode_map(&ms->tmA[m], const_cast<void*>(d_in), 5, dims, strides, box);
     } else {
       const uint64_t dims[4] = {C, X, Y, (uint64_t)n_images};
       const uint64_t strides[3] = {C, X * C, X * Y * C};
       const uint32_t box[4] = {128, (uint32_t)p.P, U->box_rows[m], 1};
-      rc = umma_encode_map(&tmA[m], const_cast<void*>(d_in), 4, dims, strides, box);
+      rc = umma_encode_map(&ms->tmA[m], const_cast<void*>(d_in), 4, dims, strides, box);
     }
     if (rc) return rc;
   }
-  CUtensorMap tmO = tmA[0];
+  ms->tmO = ms->tmA[0];
   if (p.stg_bufs > 0) {
     const uint64_t F = g.OFM, OX = g.out_x, OY = g.out_y;
     int rc;
@@ -1773,15 +1787,37 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
       const uint64_t dims[5] = {2 * F, OX / 2, 2, OY / 2, (uint64_t)n_images};
       const uint64_t strides[4] = {2 * F, OX * F, 2 * OX * F, OX * OY * F};
       const uint32_t box[5] = {128, (uint32_t)p.WT, 1, 1, 1};
-      rc = umma_encode_map_ex(&tmO, d_out, 1, 0, 5, dims, strides, box);
+      rc = umma_encode_map_ex(&ms->tmO, d_out, 1, 0, 5, dims, strides, box);
     } else {
       const uint64_t dims[4] = {F, OX, OY, (uint64_t)n_images};
       const uint64_t strides[3] = {F, OX * F, OX * OY * F};
       const uint32_t box[4] = {128, (uint32_t)(p.wl ? 32 : p.WT), 1, 1};
-      rc = umma_encode_map_ex(&tmO, d_out, 1, p.swap ? 128 : 0, 4, dims, strides, box);
+      rc = umma_encode_map_ex(&ms->tmO, d_out, 1, p.swap ? 128 : 0, 4, dims, strides, box);
     }
     if (rc) return rc;
   }
+  ms->d_in = d_in; ms->d_out = d_out; ms->n_images = n_images;
+  return FCB_OK;
+}
+
+int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStream_t st) {
+  const Geom& g = U->g;
+  Params2 p = U->p;
+  p.out = (uint8_t*)d_out;
+  p.n_images = n_images;
+  const MapSet* ms = nullptr;
+  for (const MapSet& c : U->maps)
+    if (c.n_images == n_images && c.d_in == d_in && c.d_out == d_out) { ms = &c; break; }
+  if (!ms) {
+    MapSet* slot = &U->maps[U->map_next];
+    slot->n_images = 0;  // invalid while it is being rewritten
+    int rc = umma2_encode_maps(U, slot, d_in, d_out, n_images);
+    if (rc) return rc;
+    U->map_next = (U->map_next + 1) & 3;
+    ms = slot;
+  }
+  const CUtensorMap* tmA = ms->tmA;
+  const CUtensorMap& tmO = ms->tmO;
   // sub-byte / padded output words are merged or partially written: start from zeroed words
   if (g.out_word_bytes * 8 != (size_t)g.OFM * g.out_bits && !p.dthin)  // (the thin-output deconv epilogue writes whole words)
     FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, g.out_img_bytes * n_images, st));
@@ -1789,7 +1825,7 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   const int grid = (int)std::min<long long>(total, U->num_sms / p.chb) * p.chb;
   unsigned long long* d_prof = nullptr;
 #ifdef FCB_U2_PROF
-  if (getenv("FCB_U2_PROF")) {
+  if (exp_env("FCB_U2_PROF")) {
     FCB_CUDA_OK(cudaMalloc(&d_prof, (size_t)grid * 24 * 8));
     FCB_CUDA_OK(cudaMemsetAsync(d_prof, 0, (size_t)grid * 24 * 8, st));
     p.prof = d_prof;
@@ -1803,13 +1839,15 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   else if (p.thin_in && thrp && xepi == 4) umma2_conv_kernel<2, 0, 2><<<grid, 320 + 32 * 2 + 128, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.thin_in && thrp) umma2_conv_kernel<2, 0, 1><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.thin_in && p.epi.act_kind == FCB_ACT_THRESHOLDS) umma2_conv_kernel<2, 0, 0><<<grid, 320 + 32 * 2, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (p.thin_in && p.swap && p.wl && p.epi_alt && p.NPX == 256 && !getenv("FCB_U2_NO_SWPX"))  // pixel-major bias+ReLU, warp-local stores: 16 epilogue warps
+  else if (p.thin_in && p.swap && p.wl && p.epi_alt && p.NPX == 256 && !exp_env("FCB_U2_NO_SWPX"))  // pixel-major bias+ReLU, warp-local stores: 16 epilogue warps
     umma2_conv_kernel<4, 0, 4><<<grid, 320 + 32 * 4 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.thin_in) umma2_conv_kernel<4, 0, 0><<<grid, 320 + 32 * 4, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (p.dthin == 2 && !getenv("FCB_U2_NO_DCX")) umma2_conv_kernel<1, 2, 5><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+  else if (p.dthin == 2 && !exp_env("FCB_U2_NO_DCX")) umma2_conv_kernel<1, 2, 5><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+#ifdef FCB_EXPERIMENT
   else if (p.dthin == 2) umma2_conv_kernel<1, 2, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (p.dthin) umma2_conv_kernel<1, 1, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (!thrp && p.stg_bufs == 2 && p.epi_alt && !p.swap && !getenv("FCB_U2_NO_STX"))  // staged bias+ReLU, two tiles: 16 epilogue warps
+#endif
+  else if (!thrp && p.stg_bufs == 2 && p.epi_alt && !p.swap && !exp_env("FCB_U2_NO_STX"))  // staged bias+ReLU, two tiles: 16 epilogue warps
     umma2_conv_kernel<1, 0, 6><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (thrp && xepi == 8) umma2_conv_kernel<1, 0, 3><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
   else if (thrp && xepi == 4) umma2_conv_kernel<1, 0, 2><<<grid, 320 + 32 + 128, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);

@@ -1,4 +1,4 @@
-// fcb_umma_common.h -- shared between the two generations of the umma_i8 engine.
+// fcb_umma_common.h -- shared between the host glue (fcb_plan.cu) and the kernels (fcb_umma2.cu; fcb_umma_v1.cu in experiment builds).
 #pragma once
 #include <cuda.h>
 
@@ -18,4 +18,12 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w /*[cch*128][128]*/, 
 void umma2_plan_destroy(Umma2Plan* U);
 int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStream_t st);
 const char* umma2_describe(const Umma2Plan* U, char* buf, size_t n);
+
+struct UmmaV1;  // first-generation per-tap-TMA kernel: experiment builds only (fcb_umma_v1.cu)
+#ifdef FCB_EXPERIMENT
+int umma_v1_eligible(const Geom& g);
+int umma_v1_create(const Geom& g, int8_t* d_w /*[OFMpad][K]*/, const EpiParams& epi, int num_sms, UmmaV1** out);
+void umma_v1_destroy(UmmaV1* p);
+int umma_v1_run(UmmaV1* p, const void* d_in, void* d_out, int n_images, cudaStream_t st);
+#endif
 }  // namespace fcb

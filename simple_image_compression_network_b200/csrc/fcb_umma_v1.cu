@@ -1,5 +1,6 @@
-// fcb_umma.cu -- "umma_i8": the quantized convolution as an sm_100a implicit GEMM on the 5th-generation
-// tensor cores (tcgen05.mma kind::i8, int32 accumulators in TMEM).
+// fcb_umma_v1.cu -- FIRST-GENERATION "umma_i8" kernel (one TMA box per filter tap, M = 128 pixels).  NOT part of the product
+// library: it is compiled only into experiment builds (-DFCB_EXPERIMENT, tools/libfinnconv_exp.so) where FCB_UMMA_V1=1 selects it
+// as an independent cross-check of the resident-planes kernel (fcb_umma2.cu).  Host-side plan glue lives in fcb_plan.cu.
 //
 //   D[pixel][ch] = sum_k A[pixel][k] * W[ch][k],  k = (ky*Kx + kx)*C + c   (mvau.hpp:122-178,
 //   window order slidingwindow.h:1302-1313), followed by the fused activation stage.
@@ -18,6 +19,7 @@
 // Persistent over tiles (tile = image x phase x BHxBW pixel patch); STAGES-deep smem ring of (A tile, W tile)
 // K-blocks guarded by full/empty mbarriers; two TMEM accumulator stages so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
+#ifdef FCB_EXPERIMENT
 #include <algorithm>
 #include <vector>
 
@@ -57,17 +59,12 @@ struct UmmaParams {
   Phase phases[4];
 };
 
-struct UmmaPlan {
+struct UmmaV1 {
   Geom g;
-  int device = 0;
-  int8_t* d_w = nullptr;  // [Npad][K] s8, K contiguous
-  int8_t* d_zero_bias = nullptr;  // thin-input plans with the bias folded into the weights
   CUtensorMap tmB;
   UmmaParams p;
   size_t smem = 0;
   int num_sms = 148;
-  Umma2Plan* v2 = nullptr;  // shared-memory-resident-patch main loop (fcb_umma2.cu) when the layer qualifies
-  char desc[224] = "v1 per-tap TMA";
 };
 
 // ------------------------------------------------------------------------------------------
@@ -241,66 +238,17 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)p;
-  }
-  return fn;
-}
-int umma_encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
-  return umma_encode_map_ex(m, base, 1, 128, rank, dims, strides_bytes, box);
-}
-// elem_bytes: 1 (u8) or 4 (u32 elements: boxes wider than 256 bytes); swizzle: 0 (dense box image) or 128
-int umma_encode_map_ex(CUtensorMap* m, void* base, int elem_bytes, int swizzle, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FCB_ERR_CUDA; }
-  cuuint64_t gd[5], gs[4];
-  cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
-  for (int i = 0; i + 1 < rank; i++) gs[i] = strides_bytes[i];
-  CUresult r = enc(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, base, gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return FCB_ERR_CUDA; }
-  return FCB_OK;
-}
-
-// v1 (per-tap TMA) needs whole 128-byte channel chunks and 32-channel epilogue groups
-static int v1_eligible(const Geom& g) { return g.C % KCH == 0 && g.OFM % 32 == 0 && g.OFM >= 32 && g.OFM <= 256; }
-
-int umma_eligible(const Geom& g) {
-  if (g.weight_kind != FCB_W_FIXED || g.w_bits > 8 || g.in_bits != 8) return 0;
-  if (g.in_word_bytes != (size_t)g.C) return 0;              // stream image == dense NHWC bytes
-  if (g.C % 16) return 0;                                    // TMA strides are multiples of 16 bytes
-  if (g.OFM > 256) return 0;
-  if (g.KX * g.KY > MAX_TAPS) return 0;
-  if ((uint64_t)g.K * 255ull * 128ull >= (1ull << 31)) return 0;  // exact int32 accumulation
-  if (g.pool > 2) return 0;
-  if (g.kind == FCB_KIND_DECONV522) return g.pool == 1;
-  if (g.SX != g.SY) return 0;
-  // stride 1: a partial last channel chunk is zero-filled by TMA (it then multiplies the next tap's weights by 0);
-  // stride 2: the parity view packs two pixels per row, so chunks must not straddle pixels
-  if (g.SX == 1) return 1;
-  if (g.SX == 2) return (g.C % KCH == 0) && (g.IX % 2 == 0) && (g.IY % 2 == 0);
-  return 0;
-}
-
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiParams& epi, int device, UmmaPlan** out) {
-  UmmaPlan* P = new UmmaPlan();
+// v1 (per-tap TMA) needs whole 128-byte channel chunks and 32-channel epilogue groups
+int umma_v1_eligible(const Geom& g) { return g.C % KCH == 0 && g.OFM % 32 == 0 && g.OFM >= 32 && g.OFM <= 256 && g.KX * g.KY <= MAX_TAPS; }
+
+int umma_v1_create(const Geom& g, int8_t* d_w, const EpiParams& epi, int num_sms, UmmaV1** out) {
+  *out = nullptr;
+  if (!umma_v1_eligible(g)) return FCB_ERR_UNSUPPORTED;
+  UmmaV1* P = new UmmaV1();
   P->g = g;
-  P->device = device;
+  P->num_sms = num_sms;
   UmmaParams& p = P->p;
   memset(&p, 0, sizeof(p));
   p.epi = epi;
@@ -326,7 +274,6 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   }
   p.tiles_x = (p.PX + p.BW - 1) / p.BW;
   p.tiles_y = (p.PY + p.BH - 1) / p.BH;
-  // taps
   if (!p.deconv) {
     p.nphases = 1;
     Phase& ph = p.phases[0];
@@ -365,161 +312,35 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   const int stage_bytes = TILE_M * KCH + p.N * KCH;
   p.stages = std::min(8, (int)((200 * 1024) / stage_bytes));
   P->smem = (size_t)p.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
-
-  cudaDeviceProp prop;
-  FCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  P->num_sms = prop.multiProcessorCount;
-
-  // weights: s8 [N][K], K contiguous (k = (ky*KX+kx)*C + c) -- the implicit-GEMM B operand
-  // rows padded with zeros to whole 128-channel blocks: an all-out-of-bounds TMA box row costs as much as a real one
-  // (measured on the 3-channel last layer), a zero row in memory does not
-  const int copies = 1;
-  const int rows_pad = (g.OFM + 127) / 128 * 128;
-  std::vector<int8_t> w8((size_t)rows_pad * g.K, 0);
-  for (size_t i = 0; i < (size_t)g.OFM * g.K; i++) w8[i] = (int8_t)W[i];
-  FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size()));
-  FCB_CUDA_OK(cudaMemcpy(P->d_w, w8.data(), w8.size(), cudaMemcpyHostToDevice));
-  if (v1_eligible(g)) {
-    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)p.N * copies};
-    const uint64_t strides[1] = {(uint64_t)g.K};
-    const uint32_t box[2] = {(uint32_t)KCH, (uint32_t)p.N};
-    int rc = umma_encode_map(&P->tmB, P->d_w, 2, dims, strides, box);
-    if (rc) { umma_plan_destroy(P); return rc; }
-  }
-  {
-    const char* v1only = getenv("FCB_UMMA_V1");
-    if (!(v1only && v1only[0] == '1')) {
-      int rc2 = umma2_plan_create(g, P->d_w, epi, P->num_sms, &P->v2);
-      if (rc2 == FCB_OK) umma2_describe(P->v2, P->desc, sizeof(P->desc));
-      else if (rc2 != FCB_ERR_UNSUPPORTED) { umma_plan_destroy(P); return rc2; }
-    }
-  }
-  if (!P->v2 && !v1_eligible(g)) { umma_plan_destroy(P); set_error("no tensor-core plan for this shape"); return FCB_ERR_UNSUPPORTED; }
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  FCB_CUDA_OK(cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)p.N};
+  const uint64_t strides[1] = {(uint64_t)g.K};
+  const uint32_t box[2] = {(uint32_t)KCH, (uint32_t)p.N};
+  int rc = umma_encode_map(&P->tmB, d_w, 2, dims, strides, box);
+  if (rc) { delete P; return rc; }
+  cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) { delete P; set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FCB_ERR_CUDA; }
   *out = P;
   return FCB_OK;
 }
 
-// Thin-input layers (one 4-byte word per pixel): W4 is [OFM][128], k = (ky*KX + kx)*4 + lane.
-int umma_plan_create_thin(const Geom& g, const std::vector<int32_t>& W4, const EpiParams& epi, const int8_t* bias_host, int device, UmmaPlan** out) {
-  UmmaPlan* P = new UmmaPlan();
-  P->g = g;
-  P->device = device;
-  cudaDeviceProp prop;
-  FCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  P->num_sms = prop.multiProcessorCount;
-  const int rows_pad = (g.OFM + 127) / 128 * 128;
-  std::vector<int8_t> w8((size_t)rows_pad * 128, 0);
-  for (size_t i = 0; i < (size_t)g.OFM * 128; i++) w8[i] = (int8_t)W4[i];
-  // bias + ReLU on the wrapped 8-bit lane (conv_nonsquare_top.cpp:267-278): ((acc mod 256) + bias) mod 256 = (acc + bias) mod 256, so
-  // the bias can ride in the GEMM as the weight of a constant-1 activation in the first unused window word
-  const int nw = g.KX * g.KY;
-  int bias_word = -1;
-  if (bias_host && epi.act_kind == FCB_ACT_BIAS_RELU && epi.out_bits == 8 && epi.acc_bits == 8 && (nw == 25 || nw == 9) &&
-      (uint64_t)(g.K + 1) * 255ull * 128ull < (1ull << 31) && !getenv("FCB_U2_NO_FOLD")) {
-    bias_word = nw;
-    for (int ch = 0; ch < g.OFM; ch++) w8[(size_t)ch * 128 + 4 * nw] = bias_host[ch];
-  }
-  FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size()));
-  FCB_CUDA_OK(cudaMemcpy(P->d_w, w8.data(), w8.size(), cudaMemcpyHostToDevice));
-  EpiParams epi2 = epi;
-  if (bias_word >= 0) {  // every epilogue variant now adds a zero bias
-    FCB_CUDA_OK(cudaMalloc(&P->d_zero_bias, rows_pad));
-    FCB_CUDA_OK(cudaMemset(P->d_zero_bias, 0, rows_pad));
-    epi2.bias = P->d_zero_bias;
-  }
-  int rc = umma2_plan_create_thin(g, P->d_w, epi2, P->num_sms, bias_word, &P->v2);
-  if (rc) { umma_plan_destroy(P); return rc; }
-  umma2_describe(P->v2, P->desc, sizeof(P->desc));
-  *out = P;
-  return FCB_OK;
-}
+void umma_v1_destroy(UmmaV1* P) { delete P; }
 
-// Thin-output transposed conv (deconv522, OFM 3..4): weights regrouped by input shift.  Output phase (py, px) uses tap
-// (ky, kx) = (2*offy + 2 - py, 2*offx + 2 - px) at shift (offy, offx) in {-1,0,1}^2 when that tap exists.
-int umma_plan_create_dthin(const Geom& g, const std::vector<int32_t>& W, const EpiParams& epi, int device, UmmaPlan** out) {
-  if (g.kind != FCB_KIND_DECONV522 || g.OFM < 3 || g.OFM > 4 || g.C % 128 || g.C > 256 || getenv("FCB_U2_NO_DTHIN")) return FCB_ERR_UNSUPPORTED;
-  UmmaPlan* P = new UmmaPlan();
-  P->g = g;
-  P->device = device;
-  cudaDeviceProp prop;
-  FCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  P->num_sms = prop.multiProcessorCount;
-  const int cch = g.C / 128;
-  if (!getenv("FCB_U2_NO_DCOL")) {
-    // col2im form: one GEMM over rows (tap word * 4 + channel, dcol_word()), K = the input channels; the taps are summed after the GEMM
-    std::vector<int8_t> wc((size_t)cch * 128 * 128, 0);
-    for (int cc = 0; cc < cch; cc++)
-      for (int t = 0; t < 25; t++)
-        for (int o = 0; o < g.OFM; o++)
-          for (int c = 0; c < 128; c++)
-            wc[((size_t)cc * 128 + dcol_word(t) * 4 + o) * 128 + c] = (int8_t)W[(size_t)o * g.K + t * g.C + cc * 128 + c];
-    FCB_CUDA_OK(cudaMalloc(&P->d_w, wc.size()));
-    FCB_CUDA_OK(cudaMemcpy(P->d_w, wc.data(), wc.size(), cudaMemcpyHostToDevice));
-    int rc = umma2_plan_create_dcol(g, P->d_w, epi, P->num_sms, &P->v2);
-    if (rc == FCB_OK) {
-      umma2_describe(P->v2, P->desc, sizeof(P->desc));
-      *out = P;
-      return FCB_OK;
-    }
-    cudaFree(P->d_w);
-    P->d_w = nullptr;
-    if (rc != FCB_ERR_UNSUPPORTED) { umma_plan_destroy(P); return rc; }
-  }
-  std::vector<int8_t> w8((size_t)9 * cch * 16 * 128, 0);
-  for (int cc = 0; cc < cch; cc++)
-    for (int sft = 0; sft < 9; sft++) {
-      const int offy = sft / 3 - 1, offx = sft % 3 - 1;
-      for (int ph = 0; ph < 4; ph++) {
-        const int ky = 2 * offy + 2 - ph / 2, kx = 2 * offx + 2 - ph % 2;
-        if (ky < 0 || ky > 4 || kx < 0 || kx > 4) continue;
-        for (int o = 0; o < g.OFM; o++)
-          for (int c = 0; c < 128; c++)
-            w8[(((size_t)(cc * 9 + sft) * 16) + ph * 4 + o) * 128 + c] = (int8_t)W[(size_t)o * g.K + (ky * 5 + kx) * g.C + cc * 128 + c];
-      }
-    }
-  FCB_CUDA_OK(cudaMalloc(&P->d_w, w8.size()));
-  FCB_CUDA_OK(cudaMemcpy(P->d_w, w8.data(), w8.size(), cudaMemcpyHostToDevice));
-  int rc = umma2_plan_create_dthin(g, P->d_w, epi, P->num_sms, &P->v2);
-  if (rc) { umma_plan_destroy(P); return rc; }
-  umma2_describe(P->v2, P->desc, sizeof(P->desc));
-  *out = P;
-  return FCB_OK;
-}
-
-const char* umma_plan_describe(const UmmaPlan* P) { return P ? P->desc : ""; }
-
-void umma_plan_destroy(UmmaPlan* P) {
-  if (!P) return;
-  if (P->v2) umma2_plan_destroy(P->v2);
-  cudaFree(P->d_w);
-  cudaFree(P->d_zero_bias);
-  delete P;
-}
-
-int umma_run(UmmaPlan* P, const void* d_in, void* d_out, int n_images, cudaStream_t st, uint64_t* launches) {
+int umma_v1_run(UmmaV1* P, const void* d_in, void* d_out, int n_images, cudaStream_t st) {
   const Geom& g = P->g;
   UmmaParams p = P->p;
-  if (((uintptr_t)d_in & 15) || ((uintptr_t)d_out & 15)) { set_error("device buffers must be 16-byte aligned"); return FCB_ERR_INVALID_ARG; }
-  if (P->v2) {
-    int rc2 = umma2_run(P->v2, d_in, d_out, n_images, st);
-    if (rc2 == FCB_OK && launches) (*launches)++;
-    return rc2;
-  }
   p.out = (uint8_t*)d_out;
   p.n_images = n_images;
   CUtensorMap tmA;
   int rc;
+  const uint64_t C = g.C, X = g.IX, Y = g.IY;
   if (p.stride2) {
     // [n][y/2][y%2][x/2][(x%2)*C + c] view of the dense NHWC stream
-    const uint64_t C = g.C, X = g.IX, Y = g.IY;
     const uint64_t dims[5] = {2 * C, X / 2, 2, Y / 2, (uint64_t)n_images};
     const uint64_t strides[4] = {2 * C, X * C, 2 * X * C, X * Y * C};
     const uint32_t box[5] = {(uint32_t)KCH, (uint32_t)p.BW, 1, (uint32_t)p.BH, 1};
     rc = umma_encode_map(&tmA, const_cast<void*>(d_in), 5, dims, strides, box);
   } else {
-    const uint64_t C = g.C, X = g.IX, Y = g.IY;
     const uint64_t dims[4] = {C, X, Y, (uint64_t)n_images};
     const uint64_t strides[3] = {C, X * C, X * Y * C};
     const uint32_t box[4] = {(uint32_t)KCH, (uint32_t)p.BW, (uint32_t)p.BH, 1};
@@ -533,8 +354,8 @@ int umma_run(UmmaPlan* P, const void* d_in, void* d_out, int n_images, cudaStrea
   else
     umma_conv_kernel<false><<<grid, NUM_THREADS, P->smem, st>>>(tmA, P->tmB, p);
   FCB_CUDA_OK(cudaGetLastError());
-  if (launches) (*launches)++;
   return FCB_OK;
 }
 
 }  // namespace fcb
+#endif  // FCB_EXPERIMENT

@@ -12,6 +12,8 @@ KIND_CONV, KIND_DECONV522 = 0, 1
 W_FIXED, W_BINARY_XNOR, W_BINARY_PM1 = 0, 1, 2
 ACT_PASSTHROUGH, ACT_BIAS_RELU, ACT_THRESHOLDS = 0, 1, 2
 CMP_LESS, CMP_GREATER, CMP_LESS_EQUAL, CMP_GREATER_EQUAL = 0, 1, 2, 3
+# which arithmetic unit multiplies -- the reference's resource argument R (mvau.hpp:87-98); never changes the result
+ENGINE_AUTO, ENGINE_IMAD, ENGINE_XNOR_POPC, ENGINE_TENSOR = 0, 1, 2, 3
 
 
 class CLayerDesc(ctypes.Structure):
@@ -19,8 +21,9 @@ class CLayerDesc(ctypes.Structure):
         "struct_size", "kind", "kernel_x", "kernel_y", "ifm_ch", "ofm_ch", "ifm_x", "ifm_y", "ofm_x", "ofm_y",
         "stride_x", "stride_y", "pad", "simd", "pe", "in_bits", "in_signed", "w_bits", "weight_kind",
         "acc_bits", "acc_signed", "act_kind", "out_bits", "num_th")] + [
-        ("act_val", ctypes.c_int32), ("cmp", ctypes.c_uint32), ("pool", ctypes.c_uint32),
-        ("reserved", ctypes.c_uint32 * 6)]
+        ("act_val", ctypes.c_int32), ("cmp", ctypes.c_uint32), ("pool", ctypes.c_uint32), ("engine_hint", ctypes.c_uint32),
+        ("pad_x_total", ctypes.c_uint32), ("pad_y_total", ctypes.c_uint32), ("pad_style", ctypes.c_uint32),
+        ("pool_signed", ctypes.c_uint32), ("pool_min_value", ctypes.c_int32)]
 
 
 @dataclass(frozen=True)
@@ -49,19 +52,39 @@ class LayerDesc:
     act_val: int = 0
     cmp: int = CMP_LESS
     pool: int = 0
+    engine_hint: int = ENGINE_AUTO
+    # FMPadding_nonsquare's Padding_x / Padding_y / PaddingStyle (streamtools.h:361-379), used when pad_style != 0 (then pad = 0)
+    pad_x_total: int = 0
+    pad_y_total: int = 0
+    pad_style: int = 0
+    # StreamingMaxPool_Precision's ActType signedness and min_value (maxpool.h:137-170)
+    pool_signed: int = 0
+    pool_min_value: int = 0
 
     # ---- derived geometry (conv_nonsquare_top.cpp:238-259 / :109-169) ----
+    @property
+    def pads(self):
+        """(left, right, up, down) zeros, split as FMPadding_nonsquare does (streamtools.h:374-379)."""
+        if not self.pad_style:
+            return (self.pad,) * 4
+        extra = 1 if self.pad_style == 2 else 0
+        left = self.pad_x_total // 2 + extra * (self.pad_x_total % 2)
+        up = self.pad_y_total // 2 + extra * (self.pad_y_total % 2)
+        return left, self.pad_x_total - left, up, self.pad_y_total - up
+
     @property
     def ofm_x(self) -> int:
         if self.kind == KIND_DECONV522:
             return 2 * self.ifm_x
-        return (self.ifm_x + 2 * self.pad - self.kernel_x) // self.stride_x + 1
+        left, right, _, _ = self.pads
+        return (self.ifm_x + left + right - self.kernel_x) // self.stride_x + 1
 
     @property
     def ofm_y(self) -> int:
         if self.kind == KIND_DECONV522:
             return 2 * self.ifm_y
-        return (self.ifm_y + 2 * self.pad - self.kernel_y) // self.stride_y + 1
+        _, _, up, down = self.pads
+        return (self.ifm_y + up + down - self.kernel_y) // self.stride_y + 1
 
     @property
     def out_x(self) -> int:
@@ -85,7 +108,8 @@ class LayerDesc:
         c.struct_size = ctypes.sizeof(CLayerDesc)
         for f in ("kind", "kernel_x", "kernel_y", "ifm_ch", "ofm_ch", "ifm_x", "ifm_y", "stride_x", "stride_y", "pad",
                   "simd", "pe", "in_bits", "in_signed", "w_bits", "weight_kind", "acc_bits", "acc_signed", "act_kind",
-                  "out_bits", "num_th", "act_val", "cmp", "pool"):
+                  "out_bits", "num_th", "act_val", "cmp", "pool", "engine_hint", "pad_x_total", "pad_y_total", "pad_style",
+                  "pool_signed", "pool_min_value"):
             setattr(c, f, getattr(self, f))
         c.ofm_x, c.ofm_y = self.ofm_x, self.ofm_y
         return c

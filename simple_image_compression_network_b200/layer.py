@@ -23,12 +23,12 @@ def _ptr(a):
 
 class ConvLayer:
     def __init__(self, desc: LayerDesc, weights, thresholds=None, bias=None, device: int = 0):
-        L = _lib.lib()
+        L = self._L = _lib.lib()  # the handle stays with the library build that created it
         self.desc = desc
         self.device = device
         c = desc.to_c()
         sizes = [ctypes.c_size_t() for _ in range(5)]
-        _lib.check(L.fcb_layer_query(ctypes.byref(c), *[ctypes.byref(s) for s in sizes]))
+        _lib.check(L.fcb_layer_query(ctypes.byref(c), *[ctypes.byref(s) for s in sizes]), L)
         self.in_bytes, self.out_bytes, self.weight_bytes, self.threshold_bytes, self.bias_bytes = [s.value for s in sizes]
         w = np.ascontiguousarray(weights, dtype=np.uint8)
         if w.size != self.weight_bytes:
@@ -40,7 +40,7 @@ class ConvLayer:
         if b is not None and b.size != self.bias_bytes:
             raise ValueError(f"bias image is {b.size} bytes, expected {self.bias_bytes}")
         h = ctypes.c_void_p()
-        _lib.check(L.fcb_layer_create(ctypes.byref(c), _ptr(w), _ptr(t), _ptr(b), device, ctypes.byref(h)))
+        _lib.check(L.fcb_layer_create(ctypes.byref(c), _ptr(w), _ptr(t), _ptr(b), device, ctypes.byref(h)), L)
         self._h = h
 
     def set_params(self, weights, thresholds=None, bias=None) -> None:
@@ -51,7 +51,7 @@ class ConvLayer:
         b = None if bias is None else np.ascontiguousarray(bias, dtype=np.uint8)
         if w.size != self.weight_bytes or (t is not None and t.size != self.threshold_bytes) or (b is not None and b.size != self.bias_bytes):
             raise ValueError("parameter image size does not match the layer")
-        _lib.check(_lib.lib().fcb_layer_set_params(self._h, _ptr(w), _ptr(t), _ptr(b)))
+        _lib.check(self._L.fcb_layer_set_params(self._h, _ptr(w), _ptr(t), _ptr(b)), self._L)
 
     def set_param_stream(self, param_words, thresholds=None, bias=None) -> None:
         """set_params with the weights as one period of the reference's parameter stream (GenParamStream, dma.h:214-236:
@@ -64,19 +64,19 @@ class ConvLayer:
         if w.size != tiles * pack.word_bytes(d.simd * d.pe * d.w_bits) or (t is not None and t.size != self.threshold_bytes) or \
                 (b is not None and b.size != self.bias_bytes):
             raise ValueError("parameter image size does not match the layer")
-        _lib.check(_lib.lib().fcb_layer_set_param_stream(self._h, _ptr(w), _ptr(t), _ptr(b)))
+        _lib.check(self._L.fcb_layer_set_param_stream(self._h, _ptr(w), _ptr(t), _ptr(b)), self._L)
 
     @property
     def engine(self) -> str:
-        return _lib.lib().fcb_layer_engine(self._h).decode()
+        return self._L.fcb_layer_engine(self._h).decode()
 
     @property
     def plan(self) -> str:
-        return _lib.lib().fcb_layer_plan(self._h).decode()
+        return self._L.fcb_layer_plan(self._h).decode()
 
     @property
     def launches(self) -> int:
-        return int(_lib.lib().fcb_layer_launches(self._h))
+        return int(self._L.fcb_layer_launches(self._h))
 
     def run(self, in_words, num_reps: int = 1) -> np.ndarray:
         """Host buffers in, host buffers out (H2D + kernels + D2H inside)."""
@@ -84,21 +84,26 @@ class ConvLayer:
         if x.size != self.in_bytes * num_reps:
             raise ValueError(f"input stream is {x.size} bytes, expected {self.in_bytes * num_reps}")
         out = np.empty(self.out_bytes * num_reps, dtype=np.uint8)
-        _lib.check(_lib.lib().fcb_layer_run(self._h, _ptr(x), _ptr(out), num_reps))
+        _lib.check(self._L.fcb_layer_run(self._h, _ptr(x), _ptr(out), num_reps), self._L)
         return out
 
     def run_raw(self, in_ptr: int, out_ptr: int, num_reps: int) -> None:
         """Host pointers (e.g. pinned memory) -- the same call as run() without numpy."""
-        _lib.check(_lib.lib().fcb_layer_run(self._h, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), num_reps))
+        _lib.check(self._L.fcb_layer_run(self._h, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), num_reps), self._L)
 
     def run_device(self, d_in: int, d_out: int, num_reps: int, stream: int = 0) -> None:
         """Device pointers, asynchronous on `stream` (a cudaStream_t handle as int)."""
-        _lib.check(_lib.lib().fcb_layer_run_device(self._h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), num_reps,
-                                                   ctypes.c_void_p(stream)))
+        _lib.check(self._L.fcb_layer_run_device(self._h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), num_reps,
+                                                ctypes.c_void_p(stream)), self._L)
+
+    def set_host_chunk(self, images: int) -> None:
+        """Images per staging slot of run() / run_raw() (0 = default) -- the burst length of the reference's
+        Mem2Stream_Batch / Stream2Mem_Batch (dma.h:166-176)."""
+        _lib.check(self._L.fcb_layer_set_host_chunk(self._h, images), self._L)
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib.lib().fcb_layer_destroy(self._h)
+            self._L.fcb_layer_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -113,36 +118,47 @@ class Net:
 
     def __init__(self, layers):
         self.layers = list(layers)
+        L = self._L = self.layers[0]._L
+        if any(l._L is not L for l in self.layers):
+            raise ValueError("layers of a Net must come from the same library build")
         arr = (ctypes.c_void_p * len(self.layers))(*[l._h for l in self.layers])
         h = ctypes.c_void_p()
-        _lib.check(_lib.lib().fcb_net_create(arr, len(self.layers), ctypes.byref(h)))
+        _lib.check(L.fcb_net_create(arr, len(self.layers), ctypes.byref(h)), L)
         self._h = h
         self.in_bytes = self.layers[0].in_bytes
         self.out_bytes = self.layers[-1].out_bytes
 
     @property
     def launches(self) -> int:
-        return int(_lib.lib().fcb_net_launches(self._h))
+        return int(self._L.fcb_net_launches(self._h))
 
     def run(self, in_words, num_reps: int = 1) -> np.ndarray:
         x = np.ascontiguousarray(in_words, dtype=np.uint8).reshape(-1)
         if x.size != self.in_bytes * num_reps:
             raise ValueError(f"input stream is {x.size} bytes, expected {self.in_bytes * num_reps}")
         out = np.empty(self.out_bytes * num_reps, dtype=np.uint8)
-        _lib.check(_lib.lib().fcb_net_run(self._h, _ptr(x), _ptr(out), num_reps))
+        _lib.check(self._L.fcb_net_run(self._h, _ptr(x), _ptr(out), num_reps), self._L)
         return out
 
     def run_raw(self, in_ptr: int, out_ptr: int, num_reps: int) -> None:
         """Host pointers (e.g. pinned memory): H2D, the layers and D2H of consecutive chunks overlap on three streams."""
-        _lib.check(_lib.lib().fcb_net_run(self._h, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), num_reps))
+        _lib.check(self._L.fcb_net_run(self._h, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), num_reps), self._L)
 
     def run_device(self, d_in: int, d_out: int, num_reps: int, stream: int = 0) -> None:
-        _lib.check(_lib.lib().fcb_net_run_device(self._h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), num_reps,
-                                                 ctypes.c_void_p(stream)))
+        _lib.check(self._L.fcb_net_run_device(self._h, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), num_reps,
+                                              ctypes.c_void_p(stream)), self._L)
+
+    def set_host_chunk(self, images: int) -> None:
+        """Images per staging slot of run() / run_raw() (0 = default)."""
+        _lib.check(self._L.fcb_net_set_host_chunk(self._h, images), self._L)
+
+    def set_device_chunk(self, images: int) -> None:
+        """Images per pass of the layer chain inside run_device() (0 = default); small values keep the intermediates in L2."""
+        _lib.check(self._L.fcb_net_set_device_chunk(self._h, images), self._L)
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib.lib().fcb_net_destroy(self._h)
+            self._L.fcb_net_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -4,6 +4,7 @@ import ctypes
 import dataclasses
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -86,3 +87,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "finn_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_product_library_has_no_experiment_switches(fcb_lib):
+    """No environment variable may change the kernel a production caller gets: the experiment switches (FCB_U2_*, FCB_FORCE_ENGINE,
+    ...), the first-generation kernel and the cross-check instantiations exist only in tools/libfinnconv_exp.so (-DFCB_EXPERIMENT)."""
+    from simple_image_compression_network_b200 import _lib
+    blob = open(_lib.LIB_PATH, "rb").read()
+    for needle in (b"FCB_U2_", b"FCB_FORCE_ENGINE", b"FCB_XNOR_ENGINE", b"FCB_THIN", b"FCB_NET_CHUNK", b"FCB_UMMA_V1", b"umma_conv_kernel"):
+        assert needle not in blob, needle
+    syms = subprocess.run(["nm", "-D", "--undefined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "getenv" not in syms
+
+
+def test_engine_hint_and_padding_fields_validated(fcb_lib):
+    d = cases.CASES["c2d_a"]
+    assert _query(fcb_lib, dataclasses.replace(d, engine_hint=7))[0] == -1
+    assert _query(fcb_lib, dataclasses.replace(d, pad_style=2, pad_x_total=3, pad_y_total=3))[0] == -1      # pad must be 0 with a style
+    assert _query(fcb_lib, dataclasses.replace(d, pad=0, pad_x_total=4))[0] == -1                           # totals need a style
+    ok = dataclasses.replace(d, pad=0, pad_style=2, pad_x_total=4, pad_y_total=4)                           # == pad 2 on every side
+    assert (ok.ofm_x, ok.ofm_y) == (d.ofm_x, d.ofm_y)
+    assert _query(fcb_lib, ok)[0] == 0, fcb_lib.fcb_last_error()

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import cases
+from simple_image_compression_network_b200.desc import ENGINE_IMAD, ENGINE_TENSOR, ENGINE_XNOR_POPC
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -42,23 +43,22 @@ def test_layer_matches_oracle_and_golden(name, fcb_lib, oracle_mod):
 
 
 @pytest.mark.parametrize("name", ["c2d_b", "c2d_e", "c2d_g", "dc_c", "dc_e", "th_b", "c2d_d"])
-def test_engines_agree(name, fcb_lib, oracle_mod, monkeypatch):
-    """The tensor-core engine and the universal IMAD engine give identical bytes."""
+def test_engines_agree(name, fcb_lib, oracle_mod):
+    """The tensor-core engine and the universal IMAD engine (engine_hint, the reference's resource argument R) give identical bytes."""
     d = cases.CASES[name]
     inp = cases.make_inputs(d, seed_shift=3, num_reps=3)
     want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=3)
     L = _layer(d, inp)
     got = L.run(inp["in_words"], 3)
     assert np.array_equal(got, want), f"{name} [{L.engine}]: {_diff(got, want)}"
-    monkeypatch.setenv("FCB_FORCE_ENGINE", "imad")
-    L2 = _layer(d, inp)
+    L2 = _layer(dataclasses.replace(d, engine_hint=ENGINE_IMAD), inp)
     assert L2.engine == "imad"
     got2 = L2.run(inp["in_words"], 3)
     assert np.array_equal(got2, want), f"{name} [imad]: {_diff(got2, want)}"
 
 
 @pytest.mark.parametrize("name", ["c2d_e", "c2d_g", "dc_c", "th_cfg4", "c2d_L1band", "c2d_d"])
-def test_umma_generations_agree(name, fcb_lib, oracle_mod, monkeypatch):
+def test_umma_generations_agree(name, fcb_lib, oracle_mod, monkeypatch, exp_build):
     """Resident-patch main loop (fcb_umma2.cu) and per-tap-TMA main loop (fcb_umma.cu) against the oracle."""
     d = cases.CASES[name]
     if not (d.ifm_ch % 128 == 0 and d.ofm_ch % 32 == 0):
@@ -68,6 +68,7 @@ def test_umma_generations_agree(name, fcb_lib, oracle_mod, monkeypatch):
     L = _layer(d, inp)
     got = L.run(inp["in_words"], 2)
     assert np.array_equal(got, want), f"{name} [{L.engine}: {L.plan}]: {_diff(got, want)}"
+    exp_build()  # the first-generation kernel exists only in the experiment build
     monkeypatch.setenv("FCB_UMMA_V1", "1")
     L1 = _layer(d, inp)
     assert L1.plan.startswith("v1")
@@ -255,8 +256,8 @@ def test_analysis_stack_stage_shapes(fcb_lib, oracle_mod):
 
 
 @pytest.mark.parametrize("name,pad,pool", [("xn_a", 0, 0), ("xn_b", 0, 0), ("xn_c", 0, 0), ("xn_c", 1, 0), ("xn_b", 1, 2)])
-def test_xnor_on_tensor_cores(name, pad, pool, fcb_lib, oracle_mod, monkeypatch):
-    """Opt-in +-1 int8 form of the xnor layer (sum [w==a] = (K + sum a^w^)/2, thresholds remapped to 2t-K) against the
+def test_xnor_on_tensor_cores(name, pad, pool, fcb_lib, oracle_mod):
+    """Opt-in (engine_hint = TENSOR) +-1 int8 form of the xnor layer (sum [w==a] = (K + sum a^w^)/2, thresholds remapped to 2t-K) against the
     oracle and against the default popcount engine; pad > 0 checks that border bits act as ordinary 0 activations."""
     d = dataclasses.replace(cases.CASES[name], pad=pad, pool=pool)
     inp = cases.make_inputs(d, seed_shift=21, num_reps=2)
@@ -264,8 +265,7 @@ def test_xnor_on_tensor_cores(name, pad, pool, fcb_lib, oracle_mod, monkeypatch)
     Lp = _layer(d, inp)
     assert Lp.engine in ("xnor_popc", "imad")
     assert np.array_equal(Lp.run(inp["in_words"], 2), want)
-    monkeypatch.setenv("FCB_XNOR_ENGINE", "tensor")
-    Lt = _layer(d, inp)
+    Lt = _layer(dataclasses.replace(d, engine_hint=ENGINE_TENSOR), inp)
     assert Lt.engine == "umma_i8" and "xnor as +-1" in Lt.plan, Lt.plan
     got = Lt.run(inp["in_words"], 2)
     assert np.array_equal(got, want), f"{name} pad={pad} [{Lt.plan}]: {_diff(got, want)}"
@@ -290,7 +290,7 @@ def _thin_cases():
 
 
 @pytest.mark.parametrize("name", list(_thin_cases()))
-def test_thin_input_smem_im2col(name, fcb_lib, oracle_mod, monkeypatch):
+def test_thin_input_smem_im2col(name, fcb_lib, oracle_mod, monkeypatch, exp_build):
     """Thin-input layers (one 4-byte word per pixel): sliding window built in shared memory inside the tensor-core kernel,
     against the oracle and against the older two-kernel im2col lowering."""
     d, reps = _thin_cases()[name]
@@ -300,6 +300,7 @@ def test_thin_input_smem_im2col(name, fcb_lib, oracle_mod, monkeypatch):
     assert L.engine == "umma_i8" and L.plan.startswith("smem-im2col"), L.plan
     got = L.run(inp["in_words"], reps)
     assert np.array_equal(got, want), f"{name} [{L.plan}]: {_diff(got, want)}"
+    exp_build()
     monkeypatch.setenv("FCB_THIN", "im2col")
     L2 = _layer(d, inp)
     assert not L2.plan.startswith("smem-im2col")
@@ -307,7 +308,7 @@ def test_thin_input_smem_im2col(name, fcb_lib, oracle_mod, monkeypatch):
 
 
 @pytest.mark.parametrize("ix,iy,c,ofm,reps", [(24, 16, 128, 3, 1), (50, 7, 128, 4, 2), (100, 20, 256, 3, 2), (384, 8, 128, 3, 1)])
-def test_thin_output_deconv(ix, iy, c, ofm, reps, fcb_lib, oracle_mod, monkeypatch):
+def test_thin_output_deconv(ix, iy, c, ofm, reps, fcb_lib, oracle_mod, monkeypatch, exp_build):
     """deconv522 with OFM <= 4 (the 3-channel last layer of eight_layers_net): pixels on the MMA M axis, taps regrouped by input
     shift, against the oracle and against the generic resident-planes plan."""
     d = dataclasses.replace(cases.CASES["dc_d"], ifm_x=ix, ifm_y=iy, ifm_ch=c, ofm_ch=ofm, pe=ofm)
@@ -318,6 +319,7 @@ def test_thin_output_deconv(ix, iy, c, ofm, reps, fcb_lib, oracle_mod, monkeypat
     got = L.run(inp["in_words"], reps)
     assert np.array_equal(got, want), f"[{L.plan}]: {_diff(got, want)}"
     assert "col2im" in L.plan, L.plan
+    exp_build()
     monkeypatch.setenv("FCB_U2_NO_DCOL", "1")  # the shift-block form (pixels on the MMA M axis)
     L1 = _layer(d, inp)
     assert L1.plan.startswith("thin-output deconv: pixels on M"), L1.plan
@@ -351,7 +353,7 @@ def _family_cases():
 
 
 @pytest.mark.parametrize("name", list(_family_cases()))
-def test_single_family_instantiations(name, fcb_lib, oracle_mod, monkeypatch):
+def test_single_family_instantiations(name, fcb_lib, oracle_mod, monkeypatch, exp_build):
     """The single-epilogue-family kernels with 12 / 16 epilogue warps (EPI = 2..6 of umma2_conv_kernel) against the oracle and
     against the general kernel (EPI = 0 / 8 epilogue warps) on the same plan."""
     d, switch, reps = _family_cases()[name]
@@ -361,6 +363,7 @@ def test_single_family_instantiations(name, fcb_lib, oracle_mod, monkeypatch):
     assert L.engine == "umma_i8", L.plan
     got = L.run(inp["in_words"], reps)
     assert np.array_equal(got, want), f"{name} [{L.plan}]: {_diff(got, want)}"
+    exp_build()
     monkeypatch.setenv(switch, "0" if switch == "FCB_U2_XEPI" else "1")
     L0 = _layer(d, inp)
     got0 = L0.run(inp["in_words"], reps)
@@ -444,16 +447,16 @@ def test_random_shapes_match_oracle(seed, fcb_lib, oracle_mod):
     assert len(plans) >= 4, plans
 
 
-def test_net_host_pipeline_many_chunks(fcb_lib, oracle_mod, monkeypatch):
+def test_net_host_pipeline_many_chunks(fcb_lib, oracle_mod):
     """fcb_net_run with the batch cut into many chunks (H2D / layers / D2H of neighbouring chunks overlap on three streams and two
     staging slots): every image must still come out in place and bit-exact."""
     from simple_image_compression_network_b200.layer import Net
-    monkeypatch.setenv("FCB_NET_CHUNK", "2")
     d1 = cases.CASES["c2d_e"]
     d2 = dataclasses.replace(cases.CASES["dc_c"], ifm_x=24, ifm_y=16)
     reps = 11  # 6 chunks, the last one short
     i1, i2 = cases.make_inputs(d1, num_reps=reps, relu_range=True), cases.make_inputs(d2, seed_shift=9)
     net = Net([_layer(d1, i1), _layer(d2, i2)])
+    net.set_host_chunk(2)
     got = net.run(i1["in_words"], reps)
     mid = oracle_mod.run_layer(d1, i1["in_words"], i1["weights"], None, i1["bias"], num_reps=reps)
     want = oracle_mod.run_layer(d2, mid, i2["weights"], None, i2["bias"], num_reps=reps)

@@ -6,7 +6,8 @@ import argparse, dataclasses, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from simple_image_compression_network_b200 import configs, synth
-from simple_image_compression_network_b200.desc import ACT_THRESHOLDS, KIND_CONV, KIND_DECONV522, W_BINARY_XNOR, LayerDesc
+from simple_image_compression_network_b200.desc import (ACT_THRESHOLDS, ENGINE_IMAD, ENGINE_TENSOR, KIND_CONV, KIND_DECONV522, W_BINARY_XNOR,
+                                                        LayerDesc)
 from simple_image_compression_network_b200.layer import ConvLayer, Net, synth_fill
 
 
@@ -34,11 +35,7 @@ def bench_layer(name, d, n, mask=0x7F):
     synth_fill(x.data_ptr(), x.numel(), synth.SEED_INPUT, mask)
     ms = timed(lambda: L.run_device(x.data_ptr(), y.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
     if CHECK:  # first and last image against the independent IMAD engine (itself pinned to the oracle by tests/)
-        os.environ["FCB_FORCE_ENGINE"] = "imad"
-        xe = os.environ.pop("FCB_XNOR_ENGINE", None)
-        L2 = ConvLayer(d, prm["weights"], thresholds=prm["thresholds"], bias=prm["bias"])
-        del os.environ["FCB_FORCE_ENGINE"]
-        if xe: os.environ["FCB_XNOR_ENGINE"] = xe
+        L2 = ConvLayer(dataclasses.replace(d, engine_hint=ENGINE_IMAD), prm["weights"], thresholds=prm["thresholds"], bias=prm["bias"])
         assert L2.engine != L.engine or L.engine == "imad"
         for i in sorted({0, n - 1}):
             y2 = torch.empty(L.out_bytes, dtype=torch.uint8, device="cuda")
@@ -81,8 +78,7 @@ if __name__ == "__main__":
                 bench_layer(f"stack5b_stage{i + 1}", st[i], a.images if i == 0 else a.images * 4, 0xFF)
                 continue
             if nm == "cfg3t":
-                os.environ["FCB_XNOR_ENGINE"] = "tensor"
-                bench_layer("cfg3_xnor_tensor", c3, a.images, 0xFF)
+                bench_layer("cfg3_xnor_tensor", dataclasses.replace(c3, engine_hint=ENGINE_TENSOR), a.images, 0xFF)
             elif nm == "cfg3":
                 bench_layer("cfg3_xnor", c3, a.images, 0xFF)
             elif nm == "cfg4n":
@@ -133,8 +129,6 @@ if __name__ == "__main__":
         print(json.dumps(dict(layer=name, images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3, 1), TOPs=round(2 * macs * n / ms / 1e9, 1))),
               flush=True)
     bench_layer("cfg3_xnor", c3, a.images * 16, 0xFF)
-    os.environ["FCB_XNOR_ENGINE"] = "tensor"
-    bench_layer("cfg3_xnor_as_pm1_int8_tensor", c3, a.images * 16, 0xFF)
-    del os.environ["FCB_XNOR_ENGINE"]
+    bench_layer("cfg3_xnor_as_pm1_int8_tensor", dataclasses.replace(c3, engine_hint=ENGINE_TENSOR), a.images * 16, 0xFF)
     bench_layer("cfg4_thr_pool", c4, a.images * 16, 0xFF)
     bench_layer("cfg4_thr_nopool", dataclasses.replace(c4, pool=0), a.images * 16, 0xFF)
