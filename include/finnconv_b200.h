@@ -181,6 +181,25 @@ FCB_API uint64_t fcb_net_launches(const fcb_net* net);
 FCB_API int fcb_net_set_host_chunk(fcb_net* net, uint32_t images);
 FCB_API int fcb_net_set_device_chunk(fcb_net* net, uint32_t images);
 
+/* --- the whole box behind one handle: the chain (n_layers >= 1; one layer = conv2d_layer0-style tops) replicated on `devices`
+ * (NULL / 0 = every sm_100 device; a device may be listed more than once) and numReps split into contiguous image ranges, one per
+ * replica, each served by its own host thread, streams and staging slots.  eight_layers_net(in, out, numReps)
+ * (conv_nonsquare_top.cpp:295) with numReps = 8*B then uses all 8 GPUs from ONE call; images are independent (the sliding-window
+ * buffers reset per image, slidingwindow.h:1320,1351), weights are replicated, no device talks to another.
+ * weights / thresholds / biases: one image pointer per layer (thresholds / biases may be NULL, or hold NULLs for layers without). */
+typedef struct fcb_pool fcb_pool;
+FCB_API int fcb_pool_create(const fcb_layer_desc* descs, const void* const* weights, const void* const* thresholds,
+                            const void* const* biases, uint32_t n_layers, const int* devices, uint32_t n_devices, fcb_pool** out);
+FCB_API void fcb_pool_destroy(fcb_pool* pool);
+FCB_API uint32_t fcb_pool_replicas(const fcb_pool* pool);
+/* host buffers in, host buffers out, synchronous; replica r takes images fcb_shard_range(numReps, r, replicas) */
+FCB_API int fcb_pool_run(fcb_pool* pool, const void* in_words, void* out_words, uint32_t numReps);
+/* the split itself: contiguous ranges, sizes differ by at most one image, the remainder goes to the low ranks */
+FCB_API int fcb_shard_range(uint32_t numReps, uint32_t rank, uint32_t world, uint32_t* begin, uint32_t* end);
+/* page-locked host memory, visible to every device: the host-buffer calls copy from / to it at full PCIe rate */
+FCB_API int fcb_host_alloc(void** ptr, size_t bytes);
+FCB_API void fcb_host_free(void* ptr);
+
 /* --- synthetic data (bench / tests): byte i of the buffer = splitmix64(seed ^ (offset + i)) & mask,
  * the rule of SURVEY.md 8(d); d_ptr is device memory, 16-byte aligned; asynchronous on `stream`. */
 FCB_API int fcb_synth_fill(void* d_ptr, size_t n_bytes, uint64_t seed, uint32_t mask, uint64_t offset, void* stream);

@@ -58,6 +58,17 @@ def load(path: str) -> ctypes.CDLL:
     L.fcb_net_launches.argtypes = [vp]
     L.fcb_net_launches.restype = u64
     L.fcb_synth_fill.argtypes = [vp, sz, u64, u32, u64, vp]
+    pvp = ctypes.POINTER(vp)
+    L.fcb_pool_create.argtypes = [ctypes.POINTER(CLayerDesc), pvp, pvp, pvp, u32, ctypes.POINTER(ctypes.c_int), u32, pvp]
+    L.fcb_pool_destroy.argtypes = [vp]
+    L.fcb_pool_destroy.restype = None
+    L.fcb_pool_replicas.argtypes = [vp]
+    L.fcb_pool_replicas.restype = u32
+    L.fcb_pool_run.argtypes = [vp, vp, vp, u32]
+    L.fcb_shard_range.argtypes = [u32, u32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    L.fcb_host_alloc.argtypes = [pvp, sz]
+    L.fcb_host_free.argtypes = [vp]
+    L.fcb_host_free.restype = None
     return L
 
 

@@ -284,6 +284,10 @@ static int upload_thresholds(fcb_layer* L, const std::vector<std::vector<int32_t
       }
     }
     if (ok) {
+      // entries are clamped so that the 2^levels-wide search window stays inside the 2^D - 1 table rows (thr_lut_fast relies on it;
+      // activate_thr_lut clamps again).  Exact: thresholds below the clamped index still all compare below.
+      const int levels = worst <= 7 ? 3 : 4, pmax = tn + 1 - (1 << levels);
+      for (auto& v : lut) v = (uint8_t)std::min<int>(v, pmax);
       FCB_CUDA_OK(cudaMalloc(&L->d_thr_lut, lut.size()));
       FCB_CUDA_OK(cudaMemcpy(L->d_thr_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
       FCB_CUDA_OK(cudaMalloc(&L->d_thr_lo, losh.size() * sizeof(int32_t)));

@@ -164,6 +164,45 @@ __device__ __forceinline__ void activate_thr_lut(const EpiParams& e, uint32_t to
   for (int i = 0; i < N; i++) out[i] = thr_finish(e, (int)((posb[i] - base) >> row_shift));
 }
 
+// The pooled-threshold instantiations' search (EPI = 1..3 of umma2_conv_kernel): same bucket LUT + LEVELS binary levels as
+// activate_thr_lut, with everything a level does not need hoisted out of it.  Preconditions (thrp_extra_warps(), fcb_umma2.cu):
+// comp::less / less_equal, 0 <= act_val, act_val + num_th < 256, accumulators already wrapped to TA and within +-2^30.  The
+// shared-memory table this runs on was loaded with every threshold decremented when the functor is less_equal (thr <= a  <=>
+// thr - 1 < a), so ONE strict compare serves both; INT32_MAX padding never compares below, so the position never passes num_th.
+// ROWB (bytes per table row = channels of the CTA x 4) is a compile-time constant: a level is LDS [pos + imm], ISETP, predicated add.
+// fin_base = base - act_val * ROWB, so the result is (pos - fin_base) / ROWB with no further add or mask.
+__device__ __forceinline__ int32_t min_relu_s32(int32_t a, int32_t b) {  // max(0, min(a, b)): one VIMNMX.RELU
+  int32_t d;
+  asm("min.s32.relu %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <int N, int LEVELS, int ROWB>
+__device__ __forceinline__ void thr_lut_fast(uint32_t base, uint32_t fin_base, uint32_t lut_saddr, int32_t lo, int sh, const int32_t (&a)[N],
+                                             uint32_t (&out)[N]) {
+  uint32_t posb[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const int b = min_relu_s32((a[i] - lo) >> sh, 255);
+    uint32_t p0;  // sorted index the bucket starts at, pre-clamped to thr_n + 1 - 2^LEVELS at create time
+    asm("ld.shared.u8 %0, [%1];" : "=r"(p0) : "r"(lut_saddr + (uint32_t)b));
+    posb[i] = base + p0 * (uint32_t)ROWB;
+  }
+#pragma unroll
+  for (int l = 0; l < LEVELS; l++) {
+    constexpr uint32_t top = (uint32_t)ROWB << (LEVELS - 1);
+    const uint32_t stepb = top >> l;
+    int32_t tv[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) tv[i] = lds_s32(posb[i] + stepb);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (tv[i] < a[i]) posb[i] += stepb;
+  }
+  constexpr int rsh = ROWB == 512 ? 9 : 10;
+#pragma unroll
+  for (int i = 0; i < N; i++) out[i] = (posb[i] - fin_base) >> rsh;
+}
+
 // Store one output lane per thread of a warp: lane `l` holds channel ch0 + l of one pixel.
 // `word` points at that pixel's output word; sub-byte lanes are merged across the warp.
 // Must be called by all 32 lanes (uses shuffles); `valid` masks channels >= OFM.

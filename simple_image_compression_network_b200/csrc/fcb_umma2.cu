@@ -125,6 +125,8 @@ struct Umma2Plan {
   Geom g;
   Params2 p;
   CUtensorMap tmW;
+  CUtensorMap tmW_slice;  // box of half the channel rows: the slice one CTA of a 2-CTA cluster fetches and multicasts (cluster_ok)
+  bool cluster_ok = false;
   size_t smem;
   int num_sms;
   uint32_t box_rows[2];
@@ -245,7 +247,12 @@ __device__ __forceinline__ void dcol_gather(const uint32_t (&bm)[3], uint32_t (&
 // slack for per-K-block loads of kernel parameters (each LDCU + dependent branch costs ~50 clocks of its ~580-clock budget).
 // EPI = 1: the instantiation for pooled 8-bit threshold layers (monotone compare, shared-memory tables): every other epilogue is
 // compiled out, which frees registers and instruction cache for the lock-step search.
-template <int NB, int DT, int EPI>
+// CS = CTAs per cluster (1 or 2) sharing ONE stream of weight K-blocks: each CTA fetches 1/CS of every K-block and multicasts it into
+// every ring of the cluster (the L2 -> SM weight stream -- 400 KB per 256-pixel tile on CONV_1 -- was the largest data mover of the
+// channel-heavy layers and, under the 1 kW power cap, clocks: profiles/r02_power_decomposition.log).  Each CTA still runs its own
+// tiles with cta_group::1 MMAs; only the weight ring is shared, so all CTAs of a cluster step through the same number of K-blocks
+// (a CTA with one tile fewer runs the ring protocol of a phantom tile).
+template <int NB, int DT, int EPI, int CS = 1>
 __global__ void __launch_bounds__(320 + 32 * NB + (EPI >= 4 ? 256 : EPI >= 2 ? 128 * (EPI - 1) : 0), 1)
 umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const Params2 p) {
@@ -301,15 +308,22 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   // CTA -> (channel block, tile sequence): with chb > 1 every tile is visited once per channel block
   const int chblk = blockIdx.x % p.chb, chbase = chblk * 128;
   const long long cta0 = blockIdx.x / p.chb, ncta = gridDim.x / p.chb;
+  // weight-ring passes of this CTA: its own tiles, or (clusters) the tile count of the busiest CTA -- uniform over the cluster
+  const long long my_tiles = cta0 < total_tiles ? (total_tiles - cta0 + ncta - 1) / ncta : 0;
+  const long long ring_tiles = CS > 1 ? (total_tiles + ncta - 1) / ncta : my_tiles;
+  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1u);
   if (p.thr_off >= 0) {
     // top levels of the threshold search for this CTA's channels, threshold-major (see activate_thr_hybrid)
     int32_t* ts = reinterpret_cast<int32_t*>(smem + p.thr_off);
     const int nch = p.CB * 128, ntop = (1 << p.thr_top) - 1;
     int gshift = 0;
     for (int t = p.epi.thr_n + 1; (t >> (p.thr_top + gshift)) > 1;) gshift++;
+    // pooled-threshold instantiations with a bucket LUT search with ONE strict compare (thr_lut_fast): thr <= a  <=>  thr - 1 < a
+    const int32_t thr_adj = (EPI >= 1 && EPI <= 3 && p.lut_off >= 0 && p.epi.cmp == FCB_CMP_LESS_EQUAL) ? 1 : 0;
     for (int idx = threadIdx.x; idx < ntop * nch; idx += blockDim.x) {
       const int j = idx / nch + 1, c = idx - (j - 1) * nch;
-      ts[idx] = __ldg(p.epi.thr + (size_t)((j << gshift) - 1) * p.epi.thr_stride + chbase + c);
+      ts[idx] = __ldg(p.epi.thr + (size_t)((j << gshift) - 1) * p.epi.thr_stride + chbase + c) - thr_adj;
     }
   }
 
@@ -324,7 +338,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmW);
-    for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    for (int s = 0; s < p.wstages; s++) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], CS); }  // a stage is free when EVERY CTA of the cluster has read it
     for (int i = 0; i < p.nsets * p.nplanes; i++) { mbar_init(&afull[i], p.thin_in ? NB : 1); mbar_init(&aempty[i], 1); }
     for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], THRP ? 8 + XEPI : (SWPX || DCX || STX) ? 8 : (p.epi_alt || p.epi4) ? 4 : 8); }
     for (int a = 0; a < U2_NPB; a++) { mbar_init(&pfull[a], 1); mbar_init(&pempty[a], NB); }
@@ -333,6 +347,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrival or multicast write
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -341,16 +356,19 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (lane == 0) {
       int s = 0;
       uint32_t wphase = 1;
-      for (long long t = cta0; t < total_tiles; t += ncta) {
-        if (WSTATIC && t != cta0) break;
+      for (long long t = 0; t < ring_tiles; t++) {
+        if (WSTATIC && t != 0) break;
         for (int ph = 0; ph < p.nphases; ph++) {
           const Phase2& P = p.phases[ph];
           for (int i = 0; i < P.nkb; i++) {
             mbar_wait(&wempty[s], wphase);
             if (DBG(1)) mbar_arrive(&wfull[s]);
             else {
-              mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);
+              mbar_arrive_expect_tx(&wfull[s], (uint32_t)p.w_bytes);  // the whole K-block: 1/CS of it from every CTA of the cluster
               if (DTHIN || DCOL) tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], 0, P.kb[i].w_k);  // row block w_k
+              else if (CS > 1)  // this CTA's slice of the channel rows (tmW's box is CB*128/CS rows), into every ring of the cluster
+                tma_load_2d_mc(smem + p.w_off + s * p.w_bytes + cta_rank * (uint32_t)(p.w_bytes / CS), &tmW, &wfull[s], P.kb[i].w_k,
+                               chbase + (int)cta_rank * (p.CB * 128 / CS), MC_MASK);
               else tma_load_2d(smem + p.w_off + s * p.w_bytes, &tmW, &wfull[s], P.kb[i].w_k, chbase);
             }
             if (++s == p.wstages) { s = 0; wphase ^= 1; }
@@ -520,7 +538,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 if (!THIN || ksteps > 3) umma_i8(dt, wdesc + 1030, pdesc + 6, idesc, 1u);
               }
             }
-            if (!WSTATIC) umma_commit(&wempty[s]);
+            if (!WSTATIC) { if (CS > 1) umma_commit_mc(&wempty[s], MC_MASK); else umma_commit(&wempty[s]); }
             if (flags & KB_FREE) umma_commit(&aempty[plane]);
             if (i == nkb - 1) umma_commit(&tfull[acc]);
           }
@@ -528,6 +546,18 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (++s == wstages) { s = 0; wphase ^= WSTATIC ? 0u : 1u; }
         }
       }
+    }
+    if (CS > 1) {
+      // phantom passes: a CTA with fewer tiles than the busiest one of its cluster still takes every K-block off the shared ring
+      // (its stages are written by the peers' multicasts) and frees it, without issuing MMAs
+      for (long long t = my_tiles; t < ring_tiles; t++)
+        for (int ph = 0; ph < p.nphases; ph++)
+          for (int i = 0; i < p.phases[ph].nkb; i++) {
+            mbar_wait(&wfull[s], wphase);
+            if (elect_one_sync()) umma_commit_mc(&wempty[s], MC_MASK);
+            __syncwarp();
+            if (++s == wstages) { s = 0; wphase ^= 1u; }
+          }
     }
     if (lane == 0) PROF_FLUSH(1);
   } else if (warp < 10 || XEPI > 0) {
@@ -1059,6 +1089,16 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   if (DBG(16)) {
 #pragma unroll
                     for (int w = 0; w < 8; w++) pooled[w] = (uint32_t)m8[w] & 0xFFu;
+                  } else if (THRP && use_lut) {
+                    // (m8 is already wrapped to TA; tables in shared memory carry the less_equal adjustment)
+                    const uint32_t rowb = p.CB == 2 ? 1024u : 512u, tbase = top_s - rowb, fbase = tbase - (uint32_t)p.epi.act_val * rowb;
+                    if (p.CB == 2) {
+                      if (p.epi.thr_lut_levels == 3) thr_lut_fast<8, 3, 1024>(tbase, fbase, lut_s, lut_lo, lut_sh, m8, pooled);
+                      else thr_lut_fast<8, 4, 1024>(tbase, fbase, lut_s, lut_lo, lut_sh, m8, pooled);
+                    } else {
+                      if (p.epi.thr_lut_levels == 3) thr_lut_fast<8, 3, 512>(tbase, fbase, lut_s, lut_lo, lut_sh, m8, pooled);
+                      else thr_lut_fast<8, 4, 512>(tbase, fbase, lut_s, lut_lo, lut_sh, m8, pooled);
+                    }
                   } else if (use_lut) {
                     activate_thr_lut<8>(p.epi, top_s, row_shift, lut_s, lut_lo, lut_sh, m8, pooled);
                   } else if (THRP || hybrid) {
@@ -1115,6 +1155,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 2 && lane == 0) PROF_FLUSH(2);
   if (warp >= 2 && (warp < 10 || warp >= 10 + NB) && lane == 0 && p.stg_bufs > 0) bulk_wait<0>();  // staged stores still read shared memory
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // no CTA leaves while a peer may still arrive on its barriers
   if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -1388,14 +1429,55 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     const uint32_t box[2] = {128, (uint32_t)(CBe * 128)};
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
     if (rc) { delete U; return rc; }
+    // 2-CTA clusters share the weight stream: each CTA fetches half of the rows of a K-block (a multiple of 8 rows, so the slice
+    // starts on a 1024-byte swizzle period) and multicasts it.  Not with chb > 1: neighbouring CTAs then serve different channel blocks.
+    // MEASURED (profiles/r02_cluster_multicast_ab.log, sustained, power-capped): the halved L2 stream buys ~1.5 % of SM clock, the
+    // lock-step of the two CTAs on one ring costs ~3 % of clocks per image (CONV_1 119.5 k vs 121.1 k img/s, L6 113.6 k vs 115.6 k):
+    // a net loss, so the clustered instantiations are compiled into experiment builds only (FCB_U2_CLUSTER=1).
+    U->cluster_ok = chb == 1 && exp_int("FCB_U2_CLUSTER", 0) != 0;
+    if (U->cluster_ok) {
+      const uint32_t box2[2] = {128, (uint32_t)(CBe * 64)};
+      rc = umma_encode_map(&U->tmW_slice, const_cast<int8_t*>(d_w), 2, dims, strides, box2);
+      if (rc) { delete U; return rc; }
+    }
   }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#ifdef FCB_EXPERIMENT
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#endif
   *out = U;
   return FCB_OK;
+}
+
+// launch of a resident-planes instantiation: as 2-CTA clusters sharing the weight stream when the plan allows it
+template <int EPI>
+static cudaError_t launch_resident(const Umma2Plan* U, int grid, int threads, cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1,
+                                   const CUtensorMap& o, const Params2& p) {
+#ifdef FCB_EXPERIMENT
+  if (U->cluster_ok && grid >= 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(grid & ~1), 1, 1);
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = U->smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, umma2_conv_kernel<1, 0, EPI, 2>, a0, a1, U->tmW_slice, o, p);
+  }
+#endif
+  umma2_conv_kernel<1, 0, EPI, 1><<<grid, threads, U->smem, st>>>(a0, a1, U->tmW, o, p);
+  return cudaGetLastError();
 }
 
 // Thin-input plan: d_w is [CB*128][128] s8 with k = (ky*KX + kx)*4 + lane (zero beyond the window / lanes >= C).
@@ -1749,8 +1831,8 @@ static const char* umma2_describe_base(const Umma2Plan* U, char* buf, size_t n) 
              p.tiles_x, p.tiles_y);
     return buf;
   }
-  snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d chb=%d%s planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT,
-           p.R, p.P, p.NPX, p.CB, p.chb, p.lut_off >= 0 ? " thr@smem + bucket LUT" : p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : p.epi4 ? " epi-warps=4" : ""), p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
+  snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d chb=%d%s%s planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT,
+           p.R, p.P, p.NPX, p.CB, p.chb, p.lut_off >= 0 ? " thr@smem + bucket LUT" : p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : p.epi4 ? " epi-warps=4" : ""), U->cluster_ok ? " weights-multicast x2" : "", p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
            p.tiles_x, p.tiles_y);
   return buf;
 }
@@ -1848,11 +1930,11 @@ int umma2_run(Umma2Plan* U, const void* d_in, void* d_out, int n_images, cudaStr
   else if (p.dthin) umma2_conv_kernel<1, 1, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
 #endif
   else if (!thrp && p.stg_bufs == 2 && p.epi_alt && !p.swap && !exp_env("FCB_U2_NO_STX"))  // staged bias+ReLU, two tiles: 16 epilogue warps
-    umma2_conv_kernel<1, 0, 6><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (thrp && xepi == 8) umma2_conv_kernel<1, 0, 3><<<grid, 320 + 32 + 256, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (thrp && xepi == 4) umma2_conv_kernel<1, 0, 2><<<grid, 320 + 32 + 128, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else if (thrp) umma2_conv_kernel<1, 0, 1><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
-  else umma2_conv_kernel<1, 0, 0><<<grid, 320 + 32, U->smem, st>>>(tmA[0], tmA[1], U->tmW, tmO, p);
+    FCB_CUDA_OK(launch_resident<6>(U, grid, 320 + 32 + 256, st, tmA[0], tmA[1], tmO, p));
+  else if (thrp && xepi == 8) FCB_CUDA_OK(launch_resident<3>(U, grid, 320 + 32 + 256, st, tmA[0], tmA[1], tmO, p));
+  else if (thrp && xepi == 4) FCB_CUDA_OK(launch_resident<2>(U, grid, 320 + 32 + 128, st, tmA[0], tmA[1], tmO, p));
+  else if (thrp) FCB_CUDA_OK(launch_resident<1>(U, grid, 320 + 32, st, tmA[0], tmA[1], tmO, p));
+  else FCB_CUDA_OK(launch_resident<0>(U, grid, 320 + 32, st, tmA[0], tmA[1], tmO, p));
   FCB_CUDA_OK(cudaGetLastError());
   if (d_prof) {  // debugging aid: average clocks per tile and segment over the CTAs
     FCB_CUDA_OK(cudaStreamSynchronize(st));

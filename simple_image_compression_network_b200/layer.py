@@ -168,5 +168,62 @@ class Net:
             pass
 
 
+class Pool:
+    """The chain replicated on several GPUs behind one handle (fcb_pool_*): `run(in_words, numReps)` has the meaning of
+    eight_layers_net(in, out, numReps) (conv_nonsquare_top.cpp:295) and uses every listed device from one call; the batch is split
+    into contiguous image ranges (shard.shard_range == fcb_shard_range), no device talks to another."""
+
+    def __init__(self, descs, weights, thresholds=None, biases=None, devices=None):
+        L = self._L = _lib.lib()
+        n = len(descs)
+        self.descs = list(descs)
+        keep = []
+
+        def images(seq):
+            arr = (ctypes.c_void_p * n)()
+            for i in range(n):
+                a = None if seq is None or seq[i] is None else np.ascontiguousarray(seq[i], dtype=np.uint8)
+                keep.append(a)
+                arr[i] = None if a is None else a.ctypes.data
+            return arr
+        cd = (type(descs[0].to_c()) * n)(*[d.to_c() for d in descs])
+        dev = None if not devices else (ctypes.c_int * len(devices))(*devices)
+        h = ctypes.c_void_p()
+        _lib.check(L.fcb_pool_create(cd, images(weights), images(thresholds), images(biases), n, dev, len(devices or []), ctypes.byref(h)), L)
+        self._h = h
+        sizes = [ctypes.c_size_t() for _ in range(5)]
+        c0, c1 = descs[0].to_c(), descs[-1].to_c()
+        _lib.check(L.fcb_layer_query(ctypes.byref(c0), *[ctypes.byref(s) for s in sizes]), L)
+        self.in_bytes = sizes[0].value
+        _lib.check(L.fcb_layer_query(ctypes.byref(c1), *[ctypes.byref(s) for s in sizes]), L)
+        self.out_bytes = sizes[1].value
+
+    @property
+    def replicas(self) -> int:
+        return int(self._L.fcb_pool_replicas(self._h))
+
+    def run(self, in_words, num_reps: int = 1) -> np.ndarray:
+        x = np.ascontiguousarray(in_words, dtype=np.uint8).reshape(-1)
+        if x.size != self.in_bytes * num_reps:
+            raise ValueError(f"input stream is {x.size} bytes, expected {self.in_bytes * num_reps}")
+        out = np.empty(self.out_bytes * num_reps, dtype=np.uint8)
+        _lib.check(self._L.fcb_pool_run(self._h, _ptr(x), _ptr(out), num_reps), self._L)
+        return out
+
+    def run_raw(self, in_ptr: int, out_ptr: int, num_reps: int) -> None:
+        _lib.check(self._L.fcb_pool_run(self._h, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), num_reps), self._L)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fcb_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def synth_fill(d_ptr: int, n_bytes: int, seed: int, mask: int = 0xFF, offset: int = 0, stream: int = 0) -> None:
     _lib.check(_lib.lib().fcb_synth_fill(ctypes.c_void_p(d_ptr), n_bytes, seed, mask, offset, ctypes.c_void_p(stream)))

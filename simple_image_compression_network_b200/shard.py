@@ -5,7 +5,8 @@ from __future__ import annotations
 
 
 def shard_range(n_images: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous [begin, end) of the global batch owned by `rank` (strong-scaling split, remainder to low ranks)."""
+    """Contiguous [begin, end) of the global batch owned by `rank` (strong-scaling split, remainder to low ranks) -- the rule
+    fcb_shard_range / fcb_pool_run apply inside the library (csrc/fcb_pool.cu; tests/test_multirank.py keeps the two in step)."""
     if not (0 <= rank < world):
         raise ValueError("rank out of range")
     base, rem = divmod(n_images, world)

@@ -89,7 +89,7 @@ def test_layer_host_call_many_chunks_lowered_and_direct(fcb_lib, oracle_mod):
     lowered = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=8, ofm_ch=32, ifm_x=30, ifm_y=14, stride_x=1, stride_y=1, pad=1,
                         simd=8, pe=8, in_bits=8, w_bits=4, acc_bits=8, acc_signed=0, act_kind=ACT_BIAS_RELU, out_bits=8)
     small_out = dataclasses.replace(cases.CASES["xn_a"])  # 8 x 1-bit lanes: 1-byte output words (chunk offsets need rounding)
-    for d, want_plan in ((lowered, "im2col rows"), (cases.CASES["c2d_e"], "resident-planes"), (cases.CASES["c2d_a"], "direct"), (small_out, "direct")):
+    for d, want_plan in ((lowered, "im2col rows"), (cases.CASES["c2d_e"], "resident-planes"), (cases.CASES["dc_a"], "direct"), (small_out, "direct")):
         reps = 23
         inp = cases.make_inputs(d, seed_shift=5, num_reps=reps)
         L = ConvLayer(d, inp["weights"], thresholds=inp["thresholds"], bias=inp["bias"])
@@ -117,3 +117,28 @@ def test_unmodified_reference_testbench_on_gpu_backend(fcb_lib):
     assert r.returncode == 0, out[-2000:]
     assert "passed the testing" in out, out[-2000:]
     assert "ERROR" not in out, out[-2000:]
+
+
+def test_pool_splits_the_batch_over_replicas(fcb_lib, oracle_mod):
+    """fcb_pool_*: the chain replicated behind one handle, numReps split into contiguous image ranges, one host thread per replica.
+    On a one-GPU box the replicas share device 0 (a device may be listed twice); with more GPUs every device is used."""
+    import torch
+    from oracle import cases
+    from simple_image_compression_network_b200.layer import Pool
+    d1 = cases.CASES["c2d_e"]
+    import dataclasses
+    d2 = dataclasses.replace(cases.CASES["dc_c"], ifm_x=24, ifm_y=16)
+    reps = 13
+    i1, i2 = cases.make_inputs(d1, num_reps=reps, relu_range=True), cases.make_inputs(d2, seed_shift=9)
+    mid = oracle_mod.run_layer(d1, i1["in_words"], i1["weights"], None, i1["bias"], num_reps=reps)
+    want = oracle_mod.run_layer(d2, mid, i2["weights"], None, i2["bias"], num_reps=reps)
+    ndev = torch.cuda.device_count()
+    for devices in ([0, 0, 0], None, list(range(ndev)) * 2):
+        pool = Pool([d1, d2], [i1["weights"], i2["weights"]], None, [i1["bias"], i2["bias"]], devices=devices)
+        assert pool.replicas == (len(devices) if devices else ndev)
+        for n in (reps, 2, 1):  # fewer images than replicas: the high ranks get empty ranges
+            got = pool.run(i1["in_words"][: n * pool.in_bytes], n)
+            assert np.array_equal(got, want[: n * pool.out_bytes]), f"devices={devices} n={n}"
+        pool.close()
+    one = Pool([d1], [i1["weights"]], None, [i1["bias"]], devices=[0, 0])  # single layer: fcb_layer_run underneath
+    assert np.array_equal(one.run(i1["in_words"], reps), mid)

@@ -519,3 +519,19 @@ def test_judged_configs_at_full_size(fcb_lib, oracle_mod):
         got = L.run(inp["in_words"])
         want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"])
         assert np.array_equal(got, want), f"{name} [{L.engine}: {L.plan}]: {_diff(got, want)}"
+
+
+@pytest.mark.parametrize("name,reps", [("c2d_e", 3), ("dc_c", 2), ("th_cfg4", 1), ("c2d_g", 5)])
+def test_clustered_weight_multicast(name, reps, fcb_lib, oracle_mod, monkeypatch, exp_build):
+    """Experiment build: 2-CTA clusters sharing one multicast stream of weight K-blocks (umma2_conv_kernel<.., CS = 2>), odd tile
+    counts included (a CTA with one tile fewer runs the ring protocol of a phantom tile): bit-exact against the oracle."""
+    d = cases.CASES[name]
+    inp = cases.make_inputs(d, seed_shift=17, num_reps=reps, relu_range=d.kind != 0)
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=reps)
+    exp_build()
+    monkeypatch.setenv("FCB_U2_CLUSTER", "1")
+    L = _layer(d, inp)
+    got = L.run(inp["in_words"], reps)
+    if "chb=1" in L.plan:
+        assert "weights-multicast" in L.plan, L.plan
+    assert np.array_equal(got, want), f"{name} [{L.plan}]: {_diff(got, want)}"

@@ -78,3 +78,20 @@ def test_two_rank_batch_sharding_gloo():
         assert p.exitcode == 0
     assert ok, "sharded result differs from the single-process result"
     assert tmax == 11.0
+
+
+def test_library_split_is_the_host_split(fcb_lib):
+    """fcb_shard_range (the split fcb_pool_run applies over its replicas) == shard.shard_range, and it tiles the batch."""
+    import ctypes
+    for n in (0, 1, 7, 8, 9, 4096, 4099):
+        for w in (1, 2, 3, 8):
+            prev = 0
+            for r in range(w):
+                b, e = ctypes.c_uint32(), ctypes.c_uint32()
+                assert fcb_lib.fcb_shard_range(n, r, w, ctypes.byref(b), ctypes.byref(e)) == 0
+                assert (b.value, e.value) == shard_range(n, r, w)
+                assert b.value == prev
+                prev = e.value
+            assert prev == n
+    b, e = ctypes.c_uint32(), ctypes.c_uint32()
+    assert fcb_lib.fcb_shard_range(4, 2, 2, ctypes.byref(b), ctypes.byref(e)) == -1
