@@ -387,6 +387,23 @@ def run_ours(args):
     e2e_value = world * e_img * e_steps / h.max_over_ranks(e_s)
     if not torch.equal(hy.cuda(), y[: e_img * layer.out_bytes]):
         raise SystemExit("bench: the host-buffer call and the device-resident call disagree")
+    # the denominator of e2e: the same bytes moved with NO kernel -- H2D of the inputs and D2H of the outputs of one step, on two
+    # streams at once, all ranks concurrently (what the box's PCIe / host memory sustains for this rank layout)
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    dx, dy = x[: e_img * layer.in_bytes], y[: e_img * layer.out_bytes]
+
+    def copies():
+        with torch.cuda.stream(s_up):
+            dx.copy_(hx, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            hy.copy_(dy, non_blocking=True)
+    copies()
+    h.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        copies()
+    torch.cuda.synchronize()
+    copy_value = world * e_img * e_steps / h.max_over_ranks(time.perf_counter() - t0)
 
     # ---- roofline of the dominant kernel (the only kernel in the step)
     peaks, src = _peaks()
@@ -416,7 +433,9 @@ def run_ours(args):
                     "l2": f"inputs ({n_img * layer.in_bytes / 1e9:.1f} GB per GPU) are larger than L2; no flush needed"},
             "clocks": clocks, "gpu_launches": int(launches), "parity_checked_images": checked,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e_img * layer.in_bytes,
-                    "d2h_bytes_per_step": e_img * layer.out_bytes, "images_per_step": e_img, "steps": e_steps},
+                    "d2h_bytes_per_step": e_img * layer.out_bytes, "images_per_step": e_img, "steps": e_steps,
+                    "copy_only_ceiling": copy_value, "frac_of_copy_only_ceiling": e2e_value / copy_value,
+                    "ceiling_is": "the step's H2D + D2H bytes with no kernel, both directions at once, all ranks concurrently (pinned memory)"},
             "roofline": roofline}
     del x, y, hx, hy
     torch.cuda.empty_cache()

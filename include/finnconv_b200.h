@@ -61,7 +61,23 @@ typedef enum fcb_status {
 } fcb_status;
 
 /* conv2d<> (conv_nonsquare_top.cpp:198-280) vs deconv522<> (:71-195) */
-typedef enum fcb_layer_kind { FCB_KIND_CONV = 0, FCB_KIND_DECONV522 = 1 } fcb_layer_kind;
+typedef enum fcb_layer_kind {
+  FCB_KIND_CONV = 0,
+  FCB_KIND_DECONV522 = 1,
+  /* depth-wise convolution: [FMPadding_nonsquare ->] ConvolutionInputGenerator[_NonSquare]_dws (slidingwindow.h:761-868, 1377-1488)
+   * -> Vector_Vector_Activate_Batch (vvau.hpp:80-154).  ofm_ch == ifm_ch, simd == pe (the generator's SIMD is the VVAU's PE);
+   * weights = image of FixedPointWeights<1, ap_int<w_bits>, PE, NF*Kx*Ky>::m_weights[PE][TILES], one lane per ap_uint<w_bits> word,
+   * tile = nf*Kx*Ky + ky*Kx + kx (the generator emits, per channel chunk, the taps in (ky, kx) order); any activation. */
+  FCB_KIND_DWCONV = 2,
+  /* generic pooling: the same sliding window -> Pool_batch (maxpool.h:525-577) with a pool.hpp function (pool.hpp:94-226).
+   * ofm_ch == ifm_ch, simd == pe; no weights (NULL); `weight_kind` holds the fcb_pool_fn, `act_val` its `size` argument (divisor of
+   * AvgPoolFunction, shift of QuantAvgPoolFunction); in_bits / in_signed = TSrcI lanes, acc_bits / acc_signed = the function's
+   * accumulator type, out_bits = TDstI lanes; act_kind must be FCB_ACT_PASSTHROUGH; kernel / stride / padding as for FCB_KIND_CONV. */
+  FCB_KIND_POOL = 3
+} fcb_layer_kind;
+/* MaxPoolFunction (init = type minimum) | AvgPoolFunction (sum, then / size, C++ truncation) | AccPoolFunction (sum) |
+ * QuantAvgPoolFunction (sum, then >> size) -- pool.hpp:94-226 */
+typedef enum fcb_pool_fn { FCB_POOLFN_MAX = 0, FCB_POOLFN_AVG = 1, FCB_POOLFN_ACC = 2, FCB_POOLFN_QUANTAVG = 3 } fcb_pool_fn;
 
 /* weights.hpp:110-150 FixedPointWeights | weights.hpp:66-98 BinaryWeights with
  * Recast<XnorMul> activations (interpret.hpp:57-73) | BinaryWeights with

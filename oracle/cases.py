@@ -5,11 +5,14 @@ seeded synthetic tensors each case is fed (SURVEY.md 8(d) seeding rule).
 """
 from __future__ import annotations
 
+import dataclasses
+
 import numpy as np
 
 from simple_image_compression_network_b200 import pack, synth
-from simple_image_compression_network_b200.desc import (ACT_BIAS_RELU, ACT_THRESHOLDS, KIND_CONV, KIND_DECONV522, W_BINARY_XNOR,
-                                      W_FIXED, LayerDesc)
+from simple_image_compression_network_b200.desc import (ACT_BIAS_RELU, ACT_PASSTHROUGH, ACT_THRESHOLDS, KIND_CONV, KIND_DECONV522,
+                                                        KIND_DWCONV, KIND_POOL, POOLFN_ACC, POOLFN_AVG, POOLFN_MAX, POOLFN_QUANTAVG,
+                                                        W_BINARY_XNOR, W_FIXED, LayerDesc)
 
 
 def _c2d(kx, ky, simd, pe, wb, c, ofm, ix, iy, s, p, inb, actb):
@@ -34,6 +37,20 @@ def _xn(k, simd, pe, c, ofm, ix, iy, tab):
     return LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=ix, ifm_y=iy, stride_x=1,
                      stride_y=1, pad=0, simd=simd, pe=pe, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR, acc_bits=tab,
                      acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=1, num_th=1, act_val=0)
+
+
+def _pl(k, c, pe, ix, iy, s, p, inb, ins, tab, tas, outb, fn, size=0):
+    """Pool_batch behind the depth-wise sliding window (maxpool.h:525-577, pool.hpp:94-226)."""
+    return LayerDesc(kind=KIND_POOL, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=c, ifm_x=ix, ifm_y=iy, stride_x=s, stride_y=s, pad=p,
+                     simd=pe, pe=pe, in_bits=inb, in_signed=ins, w_bits=0, weight_kind=fn, acc_bits=tab, acc_signed=tas,
+                     act_kind=ACT_PASSTHROUGH, out_bits=outb, act_val=size)
+
+
+def _dw(k, c, pe, ix, iy, s, p, wb, tab, outb, nth=0):
+    """Depth-wise convolution: dws sliding window + Vector_Vector_Activate_Batch (vvau.hpp:80-154)."""
+    return LayerDesc(kind=KIND_DWCONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=c, ifm_x=ix, ifm_y=iy, stride_x=s, stride_y=s, pad=p,
+                     simd=pe, pe=pe, in_bits=8, in_signed=0, w_bits=wb, acc_bits=tab, acc_signed=1,
+                     act_kind=ACT_THRESHOLDS if nth else ACT_PASSTHROUGH, out_bits=outb, num_th=nth)
 
 
 # name -> LayerDesc ; names and parameters mirror the X-macro tables of ref_layers.cpp
@@ -61,6 +78,22 @@ CASES = {
     "xn_a": _xn(3, 8, 4, 8, 8, 12, 10, 16),
     "xn_b": _xn(3, 64, 16, 64, 64, 16, 12, 16),
     "xn_c": _xn(3, 32, 8, 64, 32, 20, 9, 16),
+    # FMPadding_nonsquare totals + style, StreamingMaxPool_Precision forms, odd lane widths (ref_layers.cpp: run_thresh_pad_pool)
+    "px_odd2": dataclasses.replace(_th(3, 4, 2, 4, 8, 8, 10, 6, 0, 8, 15, 24, 4, 0), pad_style=2, pad_x_total=3, pad_y_total=1),
+    "px_odd1": dataclasses.replace(_th(3, 4, 2, 4, 8, 8, 10, 6, 0, 8, 15, 24, 4, 0), pad_style=1, pad_x_total=3, pad_y_total=1),
+    "pk3_signed": dataclasses.replace(_th(3, 4, 2, 4, 8, 8, 12, 12, 1, 8, 15, 24, 4, 0, pool=3), pool_signed=1, pool_min_value=-8),
+    "pk2_min5": dataclasses.replace(_th(3, 4, 2, 4, 8, 8, 12, 12, 1, 8, 15, 24, 4, 0, pool=2), pool_min_value=5),
+    "lw3": _th(3, 4, 2, 3, 8, 8, 10, 6, 1, 3, 7, 12, 3, 0),
+    "lw5x12": _th(3, 3, 4, 5, 6, 12, 9, 7, 0, 5, 40, 16, 6, 0),
+    # channel-wise units (ref_layers.cpp: run_pool_batch / run_vvau)
+    "pl_max_a": _pl(2, 8, 4, 12, 12, 2, 0, 8, 0, 8, 0, 8, POOLFN_MAX),
+    "pl_max_s": _pl(3, 4, 2, 10, 6, 1, 1, 8, 1, 8, 1, 8, POOLFN_MAX),
+    "pl_avg": _pl(2, 8, 8, 8, 8, 2, 0, 8, 0, 10, 0, 8, POOLFN_AVG, 4),
+    "pl_qavg": _pl(4, 4, 4, 16, 16, 4, 0, 8, 1, 12, 1, 8, POOLFN_QUANTAVG, 4),
+    "pl_acc": _pl(3, 6, 3, 9, 7, 1, 0, 4, 0, 8, 0, 8, POOLFN_ACC, 9),
+    "dw_a": _dw(3, 8, 4, 10, 6, 1, 1, 4, 16, 16),
+    "dw_b": _dw(3, 16, 8, 12, 12, 1, 1, 4, 16, 4, nth=15),
+    "dw_c": _dw(2, 4, 2, 8, 8, 2, 0, 4, 12, 12),
 }
 
 # cases that take long in the reference C-simulation (seconds): excluded from the quick sets
@@ -77,4 +110,6 @@ def make_inputs(d: LayerDesc, seed_shift: int = 0, num_reps: int = 1, relu_range
 
 def third_image(inp):
     """The bias-or-threshold image the ref_* entry points take as their third argument."""
-    return inp["bias"] if inp["bias"] is not None else inp["thresholds"]
+    if inp["bias"] is not None:
+        return inp["bias"]
+    return inp["thresholds"] if inp["thresholds"] is not None else np.zeros(1, np.uint8)  # (unused by pass-through / pool cases)

@@ -19,7 +19,10 @@
  *   pass-through        lane = acc truncated                   activations.hpp:127-134, mvau.hpp:167
  *   bias + ReLU         (lane+bias) mod 2^B, MSB -> 0          conv_nonsquare_top.cpp:267-278
  *   thresholds          ActVal + sum_i cmp(thr_i, acc) in TR   activations.hpp:168-190, :57-99
- *   max pool            k x k stride k, per lane (1-bit: OR)   maxpool.h:137-185, :66-96
+ *   max pool            k x k stride k, per lane (1-bit: OR)   maxpool.h:137-185, :66-96 (ActType signedness, min_value: :137-170)
+ *   padding split       left/up = P/2 (+P%2, style 2)          streamtools.h:374-379
+ *   depth-wise conv     window order (chunk, ky, kx); acc[ch] = sum_k W[pe][nf*K2+k] * a_k[ch]   slidingwindow.h:1377-1488, vvau.hpp:80-154
+ *   Pool_batch          init / pool / activate per channel    maxpool.h:525-577, pool.hpp:94-226
  * The arithmetic is done in int64 and reduced to TA once before the activation, which is
  * identical to wrapping at every += (two's-complement modular arithmetic).
  */
@@ -73,24 +76,35 @@ static inline int64_t wrap_ta(int64_t v, uint32_t bits, int is_signed) {
   return is_signed ? sext(u, bits) : (int64_t)u;
 }
 
+/* FMPadding_nonsquare split (streamtools.h:374-379) */
+static void pad_split(const fcb_layer_desc* d, uint32_t* l, uint32_t* r, uint32_t* u, uint32_t* dn) {
+  if (!d->pad_style) { *l = *r = *u = *dn = d->pad; return; }
+  *l = d->pad_x_total / 2 + (d->pad_style == 2 ? d->pad_x_total % 2 : 0); *r = d->pad_x_total - *l;
+  *u = d->pad_y_total / 2 + (d->pad_style == 2 ? d->pad_y_total % 2 : 0); *dn = d->pad_y_total - *u;
+}
+
 int fo_layer_query(const fcb_layer_desc* d, fo_sizes* s) {
   if (!d || d->struct_size != sizeof(fcb_layer_desc)) return -1;
   if (!d->simd || !d->pe || !d->ifm_ch || !d->ofm_ch || !d->kernel_x || !d->kernel_y || !d->stride_x || !d->stride_y) return -1;
   if (d->ifm_ch % d->simd) return -2;                                /* slidingwindow.h:1259 */
   if (d->ofm_ch % d->pe) return -2;                                  /* streamtools.h:505 (PE*B -> OFM*B) */
-  if (d->in_bits < 1 || d->in_bits > 16 || d->out_bits < 1 || d->out_bits > 32 || d->acc_bits < 1 || d->acc_bits > 48) return -3;
-  uint32_t ox, oy;
+  if (d->in_bits < 1 || d->in_bits > 16 || d->out_bits < 1 || d->out_bits > 32 || d->acc_bits < 1 || d->acc_bits > 64) return -3;
+  uint32_t ox, oy, pl, pr, pu, pd;
+  pad_split(d, &pl, &pr, &pu, &pd);
+  const int chanwise = d->kind == FCB_KIND_DWCONV || d->kind == FCB_KIND_POOL;
   if (d->kind == FCB_KIND_DECONV522) {
     if (d->kernel_x != 5 || d->kernel_y != 5 || d->stride_x != 2 || d->stride_y != 2 || d->pad != 2) return -2;
     ox = 2 * d->ifm_x; oy = 2 * d->ifm_y;
-  } else if (d->kind == FCB_KIND_CONV) {
-    if (d->ifm_x + 2 * d->pad < d->kernel_x || d->ifm_y + 2 * d->pad < d->kernel_y) return -2;
-    /* kept windows: stride-1 positions 0..I+2P-K with pos % S == 0 (conv_nonsquare_top.cpp:246-259) */
-    ox = (d->ifm_x + 2 * d->pad - d->kernel_x) / d->stride_x + 1;
-    oy = (d->ifm_y + 2 * d->pad - d->kernel_y) / d->stride_y + 1;
+  } else if (d->kind == FCB_KIND_CONV || chanwise) {
+    if (d->ifm_x + pl + pr < d->kernel_x || d->ifm_y + pu + pd < d->kernel_y) return -2;
+    /* kept windows: stride-1 positions 0..I+P-K with pos % S == 0 (conv_nonsquare_top.cpp:246-259) */
+    ox = (d->ifm_x + pl + pr - d->kernel_x) / d->stride_x + 1;
+    oy = (d->ifm_y + pu + pd - d->kernel_y) / d->stride_y + 1;
+    if (chanwise && (d->ofm_ch != d->ifm_ch || d->simd != d->pe)) return -2;  /* one output channel per input channel; SWG SIMD == PE */
   } else return -1;
   if (ox != d->ofm_x || oy != d->ofm_y) return -2;
-  if (d->weight_kind == FCB_W_FIXED) { if (d->w_bits < 1 || d->w_bits > 16) return -3; }
+  if (d->kind == FCB_KIND_POOL) { if (d->weight_kind > FCB_POOLFN_QUANTAVG) return -1; }
+  else if (d->weight_kind == FCB_W_FIXED) { if (d->w_bits < 1 || d->w_bits > 16) return -3; }
   else if (d->weight_kind == FCB_W_BINARY_XNOR) { if (d->w_bits != 1 || d->in_bits != 1) return -2; }
   else if (d->weight_kind == FCB_W_BINARY_PM1) { if (d->w_bits != 1) return -2; }
   else return -1;
@@ -109,11 +123,25 @@ int fo_layer_query(const fcb_layer_desc* d, fo_sizes* s) {
     s->out_bytes_per_image = s->out_word_bytes * s->out_x * s->out_y;
     s->weight_word_bytes = fo_word_bytes(d->simd * d->w_bits);
     s->weight_bytes = s->weight_word_bytes * d->pe * (size_t)s->sf * s->nf;
+    if (d->kind == FCB_KIND_DWCONV) {  /* FixedPointWeights<1, WT, PE, NF*K2>: one lane per word (vvau.hpp:128-134) */
+      s->k_total = d->kernel_x * d->kernel_y;
+      s->sf = s->k_total;
+      s->weight_word_bytes = fo_word_bytes(d->w_bits);
+      s->weight_bytes = s->weight_word_bytes * d->pe * (size_t)s->sf * s->nf;
+    } else if (d->kind == FCB_KIND_POOL) {
+      s->k_total = d->kernel_x * d->kernel_y;
+      s->sf = s->k_total;
+      s->weight_word_bytes = 0;
+      s->weight_bytes = 0;
+    }
     s->threshold_bytes = d->act_kind == FCB_ACT_THRESHOLDS ? fo_word_bytes(d->acc_bits) * d->pe * (size_t)s->nf * d->num_th : 0;
     s->bias_bytes = d->act_kind == FCB_ACT_BIAS_RELU ? d->ofm_ch : 0;
   }
   return 0;
 }
+
+static int fo_chanwise_run(const fcb_layer_desc* d, const fo_sizes* s, const void* in_words, const void* weights, const void* thresholds,
+                           const void* bias, void* out_words, uint32_t numReps);
 
 /* thresholds cmp(thr, acc) -- activations.hpp:57-99,185 */
 static inline int cmp_eval(uint32_t cmp, int64_t thr, int64_t acc) {
@@ -130,6 +158,7 @@ int fo_layer_run(const fcb_layer_desc* d, const void* in_words, const void* weig
   fo_sizes s;
   int rc = fo_layer_query(d, &s);
   if (rc) return rc;
+  if (d->kind == FCB_KIND_DWCONV || d->kind == FCB_KIND_POOL) return fo_chanwise_run(d, &s, in_words, weights, thresholds, bias, out_words, numReps);
   if (!in_words || !weights || !out_words) return -1;
   if (d->act_kind == FCB_ACT_THRESHOLDS && !thresholds) return -1;
   if (d->act_kind == FCB_ACT_BIAS_RELU && !bias) return -1;
@@ -138,8 +167,10 @@ int fo_layer_run(const fcb_layer_desc* d, const void* in_words, const void* weig
   const uint32_t OX = d->ofm_x, OY = d->ofm_y;
   const int deconv = d->kind == FCB_KIND_DECONV522;
   /* extent of the fully padded (and, for deconv, zero-inserted) frame the 5x5 / KxK windows slide over */
-  const uint32_t PX = deconv ? 2 * d->ifm_x + 4 : d->ifm_x + 2 * d->pad;
-  const uint32_t PY = deconv ? 2 * d->ifm_y + 4 : d->ifm_y + 2 * d->pad;
+  uint32_t pl, pr, pu, pd;
+  pad_split(d, &pl, &pr, &pu, &pd);
+  const uint32_t PX = deconv ? 2 * d->ifm_x + 4 : d->ifm_x + pl + pr;
+  const uint32_t PY = deconv ? 2 * d->ifm_y + 4 : d->ifm_y + pu + pd;
   const uint32_t SX = deconv ? 1 : d->stride_x, SY = deconv ? 1 : d->stride_y;
 
   /* --- weights: W[ch][k] (A.2) ------------------------------------------------ */
@@ -196,8 +227,8 @@ int fo_layer_run(const fcb_layer_desc* d, const void* in_words, const void* weig
     for (uint32_t y = 0; y < d->ifm_y; y++)
       for (uint32_t x = 0; x < d->ifm_x; x++) {
         const uint8_t* word = img + ((size_t)y * d->ifm_x + x) * s.in_word_bytes;
-        uint32_t px = deconv ? 2 * x + 2 : x + d->pad; /* A.6: Z(2i,2j) = a(i,j), then pad 2 */
-        uint32_t py = deconv ? 2 * y + 2 : y + d->pad;
+        uint32_t px = deconv ? 2 * x + 2 : x + pl; /* A.6: Z(2i,2j) = a(i,j), then pad 2 */
+        uint32_t py = deconv ? 2 * y + 2 : y + pu;
         int32_t* dst = P + ((size_t)py * PX + px) * C;
         for (uint32_t c = 0; c < C; c++) {
           uint32_t raw = get_bits(word, (uint64_t)c * d->in_bits, d->in_bits);
@@ -264,13 +295,18 @@ int fo_layer_run(const fcb_layer_desc* d, const void* in_words, const void* weig
       for (uint32_t xp = 0; xp < s.out_x; xp++) {
         uint8_t* word = oimg + ((size_t)yp * s.out_x + xp) * s.out_word_bytes;
         for (uint32_t ch = 0; ch < OFM; ch++) {
-          uint32_t m = 0; /* min_value 0 for unsigned lanes; OR == max for 1-bit */
+          /* StreamingMaxPool_Precision (maxpool.h:144-170): buf = min_value converted to ActType; `channeldata > oldMax` in ActType
+           * (ap_int<out_bits> when pool_signed); 1-bit StreamingMaxPool is an OR (:81-86) == the unsigned max from 0.
+           * pk == 1: no pool unit at all. */
+          int64_t m = pk > 1 ? wrap_ta((int64_t)d->pool_min_value, d->out_bits, d->pool_signed) : 0;
+          int first = pk == 1;
           for (uint32_t ky = 0; ky < pk; ky++)
             for (uint32_t kx = 0; kx < pk; kx++) {
-              uint32_t v = act[((size_t)(yp * pk + ky) * OX + (xp * pk + kx)) * OFM + ch];
-              if (v > m) m = v;
+              uint32_t raw = act[((size_t)(yp * pk + ky) * OX + (xp * pk + kx)) * OFM + ch];
+              int64_t v = d->pool_signed ? sext(raw, d->out_bits) : (int64_t)raw;
+              if (first || v > m) { m = v; first = 0; }
             }
-          put_bits(word, (uint64_t)ch * d->out_bits, d->out_bits, m);
+          put_bits(word, (uint64_t)ch * d->out_bits, d->out_bits, (uint32_t)((uint64_t)m & out_mask));
         }
       }
     free(P);
@@ -280,6 +316,82 @@ int fo_layer_run(const fcb_layer_desc* d, const void* in_words, const void* weig
   free(Wq);
   free(TH);
   return err;
+}
+
+/* Channel-wise units.  The sliding window is ConvolutionInputGenerator[_NonSquare]_dws (slidingwindow.h:761-868, 1377-1488): per output
+ * pixel, per channel chunk, the taps in (ky, kx) order -- so tap k = ky*Kx + kx of channel ch multiplies weight index nf*K2 + k of
+ * lane pe (ch = nf*PE + pe) in Vector_Vector_Activate_Batch (vvau.hpp:106-134), or enters function.pool() in Pool_batch
+ * (maxpool.h:548-560).  FMPadding_nonsquare zeros in front when padded. */
+static int fo_chanwise_run(const fcb_layer_desc* d, const fo_sizes* s, const void* in_words, const void* weights, const void* thresholds,
+                           const void* bias, void* out_words, uint32_t numReps) {
+  const int pool = d->kind == FCB_KIND_POOL;
+  if (!in_words || !out_words || (!pool && !weights)) return -1;
+  if (!pool && d->act_kind == FCB_ACT_THRESHOLDS && !thresholds) return -1;
+  if (!pool && d->act_kind == FCB_ACT_BIAS_RELU && !bias) return -1;
+  const uint32_t C = d->ifm_ch, KX = d->kernel_x, KY = d->kernel_y, K2 = KX * KY, OX = d->ofm_x, OY = d->ofm_y, PE = d->pe;
+  uint32_t pl, pr, pu, pd;
+  pad_split(d, &pl, &pr, &pu, &pd);
+  const uint64_t out_mask = d->out_bits >= 32 ? 0xffffffffull : ((1ull << d->out_bits) - 1ull);
+  const size_t tcb = fo_word_bytes(d->acc_bits);
+  for (uint32_t n = 0; n < numReps; n++) {
+    const uint8_t* img = (const uint8_t*)in_words + (size_t)n * s->in_bytes_per_image;
+    uint8_t* oimg = (uint8_t*)out_words + (size_t)n * s->out_bytes_per_image;
+    memset(oimg, 0, s->out_bytes_per_image);
+    for (uint32_t oy = 0; oy < OY; oy++)
+      for (uint32_t ox = 0; ox < OX; ox++) {
+        uint8_t* oword = oimg + ((size_t)oy * OX + ox) * s->out_word_bytes;
+        for (uint32_t ch = 0; ch < C; ch++) {
+          const uint32_t nf = ch / PE, pe = ch % PE;
+          int64_t acc;
+          if (!pool) acc = 0;                                            /* activation.init: 0 for PassThrough / Thresholds */
+          else if (d->weight_kind == FCB_POOLFN_MAX)                     /* pool.hpp:98-102: type minimum */
+            acc = d->acc_signed ? -((int64_t)1 << (d->acc_bits - 1)) : 0;
+          else acc = 0;                                                  /* pool.hpp:66-69 */
+          for (uint32_t ky = 0; ky < KY; ky++)
+            for (uint32_t kx = 0; kx < KX; kx++) {
+              const int64_t y = (int64_t)oy * d->stride_y + ky - pu, x = (int64_t)ox * d->stride_x + kx - pl;
+              int64_t a = 0;                                             /* FMPadding zero */
+              if (y >= 0 && y < (int64_t)d->ifm_y && x >= 0 && x < (int64_t)d->ifm_x) {
+                uint32_t raw = get_bits(img + ((size_t)y * d->ifm_x + x) * s->in_word_bytes, (uint64_t)ch * d->in_bits, d->in_bits);
+                a = d->in_signed ? sext(raw, d->in_bits) : (int64_t)raw;
+              }
+              if (!pool) {
+                const uint8_t* ww = (const uint8_t*)weights + ((size_t)pe * s->nf * K2 + (size_t)nf * K2 + ky * KX + kx) * s->weight_word_bytes;
+                const int64_t w = sext(get_bits(ww, 0, d->w_bits), d->w_bits);
+                acc = wrap_ta(acc + w * a, d->acc_bits, d->acc_signed);  /* vvau.hpp:131 */
+              } else {
+                const int64_t v = wrap_ta(a, d->acc_bits, d->acc_signed); /* the slice converts to the function's type */
+                if (d->weight_kind == FCB_POOLFN_MAX) acc = v > acc ? v : acc;         /* pool.hpp:109-112 */
+                else acc = wrap_ta(acc + v, d->acc_bits, d->acc_signed);               /* :141-144, :175-178, :211-214 */
+              }
+            }
+          uint64_t r;
+          if (pool) {
+            int64_t o = acc;
+            if (d->weight_kind == FCB_POOLFN_AVG) o = d->act_val ? acc / (int64_t)d->act_val : 0;  /* accu / size, C++ truncation (:151-154) */
+            else if (d->weight_kind == FCB_POOLFN_QUANTAVG) o = acc >> d->act_val;                  /* TO(accu >> size) (:221-224) */
+            r = (uint64_t)o & out_mask;
+          } else if (d->act_kind == FCB_ACT_PASSTHROUGH) {
+            r = (uint64_t)acc & out_mask;
+          } else if (d->act_kind == FCB_ACT_BIAS_RELU) {
+            int64_t b = (int8_t)((const uint8_t*)bias)[ch];
+            r = ((uint64_t)acc + (uint64_t)b) & out_mask;
+            if ((r >> (d->out_bits - 1)) & 1ull) r = 0;
+          } else {
+            int64_t cnt = d->act_val;
+            for (uint32_t i = 0; i < d->num_th; i++) {
+              const uint8_t* p = (const uint8_t*)thresholds + (((size_t)pe * s->nf + nf) * d->num_th + i) * tcb;
+              uint64_t raw = 0;
+              for (size_t b = 0; b < tcb && b < 8; b++) raw |= (uint64_t)p[b] << (8 * b);
+              cnt += cmp_eval(d->cmp, wrap_ta((int64_t)raw, d->acc_bits, d->acc_signed), acc);
+            }
+            r = (uint64_t)cnt & out_mask;
+          }
+          put_bits(oword, (uint64_t)ch * d->out_bits, d->out_bits, (uint32_t)r);
+        }
+      }
+  }
+  return 0;
 }
 
 /* standalone pool on a packed stream (non-square restatement of maxpool.h:137-185 / :66-96) */

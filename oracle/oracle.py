@@ -69,8 +69,10 @@ def run_layer(desc, in_words, weights, thresholds=None, bias=None, num_reps: int
     s = query(desc)
     in_words = np.ascontiguousarray(in_words, dtype=np.uint8)
     assert in_words.size == s.in_bytes_per_image * num_reps, (in_words.size, s.in_bytes_per_image, num_reps)
-    weights = np.ascontiguousarray(weights, dtype=np.uint8)
+    weights = np.ascontiguousarray(weights if weights is not None else np.zeros(0, np.uint8), dtype=np.uint8)
     assert weights.size == s.weight_bytes, (weights.size, s.weight_bytes)
+    if weights.size == 0:
+        weights = np.zeros(1, np.uint8)  # (a valid pointer; Pool_batch has no parameters)
     if thresholds is not None:
         thresholds = np.ascontiguousarray(thresholds, dtype=np.uint8)
         assert thresholds.size == s.threshold_bytes
@@ -119,6 +121,8 @@ def ref_run(case: str, in_words, weights, third, out_bytes: int):
     fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.POINTER(ctypes.c_double)]
     in_words = np.ascontiguousarray(in_words, dtype=np.uint8)
     weights = np.ascontiguousarray(weights, dtype=np.uint8)
+    if weights.size == 0:
+        weights = np.zeros(1, np.uint8)
     third = np.ascontiguousarray(third, dtype=np.uint8)
     out = np.zeros(out_bytes, dtype=np.uint8)
     secs = ctypes.c_double(0.0)

@@ -50,6 +50,7 @@ static FixedPointWeights<1, ap_int<8>, 1, CONV_7_OFM_CH> bias_layer7;
 }  // namespace PARAM
 
 #include "conv_nonsquare_top.cpp"  // the reference top, unmodified (templates conv2d<>, deconv522<>)
+#include "pool.hpp"                // pool functions of Pool_batch (not pulled in by bnn-library.h)
 
 namespace {
 
@@ -246,9 +247,140 @@ int run_pool_bin(const uint8_t* in, uint8_t* out) {
   return drain_stream<C>(s_out, out, (size_t)(DIM / PD) * (DIM / PD));
 }
 
+// ---- the threshold path with FMPadding_nonsquare's own parameters (odd / asymmetric totals, PaddingStyle; streamtools.h:361-379)
+//      and optionally StreamingMaxPool_Precision<OX, PD, OFM, ActType, MINV> behind it (maxpool.h:137-185; square maps only)
+template <unsigned K, unsigned SIMD, unsigned PE, unsigned WB, unsigned C, unsigned OFM, unsigned IX, unsigned IY, unsigned PXT, unsigned PYT,
+          unsigned STYLE, unsigned INB, unsigned NTH, int TAB, unsigned TRB, int AV, unsigned PD, typename POOLT, int MINV>
+int run_thresh_pad_pool(const uint8_t* in, const uint8_t* wts, const uint8_t* thr, uint8_t* out) {
+  constexpr unsigned PX = IX + PXT, PY = IY + PYT, OX = PX - K + 1, OY = PY - K + 1;
+  constexpr unsigned MW = K * K * C, MH = OFM, SF = MW / SIMD, NF = MH / PE;
+  static FixedPointWeights<SIMD, ap_int<WB>, PE, SF * NF> w;
+  static ThresholdsActivation<NF, PE, NTH, ap_int<TAB>, ap_uint<TRB>, AV> act;
+  load_weights(w, wts);
+  load_thresholds(act, thr);
+  hls::stream<ap_uint<C * INB> > s_in("in"), s_pad("pad");
+  hls::stream<ap_uint<SIMD * INB> > s_wa("wa"), s_win("win");
+  hls::stream<ap_uint<PE * TRB> > s_mv("mv");
+  hls::stream<ap_uint<OFM * TRB> > s_act("act"), s_out("out");
+  fill_stream<C * INB>(s_in, in, (size_t)IX * IY);
+  FMPadding_nonsquare<PX, PY, PXT, PYT, C, C, ap_uint<INB>, STYLE>(s_in, s_pad);
+  StreamingDataWidthConverter_Batch<C * INB, SIMD * INB, PX * PY>(s_pad, s_wa, 1);
+  ConvolutionInputGenerator_NonSquare<K, K, C, INB, PX, PY, OX, OY, SIMD, 1, 1>(s_wa, s_win, 1, ap_resource_dflt());
+  Matrix_Vector_Activate_Batch<MW, MH, SIMD, PE, 1, Slice<ap_uint<INB> >, Slice<ap_uint<TRB> >, Identity>(
+      s_win, s_mv, w, act, OX * OY, ap_resource_dsp());
+  StreamingDataWidthConverter_Batch<PE * TRB, OFM * TRB, OX * OY * NF>(s_mv, s_act, 1);
+  if (PD <= 1) return drain_stream<OFM * TRB>(s_act, out, (size_t)OX * OY);
+  static_assert(PD <= 1 || OX == OY, "StreamingMaxPool_Precision is square-only");
+  StreamingMaxPool_Precision<OX, (PD > 1 ? PD : 1), OFM, POOLT, MINV>(s_act, s_out);
+  return drain_stream<OFM * TRB>(s_out, out, (size_t)(OX / (PD > 1 ? PD : 1)) * (OY / (PD > 1 ? PD : 1)));
+}
+
+// ---- channel-wise units behind the depth-wise sliding window: ConvolutionInputGenerator_dws (square, any stride with K % S == 0,
+//      slidingwindow.h:761-868) or ConvolutionInputGenerator_NonSquare_dws (stride 1, :1377-1488), FMPadding_nonsquare in front.
+template <unsigned K, unsigned C, unsigned PE, unsigned IX, unsigned IY, unsigned S, unsigned PAD, unsigned INB>
+void dws_window(hls::stream<ap_uint<C * INB> >& s_in, hls::stream<ap_uint<PE * INB> >& s_win) {
+  constexpr unsigned PX = IX + 2 * PAD, PY = IY + 2 * PAD, OX = (PX - K) / S + 1, OY = (PY - K) / S + 1;
+  hls::stream<ap_uint<C * INB> > s_pad("pad");
+  hls::stream<ap_uint<PE * INB> > s_wa("wa");
+  FMPadding_nonsquare<PX, PY, 2 * PAD, 2 * PAD, C, C, ap_uint<INB> >(s_in, s_pad);
+  StreamingDataWidthConverter_Batch<C * INB, PE * INB, PX * PY>(s_pad, s_wa, 1);
+  if (PX == PY) ConvolutionInputGenerator_dws<K, C, INB, PX, OX, PE, S>(s_wa, s_win, 1, ap_resource_dflt());
+  else ConvolutionInputGenerator_NonSquare_dws<K, K, C, INB, PX, PY, OX, OY, PE, 1, 1>(s_wa, s_win, 1, ap_resource_dflt());
+}
+
+// Pool_batch (maxpool.h:525-577) with a pool.hpp function object
+template <unsigned K, unsigned C, unsigned PE, unsigned IX, unsigned IY, unsigned S, unsigned PAD, unsigned INB, typename TIN, unsigned OUTB,
+          typename FN>
+int run_pool_batch(const uint8_t* in, uint8_t* out) {
+  constexpr unsigned PX = IX + 2 * PAD, PY = IY + 2 * PAD, OX = (PX - K) / S + 1, OY = (PY - K) / S + 1;
+  static_assert(PX == PY || S == 1, "the non-square depth-wise generator is used at stride 1 only");
+  hls::stream<ap_uint<C * INB> > s_in("in");
+  hls::stream<ap_uint<PE * INB> > s_win("win");
+  hls::stream<ap_uint<PE * OUTB> > s_p("p");
+  hls::stream<ap_uint<C * OUTB> > s_out("out");
+  fill_stream<C * INB>(s_in, in, (size_t)IX * IY);
+  dws_window<K, C, PE, IX, IY, S, PAD, INB>(s_in, s_win);
+  Pool_batch<C, PE, K, Slice<TIN>, Slice<ap_uint<OUTB> > >(s_win, s_p, FN(), OX * OY);
+  StreamingDataWidthConverter_Batch<PE * OUTB, C * OUTB, OX * OY * (C / PE)>(s_p, s_out, 1);
+  return drain_stream<C * OUTB>(s_out, out, (size_t)OX * OY);
+}
+
+// Vector_Vector_Activate_Batch (vvau.hpp:80-154): FixedPointWeights<1, ap_int<WB>, PE, NF*K*K>, any activation object
+template <unsigned K, unsigned C, unsigned PE, unsigned IX, unsigned IY, unsigned S, unsigned PAD, unsigned INB, unsigned WB, unsigned OUTB,
+          typename ACT>
+int run_vvau(const uint8_t* in, const uint8_t* wts, ACT& act, uint8_t* out) {
+  constexpr unsigned PX = IX + 2 * PAD, PY = IY + 2 * PAD, OX = (PX - K) / S + 1, OY = (PY - K) / S + 1, NF = C / PE;
+  static_assert(PX == PY || S == 1, "the non-square depth-wise generator is used at stride 1 only");
+  static FixedPointWeights<1, ap_int<WB>, PE, NF * K * K> w;
+  load_weights(w, wts);
+  hls::stream<ap_uint<C * INB> > s_in("in");
+  hls::stream<ap_uint<PE * INB> > s_win("win");
+  hls::stream<ap_uint<PE * OUTB> > s_p("p");
+  hls::stream<ap_uint<C * OUTB> > s_out("out");
+  fill_stream<C * INB>(s_in, in, (size_t)IX * IY);
+  dws_window<K, C, PE, IX, IY, S, PAD, INB>(s_in, s_win);
+  Vector_Vector_Activate_Batch<C, K * K, PE, PE, 1, Slice<ap_uint<INB> >, Slice<ap_uint<OUTB> >, Identity>(s_win, s_p, w, act, OX * OY,
+                                                                                                          ap_resource_dsp());
+  StreamingDataWidthConverter_Batch<PE * OUTB, C * OUTB, OX * OY * NF>(s_p, s_out, 1);
+  return drain_stream<C * OUTB>(s_out, out, (size_t)OX * OY);
+}
+
 }  // namespace
 
 #define REF_API extern "C" __attribute__((visibility("default")))
+
+// padding / pool / lane-width forms of the threshold path: ref_<name>(in, weights, thresholds, out, secs)
+//   K SIMD PE WB  C OFM IX IY  PadX PadY Style INB NTH TAB TRB AV  PoolDim ActType MinValue
+REF_API int ref_px_odd2(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // 3 left/2... : style 2 puts the odd zero left / up
+  return run_thresh_pad_pool<3, 4, 2, 4, 8, 8, 10, 6, 3, 1, 2, 8, 15, 24, 4, 0, 1, ap_uint<4>, 0>(in, w, t, out);
+}
+REF_API int ref_px_odd1(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // other styles: the odd zero goes right / down
+  return run_thresh_pad_pool<3, 4, 2, 4, 8, 8, 10, 6, 3, 1, 1, 8, 15, 24, 4, 0, 1, ap_uint<4>, 0>(in, w, t, out);
+}
+REF_API int ref_pk3_signed(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // 12x12 map, PoolDim 3, ap_int<4> compare from -8
+  return run_thresh_pad_pool<3, 4, 2, 4, 8, 8, 12, 12, 2, 2, 2, 8, 15, 24, 4, 0, 3, ap_int<4>, -8>(in, w, t, out);
+}
+REF_API int ref_pk2_min5(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // PoolDim 2, maxima start from 5
+  return run_thresh_pad_pool<3, 4, 2, 4, 8, 8, 12, 12, 2, 2, 2, 8, 15, 24, 4, 0, 2, ap_uint<4>, 5>(in, w, t, out);
+}
+REF_API int ref_lw3(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // ap_uint<3> activations, ap_int<3> weights, ap_uint<3> outputs
+  return run_thresh_pad_pool<3, 4, 2, 3, 8, 8, 10, 6, 2, 2, 2, 3, 7, 12, 3, 0, 1, ap_uint<3>, 0>(in, w, t, out);
+}
+REF_API int ref_lw5x12(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // ap_uint<5> in, ap_int<5> weights, 12 channels of ap_uint<6> out
+  return run_thresh_pad_pool<3, 3, 4, 5, 6, 12, 9, 7, 0, 0, 2, 5, 40, 16, 6, 0, 1, ap_uint<6>, 0>(in, w, t, out);
+}
+
+// Pool_batch cases: ref_<name>(in, unused, unused, out, secs)
+//                         K  C  PE IX  IY  S PAD INB  TSrcI lane     OUTB  function
+REF_API int ref_pl_max_a(const uint8_t* in, const uint8_t*, const uint8_t*, uint8_t* out, double*) {
+  return run_pool_batch<2, 8, 4, 12, 12, 2, 0, 8, ap_uint<8>, 8, MaxPoolFunction<ap_uint<8>, 2> >(in, out);
+}
+REF_API int ref_pl_max_s(const uint8_t* in, const uint8_t*, const uint8_t*, uint8_t* out, double*) {
+  return run_pool_batch<3, 4, 2, 10, 6, 1, 1, 8, ap_int<8>, 8, MaxPoolFunction<ap_int<8>, 3> >(in, out);
+}
+REF_API int ref_pl_avg(const uint8_t* in, const uint8_t*, const uint8_t*, uint8_t* out, double*) {
+  return run_pool_batch<2, 8, 8, 8, 8, 2, 0, 8, ap_uint<8>, 8, AvgPoolFunction<ap_uint<10>, ap_uint<8>, 4> >(in, out);
+}
+REF_API int ref_pl_qavg(const uint8_t* in, const uint8_t*, const uint8_t*, uint8_t* out, double*) {
+  return run_pool_batch<4, 4, 4, 16, 16, 4, 0, 8, ap_int<8>, 8, QuantAvgPoolFunction<ap_int<12>, ap_int<8>, 4> >(in, out);
+}
+REF_API int ref_pl_acc(const uint8_t* in, const uint8_t*, const uint8_t*, uint8_t* out, double*) {
+  return run_pool_batch<3, 6, 3, 9, 7, 1, 0, 4, ap_uint<4>, 8, AccPoolFunction<ap_uint<8>, 9> >(in, out);
+}
+// depth-wise convolution cases: ref_<name>(in, weights, thresholds-or-unused, out, secs)
+REF_API int ref_dw_a(const uint8_t* in, const uint8_t* w, const uint8_t*, uint8_t* out, double*) {
+  PassThroughActivation<ap_int<16> > act;
+  return run_vvau<3, 8, 4, 10, 6, 1, 1, 8, 4, 16>(in, w, act, out);
+}
+REF_API int ref_dw_b(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {
+  static ThresholdsActivation<2, 8, 15, ap_int<16>, ap_uint<4>, 0> act;
+  load_thresholds(act, t);
+  return run_vvau<3, 16, 8, 12, 12, 1, 1, 8, 4, 4>(in, w, act, out);
+}
+REF_API int ref_dw_c(const uint8_t* in, const uint8_t* w, const uint8_t*, uint8_t* out, double*) {
+  PassThroughActivation<ap_int<12> > act;
+  return run_vvau<2, 4, 2, 8, 8, 2, 0, 8, 4, 12>(in, w, act, out);
+}
 
 // conv2d<> instantiations.  Name, KX,KY, SIMD,PE, WB, C,OFM, IX,IY, OX,OY, S, PAD, INB, ACTB
 #define CONV2D_CASES(X)                                                   \

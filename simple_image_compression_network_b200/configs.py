@@ -3,7 +3,7 @@ seeded synthetic parameters/benchmark tensors of SURVEY.md 8(d).  Host-side data
 from __future__ import annotations
 
 from . import pack, synth
-from .desc import ACT_BIAS_RELU, ACT_THRESHOLDS, KIND_CONV, KIND_DECONV522, W_BINARY_XNOR, LayerDesc
+from .desc import ACT_BIAS_RELU, ACT_THRESHOLDS, KIND_CONV, KIND_DECONV522, KIND_POOL, W_BINARY_XNOR, LayerDesc
 
 # (kind, ifm_ch, ifm_x("ROW"), ifm_y("COL"), ofm_ch, simd, pe) -- CONV_n_* of config_nonsquare.h; K5 S2 P2, 8-bit
 # activations, 4-bit weights everywhere; layers 0-3 are conv2d<>, 4-7 deconv522<> (conv_nonsquare_top.cpp:295-357)
@@ -31,8 +31,10 @@ def synthetic_params(d: LayerDesc, seed_shift: int = 0):
     """Seeded weights (+ bias or thresholds) for a descriptor -> dict of logical arrays and packed images."""
     import numpy as np
     k = d.k_total
+    if d.kind == KIND_POOL:  # Pool_batch has no parameters
+        return {"w": None, "weights": np.zeros(0, np.uint8), "bias": None, "thresholds": None, "b": None, "t": None}
     w = synth.weights(synth.SEED_WEIGHTS + seed_shift, d.ofm_ch, k, d.w_bits)
-    out = {"w": w, "weights": pack.pack_weights(w, d.simd, d.pe, d.w_bits), "bias": None, "thresholds": None, "b": None, "t": None}
+    out = {"w": w, "weights": pack.pack_weights(w, d.weight_simd, d.pe, d.w_bits), "bias": None, "thresholds": None, "b": None, "t": None}
     if d.act_kind == ACT_BIAS_RELU:
         b = synth.bias(synth.SEED_BIAS + seed_shift, d.ofm_ch)
         out["b"], out["bias"] = b, pack.pack_bias(b)

@@ -41,8 +41,20 @@ int derive_geom(const fcb_layer_desc* d, Geom* g) {
   if (!d->simd || !d->pe || !d->ifm_ch || !d->ofm_ch || !d->kernel_x || !d->kernel_y || !d->stride_x || !d->stride_y || !d->ifm_x || !d->ifm_y) {
     set_error("zero-sized parameter"); return FCB_ERR_INVALID_ARG;
   }
-  if (d->kind > FCB_KIND_DECONV522 || d->weight_kind > FCB_W_BINARY_PM1 || d->act_kind > FCB_ACT_THRESHOLDS || d->cmp > FCB_CMP_GREATER_EQUAL) {
+  const bool chanwise = d->kind == FCB_KIND_DWCONV || d->kind == FCB_KIND_POOL;
+  if (d->kind > FCB_KIND_POOL || d->act_kind > FCB_ACT_THRESHOLDS || d->cmp > FCB_CMP_GREATER_EQUAL ||
+      d->weight_kind > (d->kind == FCB_KIND_POOL ? (uint32_t)FCB_POOLFN_QUANTAVG : (uint32_t)FCB_W_BINARY_PM1)) {
     set_error("bad enum value"); return FCB_ERR_INVALID_ARG;
+  }
+  if (chanwise) {
+    // Vector_Vector_Activate_Batch / Pool_batch work channel by channel: NF = Channels / PE, and the depth-wise generator's SIMD is PE
+    if (d->ofm_ch != d->ifm_ch) { set_error("channel-wise unit: ofm_ch %u != ifm_ch %u", d->ofm_ch, d->ifm_ch); return FCB_ERR_SHAPE; }
+    if (d->simd != d->pe) { set_error("channel-wise unit: the sliding window's SIMD (%u) must equal PE (%u)", d->simd, d->pe); return FCB_ERR_SHAPE; }
+    if (d->pool >= 2) { set_error("channel-wise unit: no fused max pool (chain a FCB_KIND_POOL layer)"); return FCB_ERR_UNSUPPORTED; }
+    if (d->kind == FCB_KIND_POOL && d->act_kind != FCB_ACT_PASSTHROUGH) { set_error("FCB_KIND_POOL takes FCB_ACT_PASSTHROUGH"); return FCB_ERR_INVALID_ARG; }
+    if (d->kind == FCB_KIND_DWCONV && d->weight_kind != FCB_W_FIXED) { set_error("depth-wise convolution takes FixedPointWeights"); return FCB_ERR_UNSUPPORTED; }
+    if (d->kind == FCB_KIND_POOL && d->weight_kind == FCB_POOLFN_QUANTAVG && (d->act_val < 0 || d->act_val > 31)) { set_error("QuantAvgPoolFunction shift out of range"); return FCB_ERR_SHAPE; }
+    if (d->kind == FCB_KIND_POOL && d->weight_kind == FCB_POOLFN_AVG && d->act_val <= 0) { set_error("AvgPoolFunction needs size > 0"); return FCB_ERR_SHAPE; }
   }
   if (d->ifm_ch % d->simd) { set_error("IFM_CH %% SIMD != 0 (%u %% %u)", d->ifm_ch, d->simd); return FCB_ERR_SHAPE; }
   if (d->ofm_ch % d->pe) { set_error("OFM_CH %% PE != 0 (%u %% %u)", d->ofm_ch, d->pe); return FCB_ERR_SHAPE; }
@@ -64,21 +76,21 @@ int derive_geom(const fcb_layer_desc* d, Geom* g) {
     oy = (d->ifm_y + pu + pd - d->kernel_y) / d->stride_y + 1;
   }
   if (ox != d->ofm_x || oy != d->ofm_y) { set_error("ofm %ux%u does not match geometry %ux%u", d->ofm_x, d->ofm_y, ox, oy); return FCB_ERR_SHAPE; }
-  if (d->weight_kind == FCB_W_BINARY_XNOR && (d->w_bits != 1 || d->in_bits != 1)) { set_error("xnor needs 1-bit weights and activations"); return FCB_ERR_SHAPE; }
-  if (d->weight_kind == FCB_W_BINARY_PM1 && d->w_bits != 1) { set_error("binary weights are 1 bit"); return FCB_ERR_SHAPE; }
+  if (d->kind != FCB_KIND_POOL && d->weight_kind == FCB_W_BINARY_XNOR && (d->w_bits != 1 || d->in_bits != 1)) { set_error("xnor needs 1-bit weights and activations"); return FCB_ERR_SHAPE; }
+  if (d->kind != FCB_KIND_POOL && d->weight_kind == FCB_W_BINARY_PM1 && d->w_bits != 1) { set_error("binary weights are 1 bit"); return FCB_ERR_SHAPE; }
   const uint32_t pk = d->pool >= 2 ? d->pool : 1;
   if (ox % pk || oy % pk) { set_error("OFM %% PoolDim != 0"); return FCB_ERR_SHAPE; }
   if (d->act_kind == FCB_ACT_THRESHOLDS && d->num_th == 0) { set_error("thresholds activation with NumTH == 0"); return FCB_ERR_SHAPE; }
   // ---- what this implementation supports (a subset of what the templates can express)
-  auto pow2 = [](uint32_t v) { return v && !(v & (v - 1)); };
-  if (!pow2(d->in_bits) || d->in_bits > 16) { set_error("in_bits %u unsupported (1,2,4,8,16)", d->in_bits); return FCB_ERR_UNSUPPORTED; }
-  if (!pow2(d->out_bits) || d->out_bits > 32) { set_error("out_bits %u unsupported (1,2,4,8,16,32)", d->out_bits); return FCB_ERR_UNSUPPORTED; }
-  if (d->w_bits < 1 || d->w_bits > 16) { set_error("w_bits %u unsupported (1..16)", d->w_bits); return FCB_ERR_UNSUPPORTED; }
+  // lane widths: any ap_uint<N> / ap_int<N> the templates accept (interpret.hpp:191-217) up to 16-bit inputs and 32-bit outputs
+  if (d->in_bits < 1 || d->in_bits > 16) { set_error("in_bits %u unsupported (1..16)", d->in_bits); return FCB_ERR_UNSUPPORTED; }
+  if (d->out_bits < 1 || d->out_bits > 32) { set_error("out_bits %u unsupported (1..32)", d->out_bits); return FCB_ERR_UNSUPPORTED; }
+  if (d->kind != FCB_KIND_POOL && (d->w_bits < 1 || d->w_bits > 16)) { set_error("w_bits %u unsupported (1..16)", d->w_bits); return FCB_ERR_UNSUPPORTED; }
   if (d->in_bits == 16 && !d->in_signed) { /* lanes are staged as int32: fine */ }
   if (d->acc_bits < 1 || d->acc_bits > 32 || (d->acc_bits == 32 && !d->acc_signed && d->act_kind == FCB_ACT_THRESHOLDS)) {
     set_error("acc_bits %u unsupported (1..32)", d->acc_bits); return FCB_ERR_UNSUPPORTED;
   }
-  if (!(pk == 1 || pk == 2 || pk == 4)) { set_error("pool %u unsupported (2 or 4)", d->pool); return FCB_ERR_UNSUPPORTED; }
+  if (pk > 16) { set_error("pool %u unsupported (PoolDim <= 16)", d->pool); return FCB_ERR_UNSUPPORTED; }
   if (d->act_kind == FCB_ACT_BIAS_RELU && d->out_bits < 2) { set_error("bias+ReLU needs out_bits >= 2"); return FCB_ERR_UNSUPPORTED; }
 
   g->kind = d->kind; g->C = d->ifm_ch; g->OFM = d->ofm_ch; g->KX = d->kernel_x; g->KY = d->kernel_y;
@@ -96,6 +108,11 @@ int derive_geom(const fcb_layer_desc* d, Geom* g) {
   g->out_img_bytes = g->out_word_bytes * g->out_x * g->out_y;
   g->w_word_bytes = word_bytes(g->simd * g->w_bits);
   g->weight_bytes = g->w_word_bytes * g->pe * (size_t)g->SF * g->NF;
+  if (chanwise) {  // Kernel_2 inputs per output lane; FixedPointWeights<1, WT, PE, NF*K2> (vvau.hpp:100-134) or no weights at all (Pool_batch)
+    g->K = g->KX * g->KY; g->SF = g->K;
+    g->w_word_bytes = d->kind == FCB_KIND_POOL ? 0 : word_bytes(g->w_bits);
+    g->weight_bytes = g->w_word_bytes * g->pe * (size_t)g->SF * g->NF;
+  }
   g->threshold_bytes = g->act_kind == FCB_ACT_THRESHOLDS ? word_bytes(g->acc_bits) * g->pe * (size_t)g->NF * g->num_th : 0;
   g->bias_bytes = g->act_kind == FCB_ACT_BIAS_RELU ? g->OFM : 0;
   return FCB_OK;
@@ -142,7 +159,12 @@ size_t align_chunk(size_t chunk, size_t in_img, size_t out_img) {
 }  // namespace
 
 struct fcb_layer {
-  Geom g;
+  Geom g;   // the layer as described (public sizes)
+  Geom gi;  // what the engine computes: == g, or g without its max pool when the pool runs as a separate pass (post_pool)
+  bool post_pool = false;
+  ChanParams pool_cw{};                       // the pool pass: StreamingMaxPool_Precision as a channel-wise max from min_value
+  void* d_unpooled[2] = {nullptr, nullptr};   // the engine's un-pooled output, one buffer per staging slot
+  size_t unpooled_imgs = 0;
   fcb_layer_desc desc{};  // as given to fcb_layer_create (fcb_layer_set_params rebuilds from it)
   int device = 0;
   int engine = ENG_IMAD;
@@ -154,6 +176,7 @@ struct fcb_layer {
   int32_t* d_thr_lo = nullptr;  // [2][OFMpad]: lo, then sh
   EpiParams epi{};
   DirectParams dp{};
+  ChanParams cw{};
   size_t smem = 0;
   UmmaPlan* umma = nullptr;
   // thin-input layers (Kx*Ky*C <= 128): im2col rows in a scratch buffer, then a 1x1 layer on the tensor-core engine
@@ -190,6 +213,7 @@ struct fcb_net {
 
 static int layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, cudaStream_t st, int slot);
 static int lowered_reserve(fcb_layer* L);
+static int unpooled_reserve(fcb_layer* L);
 
 extern "C" {
 
@@ -225,7 +249,7 @@ void fcb_layer_destroy(fcb_layer* L) {
   DeviceScope ds(L->device);
   if (L->umma) umma_plan_destroy(L->umma);
   cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_thr_cm); cudaFree(L->d_thr_lut); cudaFree(L->d_thr_lo);
-  cudaFree(L->d_scratch[0]); cudaFree(L->d_scratch[1]);
+  cudaFree(L->d_scratch[0]); cudaFree(L->d_scratch[1]); cudaFree(L->d_unpooled[0]); cudaFree(L->d_unpooled[1]);
   for (int i = 0; i < 2; i++) {
     cudaFree(L->s_in[i]); cudaFree(L->s_out[i]);
     if (L->s_stream[i]) cudaStreamDestroy(L->s_stream[i]);
@@ -305,7 +329,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   Geom g;
   int rc = derive_geom(desc, &g);
   if (rc) return rc;
-  if (!weights) { set_error("weights is NULL"); return FCB_ERR_INVALID_ARG; }
+  if (!weights && g.kind != FCB_KIND_POOL) { set_error("weights is NULL"); return FCB_ERR_INVALID_ARG; }
   if (g.act_kind == FCB_ACT_THRESHOLDS && !thresholds) { set_error("thresholds is NULL"); return FCB_ERR_INVALID_ARG; }
   if (g.act_kind == FCB_ACT_BIAS_RELU && !bias) { set_error("bias is NULL"); return FCB_ERR_INVALID_ARG; }
   int ndev = 0;
@@ -330,10 +354,35 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   L->g = g;
   L->desc = *desc;
   L->device = device;
+  // StreamingMaxPool[_Precision] (maxpool.h:66-185) is fused into the epilogues for the common form: 2x2 (tensor engine) / 2x2 and 4x4
+  // (direct engines), unsigned lanes, maxima starting from 0, behind a conv2d.  Every other form the template expresses -- other
+  // PoolDim, signed ActType, a min_value that does not wrap to 0, a pool behind deconv522 -- runs the layer un-pooled into a scratch
+  // stream and then the pool as its own streaming pass (fcb_chanwise.cu).
+  {
+    const uint32_t omask = g.out_bits >= 32 ? 0xffffffffu : ((1u << g.out_bits) - 1u);
+    const bool min_is_zero = g.pool_signed ? false : (((uint32_t)g.pool_min) & omask) == 0;
+    if (g.pool >= 2 && (g.kind == FCB_KIND_DECONV522 || !(g.pool == 2 || g.pool == 4) || g.pool_signed || !min_is_zero)) {
+      L->post_pool = true;
+      ChanParams& c = L->pool_cw;
+      c.C = g.OFM; c.Cpad = (g.OFM + 31) / 32 * 32; c.KX = c.KY = g.pool; c.SX = c.SY = g.pool; c.IX = g.OX; c.IY = g.OY; c.OX = g.out_x; c.OY = g.out_y;
+      c.pad_l = c.pad_u = 0; c.in_bits = g.out_bits; c.in_signed = g.pool_signed; c.in_word_bytes = (int)g.out_word_bytes;
+      c.out_word_bytes = (int)g.out_word_bytes; c.out_bits = g.out_bits; c.acc_bits = g.out_bits; c.acc_signed = g.pool_signed;
+      c.mode = CW_POOL_MAX; c.has_init = 1; c.init = wrap_host(g.pool_min, g.out_bits, g.pool_signed);
+      c.in_img_bytes = g.out_word_bytes * (size_t)g.OX * g.OY; c.out_img_bytes = g.out_img_bytes;
+      g.pool = 1; g.out_x = g.OX; g.out_y = g.OY; g.out_img_bytes = c.in_img_bytes;  // the engine below sees the layer without its pool
+    }
+  }
+  L->gi = g;
 
   // ---- weights: m_weights[pe][nf*SF+sf] lanes -> W[ch][k] (mvau.hpp:117,148; weights.hpp:134-140)
   std::vector<int32_t> W((size_t)g.OFM * g.K);
-  {
+  if (g.kind == FCB_KIND_DWCONV) {  // one lane per word: W[ch = nf*PE + pe][k = ky*Kx + kx] = m_weights[pe][nf*K2 + k] (vvau.hpp:106-134)
+    const uint8_t* wb = (const uint8_t*)weights;
+    for (int pe = 0; pe < g.pe; pe++)
+      for (int t = 0; t < g.NF * g.K; t++)
+        W[(size_t)((t / g.K) * g.pe + pe) * g.K + t % g.K] =
+            wrap_host(get_bits(wb + ((size_t)pe * g.NF * g.K + t) * g.w_word_bytes, 0, g.w_bits), g.w_bits, 1);
+  } else if (g.kind != FCB_KIND_POOL) {
     const uint8_t* wb = (const uint8_t*)weights;
     for (int pe = 0; pe < g.pe; pe++)
       for (int nf = 0; nf < g.NF; nf++)
@@ -359,7 +408,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   }
   // The TA wrap (mvau.hpp:112: every += wraps to TA) is the identity when no partial sum can leave TA's range: with
   // |acc| <= max_ch sum_k |w| * max|a| < 2^(acc_bits-1) the device epilogue may treat the accumulator as a plain int32.
-  if (g.acc_signed && g.acc_bits < 32 && g.weight_kind == FCB_W_FIXED) {
+  if (g.acc_signed && g.acc_bits < 32 && g.weight_kind == FCB_W_FIXED && g.kind != FCB_KIND_POOL) {
     const uint64_t amax = g.in_signed ? (1ull << (g.in_bits - 1)) : ((1ull << g.in_bits) - 1);
     uint64_t worst = 0;
     for (int ch = 0; ch < g.OFM; ch++) {
@@ -388,6 +437,31 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
       }
     rc = upload_thresholds(L, thr_rows);
     if (rc) return rc;
+  }
+
+  if (g.kind == FCB_KIND_DWCONV || g.kind == FCB_KIND_POOL) {
+    // channel-wise units (fcb_chanwise.cu): streaming kernels, one engine
+    if (g.engine_hint == FCB_ENGINE_XNOR_POPC || g.engine_hint == FCB_ENGINE_TENSOR) { set_error("channel-wise units run on the CUDA cores only"); return FCB_ERR_UNSUPPORTED; }
+    ChanParams& c = L->cw;
+    c.C = g.C; c.Cpad = (g.C + 31) / 32 * 32; c.KX = g.KX; c.KY = g.KY; c.IX = g.IX; c.IY = g.IY; c.OX = g.OX; c.OY = g.OY; c.SX = g.SX; c.SY = g.SY;
+    c.pad_l = g.pad_l; c.pad_u = g.pad_u; c.in_bits = g.in_bits; c.in_signed = g.in_signed; c.in_word_bytes = (int)g.in_word_bytes;
+    c.out_word_bytes = (int)g.out_word_bytes; c.out_bits = g.out_bits; c.acc_bits = g.acc_bits; c.acc_signed = g.acc_signed;
+    c.in_img_bytes = g.in_img_bytes; c.out_img_bytes = g.out_img_bytes; c.size = g.act_val;
+    c.mode = g.kind == FCB_KIND_DWCONV ? CW_DWCONV : CW_POOL_MAX + g.weight_kind;
+    if (g.kind == FCB_KIND_DWCONV) {
+      std::vector<int16_t> Wt((size_t)g.K * c.Cpad, 0);
+      for (int ch = 0; ch < g.C; ch++)
+        for (int k = 0; k < g.K; k++) Wt[(size_t)k * c.Cpad + ch] = (int16_t)W[(size_t)ch * g.K + k];
+      FCB_CUDA_OK(cudaMalloc(&L->d_wt, Wt.size() * 2));
+      FCB_CUDA_OK(cudaMemcpy(L->d_wt, Wt.data(), Wt.size() * 2, cudaMemcpyHostToDevice));
+      c.wt = (const int16_t*)L->d_wt;
+    }
+    c.epi = L->epi;
+    L->engine = ENG_CHANWISE;
+    if (L->post_pool && (rc = unpooled_reserve(L))) return rc;
+    guard.armed = false;
+    *out = L;
+    return FCB_OK;
   }
 
   // ---- engine selection (fcb_engine_hint: the reference's resource argument R, mvau.hpp:87-98 -- never changes the result)
@@ -517,7 +591,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     DirectParams& p = L->dp;
     const int deconv = g.kind == FCB_KIND_DECONV522;
     p.C = g.C; p.OFM = g.OFM; p.OFMp = (g.OFM + 63) / 64 * 64; p.KX = g.KX; p.KY = g.KY; p.IX = g.IX; p.IY = g.IY;
-    p.OX = g.OX; p.OY = g.OY; p.SXe = deconv ? 1 : g.SX; p.SYe = deconv ? 1 : g.SY; p.PAD = g.PAD; p.deconv = deconv;
+    p.OX = g.OX; p.OY = g.OY; p.SXe = deconv ? 1 : g.SX; p.SYe = deconv ? 1 : g.SY; p.PAD = g.pad_l; p.PADY = g.pad_u; p.deconv = deconv;
     p.in_bits = g.in_bits; p.in_signed = g.in_signed; p.in_word_bytes = (int)g.in_word_bytes; p.out_word_bytes = (int)g.out_word_bytes;
     p.out_x = g.out_x; p.out_y = g.out_y; p.tiles_x = (g.OX + 15) / 16; p.tiles_y = (g.OY + 7) / 8;
     p.patch_w = 15 * p.SXe + g.KX; p.patch_h = 7 * p.SYe + g.KY; p.mul_kind = g.weight_kind;
@@ -548,6 +622,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     p.wt = L->d_wt;
   }
   if (L->lowered && (rc = lowered_reserve(L))) return rc;  // the lowering scratch is allocated here, never inside a run call
+  if (L->post_pool && (rc = unpooled_reserve(L))) return rc;
   guard.armed = false;
   *out = L;
   return FCB_OK;
@@ -564,8 +639,10 @@ int fcb_layer_set_params(fcb_layer* L, const void* weights, const void* threshol
   std::swap(L->d_wt, fresh->d_wt); std::swap(L->d_bias, fresh->d_bias);
   std::swap(L->d_thr, fresh->d_thr); std::swap(L->d_thr_cm, fresh->d_thr_cm);
   std::swap(L->d_thr_lut, fresh->d_thr_lut); std::swap(L->d_thr_lo, fresh->d_thr_lo);
-  std::swap(L->epi, fresh->epi); std::swap(L->dp, fresh->dp); std::swap(L->smem, fresh->smem);
+  std::swap(L->epi, fresh->epi); std::swap(L->dp, fresh->dp); std::swap(L->cw, fresh->cw); std::swap(L->smem, fresh->smem);
   std::swap(L->umma, fresh->umma);
+  std::swap(L->d_unpooled[0], fresh->d_unpooled[0]); std::swap(L->d_unpooled[1], fresh->d_unpooled[1]); std::swap(L->unpooled_imgs, fresh->unpooled_imgs);
+  std::swap(L->pool_cw, fresh->pool_cw); std::swap(L->post_pool, fresh->post_pool); std::swap(L->gi, fresh->gi);
   std::swap(L->lowered, fresh->lowered); std::swap(L->lower_bits, fresh->lower_bits); std::swap(L->ip, fresh->ip);
   std::swap(L->d_scratch[0], fresh->d_scratch[0]); std::swap(L->d_scratch[1], fresh->d_scratch[1]); std::swap(L->scratch_imgs, fresh->scratch_imgs); std::swap(L->scratch_img_bytes, fresh->scratch_img_bytes);
   memcpy(L->plan_desc, fresh->plan_desc, sizeof(L->plan_desc));
@@ -596,11 +673,12 @@ int fcb_layer_set_param_stream(fcb_layer* L, const void* param_words, const void
 
 const char* fcb_layer_engine(const fcb_layer* L) {
   if (!L) return "";
-  return L->engine == ENG_UMMA ? "umma_i8" : L->engine == ENG_XNOR ? "xnor_popc" : "imad";
+  return L->engine == ENG_UMMA ? "umma_i8" : L->engine == ENG_XNOR ? "xnor_popc" : L->engine == ENG_CHANWISE ? "chanwise" : "imad";
 }
 const char* fcb_layer_plan(const fcb_layer* L) {
   if (!L) return "";
   if (L->lowered) return L->plan_desc;
+  if (L->engine == ENG_CHANWISE) return "channel-wise streaming unit: warp = output pixel, lanes walk the channels";
   return L->engine == ENG_UMMA ? umma_plan_describe(L->umma) : "direct 16x8-pixel x 64-channel CTA tiles";
 }
 uint64_t fcb_layer_launches(const fcb_layer* L) { return L ? L->launches : 0; }
@@ -611,31 +689,67 @@ uint64_t fcb_layer_launches(const fcb_layer* L) { return L ? L->launches : 0; }
 // staging slot of the host-buffer call, so the lowering kernel of chunk k+1 never overwrites rows the GEMM of chunk k still reads.
 static int lowered_reserve(fcb_layer* L) {
   size_t cap = std::max<size_t>(1, ((size_t)64 << 20) / L->scratch_img_bytes);
-  cap = align_chunk(cap, L->g.in_img_bytes, L->g.out_img_bytes);
+  cap = align_chunk(cap, L->gi.in_img_bytes, L->gi.out_img_bytes);
   for (int i = 0; i < 2; i++) FCB_CUDA_OK(cudaMalloc(&L->d_scratch[i], L->scratch_img_bytes * cap));
   L->scratch_imgs = cap;
   return FCB_OK;
 }
 
+static int unpooled_reserve(fcb_layer* L) {
+  size_t cap = std::max<size_t>(1, ((size_t)128 << 20) / L->gi.out_img_bytes);
+  cap = align_chunk(cap, L->g.in_img_bytes, L->g.out_img_bytes);
+  for (int i = 0; i < 2; i++) FCB_CUDA_OK(cudaMalloc(&L->d_unpooled[i], L->gi.out_img_bytes * cap));
+  L->unpooled_imgs = cap;
+  return FCB_OK;
+}
+
+static int engine_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, cudaStream_t st, int slot);
+
 static int layer_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, cudaStream_t st, int slot) {
+  if (!L->post_pool) return engine_run_device(L, d_in, d_out, numReps, st, slot);
+  for (size_t n0 = 0; n0 < numReps; n0 += L->unpooled_imgs) {
+    const uint32_t nb = (uint32_t)std::min<size_t>(L->unpooled_imgs, numReps - n0);
+    int rc = engine_run_device(L, (const uint8_t*)d_in + n0 * L->g.in_img_bytes, L->d_unpooled[slot], nb, st, slot);
+    if (rc) return rc;
+    ChanParams c = L->pool_cw;
+    c.in = (const uint8_t*)L->d_unpooled[slot];
+    c.out = (uint8_t*)d_out + n0 * L->g.out_img_bytes;
+    if (L->g.out_word_bytes * 8 != (size_t)L->g.OFM * L->g.out_bits) FCB_CUDA_OK(cudaMemsetAsync(c.out, 0, L->g.out_img_bytes * nb, st));
+    rc = launch_chanwise(c, (int)nb, st);
+    if (rc) return rc;
+    L->launches += (nb + 65534) / 65535;
+  }
+  return FCB_OK;
+}
+
+// the layer's engine on `numReps` images (geometry L->gi: the layer without a separately-run pool)
+static int engine_run_device(fcb_layer* L, const void* d_in, void* d_out, uint32_t numReps, cudaStream_t st, int slot) {
   if (L->lowered) {
     for (size_t n0 = 0; n0 < numReps; n0 += L->scratch_imgs) {
       const int nb = (int)std::min<size_t>(L->scratch_imgs, numReps - n0);
       Im2colParams ip = L->ip;
-      ip.in = (const uint8_t*)d_in + n0 * L->g.in_img_bytes;
+      ip.in = (const uint8_t*)d_in + n0 * L->gi.in_img_bytes;
       ip.out = (uint8_t*)L->d_scratch[slot];
       int rc = L->lower_bits ? launch_expand_bits(ip, nb, st) : launch_im2col(ip, nb, st);
       if (rc) return rc;
       L->launches++;
-      rc = umma_run(L->umma, L->d_scratch[slot], (uint8_t*)d_out + n0 * L->g.out_img_bytes, nb, st, &L->launches);
+      rc = umma_run(L->umma, L->d_scratch[slot], (uint8_t*)d_out + n0 * L->gi.out_img_bytes, nb, st, &L->launches);
       if (rc) return rc;
     }
     return FCB_OK;
   }
   if (L->engine == ENG_UMMA) return umma_run(L->umma, d_in, d_out, (int)numReps, st, &L->launches);
   // containers with padding bits (e.g. ap_uint<24> in 4 bytes): writers zero them
-  if (L->g.out_word_bytes * 8 != (size_t)L->g.OFM * L->g.out_bits) {
-    FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, L->g.out_img_bytes * numReps, st));
+  if (L->gi.out_word_bytes * 8 != (size_t)L->gi.OFM * L->gi.out_bits) {
+    FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, L->gi.out_img_bytes * numReps, st));
+  }
+  if (L->engine == ENG_CHANWISE) {
+    ChanParams c = L->cw;
+    c.in = (const uint8_t*)d_in;
+    c.out = (uint8_t*)d_out;
+    int rc = launch_chanwise(c, (int)numReps, st);
+    if (rc == FCB_OK) L->launches += (numReps + 65534) / 65535;
+    return rc;
   }
   DirectParams p = L->dp;
   p.in = (const uint8_t*)d_in;

@@ -20,20 +20,6 @@ namespace fcb {
 constexpr int TX = 16, TY = 8, PXB = 4;  // tile and per-warp pixel block
 constexpr int CH_PER_CTA = 64;
 
-__device__ __forceinline__ int32_t load_lane(const uint8_t* word, int c, int bits, int sgn) {
-  // bits in {1,2,4,8,16}: a lane never straddles a byte pair boundary beyond 16 bits
-  const size_t bit = (size_t)c * bits;
-  uint32_t v;
-  if (bits == 8) v = word[bit >> 3];
-  else if (bits == 16) v = (uint32_t)word[bit >> 3] | ((uint32_t)word[(bit >> 3) + 1] << 8);
-  else v = (word[bit >> 3] >> (bit & 7)) & ((1u << bits) - 1u);
-  if (sgn) {
-    const uint32_t m = 1u << (bits - 1);
-    return (int32_t)((v ^ m) - m);
-  }
-  return (int32_t)v;
-}
-
 // Maps a coordinate of the virtual padded frame to the input image; false = structural zero.
 __device__ __forceinline__ bool map_coord(int v, int pad, int deconv, int extent, int* src) {
   if (!deconv) {
@@ -74,14 +60,14 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const DirectParams p) 
       const int px = pix % p.patch_w, py = pix / p.patch_w;
       int sx, sy;
       const bool okx = map_coord(vx0 + px, p.PAD, p.deconv, p.IX, &sx);
-      const bool oky = map_coord(vy0 + py, p.PAD, p.deconv, p.IY, &sy);
+      const bool oky = map_coord(vy0 + py, p.PADY, p.deconv, p.IY, &sy);  // (FMPadding_nonsquare may pad left / up differently)
       if (ENGINE == ENG_XNOR) {
         uint32_t v = 0;
         if (okx && oky) v = reinterpret_cast<const uint32_t*>(in + ((size_t)sy * p.IX + sx) * p.in_word_bytes)[c0 + c];
         reinterpret_cast<uint32_t*>(smem_raw)[idx] = v;
       } else {
         int32_t v = 0;
-        if (okx && oky) v = load_lane(in + ((size_t)sy * p.IX + sx) * p.in_word_bytes, c0 + c, p.in_bits, p.in_signed);
+        if (okx && oky) v = load_lane_any(in + ((size_t)sy * p.IX + sx) * p.in_word_bytes, c0 + c, p.in_bits, p.in_signed);
         reinterpret_cast<int32_t*>(smem_raw)[idx] = v;
       }
     }

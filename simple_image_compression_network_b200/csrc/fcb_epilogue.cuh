@@ -12,6 +12,23 @@
 
 namespace fcb {
 
+// Lane `c` of a packed stream word: bits [c*bits, (c+1)*bits), lane 0 at the LSB (interpret.hpp:191-217), any width 1..16,
+// reinterpreted as signed through the ap_int<bits> cast when `sgn` (interpret.hpp:213-217).
+__device__ __forceinline__ int32_t load_lane_any(const uint8_t* word, int c, int bits, int sgn) {
+  const size_t bit = (size_t)c * bits;
+  const uint8_t* b = word + (bit >> 3);
+  const int sh = (int)(bit & 7);
+  uint32_t v = b[0];
+  if (sh + bits > 8) v |= (uint32_t)b[1] << 8;
+  if (sh + bits > 16) v |= (uint32_t)b[2] << 16;
+  v = (v >> sh) & ((1u << bits) - 1u);
+  if (sgn) {
+    const uint32_t m = 1u << (bits - 1);
+    return (int32_t)((v ^ m) - m);
+  }
+  return (int32_t)v;
+}
+
 __device__ __forceinline__ int32_t wrap_ta(int32_t acc, int bits, int sgn) {
   if (bits >= 32) return acc;
   const uint32_t u = (uint32_t)acc << (32 - bits);
@@ -223,11 +240,31 @@ __device__ __forceinline__ void store_lane(uint8_t* word, int ch, bool valid, ui
         for (int b = 0; b < 4; b++)
           if ((vm >> (8 * b)) & 0xFFu) dst[b] = (uint8_t)(bits >> (8 * b));  // partially valid bytes keep zero pad bits
     }
-  } else {  // 2, 4 bits: 8/out_bits lanes share a byte
+  } else if (out_bits == 2 || out_bits == 4) {  // 8/out_bits lanes share a byte
     const int per = 8 / out_bits;
     uint32_t b = valid ? (v << ((lane % per) * out_bits)) : 0u;
     for (int s = 1; s < per; s <<= 1) b |= __shfl_xor_sync(0xffffffffu, b, s);
     if (valid && (lane % per) == 0) word[((size_t)ch * out_bits) >> 3] = (uint8_t)b;
+  } else {
+    // any other lane width (ap_uint<3>, <12>, ...): the warp's 32 lanes form a segment of out_bits 32-bit words that starts on a
+    // 4-byte boundary of the stream word (ch - lane is a multiple of 32); lanes may straddle words.  Word j = OR of the pieces of the
+    // lanes that touch it (one warp OR-reduction per word), stored by lane j byte by byte up to the last valid channel's bits.
+    const uint32_t pos = (uint32_t)lane * (uint32_t)out_bits, w0 = pos >> 5, sh = pos & 31u;
+    const uint32_t vv = valid ? (v & ((1u << out_bits) - 1u)) : 0u;
+    const uint32_t lo = vv << sh, hi = sh ? (vv >> (32u - sh)) : 0u;
+    uint32_t mine = 0;
+    for (int j = 0; j < out_bits; j++) {
+      const uint32_t c = (w0 == (uint32_t)j ? lo : 0u) | (w0 + 1u == (uint32_t)j ? hi : 0u);
+      const uint32_t wj = __reduce_or_sync(0xffffffffu, c);
+      if (lane == j) mine = wj;
+    }
+    const int nvalid = __popc(__ballot_sync(0xffffffffu, valid));   // valid channels are a prefix of the warp
+    const int seg_bytes = (nvalid * out_bits + 7) >> 3;
+    if (lane < out_bits) {
+      uint8_t* dst = word + ((((size_t)(ch - lane)) * out_bits) >> 3) + 4 * lane;
+      for (int b = 0; b < 4; b++)
+        if (4 * lane + b < seg_bytes) dst[b] = (uint8_t)(mine >> (8 * b));
+    }
   }
 }
 

@@ -68,14 +68,14 @@ struct EpiParams {
 };
 
 // ---- engines ----------------------------------------------------------------------
-enum Engine { ENG_IMAD = 0, ENG_XNOR = 1, ENG_UMMA = 2 };
+enum Engine { ENG_IMAD = 0, ENG_XNOR = 1, ENG_UMMA = 2, ENG_CHANWISE = 3 };
 
 struct DirectParams {  // imad / xnor_popc direct convolution
   const uint8_t* in;
   uint8_t* out;
   const void* wt;  // imad: int16 [K][OFMp]; xnor: uint32 [KW][OFMp]
   EpiParams epi;
-  int C, OFM, OFMp, KX, KY, IX, IY, OX, OY, SXe, SYe, PAD, deconv;
+  int C, OFM, OFMp, KX, KY, IX, IY, OX, OY, SXe, SYe, PAD, PADY, deconv;  // PAD / PADY: zeros left / up of the frame
   int in_bits, in_signed, in_word_bytes, out_word_bytes, out_x, out_y;
   int tiles_x, tiles_y, CC, patch_w, patch_h, mul_kind;
   unsigned long long in_img_bytes, out_img_bytes;
@@ -93,6 +93,21 @@ int umma_plan_create_dthin(const Geom& g, const std::vector<int32_t>& W /*[OFM][
 void umma_plan_destroy(UmmaPlan* p);
 const char* umma_plan_describe(const UmmaPlan* p);
 int umma_run(UmmaPlan* p, const void* d_in, void* d_out, int n_images, cudaStream_t st, uint64_t* launches);
+
+// channel-wise units: depth-wise convolution and Pool_batch (fcb_chanwise.cu)
+enum ChanMode { CW_DWCONV = 0, CW_POOL_MAX = 1, CW_POOL_AVG = 2, CW_POOL_ACC = 3, CW_POOL_QUANTAVG = 4 };
+struct ChanParams {
+  const uint8_t* in;
+  uint8_t* out;
+  const int16_t* wt;  // depth-wise weights [Kx*Ky][Cpad]
+  EpiParams epi;
+  int C, Cpad, KX, KY, IX, IY, OX, OY, SX, SY, pad_l, pad_u;
+  int in_bits, in_signed, in_word_bytes, out_word_bytes, out_bits;
+  int mode, size, acc_bits, acc_signed;
+  int has_init, init;  // CW_POOL_MAX started from `init` instead of the type's minimum (StreamingMaxPool_Precision's min_value)
+  unsigned long long in_img_bytes, out_img_bytes;
+};
+int launch_chanwise(const ChanParams& p, int n_images, cudaStream_t st);
 
 // thin-input lowering (fcb_im2col.cu)
 struct Im2colParams {

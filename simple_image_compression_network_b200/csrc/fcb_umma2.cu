@@ -148,6 +148,10 @@ struct PixMap {
     const int ox = p.deconv ? 2 * gx + px : gx, oy = p.deconv ? 2 * gy + py : gy;
     return img_off + ((size_t)(oy / pk) * p.out_x + (ox / pk)) * p.out_word_bytes;
   }
+  // the same for 2x2-pooled conv layers (no deconv phases), in 32-bit arithmetic below the image offset (an image is < 4 GB)
+  __device__ __forceinline__ size_t pooled2_off(int rr, int xo) const {
+    return img_off + (unsigned)(((unsigned)((y0 + rr) >> 1) * (unsigned)p.out_x + (unsigned)((x0 + xo) >> 1)) * (unsigned)p.out_word_bytes);
+  }
 };
 
 // Persistent-tile iterator: CTA c visits tiles c, c + ncta, ... ; (image, tile column, tile row) advance by precomputed
@@ -596,6 +600,15 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       pre_rr = i0 / p.WT;
       pre_xo = i0 - pre_rr * p.WT;
     }
+    // bucket-LUT constants of this thread's channel(s): tile-invariant, fetched once (two global loads per tile and warp otherwise)
+    int32_t lutlo_h[2] = {0, 0};
+    int lutsh_h[2] = {0, 0};
+    if (p.lut_off >= 0)
+      for (int cb = 0; cb < p.CB && cb < 2; cb++) {
+        const int ch = chbase + cb * 128 + q * 32 + lane, chs = chv_of(ch, p.OFM) ? ch : 0;
+        lutlo_h[cb] = p.epi.thr_lo[chs];
+        lutsh_h[cb] = p.epi.thr_sh[chs];
+      }
     const bool alt1 = alt && p.nphases == 1;
     const uint32_t acc_step = alt1 ? 2u : 1u;
     if (alt1) acc_it = (uint32_t)(half & 1);
@@ -936,8 +949,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const bool hybrid = p.thr_off >= 0;
           const bool use_lut = p.lut_off >= 0;
           const uint32_t lut_s = smem_u32(smem + (use_lut ? p.lut_off : 0)) + 256u * (uint32_t)(cb * 128 + q * 32 + lane);
-          const int32_t lut_lo = use_lut ? p.epi.thr_lo[chs] : 0;
-          const int lut_sh = use_lut ? p.epi.thr_sh[chs] : 0;
+          const int32_t lut_lo = lutlo_h[cb & 1];
+          const int lut_sh = lutsh_h[cb & 1];
           const int row_shift = p.CB == 2 ? 10 : 9;  // log2(CB * 128 channels * 4 bytes)
           const bool chv = ch < p.OFM;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
@@ -1055,7 +1068,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             // 2x2 max pool: rows rr, rr+1 of the tile are columns m and m + P of the same thread
             // work units = (row pair, 16-column block) = 8 pooled outputs; the two warps of a lane quarter take alternate units
             const int xblocks = (vcols + 15) >> 4, nunits = (vrows >> 1) * xblocks;
-            int urow = 2 * (half / xblocks), ublk = half % xblocks;  // unit -> (row pair, x block), advanced without divisions
+            int urow = 0, ublk = half;  // unit -> (row pair, x block), advanced without divisions (half < NHALF <= 4)
+            while (ublk >= xblocks) { ublk -= xblocks; urow += 2; }
 #pragma unroll 1
             for (int u = half; u < nunits; u += NHALF) {
               {
@@ -1107,11 +1121,24 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     activate_thrN<8>(p.epi, tbl, tstride, m8, pooled);
                   }
                   if (THRP || p.epi.out_bits == 8) {
-                    uint8_t* dst = p.out + pm.word_off(rr, xb, 2) + ch;  // x0 and xb are even: pooled pixel w sits w words further
+                    // x0 and xb are even: pooled pixel w sits w words further.  A warp store = 32 consecutive bytes of one word.
+                    uint8_t* dst = p.out + (THRP ? pm.pooled2_off(rr, xb) : pm.word_off(rr, xb, 2)) + ch;
+                    const int owb = p.out_word_bytes;
+                    if (chv && xb + 16 <= vcols) {  // whole unit (warp-uniform except the channel tail): no per-store predicates,
+                      if (owb == 128) {              // immediate offsets for the common word sizes
 #pragma unroll
-                    for (int w = 0; w < 8; w++) {
-                      if (xb + 2 * w < vcols && chv) *dst = (uint8_t)pooled[w];
-                      dst += p.out_word_bytes;
+                        for (int w = 0; w < 8; w++) dst[w * 128] = (uint8_t)pooled[w];
+                      } else if (owb == 256) {
+#pragma unroll
+                        for (int w = 0; w < 8; w++) dst[w * 256] = (uint8_t)pooled[w];
+                      } else {
+#pragma unroll
+                        for (int w = 0; w < 8; w++) dst[(unsigned)(w * owb)] = (uint8_t)pooled[w];
+                      }
+                    } else if (chv) {
+#pragma unroll
+                      for (int w = 0; w < 8; w++)
+                        if (xb + 2 * w < vcols) dst[(unsigned)(w * owb)] = (uint8_t)pooled[w];
                     }
                   } else {
 #pragma unroll

@@ -8,7 +8,11 @@ from __future__ import annotations
 import ctypes
 from dataclasses import dataclass
 
-KIND_CONV, KIND_DECONV522 = 0, 1
+# conv2d<> | deconv522<> | depth-wise conv (dws sliding window + Vector_Vector_Activate_Batch, vvau.hpp:80-154) |
+# generic pooling (dws sliding window + Pool_batch, maxpool.h:525-577)
+KIND_CONV, KIND_DECONV522, KIND_DWCONV, KIND_POOL = 0, 1, 2, 3
+# pool.hpp:94-226 function objects of Pool_batch (carried in `weight_kind` of a KIND_POOL descriptor; `act_val` = their `size`)
+POOLFN_MAX, POOLFN_AVG, POOLFN_ACC, POOLFN_QUANTAVG = 0, 1, 2, 3
 W_FIXED, W_BINARY_XNOR, W_BINARY_PM1 = 0, 1, 2
 ACT_PASSTHROUGH, ACT_BIAS_RELU, ACT_THRESHOLDS = 0, 1, 2
 CMP_LESS, CMP_GREATER, CMP_LESS_EQUAL, CMP_GREATER_EQUAL = 0, 1, 2, 3
@@ -96,7 +100,15 @@ class LayerDesc:
 
     @property
     def k_total(self) -> int:
+        """Inputs per output lane: the MVAU's MatrixW, or Kernel_2 for the channel-wise units."""
+        if self.kind in (KIND_DWCONV, KIND_POOL):
+            return self.kernel_x * self.kernel_y
         return self.kernel_x * self.kernel_y * self.ifm_ch
+
+    @property
+    def weight_simd(self) -> int:
+        """Lanes per weight word: SIMD, or 1 for Vector_Vector_Activate_Batch (vvau.hpp:128-134)."""
+        return 1 if self.kind == KIND_DWCONV else self.simd
 
     @property
     def macs_per_image(self) -> int:

@@ -30,7 +30,7 @@ class ConvLayer:
         sizes = [ctypes.c_size_t() for _ in range(5)]
         _lib.check(L.fcb_layer_query(ctypes.byref(c), *[ctypes.byref(s) for s in sizes]), L)
         self.in_bytes, self.out_bytes, self.weight_bytes, self.threshold_bytes, self.bias_bytes = [s.value for s in sizes]
-        w = np.ascontiguousarray(weights, dtype=np.uint8)
+        w = np.ascontiguousarray(weights if weights is not None else np.zeros(0, np.uint8), dtype=np.uint8)  # (Pool_batch: none)
         if w.size != self.weight_bytes:
             raise ValueError(f"weight image is {w.size} bytes, expected {self.weight_bytes}")
         t = None if thresholds is None else np.ascontiguousarray(thresholds, dtype=np.uint8)

@@ -62,8 +62,9 @@ def test_query_rejects_like_the_reference(fcb_lib):
     assert fcb_lib.fcb_layer_query(ctypes.byref(c), None, None, None, None, None) == -1
     dc = cases.CASES["dc_a"]
     assert _query(fcb_lib, dataclasses.replace(dc, kernel_x=3, kernel_y=3))[0] == -2  # deconv522 is k5 s2 p2
-    assert _query(fcb_lib, dataclasses.replace(d, in_bits=3))[0] == -3               # valid upstream, unsupported here
-    assert _query(fcb_lib, dataclasses.replace(cases.CASES["th_b"], pool=3))[0] in (-2, -3)
+    assert _query(fcb_lib, dataclasses.replace(d, in_bits=3))[0] == 0                # any ap_uint<N> lane width (interpret.hpp:191-217)
+    assert _query(fcb_lib, dataclasses.replace(d, in_bits=17))[0] == -3              # valid upstream, unsupported here
+    assert _query(fcb_lib, dataclasses.replace(cases.CASES["th_b"], pool=3))[0] == -2  # 16 x 12 map: ImgDim % PoolDim (maxpool.h:140)
 
 
 def test_no_cpu_fallback(fcb_lib):
