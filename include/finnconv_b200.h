@@ -216,6 +216,22 @@ FCB_API int fcb_shard_range(uint32_t numReps, uint32_t rank, uint32_t world, uin
 FCB_API int fcb_host_alloc(void** ptr, size_t bytes);
 FCB_API void fcb_host_free(void* ptr);
 
+/* --- residual add: AddStreams_Batch / AddStreamsLayer_Batch (streamtools.h:669-762).  Per stream word and channel
+ * Out_t sum = op1 + op2 + offset with op1 / op2 read as In1_t / In2_t (ap_int / ap_uint of in*_bits) and the sum wrapped to out_bits.
+ * Word images as everywhere: ap_uint<channels*bits> containers, n_words = NumTotal * numReps. */
+typedef struct fcb_add_desc {
+  uint32_t struct_size; /* = sizeof(fcb_add_desc) */
+  uint32_t channels;
+  uint32_t in1_bits, in1_signed, in2_bits, in2_signed; /* 1..32 bits */
+  uint32_t out_bits;                                   /* 1..32 */
+  int32_t offset;
+} fcb_add_desc;
+/* device buffers on `device`, asynchronous on `stream` */
+FCB_API int fcb_add_streams_device(const fcb_add_desc* desc, const void* d_in1, const void* d_in2, void* d_out, uint64_t n_words, int device,
+                                   void* stream);
+/* host buffers, synchronous */
+FCB_API int fcb_add_streams(const fcb_add_desc* desc, const void* in1, const void* in2, void* out, uint64_t n_words, int device);
+
 /* --- synthetic data (bench / tests): byte i of the buffer = splitmix64(seed ^ (offset + i)) & mask,
  * the rule of SURVEY.md 8(d); d_ptr is device memory, 16-byte aligned; asynchronous on `stream`. */
 FCB_API int fcb_synth_fill(void* d_ptr, size_t n_bytes, uint64_t seed, uint32_t mask, uint64_t offset, void* stream);

@@ -82,15 +82,92 @@ inline fcb_layer* make_layer(const fcb_layer_desc& d, const FixedPointWeights<SI
   return L;
 }
 
-// top(in, out, numReps): drain -> run -> refill.  RUN is fcb_layer_run or fcb_net_run.
+// page-locked staging buffer (fcb_host_alloc): the host-buffer calls copy from / to it at full PCIe rate
+struct HostBuf {
+  uint8_t* p = nullptr;
+  explicit HostBuf(size_t bytes) {
+    void* v = nullptr;
+    check(fcb_host_alloc(&v, bytes), "fcb_host_alloc");
+    p = (uint8_t*)v;
+  }
+  ~HostBuf() { fcb_host_free(p); }
+  HostBuf(const HostBuf&) = delete;
+  HostBuf& operator=(const HostBuf&) = delete;
+};
+
+// top(in, out, numReps): drain -> run -> refill.  RUN is fcb_layer_run, fcb_net_run or fcb_pool_run (the whole box behind one call).
 template <int WI, int WO, typename H, typename RUN>
 inline void run_streams(H* handle, RUN run, hls::stream<ap_uint<WI> >& in, hls::stream<ap_uint<WO> >& out, unsigned numReps,
                         size_t in_words_per_rep, size_t out_words_per_rep) {
   const size_t ib = fcb_word_bytes(WI), ob = fcb_word_bytes(WO);
-  std::vector<uint8_t> hin(ib * in_words_per_rep * numReps), hout(ob * out_words_per_rep * numReps);
-  for (size_t i = 0; i < in_words_per_rep * numReps; i++) word_to_bytes<WI>(in.read(), &hin[i * ib]);
-  check(run(handle, hin.data(), hout.data(), numReps), "run");
-  for (size_t i = 0; i < out_words_per_rep * numReps; i++) out.write(bytes_to_word<WO>(&hout[i * ob]));
+  HostBuf hin(ib * in_words_per_rep * numReps), hout(ob * out_words_per_rep * numReps);
+  for (size_t i = 0; i < in_words_per_rep * numReps; i++) word_to_bytes<WI>(in.read(), hin.p + i * ib);
+  check(run(handle, hin.p, hout.p, numReps), "run");
+  for (size_t i = 0; i < out_words_per_rep * numReps; i++) out.write(bytes_to_word<WO>(hout.p + i * ob));
+}
+
+#ifdef FCB_HLS_ADAPTER_QDMA
+// The same with the Vitis top-level stream type on both sides: what Qdma2Stream_Batch in front of and Stream2Qdma_Batch behind the
+// layer do (streamtools.h:1001-1037): data passes through, TKEEP is all ones, TLAST marks the last word of every frame.
+// (needs ap_axi_sdata.h; define FCB_HLS_ADAPTER_QDMA before including this header)
+template <int WI, int WO, typename H, typename RUN>
+inline void run_qdma_streams(H* handle, RUN run, hls::stream<qdma_axis<WI, 0, 0, 0> >& in, hls::stream<qdma_axis<WO, 0, 0, 0> >& out,
+                             unsigned numReps, size_t in_words_per_rep, size_t out_words_per_rep) {
+  const size_t ib = fcb_word_bytes(WI), ob = fcb_word_bytes(WO);
+  HostBuf hin(ib * in_words_per_rep * numReps), hout(ob * out_words_per_rep * numReps);
+  for (size_t i = 0; i < in_words_per_rep * numReps; i++) word_to_bytes<WI>(ap_uint<WI>(in.read().get_data()), hin.p + i * ib);
+  check(run(handle, hin.p, hout.p, numReps), "run");
+  for (unsigned rep = 0; rep < numReps; rep++)
+    for (size_t w = 0; w < out_words_per_rep; w++) {
+      qdma_axis<WO, 0, 0, 0> t;
+      t.set_data(bytes_to_word<WO>(hout.p + (rep * out_words_per_rep + w) * ob));
+      t.set_keep(-1);
+      t.set_last(w == out_words_per_rep - 1);
+      out.write(t);
+    }
+}
+#endif
+
+// AXI-memory form: what Mem2Stream_Batch -> StreamingDataWidthConverter_Batch in front of and DWC -> Stream2Mem_Batch behind the layer
+// do (dma.h:135-199, streamtools.h:463-526).  `in_mem` / `out_mem` are arrays of ap_uint<DW> memory words holding numReps frames back
+// to back; both converters move bits LSB-first, so a frame is the dense bit string of its stream words (WI or WO bits each) cut into
+// DW-bit memory words.  DW must divide or be a multiple of WI and WO, as the converters require.
+template <int WI, int WO, int DW, typename H, typename RUN>
+inline void run_axi_memory(H* handle, RUN run, const ap_uint<DW>* in_mem, ap_uint<DW>* out_mem, unsigned numReps, size_t in_words_per_rep,
+                           size_t out_words_per_rep) {
+  static_assert((WI % DW == 0 || DW % WI == 0) && (WO % DW == 0 || DW % WO == 0), "StreamingDataWidthConverter_Batch needs integer ratios");
+  const size_t ib = fcb_word_bytes(WI), ob = fcb_word_bytes(WO);
+  const size_t nin = in_words_per_rep * numReps, nout = out_words_per_rep * numReps;
+  HostBuf hin(ib * nin), hout(ob * nout);
+  for (size_t i = 0; i < nin; i++) {  // stream word i = bits [i*WI, (i+1)*WI) of the memory bit string
+    ap_uint<WI> v = 0;
+    for (int b = 0; b < WI; b++) {
+      const size_t bit = i * (size_t)WI + b;
+      v[b] = in_mem[bit / DW][(int)(bit % DW)];
+    }
+    word_to_bytes<WI>(v, hin.p + i * ib);
+  }
+  check(run(handle, hin.p, hout.p, numReps), "run");
+  const size_t out_mem_words = (nout * (size_t)WO + DW - 1) / DW;
+  for (size_t m = 0; m < out_mem_words; m++) out_mem[m] = 0;
+  for (size_t i = 0; i < nout; i++) {
+    const ap_uint<WO> v = bytes_to_word<WO>(hout.p + i * ob);
+    for (int b = 0; b < WO; b++) {
+      const size_t bit = i * (size_t)WO + b;
+      out_mem[bit / DW][(int)(bit % DW)] = v[b];
+    }
+  }
+}
+
+// The reference network on every GPU of the box behind the reference's own signature: eight_layers_net(in, out, numReps)
+// (conv_nonsquare_top.cpp:295).  `descs` / `weights` / `biases`: one entry per layer (layer_desc(), weight_image()).
+inline fcb_pool* make_pool(const std::vector<fcb_layer_desc>& descs, const std::vector<std::vector<uint8_t> >& weights,
+                           const std::vector<std::vector<uint8_t> >& biases) {
+  std::vector<const void*> w, b;
+  for (size_t i = 0; i < descs.size(); i++) { w.push_back(weights[i].data()); b.push_back(biases[i].data()); }
+  fcb_pool* P = nullptr;
+  check(fcb_pool_create(descs.data(), w.data(), nullptr, b.data(), (uint32_t)descs.size(), nullptr, 0, &P), "fcb_pool_create");
+  return P;
 }
 
 }  // namespace fcb_hls

@@ -85,6 +85,11 @@ CASES = {
     "pk2_min5": dataclasses.replace(_th(3, 4, 2, 4, 8, 8, 12, 12, 1, 8, 15, 24, 4, 0, pool=2), pool_min_value=5),
     "lw3": _th(3, 4, 2, 3, 8, 8, 10, 6, 1, 3, 7, 12, 3, 0),
     "lw5x12": _th(3, 3, 4, 5, 6, 12, 9, 7, 0, 5, 40, 16, 6, 0),
+    "acc40": LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=8, ofm_ch=8, ifm_x=10, ifm_y=6, stride_x=1, stride_y=1, pad=1, simd=4,
+                       pe=2, in_bits=16, in_signed=1, w_bits=16, acc_bits=40, acc_signed=1, act_kind=ACT_PASSTHROUGH, out_bits=32),
+    # StreamingFCLayer_Batch (fclayer.h:83-111) = a 1x1 layer over `reps` one-pixel frames, here laid out as one 7-pixel row
+    "fc_a": LayerDesc(kind=KIND_CONV, kernel_x=1, kernel_y=1, ifm_ch=64, ofm_ch=32, ifm_x=7, ifm_y=1, stride_x=1, stride_y=1, pad=0, simd=8,
+                      pe=4, in_bits=8, in_signed=0, w_bits=4, acc_bits=16, acc_signed=1, act_kind=ACT_PASSTHROUGH, out_bits=16),
     # channel-wise units (ref_layers.cpp: run_pool_batch / run_vvau)
     "pl_max_a": _pl(2, 8, 4, 12, 12, 2, 0, 8, 0, 8, 0, 8, POOLFN_MAX),
     "pl_max_s": _pl(3, 4, 2, 10, 6, 1, 1, 8, 1, 8, 1, 8, POOLFN_MAX),

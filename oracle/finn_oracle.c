@@ -414,3 +414,21 @@ int fo_maxpool(const void* in_words, void* out_words, uint32_t dim_x, uint32_t d
       }
   return 0;
 }
+
+/* AddStreams_Batch (streamtools.h:669-720): per word and channel, Out_t sum = op1 + op2 + offset, operands read as In1_t / In2_t
+ * (ap_int or ap_uint of their width), result wrapped to Out_t's width. */
+int fo_add_streams(const void* in1, const void* in2, void* out, uint64_t n_words, uint32_t channels, uint32_t in1_bits, int in1_signed,
+                   uint32_t in2_bits, int in2_signed, uint32_t out_bits, int32_t offset) {
+  if (!in1 || !in2 || !out || !channels || in1_bits < 1 || in1_bits > 32 || in2_bits < 1 || in2_bits > 32 || out_bits < 1 || out_bits > 32) return -1;
+  const size_t b1 = fo_word_bytes(channels * in1_bits), b2 = fo_word_bytes(channels * in2_bits), bo = fo_word_bytes(channels * out_bits);
+  memset(out, 0, bo * n_words);
+  for (uint64_t i = 0; i < n_words; i++)
+    for (uint32_t c = 0; c < channels; c++) {
+      uint32_t r1 = get_bits((const uint8_t*)in1 + i * b1, (uint64_t)c * in1_bits, in1_bits);
+      uint32_t r2 = get_bits((const uint8_t*)in2 + i * b2, (uint64_t)c * in2_bits, in2_bits);
+      int64_t a = in1_signed ? sext(r1, in1_bits) : (int64_t)r1, b = in2_signed ? sext(r2, in2_bits) : (int64_t)r2;
+      uint64_t sum = (uint64_t)(a + b + (int64_t)offset);
+      put_bits((uint8_t*)out + i * bo, (uint64_t)c * out_bits, out_bits, (uint32_t)(out_bits >= 32 ? sum : (sum & ((1ull << out_bits) - 1ull))));
+    }
+  return 0;
+}

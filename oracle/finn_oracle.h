@@ -26,6 +26,8 @@ FO_API int fo_layer_run(const fcb_layer_desc* d, const void* in_words, const voi
                         const void* bias, void* out_words, uint32_t numReps);
 FO_API int fo_maxpool(const void* in_words, void* out_words, uint32_t dim_x, uint32_t dim_y, uint32_t pool, uint32_t ch,
                       uint32_t bits);
+FO_API int fo_add_streams(const void* in1, const void* in2, void* out, uint64_t n_words, uint32_t channels, uint32_t in1_bits, int in1_signed,
+                          uint32_t in2_bits, int in2_signed, uint32_t out_bits, int32_t offset);
 #ifdef __cplusplus
 }
 #endif

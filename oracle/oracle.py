@@ -87,6 +87,31 @@ def run_layer(desc, in_words, weights, thresholds=None, bias=None, num_reps: int
     return out
 
 
+def add_streams(in1, in2, n_words, channels, in1_bits, in1_signed, in2_bits, in2_signed, out_bits, offset=0) -> np.ndarray:
+    """Restatement of AddStreams_Batch (streamtools.h:669-720) on packed word images."""
+    L = lib()
+    L.fo_add_streams.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32,
+                                                         ctypes.c_int, ctypes.c_uint32, ctypes.c_int32]
+    in1, in2 = np.ascontiguousarray(in1, dtype=np.uint8), np.ascontiguousarray(in2, dtype=np.uint8)
+    out = np.zeros(int(L.fo_word_bytes(channels * out_bits)) * n_words, dtype=np.uint8)
+    rc = L.fo_add_streams(_ptr(in1), _ptr(in2), _ptr(out), n_words, channels, in1_bits, in1_signed, in2_bits, in2_signed, out_bits, offset)
+    if rc:
+        raise RuntimeError(f"fo_add_streams rc={rc}")
+    return out
+
+
+def ref_add(name: str, in1, in2, out_bytes: int) -> np.ndarray:
+    """Reference AddStreams_Batch instantiation `name` of ref_layers.cpp."""
+    fn = getattr(ref_lib(), "ref_" + name)
+    fn.argtypes = [ctypes.c_void_p] * 3
+    in1, in2 = np.ascontiguousarray(in1, dtype=np.uint8), np.ascontiguousarray(in2, dtype=np.uint8)
+    out = np.zeros(out_bytes, dtype=np.uint8)
+    rc = fn(_ptr(in1), _ptr(in2), _ptr(out))
+    if rc:
+        raise RuntimeError(f"ref_{name} rc={rc}")
+    return out
+
+
 def maxpool(in_words, dim_x, dim_y, pool, ch, bits) -> np.ndarray:
     in_words = np.ascontiguousarray(in_words, dtype=np.uint8)
     wb = lib().fo_word_bytes(ch * bits)

@@ -275,6 +275,29 @@ int run_thresh_pad_pool(const uint8_t* in, const uint8_t* wts, const uint8_t* th
   return drain_stream<OFM * TRB>(s_out, out, (size_t)(OX / (PD > 1 ? PD : 1)) * (OY / (PD > 1 ? PD : 1)));
 }
 
+// ---- wide types: signed 16-bit lanes, 16-bit weights, PassThroughActivation<ap_int<TAB>> with TAB > 32 (mvau.hpp:112 allows any TA),
+//      32-bit output lanes (the range assignment at mvau.hpp:167 truncates)
+template <unsigned K, unsigned SIMD, unsigned PE, unsigned WB, unsigned C, unsigned OFM, unsigned IX, unsigned IY, unsigned PAD, unsigned INB,
+          int TAB, unsigned OUTB>
+int run_wide(const uint8_t* in, const uint8_t* wts, uint8_t* out) {
+  constexpr unsigned PX = IX + 2 * PAD, PY = IY + 2 * PAD, OX = PX - K + 1, OY = PY - K + 1;
+  constexpr unsigned MW = K * K * C, MH = OFM, SF = MW / SIMD, NF = MH / PE;
+  static FixedPointWeights<SIMD, ap_int<WB>, PE, SF * NF> w;
+  load_weights(w, wts);
+  hls::stream<ap_uint<C * INB> > s_in("in"), s_pad("pad");
+  hls::stream<ap_uint<SIMD * INB> > s_wa("wa"), s_win("win");
+  hls::stream<ap_uint<PE * OUTB> > s_mv("mv");
+  hls::stream<ap_uint<OFM * OUTB> > s_out("out");
+  fill_stream<C * INB>(s_in, in, (size_t)IX * IY);
+  FMPadding_nonsquare<PX, PY, 2 * PAD, 2 * PAD, C, C, ap_uint<INB> >(s_in, s_pad);
+  StreamingDataWidthConverter_Batch<C * INB, SIMD * INB, PX * PY>(s_pad, s_wa, 1);
+  ConvolutionInputGenerator_NonSquare<K, K, C, INB, PX, PY, OX, OY, SIMD, 1, 1>(s_wa, s_win, 1, ap_resource_dflt());
+  Matrix_Vector_Activate_Batch<MW, MH, SIMD, PE, 1, Slice<ap_int<INB> >, Slice<ap_uint<OUTB> >, Identity>(
+      s_win, s_mv, w, PassThroughActivation<ap_int<TAB> >(), OX * OY, ap_resource_dsp());
+  StreamingDataWidthConverter_Batch<PE * OUTB, OFM * OUTB, OX * OY * NF>(s_mv, s_out, 1);
+  return drain_stream<OFM * OUTB>(s_out, out, (size_t)OX * OY);
+}
+
 // ---- channel-wise units behind the depth-wise sliding window: ConvolutionInputGenerator_dws (square, any stride with K % S == 0,
 //      slidingwindow.h:761-868) or ConvolutionInputGenerator_NonSquare_dws (stride 1, :1377-1488), FMPadding_nonsquare in front.
 template <unsigned K, unsigned C, unsigned PE, unsigned IX, unsigned IY, unsigned S, unsigned PAD, unsigned INB>
@@ -348,6 +371,41 @@ REF_API int ref_lw3(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8
 }
 REF_API int ref_lw5x12(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // ap_uint<5> in, ap_int<5> weights, 12 channels of ap_uint<6> out
   return run_thresh_pad_pool<3, 3, 4, 5, 6, 12, 9, 7, 0, 0, 2, 5, 40, 16, 6, 0, 1, ap_uint<6>, 0>(in, w, t, out);
+}
+
+REF_API int ref_acc40(const uint8_t* in, const uint8_t* w, const uint8_t*, uint8_t* out, double*) {  // s16 x s16 -> ap_int<40> -> 32-bit lanes
+  return run_wide<3, 4, 2, 16, 8, 8, 10, 6, 1, 16, 40, 32>(in, w, out);
+}
+
+// AddStreams_Batch (streamtools.h:669-720): ref_<name>(in1, in2, out)
+template <unsigned CH, typename T1, typename T2, typename TO, unsigned NTOT, int OFF>
+int run_add(const uint8_t* in1, const uint8_t* in2, uint8_t* out, unsigned reps) {
+  hls::stream<ap_uint<CH * T1::width> > s1("s1");
+  hls::stream<ap_uint<CH * T2::width> > s2("s2");
+  hls::stream<ap_uint<CH * TO::width> > so("so");
+  fill_stream<CH * T1::width>(s1, in1, (size_t)NTOT * reps);
+  fill_stream<CH * T2::width>(s2, in2, (size_t)NTOT * reps);
+  AddStreams_Batch<CH, T1, T2, TO, NTOT, OFF>(s1, s2, so, reps);
+  return drain_stream<CH * TO::width>(so, out, (size_t)NTOT * reps);
+}
+REF_API int ref_add_u8(const uint8_t* a, const uint8_t* b, uint8_t* o) { return run_add<16, ap_uint<8>, ap_uint<8>, ap_uint<8>, 40, 0>(a, b, o, 3); }
+REF_API int ref_add_s8_off(const uint8_t* a, const uint8_t* b, uint8_t* o) { return run_add<6, ap_int<8>, ap_uint<4>, ap_int<10>, 33, -7>(a, b, o, 2); }
+
+// StreamingFCLayer_Batch (fclayer.h:83-111): ref_fc_<name>(in, weights, thresholds-or-unused, out, secs); one input word of MatrixW
+// lanes and one output word of MatrixH lanes per repetition
+template <unsigned MW, unsigned MH, unsigned SIMD, unsigned PE, unsigned INB, unsigned WB, int TAB, unsigned OUTB, unsigned REPS>
+int run_fc_pass(const uint8_t* in, const uint8_t* wts, uint8_t* out) {
+  static FixedPointWeights<SIMD, ap_int<WB>, PE, (MW / SIMD) * (MH / PE)> w;
+  load_weights(w, wts);
+  hls::stream<ap_uint<MW * INB> > s_in("in");
+  hls::stream<ap_uint<MH * OUTB> > s_out("out");
+  fill_stream<MW * INB>(s_in, in, REPS);
+  StreamingFCLayer_Batch<MW, MH, SIMD, PE, Slice<ap_uint<INB> >, Slice<ap_uint<OUTB> >, Identity>(s_in, s_out, w, PassThroughActivation<ap_int<TAB> >(),
+                                                                                                  REPS, ap_resource_dsp());
+  return drain_stream<MH * OUTB>(s_out, out, REPS);
+}
+REF_API int ref_fc_a(const uint8_t* in, const uint8_t* w, const uint8_t*, uint8_t* out, double*) {
+  return run_fc_pass<64, 32, 8, 4, 8, 4, 16, 16, 7>(in, w, out);
 }
 
 // Pool_batch cases: ref_<name>(in, unused, unused, out, secs)

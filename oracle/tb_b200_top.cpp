@@ -36,14 +36,20 @@ void deconv2d_layer4(stream<ap_uint<CONV_4_IFM_CH * CONV_4_IN_BIT> >& in, stream
 
 void eight_layers_net(stream<ap_uint<CONV_0_IFM_CH * CONV_0_IN_BIT> >& in, stream<ap_uint<CONV_7_OFM_CH * CONV_7_OUT_BIT> >& out,
                       unsigned int numReps) {
-  static fcb_net* N = []() {
-    fcb_layer* l[8] = {LAYER(0, FCB_KIND_CONV), LAYER(1, FCB_KIND_CONV), LAYER(2, FCB_KIND_CONV), LAYER(3, FCB_KIND_CONV),
-                       LAYER(4, FCB_KIND_DECONV522), LAYER(5, FCB_KIND_DECONV522), LAYER(6, FCB_KIND_DECONV522),
-                       LAYER(7, FCB_KIND_DECONV522)};
-    fcb_net* n = nullptr;
-    fcb_hls::check(fcb_net_create(l, 8, &n), "fcb_net_create");
-    return n;
+  // every sm_100 GPU of the box behind the one call: numReps is split into contiguous image ranges (fcb_pool_*)
+  static fcb_pool* N = []() {
+    std::vector<fcb_layer_desc> d;
+    std::vector<std::vector<uint8_t> > w, b;
+#define ADD(n, kind)                                                                                                                   \
+  d.push_back(fcb_hls::layer_desc(kind, CONV_##n##_K, CONV_##n##_S, CONV_##n##_P, CONV_##n##_IFM_CH, CONV_##n##_OFM_CH, CONV_##n##_IFM_ROW,  \
+                                  CONV_##n##_IFM_COL, CONV_##n##_SIMD, CONV_##n##_PE, CONV_##n##_W_BIT));                                 \
+  w.push_back(fcb_hls::weight_image(PARAM::weights_layer##n));                                                                          \
+  b.push_back(fcb_hls::weight_image(PARAM::bias_layer##n));
+    ADD(0, FCB_KIND_CONV) ADD(1, FCB_KIND_CONV) ADD(2, FCB_KIND_CONV) ADD(3, FCB_KIND_CONV)
+    ADD(4, FCB_KIND_DECONV522) ADD(5, FCB_KIND_DECONV522) ADD(6, FCB_KIND_DECONV522) ADD(7, FCB_KIND_DECONV522)
+#undef ADD
+    return fcb_hls::make_pool(d, w, b);
   }();
   fcb_hls::run_streams<CONV_0_IFM_CH * CONV_0_IN_BIT, CONV_7_OFM_CH * CONV_7_OUT_BIT>(
-      N, fcb_net_run, in, out, numReps, (size_t)CONV_0_IFM_ROW * CONV_0_IFM_COL, (size_t)CONV_7_OFM_ROW * CONV_7_OFM_COL);
+      N, fcb_pool_run, in, out, numReps, (size_t)CONV_0_IFM_ROW * CONV_0_IFM_COL, (size_t)CONV_7_OFM_ROW * CONV_7_OFM_COL);
 }

@@ -5,7 +5,7 @@ from __future__ import annotations
 import ctypes
 import os
 
-from .desc import CLayerDesc
+from .desc import CAddDesc, CLayerDesc
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libfinnconv_b200.so")
@@ -66,6 +66,8 @@ def load(path: str) -> ctypes.CDLL:
     L.fcb_pool_replicas.restype = u32
     L.fcb_pool_run.argtypes = [vp, vp, vp, u32]
     L.fcb_shard_range.argtypes = [u32, u32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    L.fcb_add_streams.argtypes = [ctypes.POINTER(CAddDesc), vp, vp, vp, u64, ctypes.c_int]
+    L.fcb_add_streams_device.argtypes = [ctypes.POINTER(CAddDesc), vp, vp, vp, u64, ctypes.c_int, vp]
     L.fcb_host_alloc.argtypes = [pvp, sz]
     L.fcb_host_free.argtypes = [vp]
     L.fcb_host_free.restype = None

@@ -87,8 +87,11 @@ int derive_geom(const fcb_layer_desc* d, Geom* g) {
   if (d->out_bits < 1 || d->out_bits > 32) { set_error("out_bits %u unsupported (1..32)", d->out_bits); return FCB_ERR_UNSUPPORTED; }
   if (d->kind != FCB_KIND_POOL && (d->w_bits < 1 || d->w_bits > 16)) { set_error("w_bits %u unsupported (1..16)", d->w_bits); return FCB_ERR_UNSUPPORTED; }
   if (d->in_bits == 16 && !d->in_signed) { /* lanes are staged as int32: fine */ }
-  if (d->acc_bits < 1 || d->acc_bits > 32 || (d->acc_bits == 32 && !d->acc_signed && d->act_kind == FCB_ACT_THRESHOLDS)) {
-    set_error("acc_bits %u unsupported (1..32)", d->acc_bits); return FCB_ERR_UNSUPPORTED;
+  // TA (mvau.hpp:112) up to 64 bits for pass-through and bias+ReLU: their output lanes (<= 32 bits) are the low bits of the exact
+  // sum, which 32-bit modular accumulation already carries.  Threshold compares need the whole accumulator: TA <= 32 (31 unsigned).
+  if (d->acc_bits < 1 || d->acc_bits > 64 || (d->act_kind == FCB_ACT_THRESHOLDS && (d->acc_bits > 32 || (d->acc_bits == 32 && !d->acc_signed))) ||
+      (d->kind == FCB_KIND_POOL && d->acc_bits > 32)) {
+    set_error("acc_bits %u unsupported (1..64; thresholds and pool functions: 1..32)", d->acc_bits); return FCB_ERR_UNSUPPORTED;
   }
   if (pk > 16) { set_error("pool %u unsupported (PoolDim <= 16)", d->pool); return FCB_ERR_UNSUPPORTED; }
   if (d->act_kind == FCB_ACT_BIAS_RELU && d->out_bits < 2) { set_error("bias+ReLU needs out_bits >= 2"); return FCB_ERR_UNSUPPORTED; }
@@ -959,6 +962,47 @@ uint64_t fcb_net_launches(const fcb_net* N) {
   uint64_t s = 0;
   if (N) for (auto* l : N->layers) s += l->launches;
   return s;
+}
+
+static int add_check(const fcb_add_desc* d) {
+  if (!d || d->struct_size != sizeof(fcb_add_desc)) { set_error("bad fcb_add_desc"); return FCB_ERR_INVALID_ARG; }
+  if (!d->channels || d->in1_bits < 1 || d->in1_bits > 32 || d->in2_bits < 1 || d->in2_bits > 32 || d->out_bits < 1 || d->out_bits > 32) {
+    set_error("AddStreams: lane widths 1..32, channels > 0"); return FCB_ERR_UNSUPPORTED;
+  }
+  return FCB_OK;
+}
+
+int fcb_add_streams_device(const fcb_add_desc* d, const void* d_in1, const void* d_in2, void* d_out, uint64_t n_words, int device, void* stream) {
+  int rc = add_check(d);
+  if (rc) return rc;
+  if (!d_in1 || !d_in2 || !d_out) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  FCB_ON_DEVICE(device);
+  return launch_add_streams(d_in1, d_in2, d_out, n_words, (int)d->channels, (int)d->in1_bits, d->in1_signed ? 1 : 0, (int)d->in2_bits,
+                            d->in2_signed ? 1 : 0, (int)d->out_bits, d->offset, (int)word_bytes(d->channels * d->in1_bits),
+                            (int)word_bytes(d->channels * d->in2_bits), (int)word_bytes(d->channels * d->out_bits), (cudaStream_t)stream);
+}
+
+int fcb_add_streams(const fcb_add_desc* d, const void* in1, const void* in2, void* out, uint64_t n_words, int device) {
+  int rc = add_check(d);
+  if (rc) return rc;
+  if (!in1 || !in2 || !out) { set_error("NULL argument"); return FCB_ERR_INVALID_ARG; }
+  if (!n_words) return FCB_OK;
+  FCB_ON_DEVICE(device);
+  const size_t b1 = word_bytes(d->channels * d->in1_bits) * n_words, b2 = word_bytes(d->channels * d->in2_bits) * n_words,
+               bo = word_bytes(d->channels * d->out_bits) * n_words;
+  struct Bufs {
+    void *a = nullptr, *b = nullptr, *o = nullptr;
+    ~Bufs() { cudaFree(a); cudaFree(b); cudaFree(o); }
+  } B;
+  FCB_CUDA_OK(cudaMalloc(&B.a, b1));
+  FCB_CUDA_OK(cudaMalloc(&B.b, b2));
+  FCB_CUDA_OK(cudaMalloc(&B.o, bo));
+  FCB_CUDA_OK(cudaMemcpy(B.a, in1, b1, cudaMemcpyHostToDevice));
+  FCB_CUDA_OK(cudaMemcpy(B.b, in2, b2, cudaMemcpyHostToDevice));
+  rc = fcb_add_streams_device(d, B.a, B.b, B.o, n_words, device, nullptr);
+  if (rc) return rc;
+  FCB_CUDA_OK(cudaMemcpy(out, B.o, bo, cudaMemcpyDeviceToHost));
+  return FCB_OK;
 }
 
 int fcb_synth_fill(void* d_ptr, size_t n_bytes, uint64_t seed, uint32_t mask, uint64_t offset, void* stream) {

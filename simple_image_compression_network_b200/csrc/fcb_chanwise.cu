@@ -10,6 +10,8 @@
 //
 // These are streaming units (K2 MACs or compares per output byte): a warp owns one output pixel, its lanes walk the channels,
 // so loads and stores of byte lanes are 32 consecutive bytes of one stream word; taps of neighbouring pixels hit L1/L2.
+#include <algorithm>
+
 #include "fcb_epilogue.cuh"
 
 namespace fcb {
@@ -62,6 +64,49 @@ __global__ void __launch_bounds__(256) chanwise_kernel(const ChanParams p) {
     }
     store_lane(oword, ch, chv, r, p.out_bits);
   }
+}
+
+// AddStreams_Batch (streamtools.h:669-720): Out_t sum = op1 + op2 + offset per lane; a warp owns one stream word
+__device__ __forceinline__ int32_t load_lane32(const uint8_t* word, int c, int bits, int sgn) {  // lanes up to 32 bits
+  const size_t bit = (size_t)c * bits;
+  const uint8_t* b = word + (bit >> 3);
+  const int sh = (int)(bit & 7), need = (sh + bits + 7) >> 3;
+  uint64_t v = 0;
+  for (int i = 0; i < need; i++) v |= (uint64_t)b[i] << (8 * i);
+  v >>= sh;
+  if (bits < 32) v &= (1ull << bits) - 1ull;
+  if (sgn && bits < 32) {
+    const uint64_t m = 1ull << (bits - 1);
+    v = (v ^ m) - m;
+  }
+  return (int32_t)(uint32_t)v;
+}
+__global__ void __launch_bounds__(256) add_streams_kernel(const uint8_t* __restrict__ in1, const uint8_t* __restrict__ in2, uint8_t* __restrict__ out,
+                                                          unsigned long long n_words, int ch, int b1, int s1, int b2, int s2, int ob, int offset,
+                                                          int wb1, int wb2, int wbo) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long w = (unsigned long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= n_words) return;
+  for (int c0 = 0; c0 < ch; c0 += 32) {
+    const int c = c0 + lane;
+    const bool v = c < ch;
+    uint32_t r = 0;
+    if (v) r = (uint32_t)(load_lane32(in1 + w * wb1, c, b1, s1) + load_lane32(in2 + w * wb2, c, b2, s2) + offset);  // mod 2^32, then Out_t's width
+    store_lane(out + w * wbo, c, v, ob >= 32 ? r : (r & ((1u << ob) - 1u)), ob);
+  }
+}
+int launch_add_streams(const void* d_in1, const void* d_in2, void* d_out, unsigned long long n_words, int ch, int b1, int s1, int b2, int s2, int ob,
+                       int offset, int wb1, int wb2, int wbo, cudaStream_t st) {
+  if (!n_words) return FCB_OK;
+  if ((size_t)wbo * 8 != (size_t)ch * ob) FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, (size_t)wbo * n_words, st));  // container padding bits stay zero
+  const unsigned long long blocks = (n_words + 7) / 8;
+  for (unsigned long long b0 = 0; b0 < blocks; b0 += 0x40000000ull) {
+    const unsigned nb = (unsigned)std::min<unsigned long long>(0x40000000ull, blocks - b0);
+    add_streams_kernel<<<nb, 256, 0, st>>>((const uint8_t*)d_in1 + b0 * 8 * wb1, (const uint8_t*)d_in2 + b0 * 8 * wb2, (uint8_t*)d_out + b0 * 8 * wbo,
+                                           n_words - b0 * 8, ch, b1, s1, b2, s2, ob, offset, wb1, wb2, wbo);
+    FCB_CUDA_OK(cudaGetLastError());
+  }
+  return FCB_OK;
 }
 
 int launch_chanwise(const ChanParams& p, int n_images, cudaStream_t st) {

@@ -108,6 +108,8 @@ struct ChanParams {
   unsigned long long in_img_bytes, out_img_bytes;
 };
 int launch_chanwise(const ChanParams& p, int n_images, cudaStream_t st);
+int launch_add_streams(const void* d_in1, const void* d_in2, void* d_out, unsigned long long n_words, int ch, int b1, int s1, int b2, int s2, int ob,
+                       int offset, int wb1, int wb2, int wbo, cudaStream_t st);
 
 // thin-input lowering (fcb_im2col.cu)
 struct Im2colParams {

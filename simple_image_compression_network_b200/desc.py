@@ -30,6 +30,12 @@ class CLayerDesc(ctypes.Structure):
         ("pool_signed", ctypes.c_uint32), ("pool_min_value", ctypes.c_int32)]
 
 
+class CAddDesc(ctypes.Structure):
+    """fcb_add_desc: AddStreams_Batch's template parameters (streamtools.h:669-720)."""
+    _fields_ = [(n, ctypes.c_uint32) for n in ("struct_size", "channels", "in1_bits", "in1_signed", "in2_bits", "in2_signed", "out_bits")] + [
+        ("offset", ctypes.c_int32)]
+
+
 @dataclass(frozen=True)
 class LayerDesc:
     kind: int = KIND_CONV

@@ -225,5 +225,47 @@ class Pool:
             pass
 
 
+def add_streams(in1, in2, n_words: int, channels: int, in1_bits: int, in1_signed: bool, in2_bits: int, in2_signed: bool, out_bits: int,
+                offset: int = 0, device: int = 0) -> np.ndarray:
+    """AddStreams_Batch (streamtools.h:669-720) on packed word images (host buffers): per word and channel
+    Out_t(op1 + op2 + offset), the residual add of the library."""
+    from .desc import CAddDesc
+    L = _lib.lib()
+    d = CAddDesc(ctypes.sizeof(CAddDesc), channels, in1_bits, int(in1_signed), in2_bits, int(in2_signed), out_bits, offset)
+    a, b = np.ascontiguousarray(in1, dtype=np.uint8), np.ascontiguousarray(in2, dtype=np.uint8)
+    if a.size != pack.word_bytes(channels * in1_bits) * n_words or b.size != pack.word_bytes(channels * in2_bits) * n_words:
+        raise ValueError("stream image size does not match channels x bits x n_words")
+    out = np.empty(pack.word_bytes(channels * out_bits) * n_words, dtype=np.uint8)
+    _lib.check(L.fcb_add_streams(ctypes.byref(d), _ptr(a), _ptr(b), _ptr(out), n_words, device), L)
+    return out
+
+
+class FCLayer:
+    """StreamingFCLayer_Batch (fclayer.h:83-111): a thin wrapper of the same MVAU, i.e. a 1x1 layer on one-pixel frames.  `reps`
+    repetitions are presented to the library as frames of `tile` pixels (a 1x1 layer treats every pixel on its own, and the stream
+    image -- input vectors back to back -- is the same), the remainder as one-pixel frames, so large batches fill the tensor tiles."""
+
+    def __init__(self, matrix_w: int, matrix_h: int, simd: int, pe: int, weights, thresholds=None, bias=None, tile: int = 256, device: int = 0, **numerics):
+        from .desc import KIND_CONV
+        mk = lambda x: LayerDesc(kind=KIND_CONV, kernel_x=1, kernel_y=1, ifm_ch=matrix_w, ofm_ch=matrix_h, ifm_x=x, ifm_y=1, stride_x=1,
+                                 stride_y=1, pad=0, simd=simd, pe=pe, **numerics)
+        self.tile = tile
+        self.big = ConvLayer(mk(tile), weights, thresholds=thresholds, bias=bias, device=device)
+        self.one = ConvLayer(mk(1), weights, thresholds=thresholds, bias=bias, device=device)
+        self.in_bytes, self.out_bytes = self.one.in_bytes, self.one.out_bytes
+
+    def run(self, in_words, reps: int) -> np.ndarray:
+        x = np.ascontiguousarray(in_words, dtype=np.uint8).reshape(-1)
+        if x.size != self.in_bytes * reps:
+            raise ValueError(f"input stream is {x.size} bytes, expected {self.in_bytes * reps}")
+        nbig = reps // self.tile
+        parts = []
+        if nbig:
+            parts.append(self.big.run(x[: nbig * self.tile * self.in_bytes], nbig))
+        if reps - nbig * self.tile:
+            parts.append(self.one.run(x[nbig * self.tile * self.in_bytes:], reps - nbig * self.tile))
+        return np.concatenate(parts)
+
+
 def synth_fill(d_ptr: int, n_bytes: int, seed: int, mask: int = 0xFF, offset: int = 0, stream: int = 0) -> None:
     _lib.check(_lib.lib().fcb_synth_fill(ctypes.c_void_p(d_ptr), n_bytes, seed, mask, offset, ctypes.c_void_p(stream)))

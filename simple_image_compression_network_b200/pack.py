@@ -113,3 +113,24 @@ def pack_thresholds(t: np.ndarray, pe: int, acc_bits: int) -> np.ndarray:
 def pack_bias(b: np.ndarray) -> np.ndarray:
     """bias[OFM] (s8) -> image of FixedPointWeights<1,ap_int<8>,1,OFM>::m_weights[1][OFM]."""
     return (np.asarray(b).astype(np.int64) & 0xFF).astype(np.uint8)
+
+
+def stream_to_axi_memory(stream: np.ndarray, word_bits: int, mem_bits: int = 64) -> np.ndarray:
+    """Stream image (ap-word containers of `word_bits`-bit words) -> the memory image Mem2Stream_Batch reads / Stream2Mem_Batch writes
+    (dma.h:135-199) when a StreamingDataWidthConverter_Batch (streamtools.h:463-526) sits between the `mem_bits`-bit AXI words and the
+    layer: both move bits LSB-first, so the image is the dense bit string of the words' low `word_bits` bits (the 16-image bursts of
+    the *_Batch blocks do not change the image).  The total number of bits must be a whole number of memory words."""
+    wb = word_bytes(word_bits)
+    words = np.asarray(stream, dtype=np.uint8).reshape(-1, wb)
+    bits = np.unpackbits(words, axis=1, bitorder="little")[:, :word_bits].reshape(-1)
+    if bits.size % mem_bits:
+        raise ValueError(f"{bits.size} stream bits are not a whole number of {mem_bits}-bit memory words")
+    return np.packbits(bits, bitorder="little")
+
+
+def axi_memory_to_stream(mem: np.ndarray, word_bits: int, n_words: int) -> np.ndarray:
+    """Inverse of stream_to_axi_memory: `n_words` stream words back into their ap-word containers."""
+    bits = np.unpackbits(np.asarray(mem, dtype=np.uint8), bitorder="little")[: n_words * word_bits].reshape(n_words, word_bits)
+    out = np.zeros((n_words, word_bytes(word_bits) * 8), dtype=np.uint8)
+    out[:, :word_bits] = bits
+    return np.packbits(out, axis=1, bitorder="little").reshape(-1)

@@ -142,3 +142,18 @@ def test_pool_splits_the_batch_over_replicas(fcb_lib, oracle_mod):
         pool.close()
     one = Pool([d1], [i1["weights"]], None, [i1["bias"]], devices=[0, 0])  # single layer: fcb_layer_run underneath
     assert np.array_equal(one.run(i1["in_words"], reps), mid)
+
+
+def test_adapter_against_reference_functions(fcb_lib):
+    """oracle/_ref/adapter_check: include/finnconv_hls_adapter.hpp (HLS streams, QDMA streams with TKEEP / TLAST, 64-bit AXI memory
+    images incl. the 16-image bursts of Mem2Stream_Batch / Stream2Mem_Batch, and the multi-GPU pool) against the reference's own
+    conv2d<>, Qdma2Stream_Batch / Stream2Qdma_Batch (streamtools.h:1001-1037), Mem2Stream_Batch / Stream2Mem_Batch (dma.h:135-199) and
+    StreamingDataWidthConverter_Batch (streamtools.h:463-526), compiled from /root/reference into the checker binary."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "adapter_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/adapter_check was not built (needs /root/reference at build time)")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "simple_image_compression_network_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "all 6 checks passed" in out, out[-2000:]

@@ -535,3 +535,34 @@ def test_clustered_weight_multicast(name, reps, fcb_lib, oracle_mod, monkeypatch
     if "chb=1" in L.plan:
         assert "weights-multicast" in L.plan, L.plan
     assert np.array_equal(got, want), f"{name} [{L.plan}]: {_diff(got, want)}"
+
+
+@pytest.mark.parametrize("name", ["add_u8", "add_s8_off"])
+def test_add_streams(name, fcb_lib, oracle_mod):
+    """fcb_add_streams (AddStreams_Batch, streamtools.h:669-720) against the reference-made golden and, on a larger ragged case, the oracle."""
+    from tests.test_oracle_golden import _add_cases
+    from simple_image_compression_network_b200 import pack, synth
+    from simple_image_compression_network_b200.layer import add_streams
+    a, b, n, ch, b1, s1, b2, s2, ob, off = _add_cases()[name]
+    want = np.load(os.path.join(GOLD, f"{name}.npz"))["out"]
+    assert np.array_equal(add_streams(a, b, n, ch, b1, s1, b2, s2, ob, off), want)
+    n2, ch2 = 1003, 70  # channels not a multiple of 32, odd lane widths
+    a2 = pack.pack_words(synth.lanes(21, (n2, ch2), b1), b1).reshape(-1)
+    b2w = pack.pack_words(synth.lanes(22, (n2, ch2), 5), 5).reshape(-1)
+    got = add_streams(a2, b2w, n2, ch2, b1, s1, 5, 1, 11, off)
+    assert np.array_equal(got, oracle_mod.add_streams(a2, b2w, n2, ch2, b1, s1, 5, 1, 11, off))
+
+
+def test_fc_layer_wrapper(fcb_lib, oracle_mod):
+    """StreamingFCLayer_Batch (fclayer.h:83-111) through the host wrapper: big tiles + one-pixel remainder == the 1x1 layer of the oracle
+    (pinned on the reference's own StreamingFCLayer_Batch by the `fc_a` golden)."""
+    from simple_image_compression_network_b200 import configs
+    from simple_image_compression_network_b200.layer import FCLayer
+    d = cases.CASES["fc_a"]
+    reps = 2 * 16 + 5
+    dd = dataclasses.replace(d, ifm_x=reps)
+    inp = cases.make_inputs(dd, seed_shift=3)
+    fc = FCLayer(64, 32, 8, 4, inp["weights"], tile=16, in_bits=8, in_signed=0, w_bits=4, acc_bits=16, acc_signed=1, act_kind=0, out_bits=16)
+    got = fc.run(inp["in_words"], reps)
+    want = oracle_mod.run_layer(dd, inp["in_words"], inp["weights"], None, None)
+    assert np.array_equal(got, want)

@@ -124,3 +124,22 @@ def test_oracle_rejects_bad_shapes(oracle_mod):
         oracle_mod.query(dataclasses.replace(d, simd=3))  # IFM_CH % SIMD (slidingwindow.h:1259)
     with pytest.raises(ValueError):
         oracle_mod.query(dataclasses.replace(d, pe=4))    # OFM_CH % PE
+
+
+def _add_cases():
+    from simple_image_compression_network_b200 import pack, synth
+    return {
+        # name: (in1, in2, n_words, channels, in1_bits, in1_signed, in2_bits, in2_signed, out_bits, offset) -- ref_layers.cpp run_add
+        "add_u8": (pack.pack_words(synth.lanes(5, (120, 16), 8), 8).reshape(-1), pack.pack_words(synth.lanes(6, (120, 16), 8), 8).reshape(-1),
+                   120, 16, 8, 0, 8, 0, 8, 0),
+        "add_s8_off": (pack.pack_words(synth.lanes(7, (66, 6), 8), 8).reshape(-1), pack.pack_words(synth.lanes(8, (66, 6), 4), 4).reshape(-1),
+                       66, 6, 8, 1, 4, 0, 10, -7),
+    }
+
+
+@pytest.mark.parametrize("name", ["add_u8", "add_s8_off"])
+def test_add_streams_restatement_vs_reference_golden(name, oracle_mod):
+    """AddStreams_Batch (streamtools.h:669-720): the C restatement against outputs recorded from the reference's own template."""
+    a, b, n, ch, b1, s1, b2, s2, ob, off = _add_cases()[name]
+    want = np.load(os.path.join(GOLD, f"{name}.npz"))["out"]
+    assert np.array_equal(oracle_mod.add_streams(a, b, n, ch, b1, s1, b2, s2, ob, off), want)

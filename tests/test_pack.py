@@ -61,3 +61,18 @@ def test_threshold_image_layout():
 def test_splitmix_known_answer():
     # splitmix64 reference values (seed 0 stream: first output for state 0 after one increment)
     assert int(synth.splitmix64(np.array([0], dtype=np.uint64))[0]) == 0xE220A8397B1DCDAF
+
+
+@pytest.mark.parametrize("lanes,bits,mem", [(3, 8, 64), (16, 8, 64), (12, 4, 32), (128, 8, 64), (5, 3, 8)])
+def test_axi_memory_image_roundtrip(lanes, bits, mem):
+    """Mem2Stream_Batch / Stream2Mem_Batch memory image (dma.h:135-199 + the width converter): dense LSB-first bit string."""
+    n = mem * 3  # any count that makes a whole number of memory words
+    x = synth.lanes(11, (n, lanes), bits)
+    stream = pack.pack_words(x, bits).reshape(-1)
+    img = pack.stream_to_axi_memory(stream, lanes * bits, mem)
+    assert img.size * 8 == n * lanes * bits
+    assert np.array_equal(pack.axi_memory_to_stream(img, lanes * bits, n), stream)
+    if bits == 8 and pack.word_bytes(lanes * 8) == lanes:  # byte lanes in dense containers: the memory image IS the stream image
+        assert np.array_equal(img, stream)
+    if lanes == 3 and bits == 8:  # ap_uint<24> words: the container's pad byte is not part of the memory image
+        assert np.array_equal(img.reshape(-1, 3), stream.reshape(-1, 4)[:, :3])
