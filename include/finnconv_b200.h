@@ -135,7 +135,12 @@ typedef struct fcb_layer_desc {
    * out_bits-wide integers when pool_signed != 0; every window's maximum starts from pool_min_value. */
   uint32_t pool_signed;
   int32_t pool_min_value;
+  /* Dilation_x / Dilation_y of ConvolutionInputGenerator_NonSquare_Dilated (slidingwindow.h:1515-1631): tap (ky, kx) reads the padded
+   * frame at (oy*S + ky*Dy, ox*S + kx*Dx); 0 or 1 = none.  (The reference asserts Dilation_y == 1; both axes work here.)
+   * These two fields were appended in ABI 0.2: a struct_size without them (FCB_LAYER_DESC_SIZE_V1) is accepted and means 1. */
+  uint32_t dilation_x, dilation_y;
 } fcb_layer_desc;
+#define FCB_LAYER_DESC_SIZE_V1 (sizeof(fcb_layer_desc) - 2 * sizeof(uint32_t))
 
 typedef struct fcb_layer fcb_layer; /* opaque: one layer resident on one device */
 typedef struct fcb_net fcb_net;     /* opaque: chain of layers, activations stay on device */

@@ -87,6 +87,10 @@ CASES = {
     "lw5x12": _th(3, 3, 4, 5, 6, 12, 9, 7, 0, 5, 40, 16, 6, 0),
     "acc40": LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=8, ofm_ch=8, ifm_x=10, ifm_y=6, stride_x=1, stride_y=1, pad=1, simd=4,
                        pe=2, in_bits=16, in_signed=1, w_bits=16, acc_bits=40, acc_signed=1, act_kind=ACT_PASSTHROUGH, out_bits=32),
+    # sliding-window variants (ref_layers.cpp: run_swg_variant): dilated (slidingwindow.h:1515-1631), kernel_stride (K % S != 0, :447-575)
+    "dil_x2": dataclasses.replace(_th(3, 4, 2, 4, 8, 8, 14, 8, 0, 8, 15, 24, 4, 0), dilation_x=2),
+    "dil_x3_k2": dataclasses.replace(_th(3, 8, 4, 4, 16, 8, 13, 7, 0, 8, 15, 24, 4, 0), kernel_x=2, kernel_y=3, dilation_x=3),
+    "ks_k3s2": dataclasses.replace(_th(3, 4, 2, 4, 8, 8, 11, 11, 0, 8, 15, 24, 4, 0), stride_x=2, stride_y=2),
     # StreamingFCLayer_Batch (fclayer.h:83-111) = a 1x1 layer over `reps` one-pixel frames, here laid out as one 7-pixel row
     "fc_a": LayerDesc(kind=KIND_CONV, kernel_x=1, kernel_y=1, ifm_ch=64, ofm_ch=32, ifm_x=7, ifm_y=1, stride_x=1, stride_y=1, pad=0, simd=8,
                       pe=4, in_bits=8, in_signed=0, w_bits=4, acc_bits=16, acc_signed=1, act_kind=ACT_PASSTHROUGH, out_bits=16),

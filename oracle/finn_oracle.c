@@ -76,6 +76,10 @@ static inline int64_t wrap_ta(int64_t v, uint32_t bits, int is_signed) {
   return is_signed ? sext(u, bits) : (int64_t)u;
 }
 
+/* Dilation_x / Dilation_y (slidingwindow.h:1515-1631: line index (ofm_x*Stride_x + k_x*Dilation_x), block (k_y*Dilation_y)/Stride_y) */
+static uint32_t dil_x(const fcb_layer_desc* d) { return d->struct_size == sizeof(fcb_layer_desc) && d->dilation_x > 1 ? d->dilation_x : 1; }
+static uint32_t dil_y(const fcb_layer_desc* d) { return d->struct_size == sizeof(fcb_layer_desc) && d->dilation_y > 1 ? d->dilation_y : 1; }
+
 /* FMPadding_nonsquare split (streamtools.h:374-379) */
 static void pad_split(const fcb_layer_desc* d, uint32_t* l, uint32_t* r, uint32_t* u, uint32_t* dn) {
   if (!d->pad_style) { *l = *r = *u = *dn = d->pad; return; }
@@ -84,7 +88,7 @@ static void pad_split(const fcb_layer_desc* d, uint32_t* l, uint32_t* r, uint32_
 }
 
 int fo_layer_query(const fcb_layer_desc* d, fo_sizes* s) {
-  if (!d || d->struct_size != sizeof(fcb_layer_desc)) return -1;
+  if (!d || (d->struct_size != sizeof(fcb_layer_desc) && d->struct_size != FCB_LAYER_DESC_SIZE_V1)) return -1;
   if (!d->simd || !d->pe || !d->ifm_ch || !d->ofm_ch || !d->kernel_x || !d->kernel_y || !d->stride_x || !d->stride_y) return -1;
   if (d->ifm_ch % d->simd) return -2;                                /* slidingwindow.h:1259 */
   if (d->ofm_ch % d->pe) return -2;                                  /* streamtools.h:505 (PE*B -> OFM*B) */
@@ -96,10 +100,11 @@ int fo_layer_query(const fcb_layer_desc* d, fo_sizes* s) {
     if (d->kernel_x != 5 || d->kernel_y != 5 || d->stride_x != 2 || d->stride_y != 2 || d->pad != 2) return -2;
     ox = 2 * d->ifm_x; oy = 2 * d->ifm_y;
   } else if (d->kind == FCB_KIND_CONV || chanwise) {
-    if (d->ifm_x + pl + pr < d->kernel_x || d->ifm_y + pu + pd < d->kernel_y) return -2;
+    const uint32_t kex = (d->kernel_x - 1) * dil_x(d) + 1, key = (d->kernel_y - 1) * dil_y(d) + 1;
+    if (d->ifm_x + pl + pr < kex || d->ifm_y + pu + pd < key) return -2;
     /* kept windows: stride-1 positions 0..I+P-K with pos % S == 0 (conv_nonsquare_top.cpp:246-259) */
-    ox = (d->ifm_x + pl + pr - d->kernel_x) / d->stride_x + 1;
-    oy = (d->ifm_y + pu + pd - d->kernel_y) / d->stride_y + 1;
+    ox = (d->ifm_x + pl + pr - kex) / d->stride_x + 1;
+    oy = (d->ifm_y + pu + pd - key) / d->stride_y + 1;
     if (chanwise && (d->ofm_ch != d->ifm_ch || d->simd != d->pe)) return -2;  /* one output channel per input channel; SWG SIMD == PE */
   } else return -1;
   if (ox != d->ofm_x || oy != d->ofm_y) return -2;
@@ -172,6 +177,7 @@ int fo_layer_run(const fcb_layer_desc* d, const void* in_words, const void* weig
   const uint32_t PX = deconv ? 2 * d->ifm_x + 4 : d->ifm_x + pl + pr;
   const uint32_t PY = deconv ? 2 * d->ifm_y + 4 : d->ifm_y + pu + pd;
   const uint32_t SX = deconv ? 1 : d->stride_x, SY = deconv ? 1 : d->stride_y;
+  const uint32_t DXo = deconv ? 1 : dil_x(d), DYo = deconv ? 1 : dil_y(d);
 
   /* --- weights: W[ch][k] (A.2) ------------------------------------------------ */
   int32_t* W = (int32_t*)malloc(sizeof(int32_t) * (size_t)OFM * K);
@@ -244,11 +250,12 @@ int fo_layer_run(const fcb_layer_desc* d, const void* in_words, const void* weig
       int32_t* win = (int32_t*)malloc(sizeof(int32_t) * K);
       int16_t* winq = (int16_t*)malloc(sizeof(int16_t) * K);
       for (uint32_t ox = 0; ox < OX; ox++) {
-        /* sliding window in (ky, kx, c) order */
-        for (uint32_t ky = 0; ky < KY; ky++) {
-          const int32_t* src = P + ((size_t)(oy * SY + ky) * PX + (size_t)ox * SX) * C;
-          memcpy(win + (size_t)ky * KX * C, src, sizeof(int32_t) * KX * C);
-        }
+        /* sliding window in (ky, kx, c) order; dilated taps step DX / DY frame pixels */
+        for (uint32_t ky = 0; ky < KY; ky++)
+          for (uint32_t kx = 0; kx < KX; kx++) {
+            const int32_t* src = P + ((size_t)(oy * SY + ky * DYo) * PX + (size_t)ox * SX + (size_t)kx * DXo) * C;
+            memcpy(win + ((size_t)ky * KX + kx) * C, src, sizeof(int32_t) * C);
+          }
         if (fast) for (uint32_t k = 0; k < K; k++) winq[k] = (int16_t)win[k];
         uint32_t* o = act + ((size_t)oy * OX + ox) * OFM;
         for (uint32_t ch = 0; ch < OFM; ch++) {
@@ -349,7 +356,7 @@ static int fo_chanwise_run(const fcb_layer_desc* d, const fo_sizes* s, const voi
           else acc = 0;                                                  /* pool.hpp:66-69 */
           for (uint32_t ky = 0; ky < KY; ky++)
             for (uint32_t kx = 0; kx < KX; kx++) {
-              const int64_t y = (int64_t)oy * d->stride_y + ky - pu, x = (int64_t)ox * d->stride_x + kx - pl;
+              const int64_t y = (int64_t)oy * d->stride_y + (int64_t)ky * dil_y(d) - pu, x = (int64_t)ox * d->stride_x + (int64_t)kx * dil_x(d) - pl;
               int64_t a = 0;                                             /* FMPadding zero */
               if (y >= 0 && y < (int64_t)d->ifm_y && x >= 0 && x < (int64_t)d->ifm_x) {
                 uint32_t raw = get_bits(img + ((size_t)y * d->ifm_x + x) * s->in_word_bytes, (uint64_t)ch * d->in_bits, d->in_bits);

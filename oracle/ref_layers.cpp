@@ -298,6 +298,31 @@ int run_wide(const uint8_t* in, const uint8_t* wts, uint8_t* out) {
   return drain_stream<OFM * OUTB>(s_out, out, (size_t)OX * OY);
 }
 
+// ---- ConvolutionInputGenerator_NonSquare_Dilated (slidingwindow.h:1515-1631; x dilation only) and
+//      ConvolutionInputGenerator_kernel_stride (K % S != 0, square; :447-575) in front of the MVAU with thresholds
+template <unsigned KX, unsigned KY, unsigned SIMD, unsigned PE, unsigned WB, unsigned C, unsigned OFM, unsigned IX, unsigned IY, unsigned S, unsigned DX,
+          unsigned KSTRIDE_GEN, unsigned NTH, int TAB, unsigned TRB>
+int run_swg_variant(const uint8_t* in, const uint8_t* wts, const uint8_t* thr, uint8_t* out) {
+  constexpr unsigned OX = (IX - ((KX - 1) * DX + 1)) / S + 1, OY = (IY - KY) / S + 1;
+  constexpr unsigned MW = KX * KY * C, MH = OFM, SF = MW / SIMD, NF = MH / PE;
+  static FixedPointWeights<SIMD, ap_int<WB>, PE, SF * NF> w;
+  static ThresholdsActivation<NF, PE, NTH, ap_int<TAB>, ap_uint<TRB>, 0> act;
+  load_weights(w, wts);
+  load_thresholds(act, thr);
+  hls::stream<ap_uint<C * 8> > s_in("in");
+  hls::stream<ap_uint<SIMD * 8> > s_wa("wa"), s_win("win");
+  hls::stream<ap_uint<PE * TRB> > s_mv("mv");
+  hls::stream<ap_uint<OFM * TRB> > s_out("out");
+  fill_stream<C * 8>(s_in, in, (size_t)IX * IY);
+  StreamingDataWidthConverter_Batch<C * 8, SIMD * 8, IX * IY>(s_in, s_wa, 1);
+  if (KSTRIDE_GEN) ConvolutionInputGenerator_kernel_stride<KX, C, 8, IX, OX, SIMD, S>(s_wa, s_win, 1, ap_resource_dflt());
+  else ConvolutionInputGenerator_NonSquare_Dilated<KX, KY, C, 8, IX, IY, OX, OY, SIMD, S, S, DX, 1>(s_wa, s_win, 1, ap_resource_dflt());
+  Matrix_Vector_Activate_Batch<MW, MH, SIMD, PE, 1, Slice<ap_uint<8> >, Slice<ap_uint<TRB> >, Identity>(s_win, s_mv, w, act, OX * OY,
+                                                                                                     ap_resource_dsp());
+  StreamingDataWidthConverter_Batch<PE * TRB, OFM * TRB, OX * OY * NF>(s_mv, s_out, 1);
+  return drain_stream<OFM * TRB>(s_out, out, (size_t)OX * OY);
+}
+
 // ---- channel-wise units behind the depth-wise sliding window: ConvolutionInputGenerator_dws (square, any stride with K % S == 0,
 //      slidingwindow.h:761-868) or ConvolutionInputGenerator_NonSquare_dws (stride 1, :1377-1488), FMPadding_nonsquare in front.
 template <unsigned K, unsigned C, unsigned PE, unsigned IX, unsigned IY, unsigned S, unsigned PAD, unsigned INB>
@@ -375,6 +400,16 @@ REF_API int ref_lw5x12(const uint8_t* in, const uint8_t* w, const uint8_t* t, ui
 
 REF_API int ref_acc40(const uint8_t* in, const uint8_t* w, const uint8_t*, uint8_t* out, double*) {  // s16 x s16 -> ap_int<40> -> 32-bit lanes
   return run_wide<3, 4, 2, 16, 8, 8, 10, 6, 1, 16, 40, 32>(in, w, out);
+}
+
+REF_API int ref_dil_x2(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // 3x3, Dilation_x 2, 14x8 -> 10x6
+  return run_swg_variant<3, 3, 4, 2, 4, 8, 8, 14, 8, 1, 2, 0, 15, 24, 4>(in, w, t, out);
+}
+REF_API int ref_dil_x3_k2(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // 2x3 kernel (Kx 2, Ky 3), Dilation_x 3, 16 ch
+  return run_swg_variant<2, 3, 8, 4, 4, 16, 8, 13, 7, 1, 3, 0, 15, 24, 4>(in, w, t, out);
+}
+REF_API int ref_ks_k3s2(const uint8_t* in, const uint8_t* w, const uint8_t* t, uint8_t* out, double*) {  // kernel_stride generator: K 3, S 2 (3 % 2 != 0), 11x11 -> 5x5
+  return run_swg_variant<3, 3, 4, 2, 4, 8, 8, 11, 11, 2, 1, 1, 15, 24, 4>(in, w, t, out);
 }
 
 // AddStreams_Batch (streamtools.h:669-720): ref_<name>(in1, in2, out)

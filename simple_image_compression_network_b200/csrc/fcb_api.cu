@@ -34,7 +34,14 @@ static size_t word_bytes(uint32_t bits) {
 // divisibility (maxpool.h:140), and deconv522's hard-wired k5 s2 p2 (conv_nonsquare_top.cpp:84-86).
 int derive_geom(const fcb_layer_desc* d, Geom* g) {
   if (!d) { set_error("descriptor is NULL"); return FCB_ERR_INVALID_ARG; }
-  if (d->struct_size != sizeof(fcb_layer_desc)) { set_error("struct_size %u != %zu", d->struct_size, sizeof(fcb_layer_desc)); return FCB_ERR_INVALID_ARG; }
+  if (d->struct_size != sizeof(fcb_layer_desc) && d->struct_size != FCB_LAYER_DESC_SIZE_V1) {
+    set_error("struct_size %u is neither %zu nor %zu", d->struct_size, sizeof(fcb_layer_desc), (size_t)FCB_LAYER_DESC_SIZE_V1); return FCB_ERR_INVALID_ARG;
+  }
+  const bool has_dil = d->struct_size == sizeof(fcb_layer_desc);
+  const uint32_t DX = has_dil && d->dilation_x > 1 ? d->dilation_x : 1, DY = has_dil && d->dilation_y > 1 ? d->dilation_y : 1;
+  if ((DX > 1 || DY > 1) && d->kind == FCB_KIND_DECONV522) { set_error("deconv522 has no dilation"); return FCB_ERR_SHAPE; }
+  if (DX > 64 || DY > 64) { set_error("dilation > 64"); return FCB_ERR_UNSUPPORTED; }
+  const uint32_t KEX = (d->kernel_x - 1) * DX + 1, KEY = (d->kernel_y - 1) * DY + 1;  // extent of the dilated kernel
   if (d->engine_hint > FCB_ENGINE_TENSOR || d->pad_style > 2) { set_error("bad enum value"); return FCB_ERR_INVALID_ARG; }
   if (d->pad_style && d->pad) { set_error("pad must be 0 when pad_style selects pad_x_total / pad_y_total"); return FCB_ERR_INVALID_ARG; }
   if (!d->pad_style && (d->pad_x_total || d->pad_y_total)) { set_error("pad_x_total / pad_y_total need pad_style 1 or 2"); return FCB_ERR_INVALID_ARG; }
@@ -71,9 +78,9 @@ int derive_geom(const fcb_layer_desc* d, Geom* g) {
     }
     ox = 2 * d->ifm_x; oy = 2 * d->ifm_y;
   } else {
-    if (d->ifm_x + pl + pr < d->kernel_x || d->ifm_y + pu + pd < d->kernel_y) { set_error("kernel larger than padded input"); return FCB_ERR_SHAPE; }
-    ox = (d->ifm_x + pl + pr - d->kernel_x) / d->stride_x + 1;
-    oy = (d->ifm_y + pu + pd - d->kernel_y) / d->stride_y + 1;
+    if (d->ifm_x + pl + pr < KEX || d->ifm_y + pu + pd < KEY) { set_error("kernel larger than padded input"); return FCB_ERR_SHAPE; }
+    ox = (d->ifm_x + pl + pr - KEX) / d->stride_x + 1;
+    oy = (d->ifm_y + pu + pd - KEY) / d->stride_y + 1;
   }
   if (ox != d->ofm_x || oy != d->ofm_y) { set_error("ofm %ux%u does not match geometry %ux%u", d->ofm_x, d->ofm_y, ox, oy); return FCB_ERR_SHAPE; }
   if (d->kind != FCB_KIND_POOL && d->weight_kind == FCB_W_BINARY_XNOR && (d->w_bits != 1 || d->in_bits != 1)) { set_error("xnor needs 1-bit weights and activations"); return FCB_ERR_SHAPE; }
@@ -99,6 +106,7 @@ int derive_geom(const fcb_layer_desc* d, Geom* g) {
   g->kind = d->kind; g->C = d->ifm_ch; g->OFM = d->ofm_ch; g->KX = d->kernel_x; g->KY = d->kernel_y;
   g->IX = d->ifm_x; g->IY = d->ifm_y; g->OX = ox; g->OY = oy; g->SX = d->stride_x; g->SY = d->stride_y; g->PAD = (int)pl;
   g->pad_l = (int)pl; g->pad_r = (int)pr; g->pad_u = (int)pu; g->pad_d = (int)pd;
+  g->DX = (int)DX; g->DY = (int)DY;
   g->engine_hint = (int)d->engine_hint; g->pool_signed = d->pool_signed ? 1 : 0; g->pool_min = d->pool_min_value;
   g->simd = d->simd; g->pe = d->pe; g->K = g->KX * g->KY * g->C; g->SF = g->K / g->simd; g->NF = g->OFM / g->pe;
   g->in_bits = d->in_bits; g->in_signed = d->in_signed ? 1 : 0; g->w_bits = d->w_bits; g->weight_kind = d->weight_kind;
@@ -367,7 +375,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     if (g.pool >= 2 && (g.kind == FCB_KIND_DECONV522 || !(g.pool == 2 || g.pool == 4) || g.pool_signed || !min_is_zero)) {
       L->post_pool = true;
       ChanParams& c = L->pool_cw;
-      c.C = g.OFM; c.Cpad = (g.OFM + 31) / 32 * 32; c.KX = c.KY = g.pool; c.SX = c.SY = g.pool; c.IX = g.OX; c.IY = g.OY; c.OX = g.out_x; c.OY = g.out_y;
+      c.C = g.OFM; c.Cpad = (g.OFM + 31) / 32 * 32; c.KX = c.KY = g.pool; c.SX = c.SY = g.pool; c.DX = c.DY = 1; c.IX = g.OX; c.IY = g.OY; c.OX = g.out_x; c.OY = g.out_y;
       c.pad_l = c.pad_u = 0; c.in_bits = g.out_bits; c.in_signed = g.pool_signed; c.in_word_bytes = (int)g.out_word_bytes;
       c.out_word_bytes = (int)g.out_word_bytes; c.out_bits = g.out_bits; c.acc_bits = g.out_bits; c.acc_signed = g.pool_signed;
       c.mode = CW_POOL_MAX; c.has_init = 1; c.init = wrap_host(g.pool_min, g.out_bits, g.pool_signed);
@@ -447,6 +455,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     if (g.engine_hint == FCB_ENGINE_XNOR_POPC || g.engine_hint == FCB_ENGINE_TENSOR) { set_error("channel-wise units run on the CUDA cores only"); return FCB_ERR_UNSUPPORTED; }
     ChanParams& c = L->cw;
     c.C = g.C; c.Cpad = (g.C + 31) / 32 * 32; c.KX = g.KX; c.KY = g.KY; c.IX = g.IX; c.IY = g.IY; c.OX = g.OX; c.OY = g.OY; c.SX = g.SX; c.SY = g.SY;
+    c.DX = g.DX; c.DY = g.DY;
     c.pad_l = g.pad_l; c.pad_u = g.pad_u; c.in_bits = g.in_bits; c.in_signed = g.in_signed; c.in_word_bytes = (int)g.in_word_bytes;
     c.out_word_bytes = (int)g.out_word_bytes; c.out_bits = g.out_bits; c.acc_bits = g.acc_bits; c.acc_signed = g.acc_signed;
     c.in_img_bytes = g.in_img_bytes; c.out_img_bytes = g.out_img_bytes; c.size = g.act_val;
@@ -490,7 +499,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   const bool want_xnor_tensor = g.weight_kind == FCB_W_BINARY_XNOR && (hint == FCB_ENGINE_TENSOR || env_is("FCB_XNOR_ENGINE", "tensor"));
   bool xnor_tensor_done = false;
   if (want_xnor_tensor && g.act_kind == FCB_ACT_THRESHOLDS && g.kind == FCB_KIND_CONV && dense_bits && g.SX == g.SY && g.SX == 1 && g.OFM <= 256 &&
-      g.pool <= 2 && g.pad_l == g.pad_r && g.pad_u == g.pad_d && g.pad_l == g.pad_u &&
+      g.pool <= 2 && g.pad_l == g.pad_r && g.pad_u == g.pad_d && g.pad_l == g.pad_u && g.DX == 1 && g.DY == 1 &&
       (g.acc_bits >= 31 || g.K < (1 << (g.acc_bits - (g.acc_signed ? 1 : 0))))) {
     const int Cp = (g.C + 15) / 16 * 16;
     Geom g2 = g;
@@ -553,7 +562,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   }
   // thin-input layers (one 4-byte word per pixel, e.g. the ap_uint<24> C = 3 first layer): the sliding window is built in
   // shared memory inside the tensor-core kernel (fcb_umma2.cu, thin-input mode); FCB_THIN=im2col keeps the two-kernel lowering
-  const bool sym_pad = g.pad_l == g.pad_r && g.pad_u == g.pad_d && g.pad_l == g.pad_u;
+  const bool sym_pad = g.pad_l == g.pad_r && g.pad_u == g.pad_d && g.pad_l == g.pad_u && g.DX == 1 && g.DY == 1;  // (and no dilation)
   if (engine == ENG_IMAD && !force_imad && !env_is("FCB_THIN", "im2col") && g.kind == FCB_KIND_CONV && sym_pad &&
       g.weight_kind == FCB_W_FIXED && g.w_bits <= 8 && g.in_bits == 8 && g.in_word_bytes == 4 && g.KX * g.KY <= 32 && g.OFM <= 256 &&
       g.pool <= 2 && g.SX == g.SY && g.SX <= 2 && g.IX % 4 == 0 && (uint64_t)g.K * 255ull * 128ull < (1ull << 31)) {
@@ -597,7 +606,8 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     p.OX = g.OX; p.OY = g.OY; p.SXe = deconv ? 1 : g.SX; p.SYe = deconv ? 1 : g.SY; p.PAD = g.pad_l; p.PADY = g.pad_u; p.deconv = deconv;
     p.in_bits = g.in_bits; p.in_signed = g.in_signed; p.in_word_bytes = (int)g.in_word_bytes; p.out_word_bytes = (int)g.out_word_bytes;
     p.out_x = g.out_x; p.out_y = g.out_y; p.tiles_x = (g.OX + 15) / 16; p.tiles_y = (g.OY + 7) / 8;
-    p.patch_w = 15 * p.SXe + g.KX; p.patch_h = 7 * p.SYe + g.KY; p.mul_kind = g.weight_kind;
+    p.DX = g.DX; p.DY = g.DY;
+    p.patch_w = 15 * p.SXe + (g.KX - 1) * g.DX + 1; p.patch_h = 7 * p.SYe + (g.KY - 1) * g.DY + 1; p.mul_kind = g.weight_kind;
     p.in_img_bytes = g.in_img_bytes; p.out_img_bytes = g.out_img_bytes; p.epi = L->epi;
     const int cu = engine == ENG_XNOR ? g.C / 32 : g.C;
     const size_t budget = 96 * 1024;

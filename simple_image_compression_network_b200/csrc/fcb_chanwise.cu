@@ -37,9 +37,9 @@ __global__ void __launch_bounds__(256) chanwise_kernel(const ChanParams p) {
     if (p.mode == CW_POOL_MAX)  // pool.hpp:98-102: the type's minimum; StreamingMaxPool_Precision: min_value (maxpool.h:144-150)
       acc = p.has_init ? (int64_t)p.init : (p.acc_signed ? -((int64_t)1 << (p.acc_bits - 1)) : 0);
     for (int ky = 0; ky < p.KY; ky++) {
-      const int y = y0 + ky;
+      const int y = y0 + ky * p.DY;
       for (int kx = 0; kx < p.KX; kx++) {
-        const int x = x0 + kx;
+        const int x = x0 + kx * p.DX;
         int32_t a = 0;  // FMPadding zero
         if (chv && y >= 0 && y < p.IY && x >= 0 && x < p.IX)
           a = load_lane_any(in + ((size_t)y * p.IX + x) * p.in_word_bytes, ch, p.in_bits, p.in_signed);

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const DirectParams p) 
       }
       for (int it = 0; it < nit; it++) {
         const uint32_t w00 = wn[0], w01 = wn[1], w10 = wn[2], w11 = wn[3];
-        const int poff = (ky * p.patch_w + kx) * cc2 + c2;
+        const int poff = (ky * p.DY * p.patch_w + kx * p.DX) * cc2 + c2;
         if (++c2 == cc2) { c2 = 0; if (++kx == p.KX) { kx = 0; ++ky; } }
         if (it + 1 < nit) {
           const size_t r = wrow_of(ky, kx, c2);
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const DirectParams p) 
 #pragma unroll
             for (int i = 0; i < PXB * PXB; i++) {
               const int ly = wy + (i >> 2), lx = wx + (i & 3);
-              const uint32_t a = patch[((ly * p.SYe + ky) * p.patch_w + (lx * p.SXe + kx)) * cc + c];
+              const uint32_t a = patch[((ly * p.SYe + ky * p.DY) * p.patch_w + (lx * p.SXe + kx * p.DX)) * cc + c];
               acc[i][0] += __popc(~(a ^ w0));
               acc[i][1] += __popc(~(a ^ w1));
             }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const DirectParams p) 
 #pragma unroll
             for (int i = 0; i < PXB * PXB; i++) {
               const int ly = wy + (i >> 2), lx = wx + (i & 3);
-              const int32_t a = patch[((ly * p.SYe + ky) * p.patch_w + (lx * p.SXe + kx)) * cc + c];
+              const int32_t a = patch[((ly * p.SYe + ky * p.DY) * p.patch_w + (lx * p.SXe + kx * p.DX)) * cc + c];
               if (p.mul_kind == FCB_W_BINARY_XNOR) {
                 acc[i][0] += (a == w0);
                 acc[i][1] += (a == w1);

@@ -38,6 +38,7 @@ inline int exp_int(const char* name, int dflt) {
 // ---- derived geometry -------------------------------------------------------------
 struct Geom {
   int kind, C, OFM, KX, KY, IX, IY, OX, OY, SX, SY, PAD;
+  int DX, DY;                      // dilation (slidingwindow.h:1515-1631), 1 = none
   int pad_l, pad_r, pad_u, pad_d;  // FMPadding_nonsquare split (streamtools.h:374-379); PAD = pad_l when all four are equal
   int engine_hint, pool_signed, pool_min;
   int simd, pe, SF, NF, K;
@@ -75,7 +76,7 @@ struct DirectParams {  // imad / xnor_popc direct convolution
   uint8_t* out;
   const void* wt;  // imad: int16 [K][OFMp]; xnor: uint32 [KW][OFMp]
   EpiParams epi;
-  int C, OFM, OFMp, KX, KY, IX, IY, OX, OY, SXe, SYe, PAD, PADY, deconv;  // PAD / PADY: zeros left / up of the frame
+  int C, OFM, OFMp, KX, KY, DX, DY, IX, IY, OX, OY, SXe, SYe, PAD, PADY, deconv;  // PAD / PADY: zeros left / up of the frame
   int in_bits, in_signed, in_word_bytes, out_word_bytes, out_x, out_y;
   int tiles_x, tiles_y, CC, patch_w, patch_h, mul_kind;
   unsigned long long in_img_bytes, out_img_bytes;
@@ -101,7 +102,7 @@ struct ChanParams {
   uint8_t* out;
   const int16_t* wt;  // depth-wise weights [Kx*Ky][Cpad]
   EpiParams epi;
-  int C, Cpad, KX, KY, IX, IY, OX, OY, SX, SY, pad_l, pad_u;
+  int C, Cpad, KX, KY, DX, DY, IX, IY, OX, OY, SX, SY, pad_l, pad_u;
   int in_bits, in_signed, in_word_bytes, out_word_bytes, out_bits;
   int mode, size, acc_bits, acc_signed;
   int has_init, init;  // CW_POOL_MAX started from `init` instead of the type's minimum (StreamingMaxPool_Precision's min_value)

@@ -1206,7 +1206,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   if (!deconv) {
     for (int ky = 0; ky < g.KY; ky++)
       for (int kx = 0; kx < g.KX; kx++) {
-        const int dx = kx - g.PAD, dy = ky - g.PAD;
+        const int dx = kx * g.DX - g.PAD, dy = ky * g.DY - g.PAD;  // (a dilated tap is just another plane offset)
         taps.push_back({fdiv(dx, s), fdiv(dy, s), dx - fdiv(dx, s) * s, dy - fdiv(dy, s) * s, ky * g.KX + kx, 0});
       }
   } else {
@@ -1511,7 +1511,7 @@ static cudaError_t launch_resident(const Umma2Plan* U, int grid, int threads, cu
 int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& epi, int num_sms, int bias_word, Umma2Plan** out) {
   *out = nullptr;
   const int s = g.SX, nw = g.KX * g.KY;
-  if (g.kind != FCB_KIND_CONV || g.in_word_bytes != 4 || g.in_bits != 8 || nw > 32 || g.SX != g.SY || s < 1 || s > 2 || g.pool > 2 ||
+  if (g.kind != FCB_KIND_CONV || g.in_word_bytes != 4 || g.in_bits != 8 || nw > 32 || g.SX != g.SY || s < 1 || s > 2 || g.pool > 2 || g.DX != 1 || g.DY != 1 ||
       (g.IX % 4) || g.OFM > 256)
     return FCB_ERR_UNSUPPORTED;
   const int CB = (g.OFM + 127) / 128;

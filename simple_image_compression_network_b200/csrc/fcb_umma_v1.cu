@@ -241,7 +241,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // v1 (per-tap TMA) needs whole 128-byte channel chunks and 32-channel epilogue groups
-int umma_v1_eligible(const Geom& g) { return g.C % KCH == 0 && g.OFM % 32 == 0 && g.OFM >= 32 && g.OFM <= 256 && g.KX * g.KY <= MAX_TAPS; }
+int umma_v1_eligible(const Geom& g) { return g.DX == 1 && g.DY == 1 && g.C % KCH == 0 && g.OFM % 32 == 0 && g.OFM >= 32 && g.OFM <= 256 && g.KX * g.KY <= MAX_TAPS; }
 
 int umma_v1_create(const Geom& g, int8_t* d_w, const EpiParams& epi, int num_sms, UmmaV1** out) {
   *out = nullptr;

@@ -27,7 +27,7 @@ class CLayerDesc(ctypes.Structure):
         "acc_bits", "acc_signed", "act_kind", "out_bits", "num_th")] + [
         ("act_val", ctypes.c_int32), ("cmp", ctypes.c_uint32), ("pool", ctypes.c_uint32), ("engine_hint", ctypes.c_uint32),
         ("pad_x_total", ctypes.c_uint32), ("pad_y_total", ctypes.c_uint32), ("pad_style", ctypes.c_uint32),
-        ("pool_signed", ctypes.c_uint32), ("pool_min_value", ctypes.c_int32)]
+        ("pool_signed", ctypes.c_uint32), ("pool_min_value", ctypes.c_int32), ("dilation_x", ctypes.c_uint32), ("dilation_y", ctypes.c_uint32)]
 
 
 class CAddDesc(ctypes.Structure):
@@ -70,6 +70,9 @@ class LayerDesc:
     # StreamingMaxPool_Precision's ActType signedness and min_value (maxpool.h:137-170)
     pool_signed: int = 0
     pool_min_value: int = 0
+    # ConvolutionInputGenerator_NonSquare_Dilated (slidingwindow.h:1515-1631); 1 = none
+    dilation_x: int = 1
+    dilation_y: int = 1
 
     # ---- derived geometry (conv_nonsquare_top.cpp:238-259 / :109-169) ----
     @property
@@ -87,14 +90,14 @@ class LayerDesc:
         if self.kind == KIND_DECONV522:
             return 2 * self.ifm_x
         left, right, _, _ = self.pads
-        return (self.ifm_x + left + right - self.kernel_x) // self.stride_x + 1
+        return (self.ifm_x + left + right - ((self.kernel_x - 1) * self.dilation_x + 1)) // self.stride_x + 1
 
     @property
     def ofm_y(self) -> int:
         if self.kind == KIND_DECONV522:
             return 2 * self.ifm_y
         _, _, up, down = self.pads
-        return (self.ifm_y + up + down - self.kernel_y) // self.stride_y + 1
+        return (self.ifm_y + up + down - ((self.kernel_y - 1) * self.dilation_y + 1)) // self.stride_y + 1
 
     @property
     def out_x(self) -> int:
@@ -127,7 +130,7 @@ class LayerDesc:
         for f in ("kind", "kernel_x", "kernel_y", "ifm_ch", "ofm_ch", "ifm_x", "ifm_y", "stride_x", "stride_y", "pad",
                   "simd", "pe", "in_bits", "in_signed", "w_bits", "weight_kind", "acc_bits", "acc_signed", "act_kind",
                   "out_bits", "num_th", "act_val", "cmp", "pool", "engine_hint", "pad_x_total", "pad_y_total", "pad_style",
-                  "pool_signed", "pool_min_value"):
+                  "pool_signed", "pool_min_value", "dilation_x", "dilation_y"):
             setattr(c, f, getattr(self, f))
         c.ofm_x, c.ofm_y = self.ofm_x, self.ofm_y
         return c
