@@ -32,12 +32,26 @@ static size_t word_bytes(uint32_t bits) {
 // Validation mirrors the reference's preconditions: IFMChannels % SIMD (slidingwindow.h:1259),
 // DWC divisibility PE*B | OFM*B (streamtools.h:505), TILES == NF*SF (mvau.hpp:101-105,117), pool
 // divisibility (maxpool.h:140), and deconv522's hard-wired k5 s2 p2 (conv_nonsquare_top.cpp:84-86).
-int derive_geom(const fcb_layer_desc* d, Geom* g) {
-  if (!d) { set_error("descriptor is NULL"); return FCB_ERR_INVALID_ARG; }
-  if (d->struct_size != sizeof(fcb_layer_desc) && d->struct_size != FCB_LAYER_DESC_SIZE_V1) {
-    set_error("struct_size %u is neither %zu nor %zu", d->struct_size, sizeof(fcb_layer_desc), (size_t)FCB_LAYER_DESC_SIZE_V1); return FCB_ERR_INVALID_ARG;
+// A caller built against ABI 0.1 passes the shorter struct (FCB_LAYER_DESC_SIZE_V1): copy what it has into the current layout, the
+// appended fields read as zero.  Nothing past the caller's struct_size is ever touched.
+int normalize_desc(const fcb_layer_desc* in, fcb_layer_desc* out) {
+  if (!in) { set_error("descriptor is NULL"); return FCB_ERR_INVALID_ARG; }
+  if (in->struct_size != sizeof(fcb_layer_desc) && in->struct_size != FCB_LAYER_DESC_SIZE_V1) {
+    set_error("struct_size %u is neither %zu nor %zu", in->struct_size, sizeof(fcb_layer_desc), (size_t)FCB_LAYER_DESC_SIZE_V1);
+    return FCB_ERR_INVALID_ARG;
   }
-  const bool has_dil = d->struct_size == sizeof(fcb_layer_desc);
+  memset(out, 0, sizeof(*out));
+  memcpy(out, in, in->struct_size);
+  out->struct_size = sizeof(fcb_layer_desc);
+  return FCB_OK;
+}
+
+int derive_geom(const fcb_layer_desc* d_in, Geom* g) {
+  fcb_layer_desc dn;
+  int nrc = normalize_desc(d_in, &dn);
+  if (nrc) return nrc;
+  const fcb_layer_desc* d = &dn;
+  const bool has_dil = true;
   const uint32_t DX = has_dil && d->dilation_x > 1 ? d->dilation_x : 1, DY = has_dil && d->dilation_y > 1 ? d->dilation_y : 1;
   if ((DX > 1 || DY > 1) && d->kind == FCB_KIND_DECONV522) { set_error("deconv522 has no dilation"); return FCB_ERR_SHAPE; }
   if (DX > 64 || DY > 64) { set_error("dilation > 64"); return FCB_ERR_UNSUPPORTED; }
@@ -363,7 +377,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     ~Guard() { if (armed && L) fcb_layer_destroy(L); }
   } guard{L};
   L->g = g;
-  L->desc = *desc;
+  normalize_desc(desc, &L->desc);
   L->device = device;
   // StreamingMaxPool[_Precision] (maxpool.h:66-185) is fused into the epilogues for the common form: 2x2 (tensor engine) / 2x2 and 4x4
   // (direct engines), unsigned lanes, maxima starting from 0, behind a conv2d.  Every other form the template expresses -- other
@@ -410,6 +424,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         }
   }
   // ---- activation parameters
+  L->epi.ta_bits = g.acc_bits;
   L->epi.act_kind = g.act_kind; L->epi.acc_bits = g.acc_bits; L->epi.acc_signed = g.acc_signed; L->epi.out_bits = g.out_bits;
   L->epi.num_th = g.num_th; L->epi.act_val = g.act_val; L->epi.cmp = g.cmp; L->epi.pool = g.pool;
   if (g.act_kind == FCB_ACT_BIAS_RELU) {
@@ -524,7 +539,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
       rc = upload_thresholds(L, rows2);
       if (rc) return rc;
       EpiParams e2 = L->epi;
-      e2.acc_bits = 32; e2.acc_signed = 1;
+      e2.acc_bits = 32; e2.acc_signed = 1; e2.ta_bits = 32;
       rc = umma_plan_create(g2, W2, e2, device, &L->umma);
       if (rc == FCB_OK) {
         L->epi = e2;

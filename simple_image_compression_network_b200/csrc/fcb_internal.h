@@ -49,10 +49,12 @@ struct Geom {
   size_t w_word_bytes, weight_bytes, threshold_bytes, bias_bytes;
 };
 int derive_geom(const fcb_layer_desc* d, Geom* g);  // validates like the reference's CASSERTs
+int normalize_desc(const fcb_layer_desc* in, fcb_layer_desc* out);  // either ABI struct size -> the current layout
 
 // ---- epilogue parameters (device-visible POD) -----------------------------------------
 struct EpiParams {
   int act_kind, acc_bits, acc_signed, out_bits, num_th, act_val, cmp, pool;
+  int ta_bits;  // TA's declared width: accumulators and thresholds lie within it even when the wrap itself was elided (acc_bits = 32)
   const int8_t* bias;    // [OFM]            (FCB_ACT_BIAS_RELU)
   const int32_t* thr;    // [thr_n][thr_stride]: threshold i of channel ch at thr[i*thr_stride + ch]; per channel sorted
                          // ascending, wrapped to TA, padded with INT32_MAX up to thr_n = 2^k - 1 entries (FCB_ACT_THRESHOLDS)

@@ -60,6 +60,13 @@ int fcb_pool_create(const fcb_layer_desc* descs, const void* const* weights, con
     }
   }
   if (devs.empty()) { set_error("no usable sm_100 device (this library has no CPU path)"); return FCB_ERR_CUDA; }
+  // the array's element size is the caller's struct_size (a client built against ABI 0.1 passes shorter structs)
+  std::vector<fcb_layer_desc> dn(n_layers);
+  for (uint32_t i = 0; i < n_layers; i++) {
+    int rc = normalize_desc((const fcb_layer_desc*)((const uint8_t*)descs + (size_t)i * descs->struct_size), &dn[i]);
+    if (rc) return rc;
+  }
+  descs = dn.data();
   fcb_pool* P = new fcb_pool();
   P->reps.resize(devs.size());
   for (size_t r = 0; r < devs.size(); r++) {

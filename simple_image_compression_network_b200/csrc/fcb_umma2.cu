@@ -1115,6 +1115,11 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     }
                   } else if (use_lut) {
                     activate_thr_lut<8>(p.epi, top_s, row_shift, lut_s, lut_lo, lut_sh, m8, pooled);
+                  } else if (THRP && gshift == 2 && p.thr_top == 6 && p.epi.thr_n == 255 && p.epi.ta_bits <= 30) {
+                    // 255 thresholds, 63 of them in shared memory (every 4th), m8 already wrapped to TA
+                    const int ns = p.epi.cmp == FCB_CMP_LESS_EQUAL ? 1 : 0;
+                    if (p.CB == 2) thr_hybrid_fast<8, 6, 1024>(top_s - 1024u, ns, p.epi.act_val, row_cm, m8, pooled);
+                    else thr_hybrid_fast<8, 6, 512>(top_s - 512u, ns, p.epi.act_val, row_cm, m8, pooled);
                   } else if (THRP || hybrid) {
                     activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, m8, pooled);
                   } else {

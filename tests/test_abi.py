@@ -109,3 +109,15 @@ def test_engine_hint_and_padding_fields_validated(fcb_lib):
     ok = dataclasses.replace(d, pad=0, pad_style=2, pad_x_total=4, pad_y_total=4)                           # == pad 2 on every side
     assert (ok.ofm_x, ok.ofm_y) == (d.ofm_x, d.ofm_y)
     assert _query(fcb_lib, ok)[0] == 0, fcb_lib.fcb_last_error()
+
+
+def test_v1_descriptor_size_still_accepted(fcb_lib):
+    """A client compiled against ABI 0.1 passes fcb_layer_desc without the appended dilation fields (FCB_LAYER_DESC_SIZE_V1)."""
+    d = cases.CASES["c2d_a"]
+    c = d.to_c()
+    c.struct_size = ctypes.sizeof(c) - 8
+    c.dilation_x = 77  # garbage past the caller's struct must not be read
+    sizes = [ctypes.c_size_t() for _ in range(5)]
+    assert fcb_lib.fcb_layer_query(ctypes.byref(c), *[ctypes.byref(s) for s in sizes]) == 0, fcb_lib.fcb_last_error()
+    c.struct_size = ctypes.sizeof(c) - 4
+    assert fcb_lib.fcb_layer_query(ctypes.byref(c), *[ctypes.byref(s) for s in sizes]) == -1
