@@ -626,10 +626,12 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     p.in_img_bytes = g.in_img_bytes; p.out_img_bytes = g.out_img_bytes; p.epi = L->epi;
     const int cu = engine == ENG_XNOR ? g.C / 32 : g.C;
     const size_t budget = 96 * 1024;
-    int cc = (int)(budget / ((size_t)p.patch_w * p.patch_h * 4));
+    const bool imad2 = engine == ENG_IMAD && g.weight_kind != FCB_W_BINARY_XNOR;  // imad_conv_kernel: weights share the budget
+    int cc = imad2 ? (int)(budget / ((size_t)p.patch_w * p.patch_h * 4 + (size_t)g.KX * g.KY * 128)) & ~3
+                   : (int)(budget / ((size_t)p.patch_w * p.patch_h * 4));
     if (cc < 1) { set_error("kernel %dx%d stride %d: patch does not fit shared memory", g.KX, g.KY, g.SX); return FCB_ERR_UNSUPPORTED; }
     p.CC = std::min(cc, cu);
-    L->smem = direct_smem_bytes(engine, p.patch_w, p.patch_h, p.CC);
+    L->smem = imad2 ? imad_smem_bytes(p.patch_w, p.patch_h, g.KX * g.KY, p.CC) : direct_smem_bytes(engine, p.patch_w, p.patch_h, p.CC);
     if (engine == ENG_XNOR) {
       const int KW = g.KX * g.KY * (g.C / 32);
       std::vector<uint32_t> Wb((size_t)KW * p.OFMp, 0u);
@@ -707,7 +709,7 @@ const char* fcb_layer_plan(const fcb_layer* L) {
   if (!L) return "";
   if (L->lowered) return L->plan_desc;
   if (L->engine == ENG_CHANWISE) return "channel-wise streaming unit: warp = output pixel, lanes walk the channels";
-  return L->engine == ENG_UMMA ? umma_plan_describe(L->umma) : "direct 16x8-pixel x 64-channel CTA tiles";
+  return L->engine == ENG_UMMA ? umma_plan_describe(L->umma) : "direct 16x8-pixel x 64-channel CTA tiles (patch and weight pairs in shared memory)";
 }
 uint64_t fcb_layer_launches(const fcb_layer* L) { return L ? L->launches : 0; }
 

@@ -32,6 +32,50 @@ __device__ __forceinline__ bool map_coord(int v, int pad, int deconv, int extent
   return s >= 0 && !(s & 1) && (s >> 1) < extent;
 }
 
+// activation, pool, store of one warp's 4x4 pixel block x 2 channels per lane (shared by both direct kernels)
+__device__ __forceinline__ void direct_epilogue(const DirectParams& p, const int32_t (&acc)[PXB * PXB][2], int img, int ch0, int ox0, int oy0, int wx,
+                                                int wy, int lane) {
+  // ---- activation, pool, store -----------------------------------------------------------
+  const int pk = p.epi.pool >= 2 ? p.epi.pool : 1;
+  uint8_t* out = p.out + (size_t)img * p.out_img_bytes;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int ch = ch0 + 32 * j;
+    const bool chv = ch < p.OFM;
+    uint32_t val[PXB * PXB];
+#pragma unroll
+    for (int i = 0; i < PXB * PXB; i++) val[i] = chv ? activate(p.epi, ch, acc[i][j]) : 0u;
+    if (p.epi.out_bits == 1 && pk == 1) {
+      // 1-bit lanes: one ballot per pixel; lane i keeps pixel i of the 4x4 block, then one store instruction for all 16
+      uint32_t mine = 0;
+#pragma unroll
+      for (int i = 0; i < PXB * PXB; i++) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, chv && (val[i] & 1u));
+        if (lane == i) mine = bits;
+      }
+      const int oy = oy0 + wy + (lane >> 2), ox = ox0 + wx + (lane & 3), c0 = ch - lane;  // c0: first channel of this warp
+      if (lane < PXB * PXB && oy < p.OY && ox < p.OX && c0 < p.OFM) {
+        uint8_t* dst = out + ((size_t)oy * p.out_x + ox) * p.out_word_bytes + (c0 >> 3);
+        if (c0 + 32 <= p.OFM && p.out_word_bytes >= 4) *reinterpret_cast<uint32_t*>(dst) = mine;
+        else
+          for (int b = 0; b < 4; b++)
+            if (c0 + 8 * b < p.OFM) dst[b] = (uint8_t)(mine >> (8 * b));
+      }
+      continue;
+    }
+    for (int by = 0; by < PXB; by += pk)
+      for (int bx = 0; bx < PXB; bx += pk) {
+        const int oy = oy0 + wy + by, ox = ox0 + wx + bx;  // pre-pool pixel (warp-uniform)
+        if (oy >= p.OY || ox >= p.OX) continue;
+        uint32_t m = 0;
+        for (int dy = 0; dy < pk; dy++)
+          for (int dx = 0; dx < pk; dx++) m = max(m, val[(by + dy) * PXB + bx + dx]);
+        uint8_t* word = out + ((size_t)(oy / pk) * p.out_x + (ox / pk)) * p.out_word_bytes;
+        store_lane(word, ch, chv, m, p.epi.out_bits);
+      }
+  }
+}
+
 template <int ENGINE>
 __global__ void __launch_bounds__(256) direct_conv_kernel(const DirectParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -140,51 +184,110 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const DirectParams p) 
       }
     __syncthreads();
   }
+  direct_epilogue(p, acc, img, ch0, ox0, oy0, wx, wy, lane);
+}
 
-  // ---- activation, pool, store -----------------------------------------------------------
-  const int pk = p.epi.pool >= 2 ? p.epi.pool : 1;
-  uint8_t* out = p.out + (size_t)img * p.out_img_bytes;
+// ------------------------------------------------------------------------------------------------------------------------
+// imad_conv_kernel -- the IMAD engine proper (FixedPoint / +-1 weights; north_star: "IMAD for wider types").
+// Same decomposition as above (CTA = 16x8 pixels x 64 channels, warp = 4x4 pixels, lane = channels {l, l+32}), with the inner loop
+// built around the shared-memory pipe instead of L1:
+//   * the weights of the channel chunk are staged in shared memory as packed pairs, word [tap][c][lane] = w(ch l) | w(ch l+32) << 16:
+//     one conflict-free LDS per (tap, channel) instead of two L1 loads whose latency nothing hid;
+//   * the patch is stored with a channel pitch that is a multiple of 4, so one LDS.128 brings 4 channels of a pixel: per 4 channels
+//     a lane issues 16 + 4 shared loads for 128 IMADs (16 + 2 per 32 before);
+//   * deconv522: taps are walked by parity class and only the pixels whose (row + ky, column + kx) parities hit a non-zero sample
+//     of the zero-inserted frame are unrolled: 4x fewer IMADs, the structural zeros are never multiplied.
+template <bool DECONV, int PKY, int PKX>
+__device__ __forceinline__ void imad_taps(const DirectParams& p, const int32_t* __restrict__ patch, const uint32_t* __restrict__ wsm, int cc4, int lane,
+                                          int wx, int wy, int32_t (&acc)[PXB * PXB][2]) {
+  const int rowstep = p.SYe * p.patch_w * cc4, colstep = p.SXe * cc4;
+  for (int ky = DECONV ? PKY : 0; ky < p.KY; ky += DECONV ? 2 : 1)
+    for (int kx = DECONV ? PKX : 0; kx < p.KX; kx += DECONV ? 2 : 1) {
+      const uint32_t* wrow = wsm + (size_t)(ky * p.KX + kx) * cc4 * 32 + lane;
+      const int32_t* prow = patch + ((size_t)(wy * p.SYe + ky * p.DY) * p.patch_w + wx * p.SXe + kx * p.DX) * cc4;
+      for (int c = 0; c < cc4; c += 4) {
+        int32_t w0[4], w1[4];
 #pragma unroll
-  for (int j = 0; j < 2; j++) {
-    const int ch = ch0 + 32 * j;
-    const bool chv = ch < p.OFM;
-    uint32_t val[PXB * PXB];
+        for (int j = 0; j < 4; j++) {
+          const uint32_t wp = wrow[(c + j) * 32];
+          w0[j] = (int32_t)(int16_t)(wp & 0xFFFFu);
+          w1[j] = (int32_t)wp >> 16;
+        }
 #pragma unroll
-    for (int i = 0; i < PXB * PXB; i++) val[i] = chv ? activate(p.epi, ch, acc[i][j]) : 0u;
-    if (p.epi.out_bits == 1 && pk == 1) {
-      // 1-bit lanes: one ballot per pixel; lane i keeps pixel i of the 4x4 block, then one store instruction for all 16
-      uint32_t mine = 0;
-#pragma unroll
-      for (int i = 0; i < PXB * PXB; i++) {
-        const uint32_t bits = __ballot_sync(0xffffffffu, chv && (val[i] & 1u));
-        if (lane == i) mine = bits;
+        for (int i = 0; i < PXB * PXB; i++) {
+          const int ly = i >> 2, lx = i & 3;
+          if (DECONV && (((ly ^ PKY) & 1) || ((lx ^ PKX) & 1))) continue;  // compile-time: structural zero of the inserted frame
+          const int4 a = *reinterpret_cast<const int4*>(prow + ly * rowstep + lx * colstep + c);
+          acc[i][0] += a.x * w0[0] + a.y * w0[1] + a.z * w0[2] + a.w * w0[3];
+          acc[i][1] += a.x * w1[0] + a.y * w1[1] + a.z * w1[2] + a.w * w1[3];
+        }
       }
-      const int oy = oy0 + wy + (lane >> 2), ox = ox0 + wx + (lane & 3), c0 = ch - lane;  // c0: first channel of this warp
-      if (lane < PXB * PXB && oy < p.OY && ox < p.OX && c0 < p.OFM) {
-        uint8_t* dst = out + ((size_t)oy * p.out_x + ox) * p.out_word_bytes + (c0 >> 3);
-        if (c0 + 32 <= p.OFM && p.out_word_bytes >= 4) *reinterpret_cast<uint32_t*>(dst) = mine;
-        else
-          for (int b = 0; b < 4; b++)
-            if (c0 + 8 * b < p.OFM) dst[b] = (uint8_t)(mine >> (8 * b));
-      }
-      continue;
     }
-    for (int by = 0; by < PXB; by += pk)
-      for (int bx = 0; bx < PXB; bx += pk) {
-        const int oy = oy0 + wy + by, ox = ox0 + wx + bx;  // pre-pool pixel (warp-uniform)
-        if (oy >= p.OY || ox >= p.OX) continue;
-        uint32_t m = 0;
-        for (int dy = 0; dy < pk; dy++)
-          for (int dx = 0; dx < pk; dx++) m = max(m, val[(by + dy) * PXB + bx + dx]);
-        uint8_t* word = out + ((size_t)(oy / pk) * p.out_x + (ox / pk)) * p.out_word_bytes;
-        store_lane(word, ch, chv, m, p.epi.out_bits);
+}
+
+__global__ void __launch_bounds__(256, 2) imad_conv_kernel(const DirectParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+  const int img = blockIdx.z;
+  const int chb = blockIdx.y * CH_PER_CTA, ch0 = chb + lane;
+  const int ox0 = tx * TX, oy0 = ty * TY;
+  const int wx = (warp & 3) * PXB, wy = (warp >> 2) * PXB;
+  const uint8_t* in = p.in + (size_t)img * p.in_img_bytes;
+  int32_t acc[PXB * PXB][2];
+#pragma unroll
+  for (int i = 0; i < PXB * PXB; i++) acc[i][0] = acc[i][1] = 0;
+  const int vx0 = ox0 * p.SXe, vy0 = oy0 * p.SYe;
+  int32_t* patch = reinterpret_cast<int32_t*>(smem_raw);
+  const int16_t* wt = reinterpret_cast<const int16_t*>(p.wt);
+  for (int c0 = 0; c0 < p.C; c0 += p.CC) {
+    const int cc = min(p.CC, p.C - c0), cc4 = (cc + 3) & ~3;
+    uint32_t* wsm = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)p.patch_h * p.patch_w * cc4;
+    // ---- stage the patch: zero padding / zero insertion resolved here; channels cc..cc4 are zeros
+    const int total = p.patch_h * p.patch_w * cc4;
+    for (int idx = tid; idx < total; idx += blockDim.x) {
+      const int c = idx % cc4, pix = idx / cc4;
+      const int px = pix % p.patch_w, py = pix / p.patch_w;
+      int sx, sy;
+      const bool okx = map_coord(vx0 + px, p.PAD, p.deconv, p.IX, &sx);
+      const bool oky = map_coord(vy0 + py, p.PADY, p.deconv, p.IY, &sy);
+      int32_t v = 0;
+      if (c < cc && okx && oky) v = load_lane_any(in + ((size_t)sy * p.IX + sx) * p.in_word_bytes, c0 + c, p.in_bits, p.in_signed);
+      patch[idx] = v;
+    }
+    // ---- stage the weights of this channel chunk as packed pairs
+    const int wtotal = p.KX * p.KY * cc4 * 32;
+    for (int idx = tid; idx < wtotal; idx += blockDim.x) {
+      const int l = idx & 31, c = (idx >> 5) % cc4, tap = (idx >> 5) / cc4;
+      uint32_t wp = 0;
+      if (c < cc) {
+        const size_t row = (size_t)(tap * p.C + c0 + c) * p.OFMp + chb + l;
+        wp = ((uint32_t)(uint16_t)__ldg(wt + row)) | ((uint32_t)(uint16_t)__ldg(wt + row + 32) << 16);
       }
+      wsm[idx] = wp;
+    }
+    __syncthreads();
+    if (p.deconv) {
+      imad_taps<true, 0, 0>(p, patch, wsm, cc4, lane, wx, wy, acc);
+      imad_taps<true, 0, 1>(p, patch, wsm, cc4, lane, wx, wy, acc);
+      imad_taps<true, 1, 0>(p, patch, wsm, cc4, lane, wx, wy, acc);
+      imad_taps<true, 1, 1>(p, patch, wsm, cc4, lane, wx, wy, acc);
+    } else {
+      imad_taps<false, 0, 0>(p, patch, wsm, cc4, lane, wx, wy, acc);
+    }
+    __syncthreads();
   }
+  direct_epilogue(p, acc, img, ch0, ox0, oy0, wx, wy, lane);
 }
 
 size_t direct_smem_bytes(int engine, int patch_w, int patch_h, int cc) {
   (void)engine;
   return (size_t)patch_w * patch_h * cc * 4;
+}
+// imad_conv_kernel: patch (channel pitch rounded up to 4) + packed weight pairs of the chunk
+size_t imad_smem_bytes(int patch_w, int patch_h, int taps, int cc) {
+  const size_t cc4 = (size_t)((cc + 3) & ~3);
+  return (size_t)patch_w * patch_h * cc4 * 4 + (size_t)taps * cc4 * 128;
 }
 
 int launch_direct(const DirectParams& p, int engine, int n_images, size_t smem_bytes, cudaStream_t st) {
@@ -199,9 +302,12 @@ int launch_direct(const DirectParams& p, int engine, int n_images, size_t smem_b
     if (engine == ENG_XNOR) {
       FCB_CUDA_OK(cudaFuncSetAttribute(direct_conv_kernel<ENG_XNOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       direct_conv_kernel<ENG_XNOR><<<grid, 256, smem_bytes, st>>>(q);
-    } else {
+    } else if (p.mul_kind == FCB_W_BINARY_XNOR) {  // xnor layers the popcount engine cannot take (IFM_CH % 32 != 0): a == w per lane
       FCB_CUDA_OK(cudaFuncSetAttribute(direct_conv_kernel<ENG_IMAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       direct_conv_kernel<ENG_IMAD><<<grid, 256, smem_bytes, st>>>(q);
+    } else {
+      FCB_CUDA_OK(cudaFuncSetAttribute(imad_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      imad_conv_kernel<<<grid, 256, smem_bytes, st>>>(q);
     }
     FCB_CUDA_OK(cudaGetLastError());
   }

@@ -220,38 +220,6 @@ __device__ __forceinline__ void thr_lut_fast(uint32_t base, uint32_t fin_base, u
   for (int i = 0; i < N; i++) out[i] = (posb[i] - fin_base) >> rsh;
 }
 
-// The pooled-threshold instantiations' hybrid search when the full table does not fit shared memory: TOP binary levels on the
-// shared-memory table of every G-th sorted threshold (G = 4), then one aligned 16-byte group of the channel-major global copy.
-// Same preconditions as thr_lut_fast; comp::less_equal is folded into the operand (thr <= a  <=>  thr < a + 1; |a| < 2^30), ROWB is
-// a compile-time constant, and the position stays a byte offset into the thread's column: a level is LDS [pos + imm], ISETP, predicated add.
-template <int N, int TOP, int ROWB>
-__device__ __forceinline__ void thr_hybrid_fast(uint32_t base /* column address - ROWB */, int nonstrict, int act_val,
-                                                const int32_t* __restrict__ row_cm, const int32_t (&acc)[N], uint32_t (&out)[N]) {
-  int32_t a[N];
-  uint32_t posb[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) { a[i] = acc[i] + nonstrict; posb[i] = base; }
-#pragma unroll
-  for (int l = 0; l < TOP; l++) {
-    constexpr uint32_t top = (uint32_t)ROWB << (TOP - 1);
-    const uint32_t stepb = top >> l;
-    int32_t tv[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) tv[i] = lds_s32(posb[i] + stepb);
-#pragma unroll
-    for (int i = 0; i < N; i++)
-      if (tv[i] < a[i]) posb[i] += stepb;
-  }
-  constexpr int rsh = ROWB == 512 ? 9 : 10;
-  int4 qv[N];
-  const char* rowb = reinterpret_cast<const char*>(row_cm);
-#pragma unroll
-  for (int i = 0; i < N; i++) qv[i] = __ldg(reinterpret_cast<const int4*>(rowb + (((posb[i] - base) >> rsh) << 4)));  // group index * 16 bytes
-#pragma unroll
-  for (int i = 0; i < N; i++)
-    out[i] = (uint32_t)(act_val + (int)(((posb[i] - base) >> rsh) << 2) + (qv[i].x < a[i]) + (qv[i].y < a[i]) + (qv[i].z < a[i]));
-}
-
 // Store one output lane per thread of a warp: lane `l` holds channel ch0 + l of one pixel.
 // `word` points at that pixel's output word; sub-byte lanes are merged across the warp.
 // Must be called by all 32 lanes (uses shuffles); `valid` masks channels >= OFM.

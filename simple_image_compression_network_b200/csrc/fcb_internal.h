@@ -85,6 +85,7 @@ struct DirectParams {  // imad / xnor_popc direct convolution
 };
 int launch_direct(const DirectParams& p, int engine, int n_images, size_t smem_bytes, cudaStream_t st);
 size_t direct_smem_bytes(int engine, int patch_w, int patch_h, int cc);
+size_t imad_smem_bytes(int patch_w, int patch_h, int taps, int cc);
 
 // tcgen05 implicit GEMM (fcb_plan.cu: host glue; fcb_umma2.cu: kernels)
 struct UmmaPlan;  // opaque to the API file

@@ -601,14 +601,17 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       pre_xo = i0 - pre_rr * p.WT;
     }
     // bucket-LUT constants of this thread's channel(s): tile-invariant, fetched once (two global loads per tile and warp otherwise)
-    int32_t lutlo_h[2] = {0, 0};
-    int lutsh_h[2] = {0, 0};
-    if (p.lut_off >= 0)
-      for (int cb = 0; cb < p.CB && cb < 2; cb++) {
-        const int ch = chbase + cb * 128 + q * 32 + lane, chs = chv_of(ch, p.OFM) ? ch : 0;
-        lutlo_h[cb] = p.epi.thr_lo[chs];
-        lutsh_h[cb] = p.epi.thr_sh[chs];
+    int32_t lutlo0 = 0, lutlo1 = 0;  // (scalars, not an indexed array: no local-memory frame in the epilogue)
+    int lutsh0 = 0, lutsh1 = 0;
+    if (p.lut_off >= 0) {
+      const int cha = chbase + q * 32 + lane, chb_ = cha + 128;
+      lutlo0 = p.epi.thr_lo[chv_of(cha, p.OFM) ? cha : 0];
+      lutsh0 = p.epi.thr_sh[chv_of(cha, p.OFM) ? cha : 0];
+      if (p.CB > 1) {
+        lutlo1 = p.epi.thr_lo[chv_of(chb_, p.OFM) ? chb_ : 0];
+        lutsh1 = p.epi.thr_sh[chv_of(chb_, p.OFM) ? chb_ : 0];
       }
+    }
     const bool alt1 = alt && p.nphases == 1;
     const uint32_t acc_step = alt1 ? 2u : 1u;
     if (alt1) acc_it = (uint32_t)(half & 1);
@@ -949,8 +952,8 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const bool hybrid = p.thr_off >= 0;
           const bool use_lut = p.lut_off >= 0;
           const uint32_t lut_s = smem_u32(smem + (use_lut ? p.lut_off : 0)) + 256u * (uint32_t)(cb * 128 + q * 32 + lane);
-          const int32_t lut_lo = lutlo_h[cb & 1];
-          const int lut_sh = lutsh_h[cb & 1];
+          const int32_t lut_lo = cb ? lutlo1 : lutlo0;
+          const int lut_sh = cb ? lutsh1 : lutsh0;
           const int row_shift = p.CB == 2 ? 10 : 9;  // log2(CB * 128 channels * 4 bytes)
           const bool chv = ch < p.OFM;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + cb * p.NPX);
@@ -1080,7 +1083,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   // count-of-thresholds-below is non-decreasing in the TA-wrapped accumulator: pool first, then ONE search
                   int32_t m8[8];
                   uint32_t pooled[8];
-                  uint32_t va[2][8], vb[2][8];
+                  uint32_t va[2][8] = {}, vb[2][8] = {};
                   const bool second = xb + 8 < vcols;  // warp-uniform; 8-column groups keep reads inside the accumulator stage
                   tmem_ld8(taddr + (uint32_t)(rr * p.P + xb), va[0]);
                   tmem_ld8(taddr + (uint32_t)((rr + 1) * p.P + xb), vb[0]);
@@ -1115,11 +1118,6 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     }
                   } else if (use_lut) {
                     activate_thr_lut<8>(p.epi, top_s, row_shift, lut_s, lut_lo, lut_sh, m8, pooled);
-                  } else if (THRP && gshift == 2 && p.thr_top == 6 && p.epi.thr_n == 255 && p.epi.ta_bits <= 30) {
-                    // 255 thresholds, 63 of them in shared memory (every 4th), m8 already wrapped to TA
-                    const int ns = p.epi.cmp == FCB_CMP_LESS_EQUAL ? 1 : 0;
-                    if (p.CB == 2) thr_hybrid_fast<8, 6, 1024>(top_s - 1024u, ns, p.epi.act_val, row_cm, m8, pooled);
-                    else thr_hybrid_fast<8, 6, 512>(top_s - 512u, ns, p.epi.act_val, row_cm, m8, pooled);
                   } else if (THRP || hybrid) {
                     activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, m8, pooled);
                   } else {

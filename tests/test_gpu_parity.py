@@ -566,3 +566,19 @@ def test_fc_layer_wrapper(fcb_lib, oracle_mod):
     got = fc.run(inp["in_words"], reps)
     want = oracle_mod.run_layer(dd, inp["in_words"], inp["weights"], None, None)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("c,ofm,x,y,nth,k", [(3, 16, 64, 14, 15, 5), (3, 128, 64, 14, 15, 3), (128, 128, 40, 12, 15, 3), (128, 64, 22, 8, 63, 3),
+                                              (32, 256, 36, 10, 15, 3), (4, 256, 48, 6, 127, 3)])
+def test_pooled_thresholds_small_tables(c, ofm, x, y, nth, k, fcb_lib, oracle_mod):
+    """Pooled 8-bit threshold layers whose tables are SHORT (15 / 63 / 127 thresholds: no bucket LUT, every level in shared memory), on the
+    thin-input and the resident-planes instantiations with 8 epilogue warps -- the corner the seeded fuzz found (seed 101, layer 28)."""
+    from simple_image_compression_network_b200.desc import ACT_THRESHOLDS, KIND_CONV, LayerDesc
+    d = LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=1, stride_y=1, pad=k // 2,
+                  simd=c if c < 8 else 8, pe=16, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8, num_th=nth, pool=2)
+    for reps in (2, 1):
+        inp = cases.make_inputs(d, seed_shift=129, num_reps=reps, relu_range=True)
+        L = _layer(d, inp)
+        got = L.run(inp["in_words"], reps)
+        want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], None, num_reps=reps)
+        assert np.array_equal(got, want), f"[{L.engine}: {L.plan}]: {_diff(got, want)}"
