@@ -29,6 +29,7 @@
 // 6 = plane TMA producer.  plane i: full/empty barrier pair, refilled for the next tile as soon as its last tap has
 // retired; weight ring of WSTAGES K-blocks; accumulator stages double buffered in TMEM when they fit.
 #include <algorithm>
+#include <memory>
 #include <vector>
 
 #include "fcb_epilogue.cuh"
@@ -1322,7 +1323,8 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   }
   if (!bWT) return FCB_ERR_UNSUPPORTED;
 
-  Umma2Plan* U = new Umma2Plan();
+  std::unique_ptr<Umma2Plan> U_owner(new Umma2Plan());  // released to the caller on success; every early return frees it
+  Umma2Plan* U = U_owner.get();
   U->g = g; U->num_sms = num_sms;
   Params2& p = U->p;
   memset(&p, 0, sizeof(p));
@@ -1350,7 +1352,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     int map = -1;
     for (int m = 0; m < nmaps; m++) if (map_rows[m] == rows) map = m;
     if (map < 0) {
-      if (nmaps == 2) { delete U; return FCB_ERR_UNSUPPORTED; }
+      if (nmaps == 2) return FCB_ERR_UNSUPPORTED;
       map = nmaps; map_rows[nmaps++] = rows;
     }
     const int a_off_max = (h.maxy - h.miny) * p.P + (h.maxx - h.minx);
@@ -1421,7 +1423,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     p.epi4 = (reg_fast && p.acc_stages == 2 && exp_int("FCB_U2_EPI4", 0)) ? 1 : 0;
   }
   U->smem = (size_t)off + 1024;
-  if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
+  if (U->smem > 227 * 1024) return FCB_ERR_UNSUPPORTED;
   // K-block lists: plane-major within each phase so planes are released progressively
   std::vector<int> last_use(np, -1), first_use(np, -1);
   int ord = 0;
@@ -1458,7 +1460,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     const uint64_t strides[1] = {(uint64_t)g.K};
     const uint32_t box[2] = {128, (uint32_t)(CBe * 128)};
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
-    if (rc) { delete U; return rc; }
+    if (rc) return rc;
     // 2-CTA clusters share the weight stream: each CTA fetches half of the rows of a K-block (a multiple of 8 rows, so the slice
     // starts on a 1024-byte swizzle period) and multicasts it.  Not with chb > 1: neighbouring CTAs then serve different channel blocks.
     // MEASURED (profiles/r02_cluster_multicast_ab.log, sustained, power-capped): the halved L2 stream buys ~1.5 % of SM clock, the
@@ -1468,7 +1470,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     if (U->cluster_ok) {
       const uint32_t box2[2] = {128, (uint32_t)(CBe * 64)};
       rc = umma_encode_map(&U->tmW_slice, const_cast<int8_t*>(d_w), 2, dims, strides, box2);
-      if (rc) { delete U; return rc; }
+      if (rc) return rc;
     }
   }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1483,7 +1485,7 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 0, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #endif
-  *out = U;
+  *out = U_owner.release();
   return FCB_OK;
 }
 
@@ -1562,7 +1564,8 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     }
   }
   if (!bWT) return FCB_ERR_UNSUPPORTED;
-  Umma2Plan* U = new Umma2Plan();
+  std::unique_ptr<Umma2Plan> U_owner(new Umma2Plan());  // released to the caller on success; every early return frees it
+  Umma2Plan* U = U_owner.get();
   U->g = g; U->num_sms = num_sms;
   Params2& p = U->p;
   memset(&p, 0, sizeof(p));
@@ -1633,7 +1636,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.wl = (p.swap && p.epi_alt && bWT % 32 == 0 && !exp_env("FCB_U2_NO_WL")) ? 1 : 0;
   p.patch_off = off; off += (int)U2_NPB * p.patch_bytes;
   U->smem = (size_t)off + 1024;
-  if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
+  if (U->smem > 227 * 1024) return FCB_ERR_UNSUPPORTED;
   Phase2& P = p.phases[0];
   P.nkb = 1; P.px = P.py = 0;
   P.kb[0].plane = 0; P.kb[0].flags = KB_WAIT | KB_FREE; P.kb[0].a_off = 0; P.kb[0].w_k = 0; P.kb[0].d_off = 0;
@@ -1642,7 +1645,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
     const uint64_t strides[1] = {128};
     const uint32_t box[2] = {128, (uint32_t)(CB * 128)};
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
-    if (rc) { delete U; return rc; }
+    if (rc) return rc;
   }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<4, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1650,7 +1653,7 @@ int umma2_plan_create_thin(const Geom& g, const int8_t* d_w, const EpiParams& ep
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<2, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  *out = U;
+  *out = U_owner.release();
   return FCB_OK;
 }
 
@@ -1679,7 +1682,8 @@ int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& e
     if (cost < best * 0.999) { best = cost; bWT = WT; bR = R; }
   }
   if (!bWT) return FCB_ERR_UNSUPPORTED;
-  Umma2Plan* U = new Umma2Plan();
+  std::unique_ptr<Umma2Plan> U_owner(new Umma2Plan());  // released to the caller on success; every early return frees it
+  Umma2Plan* U = U_owner.get();
   U->g = g; U->num_sms = num_sms;
   Params2& p = U->p;
   memset(&p, 0, sizeof(p));
@@ -1709,7 +1713,7 @@ int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& e
   p.stage_off = off; off += 8 * 256;
   p.thr_off = -1; p.lut_off = -1;
   U->smem = (size_t)off + 1024;
-  if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
+  if (U->smem > 227 * 1024) return FCB_ERR_UNSUPPORTED;
   // K-blocks: (channel chunk, shift); shift s = (offy + 1) * 3 + (offx + 1)
   Phase2& P = p.phases[0];
   P.nkb = 0; P.px = P.py = 0;
@@ -1727,10 +1731,10 @@ int umma2_plan_create_dthin(const Geom& g, const int8_t* d_w, const EpiParams& e
     const uint64_t strides[1] = {128};
     const uint32_t box[2] = {128, 16};
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
-    if (rc) { delete U; return rc; }
+    if (rc) return rc;
   }
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  *out = U;
+  *out = U_owner.release();
   return FCB_OK;
 #endif
 }
@@ -1753,7 +1757,8 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
     if (cost < best * 0.999) { best = cost; bWT = WT; bR = R; }
   }
   if (!bWT) return FCB_ERR_UNSUPPORTED;
-  Umma2Plan* U = new Umma2Plan();
+  std::unique_ptr<Umma2Plan> U_owner(new Umma2Plan());  // released to the caller on success; every early return frees it
+  Umma2Plan* U = U_owner.get();
   U->g = g; U->num_sms = num_sms;
   Params2& p = U->p;
   memset(&p, 0, sizeof(p));
@@ -1792,7 +1797,7 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
   p.stg_off = off; p.stg_bytes = NPX * DCOL_PIX; p.stg_bufs = 0;  // (stg_bufs stays 0: not the TMA-store path)
   off += 2 * p.stg_bytes;
   U->smem = (size_t)off + 1024;
-  if (U->smem > 227 * 1024) { delete U; return FCB_ERR_UNSUPPORTED; }
+  if (U->smem > 227 * 1024) return FCB_ERR_UNSUPPORTED;
   Phase2& P = p.phases[0];
   P.nkb = 0; P.px = P.py = 0;
   for (int cc = 0; cc < cch; cc++) {
@@ -1805,13 +1810,13 @@ int umma2_plan_create_dcol(const Geom& g, const int8_t* d_w, const EpiParams& ep
     const uint64_t strides[1] = {128};
     const uint32_t box[2] = {128, 128};
     int rc = umma_encode_map(&U->tmW, const_cast<int8_t*>(d_w), 2, dims, strides, box);
-    if (rc) { delete U; return rc; }
+    if (rc) return rc;
   }
 #ifdef FCB_EXPERIMENT
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #endif
   FCB_CUDA_OK(cudaFuncSetAttribute(umma2_conv_kernel<1, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  *out = U;
+  *out = U_owner.release();
   return FCB_OK;
 }
 

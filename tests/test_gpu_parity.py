@@ -502,8 +502,8 @@ def test_set_param_stream(name, fcb_lib, oracle_mod):
 
 
 def test_judged_configs_at_full_size(fcb_lib, oracle_mod):
-    """BASELINE.json configs 3 and 5b (first and last stage) at their full sizes against the oracle (config 4 at full size is
-    `th_cfg4` above; config 2 is `c2d_L1`; config 5a / the full network are tests/test_net8.py)."""
+    """BASELINE.json configs 3 and 5b (all four stages) at their full sizes against the oracle (config 4 at full size is
+    `th_cfg4` above; config 2 is `c2d_L1` and tests/test_bench_scale.py; config 5a / the full network are tests/test_net8.py)."""
     from simple_image_compression_network_b200.desc import ACT_THRESHOLDS, KIND_CONV, W_BINARY_XNOR, LayerDesc
     c3 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=64, ofm_ch=64, ifm_x=128, ifm_y=96, stride_x=1, stride_y=1, pad=0,
                    simd=64, pe=16, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR, acc_bits=16, acc_signed=1, act_kind=ACT_THRESHOLDS,
@@ -513,7 +513,8 @@ def test_judged_configs_at_full_size(fcb_lib, oracle_mod):
         return LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=1, stride_y=1, pad=1,
                          simd=simd, pe=pe, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8,
                          num_th=255, pool=2)
-    for name, d in (("config 3", c3), ("config 5b stage 1", stage(3, 128, 768, 512, 3, 16)), ("config 5b stage 4", stage(128, 192, 96, 64, 32, 24))):
+    for name, d in (("config 3", c3), ("config 5b stage 1", stage(3, 128, 768, 512, 3, 16)), ("config 5b stage 2", stage(128, 128, 384, 256, 32, 16)),
+                    ("config 5b stage 3", stage(128, 128, 192, 128, 32, 16)), ("config 5b stage 4", stage(128, 192, 96, 64, 32, 24))):
         inp = cases.make_inputs(d, seed_shift=61)
         L = _layer(d, inp)
         got = L.run(inp["in_words"])
@@ -582,3 +583,62 @@ def test_pooled_thresholds_small_tables(c, ofm, x, y, nth, k, fcb_lib, oracle_mo
         got = L.run(inp["in_words"], reps)
         want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], None, num_reps=reps)
         assert np.array_equal(got, want), f"[{L.engine}: {L.plan}]: {_diff(got, want)}"
+
+
+@pytest.mark.parametrize("c,ofm,k,s,dx,dy,pad,x,y,engine", [
+    (128, 128, 3, 1, 2, 1, 2, 40, 12, "umma_i8"),   # resident planes: a dilated tap is just another plane offset
+    (128, 64, 3, 2, 2, 2, 2, 44, 16, "umma_i8"),    # stride 2 + dilation on both axes
+    (256, 192, 3, 1, 3, 2, 0, 30, 14, "umma_i8"),
+    (8, 12, 3, 1, 2, 3, 1, 21, 13, "imad"),
+    (6, 5, 2, 2, 3, 1, 0, 17, 9, "imad"),
+])
+def test_dilation_on_the_engines(c, ofm, k, s, dx, dy, pad, x, y, engine, fcb_lib, oracle_mod):
+    """ConvolutionInputGenerator_NonSquare_Dilated (slidingwindow.h:1515-1631) on the tensor and IMAD engines; the oracle's dilation is
+    pinned on the reference generator by the dil_* goldens (x axis; the reference asserts Dilation_y == 1, y follows by symmetry)."""
+    from simple_image_compression_network_b200.desc import ACT_BIAS_RELU, KIND_CONV, LayerDesc
+    d = LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=s, stride_y=s, pad=pad,
+                  simd=2, pe=1, in_bits=8, w_bits=4, acc_bits=8, acc_signed=0, act_kind=ACT_BIAS_RELU, out_bits=8, dilation_x=dx, dilation_y=dy)
+    inp = cases.make_inputs(d, seed_shift=77, num_reps=2, relu_range=True)
+    L = _layer(d, inp)
+    assert L.engine == engine, L.plan
+    got = L.run(inp["in_words"], 2)
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], None, inp["bias"], num_reps=2)
+    assert np.array_equal(got, want), f"[{L.engine}: {L.plan}]: {_diff(got, want)}"
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_channelwise_units_fuzz(seed, fcb_lib, oracle_mod):
+    """Depth-wise convolution (VVAU) and Pool_batch with random geometry, lane widths, signedness, functions, padding, stride and dilation
+    against the oracle (whose semantics are pinned on the reference's templates by the pl_* / dw_* goldens)."""
+    from simple_image_compression_network_b200._lib import FcbError
+    from simple_image_compression_network_b200.desc import (ACT_PASSTHROUGH, ACT_THRESHOLDS, KIND_DWCONV, KIND_POOL, LayerDesc)
+    rng = np.random.default_rng(seed)
+    ran = 0
+    for i in range(30):
+        c = int(rng.choice([3, 8, 24, 40, 128])); pe = int(rng.choice([p for p in (1, 2, 4, 8) if c % p == 0]))
+        k = int(rng.choice([2, 3])); s = int(rng.choice([1, 2])); pad = int(rng.integers(0, 2))
+        x = int(rng.integers(k + 2, 30)); y = int(rng.integers(k + 2, 14))
+        inb = int(rng.choice([3, 4, 8])); ins = int(rng.integers(0, 2))
+        common = dict(kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=c, ifm_x=x, ifm_y=y, stride_x=s, stride_y=s, pad=pad, simd=pe, pe=pe, in_bits=inb,
+                      in_signed=ins, dilation_x=int(rng.choice([1, 1, 2])))
+        if rng.integers(0, 2):
+            fn = int(rng.integers(0, 4)); tab = int(rng.choice([inb, inb + 4, 16]))
+            d = LayerDesc(kind=KIND_POOL, w_bits=0, weight_kind=fn, acc_bits=tab, acc_signed=ins, act_kind=ACT_PASSTHROUGH,
+                          out_bits=int(rng.choice([inb, 8, 12])), act_val=int(rng.choice([2, 3, 4])), **common)
+        else:
+            thr = bool(rng.integers(0, 2))
+            d = LayerDesc(kind=KIND_DWCONV, w_bits=int(rng.choice([3, 4, 8])), acc_bits=int(rng.choice([12, 16, 24])), acc_signed=1,
+                          act_kind=ACT_THRESHOLDS if thr else ACT_PASSTHROUGH, out_bits=4 if thr else int(rng.choice([8, 12, 16])),
+                          num_th=15 if thr else 0, **common)
+        reps = 1 + i % 3
+        try:
+            inp = cases.make_inputs(d, seed_shift=seed + i, num_reps=reps)
+            L = _layer(d, inp)
+        except (FcbError, ValueError, AssertionError):
+            continue
+        got = L.run(inp["in_words"], reps)
+        want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=reps)
+        assert L.engine == "chanwise"
+        assert np.array_equal(got, want), f"case {i} {d}: {_diff(got, want)}"
+        ran += 1
+    assert ran >= 20, ran

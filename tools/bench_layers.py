@@ -9,6 +9,9 @@ from simple_image_compression_network_b200 import configs, synth
 from simple_image_compression_network_b200.desc import (ACT_THRESHOLDS, ENGINE_IMAD, ENGINE_TENSOR, KIND_CONV, KIND_DECONV522, W_BINARY_XNOR,
                                                         LayerDesc)
 from simple_image_compression_network_b200.layer import ConvLayer, Net, synth_fill
+if os.environ.get("FCB_EXP"):  # the experiment build (environment switches that bend plans): measurements only
+    from simple_image_compression_network_b200 import _lib
+    _lib.set_default(_lib.load(_lib.EXP_LIB_PATH))
 
 
 def timed(fn, steps=5, warm=2):
