@@ -629,9 +629,21 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
     const bool imad2 = engine == ENG_IMAD && g.weight_kind != FCB_W_BINARY_XNOR;  // imad_conv_kernel: weights share the budget
     int cc = imad2 ? (int)(budget / ((size_t)p.patch_w * p.patch_h * 4 + (size_t)g.KX * g.KY * 128)) & ~3
                    : (int)(budget / ((size_t)p.patch_w * p.patch_h * 4));
+    // weights that fit 8 bits (every reference config) run on the packed dot-product instructions: 4 MACs per instruction for lanes
+    // of <= 8 bits, 2 for lanes of <= 16 bits (fcb_direct.cu, dot_conv_kernel)
+    p.dot_pack = 0;
+    if (imad2 && exp_int("FCB_DOT", 1)) {
+      bool w8 = true;
+      for (int32_t w : W) if (w < -128 || w > 127) { w8 = false; break; }
+      const int pk = g.in_bits <= 8 ? 4 : 2;
+      const int dcc = w8 ? dot_chunk_channels(p.patch_w, p.patch_h, g.KX * g.KY, g.C, pk, budget) : 0;
+      if (dcc) { p.dot_pack = pk; cc = dcc; }
+    }
     if (cc < 1) { set_error("kernel %dx%d stride %d: patch does not fit shared memory", g.KX, g.KY, g.SX); return FCB_ERR_UNSUPPORTED; }
-    p.CC = std::min(cc, cu);
-    L->smem = imad2 ? imad_smem_bytes(p.patch_w, p.patch_h, g.KX * g.KY, p.CC) : direct_smem_bytes(engine, p.patch_w, p.patch_h, p.CC);
+    p.CC = std::min(cc, p.dot_pack ? cc : cu);
+    L->smem = p.dot_pack ? dot_smem_bytes(p.patch_w, p.patch_h, g.KX * g.KY, p.CC, p.dot_pack)
+              : imad2    ? imad_smem_bytes(p.patch_w, p.patch_h, g.KX * g.KY, p.CC)
+                         : direct_smem_bytes(engine, p.patch_w, p.patch_h, p.CC);
     if (engine == ENG_XNOR) {
       const int KW = g.KX * g.KY * (g.C / 32);
       std::vector<uint32_t> Wb((size_t)KW * p.OFMp, 0u);
@@ -642,6 +654,10 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         }
       FCB_CUDA_OK(cudaMalloc(&L->d_wt, Wb.size() * 4));
       FCB_CUDA_OK(cudaMemcpy(L->d_wt, Wb.data(), Wb.size() * 4, cudaMemcpyHostToDevice));
+    } else if (p.dot_pack) {
+      const std::vector<uint32_t> Wd = dot_pack_weights(W, g.OFM, p.OFMp, g.C, g.KX * g.KY, p.dot_pack);
+      FCB_CUDA_OK(cudaMalloc(&L->d_wt, Wd.size() * 4));
+      FCB_CUDA_OK(cudaMemcpy(L->d_wt, Wd.data(), Wd.size() * 4, cudaMemcpyHostToDevice));
     } else {
       std::vector<int16_t> Wt((size_t)g.K * p.OFMp, 0);
       for (int ch = 0; ch < g.OFM; ch++)
@@ -709,7 +725,10 @@ const char* fcb_layer_plan(const fcb_layer* L) {
   if (!L) return "";
   if (L->lowered) return L->plan_desc;
   if (L->engine == ENG_CHANWISE) return "channel-wise streaming unit: warp = output pixel, lanes walk the channels";
-  return L->engine == ENG_UMMA ? umma_plan_describe(L->umma) : "direct 16x8-pixel x 64-channel CTA tiles (patch and weight pairs in shared memory)";
+  if (L->engine == ENG_UMMA) return umma_plan_describe(L->umma);
+  if (L->dp.dot_pack == 4) return "direct 16x8-pixel x 64-channel CTA tiles, IDP.4A (4 channels per patch word, weights as bytes in shared memory)";
+  if (L->dp.dot_pack == 2) return "direct 16x8-pixel x 64-channel CTA tiles, IDP.2A (2 channels per patch word, weights as bytes in shared memory)";
+  return "direct 16x8-pixel x 64-channel CTA tiles (patch and weight pairs in shared memory)";
 }
 uint64_t fcb_layer_launches(const fcb_layer* L) { return L ? L->launches : 0; }
 

@@ -76,16 +76,20 @@ enum Engine { ENG_IMAD = 0, ENG_XNOR = 1, ENG_UMMA = 2, ENG_CHANWISE = 3 };
 struct DirectParams {  // imad / xnor_popc direct convolution
   const uint8_t* in;
   uint8_t* out;
-  const void* wt;  // imad: int16 [K][OFMp]; xnor: uint32 [KW][OFMp]
+  const void* wt;  // imad: int16 [K][OFMp]; dot: dot_pack_weights(); xnor: uint32 [KW][OFMp]
   EpiParams epi;
   int C, OFM, OFMp, KX, KY, DX, DY, IX, IY, OX, OY, SXe, SYe, PAD, PADY, deconv;  // PAD / PADY: zeros left / up of the frame
   int in_bits, in_signed, in_word_bytes, out_word_bytes, out_x, out_y;
   int tiles_x, tiles_y, CC, patch_w, patch_h, mul_kind;
+  int dot_pack;  // 0: imad_conv_kernel; 2 / 4: dot_conv_kernel on IDP.2A / IDP.4A (weights fit 8 bits, lanes <= 16 / <= 8 bits)
   unsigned long long in_img_bytes, out_img_bytes;
 };
 int launch_direct(const DirectParams& p, int engine, int n_images, size_t smem_bytes, cudaStream_t st);
 size_t direct_smem_bytes(int engine, int patch_w, int patch_h, int cc);
 size_t imad_smem_bytes(int patch_w, int patch_h, int taps, int cc);
+int dot_chunk_channels(int patch_w, int patch_h, int taps, int C, int pk, size_t budget);
+size_t dot_smem_bytes(int patch_w, int patch_h, int taps, int cc, int pk);
+std::vector<uint32_t> dot_pack_weights(const std::vector<int32_t>& W /*[OFM][taps * C]*/, int OFM, int OFMp, int C, int taps, int pk);
 
 // tcgen05 implicit GEMM (fcb_plan.cu: host glue; fcb_umma2.cu: kernels)
 struct UmmaPlan;  // opaque to the API file

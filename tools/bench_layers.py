@@ -88,6 +88,12 @@ if __name__ == "__main__":
                 bench_layer("cfg4_thr_nopool", dataclasses.replace(c4, pool=0), a.images, 0xFF)
             elif nm == "cfg4":
                 bench_layer("cfg4_thr_pool", c4, a.images, 0xFF)
+            elif nm == "imad16":  # 16-bit lanes x 8-bit weights: the universal engine's own shape (workloads.imad16)
+                from simple_image_compression_network_b200 import workloads
+                bench_layer("wide16_imad", workloads.imad16(), a.images * 8, 0xFF)
+            elif nm.endswith("i"):  # L2i: layer 2 of the reference net forced onto the universal engine
+                i = int(nm[1:-1])
+                bench_layer(nm, dataclasses.replace(configs.net_layer(i), engine_hint=ENGINE_IMAD), a.images, 0xFF if i == 0 else 0x7F)
             else:
                 i = int(nm[1:])
                 bench_layer(nm, configs.net_layer(i), a.images, 0xFF if i == 0 else 0x7F)
