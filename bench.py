@@ -225,7 +225,7 @@ class Harness:
 
 
 def _bound_entry(name, bound, img_s, ms_step, n_img, steps, clk, world, peaks, *, ops_per_image=None, bytes_per_image=None,
-                 popc_words_per_image=None, extra=None):
+                 popc_words_per_image=None, alu_macs_per_image=None, alu_macs_per_s=None, extra=None):
     from simple_image_compression_network_b200 import workloads as W
     e = {"name": name, "images_per_gpu": n_img, "steps": steps, "ms_per_step": ms_step, "img_s": img_s, "n_gpus": world, "bound": bound,
          "sm_mhz": clk.get("sm_mhz"), "clock_reasons": clk.get("reasons")}
@@ -238,8 +238,11 @@ def _bound_entry(name, bound, img_s, ms_step, n_img, steps, clk, world, peaks, *
         e.update({"GBs_per_gpu": gbs, "frac_of_hbm_measured": gbs / float(peaks["hbm_gbs"]), "algorithmic_bytes_per_image": bytes_per_image})
     if popc_words_per_image is not None:
         e.update({"popc_Twords_s_per_gpu": per_gpu * popc_words_per_image / 1e12, "frac_of_popc_peak": per_gpu * popc_words_per_image / W.POPC_WORDS_PER_S})
+    if alu_macs_per_s is not None:  # universal direct engine: the packed dot-product issue rate (workloads.direct_macs_per_s)
+        e.update({"TMACs_per_gpu": per_gpu * alu_macs_per_image / 1e12, "alu_peak_TMACs": alu_macs_per_s / 1e12,
+                  "frac_of_dot_issue_rate": per_gpu * alu_macs_per_image / alu_macs_per_s})
     e["frac"] = {"tensor": e.get("frac_of_int8_spec_4500"), "hbm": e.get("frac_of_hbm_measured"), "popc": e.get("frac_of_popc_peak"),
-                 "alu": None}[bound]
+                 "alu": e.get("frac_of_dot_issue_rate")}[bound]
     if extra:
         e.update(extra)
     return e
@@ -282,6 +285,8 @@ def run_configs(h: Harness, peaks, n_scale: float):
             kw["bytes_per_image"] = L.in_bytes + L.out_bytes
         if bound == "alu":
             kw["bytes_per_image"] = L.in_bytes + L.out_bytes
+            kw["alu_macs_per_image"] = float(d.macs_per_image)
+            kw["alu_macs_per_s"] = W.direct_macs_per_s(d)
         run_one(name, L.run_device, L.in_bytes, L.out_bytes, n, mask, kw, extra={"engine": L.engine, "plan": L.plan,
                                                                                  "GMAC_per_image_nonzero": W.nonzero_macs(d) / 1e9})
         return L

@@ -15,6 +15,14 @@ from .desc import ACT_PASSTHROUGH, ACT_THRESHOLDS, KIND_CONV, W_BINARY_XNOR, Lay
 INT8_SPEC_TOPS = 4500.0        # dense INT8, B200 data sheet (the sparse figure is twice that and is not used)
 INT8_MMA_ONLY_TOPS = 4380.0    # tools/umma_peak.cu, profiles/r01_umma_peak_int8.log (MMA issue only, operands resident)
 POPC_WORDS_PER_S = 4.58e12     # tools/popc_peak.cu, profiles/r01_popc_peak.log (15.7 lane-popc / clk / SM at 1965 MHz)
+# integer multiply-add and the packed dot products issue on the heavy half of the FMA pipe: 64 lanes / clk / SM at 1965 MHz
+# (profiles/r02_imad_ncu_full_summary.txt: sm__pipe_fmaheavy_cycles_active); MACs per instruction: IMAD 1, IDP.2A 2, IDP.4A 4
+INT_DOT_INSTR_PER_S = 148 * 64 * 1.965e9
+
+
+def direct_macs_per_s(d: LayerDesc) -> float:
+    """Ceiling of the universal direct engine for a layer with weights of at most 8 bits (csrc/fcb_direct.cu, dot_conv_kernel)."""
+    return INT_DOT_INSTR_PER_S * (4 if d.in_bits <= 8 else 2)
 
 
 def config3() -> LayerDesc:

@@ -541,7 +541,7 @@ def test_set_param_stream(name, fcb_lib, oracle_mod):
 
 
 def test_judged_configs_at_full_size(fcb_lib, oracle_mod):
-    """BASELINE.json configs 3 and 5b (all four stages) at their full sizes against the oracle (config 4 at full size is
+    """BASELINE.json configs 3 and 5b (all four stages) and the wide-lane config of bench.py at their full sizes against the oracle (config 4 at full size is
     `th_cfg4` above; config 2 is `c2d_L1` and tests/test_bench_scale.py; config 5a / the full network are tests/test_net8.py)."""
     from simple_image_compression_network_b200.desc import ACT_THRESHOLDS, KIND_CONV, W_BINARY_XNOR, LayerDesc
     c3 = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=64, ofm_ch=64, ifm_x=128, ifm_y=96, stride_x=1, stride_y=1, pad=0,
@@ -552,8 +552,10 @@ def test_judged_configs_at_full_size(fcb_lib, oracle_mod):
         return LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=1, stride_y=1, pad=1,
                          simd=simd, pe=pe, in_bits=8, w_bits=4, acc_bits=24, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=8,
                          num_th=255, pool=2)
+    from simple_image_compression_network_b200 import workloads
     for name, d in (("config 3", c3), ("config 5b stage 1", stage(3, 128, 768, 512, 3, 16)), ("config 5b stage 2", stage(128, 128, 384, 256, 32, 16)),
-                    ("config 5b stage 3", stage(128, 128, 192, 128, 32, 16)), ("config 5b stage 4", stage(128, 192, 96, 64, 32, 24))):
+                    ("config 5b stage 3", stage(128, 128, 192, 128, 32, 16)), ("config 5b stage 4", stage(128, 192, 96, 64, 32, 24)),
+                    ("16-bit lanes on the universal engine", workloads.imad16())):
         inp = cases.make_inputs(d, seed_shift=61)
         L = _layer(d, inp)
         got = L.run(inp["in_words"])
