@@ -29,5 +29,16 @@ for seed in range(first, first + n):
         if not np.array_equal(got, want):
             bad += 1
             print(f"MISMATCH seed {seed} case {i} reps {reps} {d} [{L.engine}: {L.plan}]", flush=True)
+    for i, d in enumerate(T._direct_descs(seed, per)):  # the universal engine's three inner loops
+        inp = cases.make_inputs(d, seed_shift=seed * 100 + i, num_reps=2)
+        L = T._layer(d, inp)
+        got = L.run(inp["in_words"], 2)
+        want = oracle.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=2)
+        ran += 1
+        key = "direct:" + ("IDP.4A" if "IDP.4A" in L.plan else "IDP.2A" if "IDP.2A" in L.plan else "IMAD")
+        plans[key] = plans.get(key, 0) + 1
+        if not np.array_equal(got, want):
+            bad += 1
+            print(f"MISMATCH seed {seed} direct case {i} {d} [{L.engine}: {L.plan}]", flush=True)
 print(f"fuzz: {ran} layers run, {bad} mismatches; plans: {plans}")
 sys.exit(1 if bad else 0)

@@ -447,16 +447,13 @@ def test_random_shapes_match_oracle(seed, fcb_lib, oracle_mod):
     assert len(plans) >= 4, plans
 
 
-@pytest.mark.parametrize("seed", [7, 8])
-def test_direct_engine_kernels_match_oracle(seed, fcb_lib, oracle_mod):
-    """The three inner loops of the universal engine (fcb_direct.cu): IDP.4A (lanes <= 8 bits, weights <= 8 bits), IDP.2A (lanes of
-    9..16 bits) and plain IMAD (weights of 9..16 bits), signed and unsigned lanes, conv (strides, dilation, ragged channel counts that
-    leave the last packed word / group partly empty, several channel chunks) and deconv522 -- forced with engine_hint, bit-exact
-    against the oracle."""
+def _direct_descs(seed, count):
+    """Random layers forced onto the universal engine (engine_hint): lane widths on both sides of the IDP.4A / IDP.2A / IMAD split,
+    signed and unsigned lanes, strides, dilation, ragged channel counts, several channel chunks, deconv522."""
     from simple_image_compression_network_b200.desc import ACT_PASSTHROUGH, KIND_CONV, KIND_DECONV522, LayerDesc
     rng = np.random.default_rng(seed)
-    seen = set()
-    for i in range(36):
+    out = []
+    for i in range(count):
         inb, wb = [(8, 8), (4, 3), (16, 8), (12, 5), (16, 16), (8, 12)][i % 6]
         ins = int(rng.integers(0, 2))
         c = int(rng.choice([1, 3, 7, 16, 20, 33, 64, 130])); ofm = int(rng.choice([1, 5, 32, 64, 70]))
@@ -466,20 +463,32 @@ def test_direct_engine_kernels_match_oracle(seed, fcb_lib, oracle_mod):
                           act_kind=ACT_PASSTHROUGH, out_bits=32, engine_hint=ENGINE_IMAD)
         else:
             kx, ky = int(rng.choice([1, 3, 5])), int(rng.choice([1, 3]))
-            sx, sy = int(rng.choice([1, 2])), int(rng.choice([1, 2]))
+            sx, sy = int(rng.choice([1, 2, 3])), int(rng.choice([1, 2]))
             dx, dy = (int(rng.choice([1, 2])), int(rng.choice([1, 2]))) if (sx, sy) == (1, 1) else (1, 1)
             x = (kx - 1) * dx + 1 + int(rng.integers(0, 24)); y = (ky - 1) * dy + 1 + int(rng.integers(0, 10))
             x += (-(x - ((kx - 1) * dx + 1))) % sx; y += (-(y - ((ky - 1) * dy + 1))) % sy
             d = LayerDesc(kind=KIND_CONV, kernel_x=kx, kernel_y=ky, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=sx, stride_y=sy, pad=0,
                           simd=1, pe=1, in_bits=inb, in_signed=ins, w_bits=wb, acc_bits=32, acc_signed=1, act_kind=ACT_PASSTHROUGH, out_bits=32,
                           dilation_x=dx, dilation_y=dy, engine_hint=ENGINE_IMAD)
+        out.append(d)
+    return out
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+def test_direct_engine_kernels_match_oracle(seed, fcb_lib, oracle_mod):
+    """The three inner loops of the universal engine (fcb_direct.cu): IDP.4A (lanes <= 8 bits, weights <= 8 bits), IDP.2A (lanes of
+    9..16 bits) and plain IMAD (weights of 9..16 bits), signed and unsigned lanes, conv (strides 1 / 2 / generic, dilation, ragged
+    channel counts that leave the last packed word / group partly empty, several channel chunks) and deconv522 -- forced with
+    engine_hint, bit-exact against the oracle."""
+    seen = set()
+    for i, d in enumerate(_direct_descs(seed, 36)):
         inp = cases.make_inputs(d, seed_shift=seed * 100 + i, num_reps=2)
         L = _layer(d, inp)
         assert L.engine == "imad"
         kern = "IDP.4A" if "IDP.4A" in L.plan else "IDP.2A" if "IDP.2A" in L.plan else "IMAD"
         w8 = int(np.abs(inp["w"].astype(np.int64) * 2 + 1).max()) <= 255  # every weight in [-128, 127]
-        assert kern == ("IMAD" if not w8 else "IDP.4A" if inb <= 8 else "IDP.2A"), (d, L.plan)
-        seen.add((kern, ins, d.kind))
+        assert kern == ("IMAD" if not w8 else "IDP.4A" if d.in_bits <= 8 else "IDP.2A"), (d, L.plan)
+        seen.add((kern, d.in_signed, d.kind))
         got = L.run(inp["in_words"], 2)
         want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=2)
         assert np.array_equal(got, want), f"seed {seed} case {i} {d} [{L.plan}]: {_diff(got, want)}"
