@@ -63,6 +63,7 @@ struct Params2 {
   uint8_t* out;
   EpiParams epi;
   int OFM, CB, NPX, stride2, deconv, nphases, nplanes;
+  int n_mma;  // N of the resident-planes MMA (<= NPX)
   int WT, R, P, tiles_x, tiles_y, PX, PY;
   int out_x, out_y, out_word_bytes, n_images;
   int wstages, w_bytes, acc_stages, acc_stride, tmem_cols;
@@ -1298,7 +1299,10 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
           if (!ok || (long long)plane_bytes + (long long)WS * w_bytes_c > (long long)smem_limit) continue;
           const double tiles = (double)((PX + WT - 1) / WT) * ((PY + R - 1) / R) * cd.chb;  // tile visits per CTA group
           const double nkb = (double)taps.size() * cch;  // all phases
-          const double mma_clk = nkb * cbe * 4 * (NPX == 256 ? 146.0 : 102.0);  // measured clocks per instruction
+          // clocks per instruction: measured 146 at N = 256 and 102 at N = 128 = shared-memory operand reads at ~84 B/clk
+          // (4 KB of weights + 32 B per column); N is trimmed to the tile's last useful column below
+          const int n_eff = std::min(NPX, ((R - 1) * P + WT + 15) / 16 * 16);
+          const double mma_clk = nkb * cbe * 4 * (58.0 + 0.344 * n_eff);
           const double fill_clk = ((double)plane_bytes + nkb * w_bytes_c) / 38.0;  // measured L2->SM fill, B/clk/SM
           // epilogue: bias/ReLU ~7 clk per pixel and channel block.  Threshold search: instruction bound, epi_factor issue clocks
           // per warp-level output (32 channels), counted with the padding of the 16-wide search batches
@@ -1339,7 +1343,12 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   int tc = 32;
   while (tc < p.acc_stages * p.acc_stride) tc *= 2;
   p.tmem_cols = tc;
-  p.idesc = make_idesc_i8(128, bNPX, /*A = weights*/ 1, /*B = activations*/ g.in_signed);
+  // MMA width: the last accumulator column any output of the tile maps to is (R-1)*P + WT - 1; columns past it (the tail of the 256)
+  // are never read back as results, so N stops at the next multiple of 16 (an MMA costs ~(4 KB of A + 32 B x N of B) / 84 B/clk)
+  int n_mma = bNPX;
+  if (exp_int("FCB_U2_NTRIM", 1)) n_mma = std::min(bNPX, ((bR - 1) * (bWT + halo_x) + bWT + 15) / 16 * 16);
+  p.idesc = make_idesc_i8(128, n_mma, /*A = weights*/ 1, /*B = activations*/ g.in_signed);
+  p.n_mma = n_mma;
   p.debug = exp_int("FCB_U2_DEBUG", 0);
   // planes
   int plane_of[4][4];
@@ -1866,8 +1875,8 @@ static const char* umma2_describe_base(const Umma2Plan* U, char* buf, size_t n) 
              p.tiles_x, p.tiles_y);
     return buf;
   }
-  snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d CB=%d chb=%d%s%s planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT,
-           p.R, p.P, p.NPX, p.CB, p.chb, p.lut_off >= 0 ? " thr@smem + bucket LUT" : p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : p.epi4 ? " epi-warps=4" : ""), U->cluster_ok ? " weights-multicast x2" : "", p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
+  snprintf(buf, n, "resident-planes WT=%d R=%d P=%d NPX=%d N=%d CB=%d chb=%d%s%s planes=%dx%d wstages=%d acc_stages=%d smem=%zu tiles=%dx%d", p.WT,
+           p.R, p.P, p.NPX, p.n_mma, p.CB, p.chb, p.lut_off >= 0 ? " thr@smem + bucket LUT" : p.thr_off >= 0 ? " thr-top@smem" : (p.stg_bufs == 2 ? " tma-store x2" : p.stg_bufs == 1 ? " tma-store x1" : p.epi4 ? " epi-warps=4" : ""), U->cluster_ok ? " weights-multicast x2" : "", p.nplanes, p.nsets, p.wstages, p.acc_stages, U->smem,
            p.tiles_x, p.tiles_y);
   return buf;
 }
