@@ -194,6 +194,7 @@ struct fcb_layer {
   int device = 0;
   int engine = ENG_IMAD;
   void* d_wt = nullptr;
+  void* d_wt4 = nullptr;  // depth-wise weights as bytes, four taps per word (fcb_chanwise.cu)
   int8_t* d_bias = nullptr;
   int32_t* d_thr = nullptr;
   int32_t* d_thr_cm = nullptr;
@@ -273,7 +274,7 @@ void fcb_layer_destroy(fcb_layer* L) {
   if (!L) return;
   DeviceScope ds(L->device);
   if (L->umma) umma_plan_destroy(L->umma);
-  cudaFree(L->d_wt); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_thr_cm); cudaFree(L->d_thr_lut); cudaFree(L->d_thr_lo);
+  cudaFree(L->d_wt); cudaFree(L->d_wt4); cudaFree(L->d_bias); cudaFree(L->d_thr); cudaFree(L->d_thr_cm); cudaFree(L->d_thr_lut); cudaFree(L->d_thr_lo);
   cudaFree(L->d_scratch[0]); cudaFree(L->d_scratch[1]); cudaFree(L->d_unpooled[0]); cudaFree(L->d_unpooled[1]);
   for (int i = 0; i < 2; i++) {
     cudaFree(L->s_in[i]); cudaFree(L->s_out[i]);
@@ -482,6 +483,18 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
       FCB_CUDA_OK(cudaMalloc(&L->d_wt, Wt.size() * 2));
       FCB_CUDA_OK(cudaMemcpy(L->d_wt, Wt.data(), Wt.size() * 2, cudaMemcpyHostToDevice));
       c.wt = (const int16_t*)L->d_wt;
+      // byte form for the dot-product inner loop of chanwise_bytes_kernel: word [chunk][ch] = weights of taps 4*chunk .. 4*chunk+3
+      bool w8 = true;
+      for (int32_t w : W) if (w < -128 || w > 127) { w8 = false; break; }
+      if (w8) {
+        const int chunks = (g.K + 3) / 4;
+        std::vector<uint32_t> W4((size_t)chunks * c.Cpad, 0u);
+        for (int ch = 0; ch < g.C; ch++)
+          for (int k = 0; k < g.K; k++) W4[(size_t)(k >> 2) * c.Cpad + ch] |= (uint32_t)(uint8_t)(int8_t)W[(size_t)ch * g.K + k] << (8 * (k & 3));
+        FCB_CUDA_OK(cudaMalloc(&L->d_wt4, W4.size() * 4));
+        FCB_CUDA_OK(cudaMemcpy(L->d_wt4, W4.data(), W4.size() * 4, cudaMemcpyHostToDevice));
+        c.wt4 = (const uint32_t*)L->d_wt4;
+      }
     }
     c.epi = L->epi;
     L->engine = ENG_CHANWISE;
@@ -682,7 +695,7 @@ int fcb_layer_set_params(fcb_layer* L, const void* weights, const void* threshol
   int rc = fcb_layer_create(&L->desc, weights, thresholds, bias, L->device, &fresh);
   if (rc) return rc;
   std::swap(L->engine, fresh->engine);
-  std::swap(L->d_wt, fresh->d_wt); std::swap(L->d_bias, fresh->d_bias);
+  std::swap(L->d_wt, fresh->d_wt); std::swap(L->d_wt4, fresh->d_wt4); std::swap(L->d_bias, fresh->d_bias);
   std::swap(L->d_thr, fresh->d_thr); std::swap(L->d_thr_cm, fresh->d_thr_cm);
   std::swap(L->d_thr_lut, fresh->d_thr_lut); std::swap(L->d_thr_lo, fresh->d_thr_lo);
   std::swap(L->epi, fresh->epi); std::swap(L->dp, fresh->dp); std::swap(L->cw, fresh->cw); std::swap(L->smem, fresh->smem);
@@ -724,7 +737,12 @@ const char* fcb_layer_engine(const fcb_layer* L) {
 const char* fcb_layer_plan(const fcb_layer* L) {
   if (!L) return "";
   if (L->lowered) return L->plan_desc;
-  if (L->engine == ENG_CHANWISE) return "channel-wise streaming unit: warp = output pixel, lanes walk the channels";
+  if (L->engine == ENG_CHANWISE) {
+    const int v = chanwise_vector_words(L->cw);
+    return v == 4   ? "channel-wise streaming unit, byte lanes: thread = 16 channels of an output pixel (16-byte loads per tap)"
+           : v == 1 ? "channel-wise streaming unit, byte lanes: thread = 4 channels of an output pixel (4-byte loads per tap)"
+                    : "channel-wise streaming unit: warp = output pixel, lanes walk the channels";
+  }
   if (L->engine == ENG_UMMA) return umma_plan_describe(L->umma);
   if (L->dp.dot_pack == 4) return "direct 16x8-pixel x 64-channel CTA tiles, IDP.4A (4 channels per patch word, weights as bytes in shared memory)";
   if (L->dp.dot_pack == 2) return "direct 16x8-pixel x 64-channel CTA tiles, IDP.2A (2 channels per patch word, weights as bytes in shared memory)";

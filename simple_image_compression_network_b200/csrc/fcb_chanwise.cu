@@ -66,6 +66,222 @@ __global__ void __launch_bounds__(256) chanwise_kernel(const ChanParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Byte-lane form of the same units (8-bit input lanes, 8 / 16 / 32-bit output lanes, channel count a multiple of 4, words without
+// container padding): a thread owns 4*V consecutive channels of one output pixel and moves them as one 4*V-byte load per tap and one
+// vector store, so a warp reads 128*V consecutive bytes per tap -- these units are HBM-bound (K2 operations per byte) and what they
+// need is bytes in flight, not arithmetic: 2048 threads x 16 B per SM cover the ~23 B/clk/SM that HBM delivers.  Same functions,
+// same order of operations as chanwise_kernel, in 32-bit arithmetic (launch_chanwise sends here only what is exact in 32 bits:
+// accumulator types of at most 31 bits for the pool functions, Kx*Ky <= 128 for the depth-wise sum of 8-bit x 16-bit products).
+__device__ __forceinline__ int32_t wrap32(int32_t v, int bits, int sgn) {
+  if (bits >= 32) return v;
+  const uint32_t u = (uint32_t)v << (32 - bits);
+  return sgn ? ((int32_t)u >> (32 - bits)) : (int32_t)(u >> (32 - bits));
+}
+
+// BM: 0 depth-wise MAC (3: the same through IDP.4A, weights of at most 8 bits), 1 max (the tap converts to the function's type without changing value: checked by the launcher), 2 the three
+// sums (Avg / Acc / QuantAvg: converting every tap and wrapping every += is congruent mod 2^TA to wrapping the exact sum once).
+// INS: signed input lanes.  Both are template parameters: these kernels are bound by instruction issue once the loads are wide.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {  // generic mode: selector bit 3 replicates the byte's sign
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+template <bool AS>  // d = c + sum of four (8-bit lanes of a, signed iff AS) x (signed 8-bit lanes of b)
+__device__ __forceinline__ int32_t dp4a_mixed(uint32_t a, uint32_t b, int32_t c) {
+  int32_t d;
+  if (AS) asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  else asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+template <int V, int BM, bool INS>
+__global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p) {
+  constexpr int N = 4 * V;  // channels per thread
+  const int groups = p.C / N;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)p.OX * p.OY * groups) return;
+  const int g = (int)(t % groups), pix = (int)(t / groups);
+  const int oy = pix / p.OX, ox = pix - oy * p.OX, ch0 = g * N;
+  const uint8_t* in = p.in + (size_t)blockIdx.y * p.in_img_bytes + (size_t)ch0;
+  const int y0 = oy * p.SY - p.pad_u, x0 = ox * p.SX - p.pad_l;
+  int32_t acc[N];
+  uint32_t mx[N / 2];  // max and sums: two channels per register as 16-bit halves (VIMNMX.S16x2 / one IADD; byte lanes widen with one PRMT per pair)
+  {
+    // pool.hpp:98-102: the type's minimum, or min_value (maxpool.h:144-150); anything below -32768 is below every 8-bit tap
+    int32_t first = BM == 1 ? (p.has_init ? p.init : (p.acc_signed ? -(1 << (p.acc_bits - 1)) : 0)) : 0;
+    first = max(first, -32768);
+#pragma unroll
+    for (int j = 0; j < N; j++) acc[j] = 0;
+#pragma unroll
+    for (int j = 0; j < N / 2; j++) mx[j] = BM == 1 ? ((uint32_t)first & 0xFFFFu) * 0x10001u : 0u;
+  }
+  // taps in (ky, kx) order, four at a time: the loads of a chunk are issued together (what these units need is bytes in flight)
+  const int taps = p.KX * p.KY;
+  int ky = 0, kx = 0;
+  for (int t0 = 0; t0 < taps; t0 += 4) {
+    uint32_t w[4][V];
+    uint2 wq[4][V];  // depth-wise weights of the taps: 4 int16 per word of channels
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int i = 0; i < V; i++) w[u][i] = 0u;  // FMPadding zero
+      const int y = y0 + ky * p.DY, x = x0 + kx * p.DX;
+      if (t0 + u < taps) {
+        if (y >= 0 && y < p.IY && x >= 0 && x < p.IX) {
+          const uint8_t* src = in + ((size_t)y * p.IX + x) * p.in_word_bytes;
+          if (V == 4) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+            w[u][0] = q.x; w[u][1 % V] = q.y; w[u][2 % V] = q.z; w[u][3 % V] = q.w;
+          } else {
+            w[u][0] = __ldg(reinterpret_cast<const uint32_t*>(src));
+          }
+        }
+        if (BM == 0) {
+#pragma unroll
+          for (int i = 0; i < V; i++) wq[u][i] = __ldg(reinterpret_cast<const uint2*>(p.wt + (size_t)(t0 + u) * p.Cpad + ch0) + i);
+        }
+      }
+      if (++kx == p.KX) { kx = 0; ++ky; }
+    }
+    if (BM == 3) {
+      // depth-wise with weights of at most 8 bits: the four taps of the chunk go through the dot-product unit.  Per word of four
+      // channels the 4x4 bytes (tap x channel) are transposed with 8 PRMTs into one register per channel holding its four taps, and
+      // one IDP.4A per channel multiplies them with that channel's four weights (table wt4: [chunk][channel] words, zero past the
+      // last tap): 12 instructions per 16 MACs instead of ~70.
+#pragma unroll
+      for (int i = 0; i < V; i++) {
+        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.wt4 + (size_t)(t0 >> 2) * p.Cpad + ch0) + i);
+        const uint32_t lo01 = prmt(w[0][i], w[1][i], 0x5140u), hi01 = prmt(w[0][i], w[1][i], 0x7362u);
+        const uint32_t lo23 = prmt(w[2][i], w[3][i], 0x5140u), hi23 = prmt(w[2][i], w[3][i], 0x7362u);
+        acc[4 * i] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x5410u), wv.x, acc[4 * i]);
+        acc[4 * i + 1] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x7632u), wv.y, acc[4 * i + 1]);
+        acc[4 * i + 2] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x5410u), wv.z, acc[4 * i + 2]);
+        acc[4 * i + 3] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x7632u), wv.w, acc[4 * i + 3]);
+      }
+    } else {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (t0 + u >= taps) break;
+      if (BM == 2) {
+        // sums: two channels per register as 16-bit halves, plain 32-bit adds (<= 128 taps x 255 < 2^16: no carry between the halves);
+        // signed lanes are summed as a + 128 (padding zeros included: 0x80 after the flip) and corrected once at the end
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+          const uint32_t b = INS ? (w[u][i] ^ 0x80808080u) : w[u][i];
+          mx[2 * i] += prmt(b, 0u, 0x4140u);
+          mx[2 * i + 1] += prmt(b, 0u, 0x4342u);
+        }
+      } else if (BM == 1) {
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+          mx[2 * i] = __vmaxs2(mx[2 * i], prmt(w[u][i], 0u, INS ? 0x9180u : 0x4140u));          // bytes 0, 1 sign- / zero-extended to 16 bits
+          mx[2 * i + 1] = __vmaxs2(mx[2 * i + 1], prmt(w[u][i], 0u, INS ? 0xB3A2u : 0x4342u));  // bytes 2, 3
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          const uint32_t sh = w[u][j >> 2] >> (8 * (j & 3));
+          const int32_t a = INS ? (int32_t)(int8_t)sh : (int32_t)(sh & 0xFFu);
+          const uint32_t pair = (j & 2) ? wq[u][j >> 2].y : wq[u][j >> 2].x;
+          acc[j] += ((j & 1) ? ((int32_t)pair >> 16) : (int32_t)(int16_t)(pair & 0xFFFFu)) * a;
+        }
+      }
+    }
+    }
+  }
+  if (BM == 1) {
+#pragma unroll
+    for (int j = 0; j < N; j++) acc[j] = (j & 1) ? ((int32_t)mx[j >> 1] >> 16) : (int32_t)(int16_t)(mx[j >> 1] & 0xFFFFu);
+  } else if (BM == 2) {
+    const int32_t bias = INS ? 128 * taps : 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) acc[j] = (int32_t)((j & 1) ? (mx[j >> 1] >> 16) : (mx[j >> 1] & 0xFFFFu)) - bias;
+  }
+  uint32_t r[N];
+  const uint32_t omask = p.out_bits >= 32 ? 0xffffffffu : ((1u << p.out_bits) - 1u);
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    if (BM == 0 || BM == 3) {
+      r[j] = activate(p.epi, ch0 + j, acc[j]);
+    } else {
+      int32_t o = acc[j];
+      if (BM == 2) {
+        o = wrap32(o, p.acc_bits, p.acc_signed);
+        // accu / size with C++ truncation; |accu| <= 128 taps x 255 < 2^24, so the float quotient truncates to the same integer
+        if (p.mode == CW_POOL_AVG) o = p.size ? (int32_t)((float)o / (float)p.size) : 0;
+        else if (p.mode == CW_POOL_QUANTAVG) o = o >> p.size;
+      }
+      r[j] = (uint32_t)o & omask;
+    }
+  }
+  uint8_t* dst = p.out + (size_t)blockIdx.y * p.out_img_bytes + (size_t)pix * p.out_word_bytes + (size_t)ch0 * (p.out_bits >> 3);
+  if (p.out_bits == 8) {
+    uint32_t o[V];
+#pragma unroll
+    for (int i = 0; i < V; i++) o[i] = (r[4 * i] & 0xFFu) | ((r[4 * i + 1] & 0xFFu) << 8) | ((r[4 * i + 2] & 0xFFu) << 16) | (r[4 * i + 3] << 24);
+    if (V == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1 % V], o[2 % V], o[3 % V]);
+    else *reinterpret_cast<uint32_t*>(dst) = o[0];
+  } else if (p.out_bits == 16) {
+    uint32_t o[2 * V];
+#pragma unroll
+    for (int i = 0; i < 2 * V; i++) o[i] = (r[2 * i] & 0xFFFFu) | (r[2 * i + 1] << 16);
+    if (V == 4) {
+#pragma unroll
+      for (int i = 0; i < V / 2; i++) reinterpret_cast<uint4*>(dst)[i] = make_uint4(o[4 * i], o[(4 * i + 1) % (2 * V)], o[(4 * i + 2) % (2 * V)], o[(4 * i + 3) % (2 * V)]);
+    } else {
+      *reinterpret_cast<uint2*>(dst) = make_uint2(o[0], o[1]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; i++) reinterpret_cast<uint4*>(dst)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+  }
+}
+
+template <int V>
+static void launch_bytes(const ChanParams& q, dim3 grid, cudaStream_t st) {
+  const int bm = q.mode == CW_DWCONV ? (q.wt4 ? 3 : 0) : q.mode == CW_POOL_MAX ? 1 : 2;
+  if (bm == 3) {
+    if (q.in_signed) chanwise_bytes_kernel<V, 3, true><<<grid, 256, 0, st>>>(q);
+    else chanwise_bytes_kernel<V, 3, false><<<grid, 256, 0, st>>>(q);
+  } else if (q.in_signed) {
+    if (bm == 0) chanwise_bytes_kernel<V, 0, true><<<grid, 256, 0, st>>>(q);
+    else if (bm == 1) chanwise_bytes_kernel<V, 1, true><<<grid, 256, 0, st>>>(q);
+    else chanwise_bytes_kernel<V, 2, true><<<grid, 256, 0, st>>>(q);
+  } else {
+    if (bm == 0) chanwise_bytes_kernel<V, 0, false><<<grid, 256, 0, st>>>(q);
+    else if (bm == 1) chanwise_bytes_kernel<V, 1, false><<<grid, 256, 0, st>>>(q);
+    else chanwise_bytes_kernel<V, 2, false><<<grid, 256, 0, st>>>(q);
+  }
+}
+
+// AddStreams_Batch on byte lanes (8-bit operands, 8- or 16-bit sums): 16 lanes per thread
+__global__ void __launch_bounds__(256) add_streams_bytes_kernel(const uint4* __restrict__ in1, const uint4* __restrict__ in2, uint8_t* __restrict__ out,
+                                                                unsigned long long n16, int s1, int s2, int ob, int offset) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= n16) return;
+  const uint4 a = __ldg(in1 + t), b = __ldg(in2 + t);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t r[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const uint32_t x = (aw[j >> 2] >> (8 * (j & 3))) & 0xFFu, y = (bw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+    r[j] = (uint32_t)((s1 ? (int32_t)(int8_t)x : (int32_t)x) + (s2 ? (int32_t)(int8_t)y : (int32_t)y) + offset);
+  }
+  if (ob == 8) {
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = (r[4 * i] & 0xFFu) | ((r[4 * i + 1] & 0xFFu) << 8) | ((r[4 * i + 2] & 0xFFu) << 16) | (r[4 * i + 3] << 24);
+    reinterpret_cast<uint4*>(out)[t] = make_uint4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+      reinterpret_cast<uint4*>(out)[2 * t + i] = make_uint4((r[8 * i] & 0xFFFFu) | (r[8 * i + 1] << 16), (r[8 * i + 2] & 0xFFFFu) | (r[8 * i + 3] << 16),
+                                                           (r[8 * i + 4] & 0xFFFFu) | (r[8 * i + 5] << 16), (r[8 * i + 6] & 0xFFFFu) | (r[8 * i + 7] << 16));
+  }
+}
+
 // AddStreams_Batch (streamtools.h:669-720): Out_t sum = op1 + op2 + offset per lane; a warp owns one stream word
 __device__ __forceinline__ int32_t load_lane32(const uint8_t* word, int c, int bits, int sgn) {  // lanes up to 32 bits
   const size_t bit = (size_t)c * bits;
@@ -98,6 +314,19 @@ __global__ void __launch_bounds__(256) add_streams_kernel(const uint8_t* __restr
 int launch_add_streams(const void* d_in1, const void* d_in2, void* d_out, unsigned long long n_words, int ch, int b1, int s1, int b2, int s2, int ob,
                        int offset, int wb1, int wb2, int wbo, cudaStream_t st) {
   if (!n_words) return FCB_OK;
+  const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (b1 == 8 && b2 == 8 && (ob == 8 || ob == 16) && wb1 == ch && wb2 == ch && wbo == ch * ob / 8 && ((unsigned long long)ch * n_words) % 16 == 0 &&
+      al16(d_in1) && al16(d_in2) && al16(d_out)) {
+    // byte lanes without container padding: the word structure does not matter, the stream is a flat array of lanes
+    const unsigned long long n16 = (unsigned long long)ch * n_words / 16, blocks = (n16 + 255) / 256;
+    for (unsigned long long b0 = 0; b0 < blocks; b0 += 0x40000000ull) {
+      const unsigned nb = (unsigned)std::min<unsigned long long>(0x40000000ull, blocks - b0);
+      add_streams_bytes_kernel<<<nb, 256, 0, st>>>((const uint4*)d_in1 + b0 * 256, (const uint4*)d_in2 + b0 * 256, (uint8_t*)d_out + b0 * 256 * 2 * ob,
+                                                   n16 - b0 * 256, s1, s2, ob, offset);
+      FCB_CUDA_OK(cudaGetLastError());
+    }
+    return FCB_OK;
+  }
   if ((size_t)wbo * 8 != (size_t)ch * ob) FCB_CUDA_OK(cudaMemsetAsync(d_out, 0, (size_t)wbo * n_words, st));  // container padding bits stay zero
   const unsigned long long blocks = (n_words + 7) / 8;
   for (unsigned long long b0 = 0; b0 < blocks; b0 += 0x40000000ull) {
@@ -109,13 +338,41 @@ int launch_add_streams(const void* d_in1, const void* d_in2, void* d_out, unsign
   return FCB_OK;
 }
 
+// 32-bit words of channels a thread of chanwise_bytes_kernel would own for this unit (4 or 1), 0 = the general kernel: what the
+// byte-lane form computes exactly in 32 bits, on words it can move as vectors (buffer alignment is checked again per launch)
+int chanwise_vector_words(const ChanParams& p) {
+  // depth-wise / sums: exact in 32 bits (8-bit lanes x 16-bit weights x <= 128 taps); max: the tap must convert to the function's
+  // type without changing value (same signedness and >= 8 bits, or unsigned lanes in a signed type of >= 9 bits)
+  const bool exact32 = p.KX * p.KY <= 128 &&
+                       (p.mode == CW_DWCONV ? true
+                        : p.mode == CW_POOL_MAX
+                            ? (p.acc_bits <= 31 && (!p.has_init || p.init <= 32767) &&
+                               ((p.acc_signed == p.in_signed && p.acc_bits >= 8) || (p.acc_signed && !p.in_signed && p.acc_bits >= 9)))
+                            : (p.acc_bits <= 31 && p.size >= 0 && p.size < 32));
+  if (!(exact32 && p.in_bits == 8 && (p.out_bits == 8 || p.out_bits == 16 || p.out_bits == 32) && p.C % 4 == 0 && p.in_word_bytes == p.C &&
+        p.out_word_bytes == p.C * (p.out_bits / 8) && (p.mode != CW_DWCONV || p.Cpad % 4 == 0) && p.in_img_bytes % 16 == 0 &&
+        p.out_img_bytes % 16 == 0))
+    return 0;
+  return p.C % 16 == 0 ? 4 : 1;
+}
+
 int launch_chanwise(const ChanParams& p, int n_images, cudaStream_t st) {
   const int blocks = (p.OX * p.OY + 7) / 8;
+  int V = chanwise_vector_words(p);
+  if (((reinterpret_cast<uintptr_t>(p.in) | reinterpret_cast<uintptr_t>(p.out)) & 15) ||
+      (p.mode == CW_DWCONV && ((reinterpret_cast<uintptr_t>(p.wt) & 7) || (reinterpret_cast<uintptr_t>(p.wt4) & 15))))
+    V = 0;
   for (int n0 = 0; n0 < n_images; n0 += 65535) {
     ChanParams q = p;
     const int nb = n_images - n0 < 65535 ? n_images - n0 : 65535;
     q.in = p.in + (size_t)n0 * p.in_img_bytes;
     q.out = p.out + (size_t)n0 * p.out_img_bytes;
+    if (V) {
+      const long long threads = (long long)p.OX * p.OY * (p.C / (4 * V));
+      const dim3 grid((unsigned)((threads + 255) / 256), nb, 1);
+      if (V == 4) launch_bytes<4>(q, grid, st);
+      else launch_bytes<1>(q, grid, st);
+    } else
     chanwise_kernel<<<dim3(blocks, nb, 1), 256, 0, st>>>(q);
     FCB_CUDA_OK(cudaGetLastError());
   }

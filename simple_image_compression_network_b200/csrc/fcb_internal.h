@@ -108,6 +108,7 @@ struct ChanParams {
   const uint8_t* in;
   uint8_t* out;
   const int16_t* wt;  // depth-wise weights [Kx*Ky][Cpad]
+  const uint32_t* wt4; // the same as bytes, four taps per word: [ceil(Kx*Ky / 4)][Cpad] (NULL when a weight does not fit 8 bits)
   EpiParams epi;
   int C, Cpad, KX, KY, DX, DY, IX, IY, OX, OY, SX, SY, pad_l, pad_u;
   int in_bits, in_signed, in_word_bytes, out_word_bytes, out_bits;
@@ -116,6 +117,7 @@ struct ChanParams {
   unsigned long long in_img_bytes, out_img_bytes;
 };
 int launch_chanwise(const ChanParams& p, int n_images, cudaStream_t st);
+int chanwise_vector_words(const ChanParams& p);  // 4 / 1: byte-lane kernel with 16 / 4 channels per thread; 0: general kernel
 int launch_add_streams(const void* d_in1, const void* d_in2, void* d_out, unsigned long long n_words, int ch, int b1, int s1, int b2, int s2, int ob,
                        int offset, int wb1, int wb2, int wbo, cudaStream_t st);
 

@@ -1264,6 +1264,9 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
     if (D - 2 >= 1) cands.push_back({D - 2, 1, 60.0});
   }
   cands.push_back({0, 1, thr ? 120.0 : 0.0});
+  // two channel blocks without shared-memory tables: one CTA group per block keeps 256 accumulator columns free, so the epilogue of
+  // a tile overlaps the MMAs of the next (CB = 2 in one CTA fills all 512 columns: acc_stages = 1, epilogue serial with the MMAs)
+  if (!thr && CB == 2 && !exp_env("FCB_U2_NO_CHB")) cands.push_back({0, 2, 0.0});
   double best = 1e30;
   int bWT = 0, bR = 0, bNPX = 0, bWS = 0, thr_top = 0, thr_bytes = 0, chb = 1, CBe = CB;
   const int only_cand = exp_int("FCB_U2_CAND", -1);  // experiments: evaluate one candidate only

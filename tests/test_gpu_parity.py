@@ -656,6 +656,67 @@ def test_dilation_on_the_engines(c, ofm, k, s, dx, dy, pad, x, y, engine, fcb_li
     assert np.array_equal(got, want), f"[{L.engine}: {L.plan}]: {_diff(got, want)}"
 
 
+@pytest.mark.parametrize("seed", [21, 22])
+def test_channelwise_byte_lane_forms(seed, fcb_lib, oracle_mod):
+    """chanwise_bytes_kernel (8-bit lanes moved as 4- / 16-byte vectors): every pool function, depth-wise with pass-through and
+    thresholds, 8 / 16 / 32-bit outputs, signed and unsigned lanes, padding, stride, dilation; channel counts that take the 16-channel,
+    the 4-channel and the general kernel -- against the oracle."""
+    from simple_image_compression_network_b200.desc import (ACT_PASSTHROUGH, ACT_THRESHOLDS, KIND_DWCONV, KIND_POOL, LayerDesc)
+    rng = np.random.default_rng(seed)
+    forms = set()
+    for i in range(40):
+        c = int(rng.choice([4, 8, 16, 48, 128, 6])); pe = int(rng.choice([p for p in (1, 2, 4) if c % p == 0]))
+        k = int(rng.choice([2, 3])); s = int(rng.choice([1, 2])); pad = int(rng.integers(0, 2))
+        x = 4 * int(rng.integers(2, 8)); y = 4 * int(rng.integers(1, 4))
+        ins = int(rng.integers(0, 2)); outb = int(rng.choice([8, 16, 32]))
+        common = dict(kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=c, ifm_x=x, ifm_y=y, stride_x=s, stride_y=s, pad=pad, simd=pe, pe=pe, in_bits=8,
+                      in_signed=ins, dilation_x=int(rng.choice([1, 1, 2])))
+        if i % 2:
+            fn = i // 2 % 4
+            d = LayerDesc(kind=KIND_POOL, w_bits=0, weight_kind=fn, acc_bits=int(rng.choice([8, 12, 16])), acc_signed=ins, act_kind=ACT_PASSTHROUGH,
+                          out_bits=outb, act_val=int(rng.choice([2, 3, 4])), **common)
+        else:
+            thr = i % 4 == 0
+            d = LayerDesc(kind=KIND_DWCONV, w_bits=int(rng.choice([4, 8])), acc_bits=int(rng.choice([16, 24])), acc_signed=1,
+                          act_kind=ACT_THRESHOLDS if thr else ACT_PASSTHROUGH, out_bits=8 if thr else outb, num_th=255 if thr else 0, **common)
+        inp = cases.make_inputs(d, seed_shift=seed + i, num_reps=3)
+        L = _layer(d, inp)
+        assert L.engine == "chanwise"
+        form = "16" if "16 channels" in L.plan else "4" if "4 channels" in L.plan else "general"
+        assert form == ("general" if (c % 4 or L.in_bytes % 16 or L.out_bytes % 16) else "16" if c % 16 == 0 else "4"), (d, L.plan)
+        forms.add(form)
+        got = L.run(inp["in_words"], 3)
+        want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=3)
+        assert np.array_equal(got, want), f"case {i} {d} [{L.plan}]: {_diff(got, want)}"
+    assert forms == {"16", "4", "general"}
+
+
+def test_channelwise_units_at_bench_size(fcb_lib, oracle_mod):
+    """The channel-wise shapes tools/bench_layers.py times (384x256 frames, 128 channels): 2x2 max pool, 3x3 signed max pool with padding,
+    2x2 average, depth-wise 3x3 with pass-through and with 255 thresholds, AddStreams on the same frames -- full size against the oracle."""
+    from simple_image_compression_network_b200.desc import (ACT_PASSTHROUGH, ACT_THRESHOLDS, KIND_DWCONV, KIND_POOL, POOLFN_AVG, POOLFN_MAX, LayerDesc)
+    from simple_image_compression_network_b200.layer import add_streams
+    geo = dict(ifm_ch=128, ofm_ch=128, ifm_x=384, ifm_y=256, simd=16, pe=16, in_bits=8)
+    descs = [LayerDesc(kind=KIND_POOL, kernel_x=k, kernel_y=k, stride_x=st, stride_y=st, pad=pad, in_signed=ins, w_bits=0, weight_kind=fn, acc_bits=tab,
+                       acc_signed=ins, act_kind=ACT_PASSTHROUGH, out_bits=8, act_val=size, **geo)
+             for k, st, pad, ins, fn, tab, size in ((2, 2, 0, 0, POOLFN_MAX, 8, 0), (3, 1, 1, 1, POOLFN_MAX, 8, 0), (2, 2, 0, 0, POOLFN_AVG, 10, 4))]
+    descs += [LayerDesc(kind=KIND_DWCONV, kernel_x=3, kernel_y=3, stride_x=1, stride_y=1, pad=1, in_signed=0, w_bits=4, acc_bits=16, acc_signed=1,
+                        act_kind=ACT_THRESHOLDS if thr else ACT_PASSTHROUGH, out_bits=8 if thr else 16, num_th=255 if thr else 0, **geo) for thr in (False, True)]
+    for d in descs:
+        inp = cases.make_inputs(d, seed_shift=5)
+        L = _layer(d, inp)
+        assert "16 channels" in L.plan
+        got = L.run(inp["in_words"])
+        want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"])
+        assert np.array_equal(got, want), f"{d} [{L.plan}]: {_diff(got, want)}"
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, 384 * 256 * 128, dtype=np.uint8); b = rng.integers(0, 256, a.size, dtype=np.uint8)
+    for ob, s1 in ((8, False), (16, True)):
+        got = add_streams(a, b, 384 * 256, 128, 8, s1, 8, False, ob, offset=-3)
+        want = oracle_mod.add_streams(a, b, 384 * 256, 128, 8, s1, 8, False, ob, -3)
+        assert np.array_equal(got, want), f"add_streams ob={ob}"
+
+
 @pytest.mark.parametrize("seed", [11, 12])
 def test_channelwise_units_fuzz(seed, fcb_lib, oracle_mod):
     """Depth-wise convolution (VVAU) and Pool_batch with random geometry, lane widths, signedness, functions, padding, stride and dilation

@@ -88,6 +88,34 @@ if __name__ == "__main__":
                 bench_layer("cfg4_thr_nopool", dataclasses.replace(c4, pool=0), a.images, 0xFF)
             elif nm == "cfg4":
                 bench_layer("cfg4_thr_pool", c4, a.images, 0xFF)
+            elif nm in ("pool", "pool3s", "avg", "dw", "dwthr"):  # channel-wise streaming units (fcb_chanwise.cu), HBM-bound
+                from simple_image_compression_network_b200.desc import ACT_PASSTHROUGH, KIND_DWCONV, KIND_POOL, POOLFN_AVG, POOLFN_MAX
+                if nm == "dw" or nm == "dwthr":  # depth-wise 3x3, 128 channels, 384x256 (u8 x s4)
+                    d = LayerDesc(kind=KIND_DWCONV, kernel_x=3, kernel_y=3, ifm_ch=128, ofm_ch=128, ifm_x=384, ifm_y=256, stride_x=1, stride_y=1, pad=1,
+                                  simd=16, pe=16, in_bits=8, in_signed=0, w_bits=4, acc_bits=16, acc_signed=1,
+                                  act_kind=ACT_THRESHOLDS if nm == "dwthr" else ACT_PASSTHROUGH, out_bits=8 if nm == "dwthr" else 16,
+                                  num_th=255 if nm == "dwthr" else 0)
+                else:
+                    k, st, pad, ins, fn, tab, size = {"pool": (2, 2, 0, 0, POOLFN_MAX, 8, 0), "pool3s": (3, 1, 1, 1, POOLFN_MAX, 8, 0),
+                                                      "avg": (2, 2, 0, 0, POOLFN_AVG, 10, 4)}[nm]
+                    d = LayerDesc(kind=KIND_POOL, kernel_x=k, kernel_y=k, ifm_ch=128, ofm_ch=128, ifm_x=384, ifm_y=256, stride_x=st, stride_y=st, pad=pad,
+                                  simd=16, pe=16, in_bits=8, in_signed=ins, w_bits=0, weight_kind=fn, acc_bits=tab, acc_signed=ins,
+                                  act_kind=ACT_PASSTHROUGH, out_bits=8, act_val=size)
+                bench_layer(f"chanwise_{nm}", d, a.images, 0xFF)
+            elif nm == "add":  # AddStreams_Batch on two 384x256x128-byte streams per image
+                import ctypes
+                from simple_image_compression_network_b200 import _lib
+                from simple_image_compression_network_b200.desc import CAddDesc
+                n = a.images; words = 384 * 256 * n
+                x1 = torch.empty(words * 128, dtype=torch.uint8, device="cuda"); x2 = torch.empty_like(x1); y = torch.empty_like(x1)
+                synth_fill(x1.data_ptr(), x1.numel(), synth.SEED_INPUT, 0x7F); synth_fill(x2.data_ptr(), x2.numel(), synth.SEED_INPUT + 1, 0x7F)
+                cd = CAddDesc(ctypes.sizeof(CAddDesc), 128, 8, 0, 8, 0, 8, 0)
+                Lb = _lib.lib()
+                run = lambda: _lib.check(Lb.fcb_add_streams_device(ctypes.byref(cd), ctypes.c_void_p(x1.data_ptr()), ctypes.c_void_p(x2.data_ptr()),
+                                                                   ctypes.c_void_p(y.data_ptr()), words, 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), Lb)
+                ms = timed(run)
+                print(json.dumps(dict(layer="add_streams_u8_128ch_384x256", images=n, ms=round(ms, 3), img_s=round(n / ms * 1e3),
+                                      GBs=round(3 * x1.numel() / ms / 1e6, 1))), flush=True)
             elif nm == "imad16":  # 16-bit lanes x 8-bit weights: the universal engine's own shape (workloads.imad16)
                 from simple_image_compression_network_b200 import workloads
                 bench_layer("wide16_imad", workloads.imad16(), a.images * 8, 0xFF)
