@@ -96,7 +96,77 @@ __device__ __forceinline__ int32_t dp4a_mixed(uint32_t a, uint32_t b, int32_t c)
   return d;
 }
 
+// One chunk of up to four taps (cnt valid ones, t0 = index of the first) into the accumulators.  w[u][i]: word i (4 channels) of tap u,
+// zeros for FMPadding and past the last tap.
 template <int V, int BM, bool INS>
+__device__ __forceinline__ void chanwise_consume(const ChanParams& p, const uint32_t (&w)[4][V], int t0, int cnt, int ch0, int32_t (&acc)[4 * V],
+                                                 uint32_t (&mx)[2 * V]) {
+  if (BM == 3) {
+    // depth-wise with weights of at most 8 bits: the four taps of the chunk go through the dot-product unit.  Per word of four
+    // channels the 4x4 bytes (tap x channel) are transposed with 8 PRMTs into one register per channel holding its four taps, and
+    // one IDP.4A per channel multiplies them with that channel's four weights (table wt4: [chunk][channel] words, zero past the
+    // last tap): 12 instructions per 16 MACs instead of ~70.
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.wt4 + (size_t)(t0 >> 2) * p.Cpad + ch0) + i);
+      const uint32_t lo01 = prmt(w[0][i], w[1][i], 0x5140u), hi01 = prmt(w[0][i], w[1][i], 0x7362u);
+      const uint32_t lo23 = prmt(w[2][i], w[3][i], 0x5140u), hi23 = prmt(w[2][i], w[3][i], 0x7362u);
+      acc[4 * i] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x5410u), wv.x, acc[4 * i]);
+      acc[4 * i + 1] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x7632u), wv.y, acc[4 * i + 1]);
+      acc[4 * i + 2] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x5410u), wv.z, acc[4 * i + 2]);
+      acc[4 * i + 3] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x7632u), wv.w, acc[4 * i + 3]);
+    }
+  } else {
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    if (u < cnt) {
+      if (BM == 2) {
+        // sums: two channels per register as 16-bit halves, plain 32-bit adds (<= 128 taps x 255 < 2^16: no carry between the halves);
+        // signed lanes are summed as a + 128 (padding zeros included: 0x80 after the flip) and corrected once at the end
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+          const uint32_t b = INS ? (w[u][i] ^ 0x80808080u) : w[u][i];
+          mx[2 * i] += prmt(b, 0u, 0x4140u);
+          mx[2 * i + 1] += prmt(b, 0u, 0x4342u);
+        }
+      } else if (BM == 1) {
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+          mx[2 * i] = __vmaxs2(mx[2 * i], prmt(w[u][i], 0u, INS ? 0x9180u : 0x4140u));          // bytes 0, 1 sign- / zero-extended to 16 bits
+          mx[2 * i + 1] = __vmaxs2(mx[2 * i + 1], prmt(w[u][i], 0u, INS ? 0xB3A2u : 0x4342u));  // bytes 2, 3
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+          const uint2 wq = __ldg(reinterpret_cast<const uint2*>(p.wt + (size_t)(t0 + u) * p.Cpad + ch0) + i);  // 4 int16 weights
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t sh = w[u][i] >> (8 * j);
+            const int32_t a = INS ? (int32_t)(int8_t)sh : (int32_t)(sh & 0xFFu);
+            const uint32_t pair = (j & 2) ? wq.y : wq.x;
+            acc[4 * i + j] += ((j & 1) ? ((int32_t)pair >> 16) : (int32_t)(int16_t)(pair & 0xFFFFu)) * a;
+          }
+        }
+      }
+    }
+  }
+  }
+}
+
+template <int V>
+__device__ __forceinline__ void chanwise_load(const uint8_t* src, bool ok, uint32_t (&w)[V]) {
+  if (V == 4) {
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);  // FMPadding zero
+    if (ok) q = __ldg(reinterpret_cast<const uint4*>(src));
+    w[0] = q.x; w[1 % V] = q.y; w[2 % V] = q.z; w[3 % V] = q.w;
+  } else {
+    w[0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(src)) : 0u;
+  }
+}
+
+// KS: 2 / 3 = square window of that size with unit dilation, fully unrolled (all loads of the window issued first, tap addresses from
+// one row pointer per ky); 0 = any window, taps in (ky, kx) order four at a time.
+template <int V, int BM, bool INS, int KS>
 __global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p) {
   constexpr int N = 4 * V;  // channels per thread
   const int groups = p.C / N;
@@ -117,78 +187,48 @@ __global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p)
 #pragma unroll
     for (int j = 0; j < N / 2; j++) mx[j] = BM == 1 ? ((uint32_t)first & 0xFFFFu) * 0x10001u : 0u;
   }
-  // taps in (ky, kx) order, four at a time: the loads of a chunk are issued together (what these units need is bytes in flight)
   const int taps = p.KX * p.KY;
-  int ky = 0, kx = 0;
-  for (int t0 = 0; t0 < taps; t0 += 4) {
-    uint32_t w[4][V];
-    uint2 wq[4][V];  // depth-wise weights of the taps: 4 int16 per word of channels
+  if constexpr (KS > 0) {
+    constexpr int T = KS * KS, TC = KS ? (T + 3) / 4 * 4 : 4;  // (KS = 0 never runs this branch; the array must still have a size)
+    uint32_t w[TC][V];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int ky = 0; ky < KS; ky++) {
+      const int y = y0 + ky;
+      const bool yok = y >= 0 && y < p.IY;
+      const uint8_t* row = in + ((size_t)(yok ? y : 0) * p.IX) * p.in_word_bytes;
 #pragma unroll
-      for (int i = 0; i < V; i++) w[u][i] = 0u;  // FMPadding zero
-      const int y = y0 + ky * p.DY, x = x0 + kx * p.DX;
-      if (t0 + u < taps) {
-        if (y >= 0 && y < p.IY && x >= 0 && x < p.IX) {
-          const uint8_t* src = in + ((size_t)y * p.IX + x) * p.in_word_bytes;
-          if (V == 4) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
-            w[u][0] = q.x; w[u][1 % V] = q.y; w[u][2 % V] = q.z; w[u][3 % V] = q.w;
-          } else {
-            w[u][0] = __ldg(reinterpret_cast<const uint32_t*>(src));
-          }
-        }
-        if (BM == 0) {
-#pragma unroll
-          for (int i = 0; i < V; i++) wq[u][i] = __ldg(reinterpret_cast<const uint2*>(p.wt + (size_t)(t0 + u) * p.Cpad + ch0) + i);
-        }
-      }
-      if (++kx == p.KX) { kx = 0; ++ky; }
-    }
-    if (BM == 3) {
-      // depth-wise with weights of at most 8 bits: the four taps of the chunk go through the dot-product unit.  Per word of four
-      // channels the 4x4 bytes (tap x channel) are transposed with 8 PRMTs into one register per channel holding its four taps, and
-      // one IDP.4A per channel multiplies them with that channel's four weights (table wt4: [chunk][channel] words, zero past the
-      // last tap): 12 instructions per 16 MACs instead of ~70.
-#pragma unroll
-      for (int i = 0; i < V; i++) {
-        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.wt4 + (size_t)(t0 >> 2) * p.Cpad + ch0) + i);
-        const uint32_t lo01 = prmt(w[0][i], w[1][i], 0x5140u), hi01 = prmt(w[0][i], w[1][i], 0x7362u);
-        const uint32_t lo23 = prmt(w[2][i], w[3][i], 0x5140u), hi23 = prmt(w[2][i], w[3][i], 0x7362u);
-        acc[4 * i] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x5410u), wv.x, acc[4 * i]);
-        acc[4 * i + 1] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x7632u), wv.y, acc[4 * i + 1]);
-        acc[4 * i + 2] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x5410u), wv.z, acc[4 * i + 2]);
-        acc[4 * i + 3] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x7632u), wv.w, acc[4 * i + 3]);
-      }
-    } else {
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (t0 + u >= taps) break;
-      if (BM == 2) {
-        // sums: two channels per register as 16-bit halves, plain 32-bit adds (<= 128 taps x 255 < 2^16: no carry between the halves);
-        // signed lanes are summed as a + 128 (padding zeros included: 0x80 after the flip) and corrected once at the end
-#pragma unroll
-        for (int i = 0; i < V; i++) {
-          const uint32_t b = INS ? (w[u][i] ^ 0x80808080u) : w[u][i];
-          mx[2 * i] += prmt(b, 0u, 0x4140u);
-          mx[2 * i + 1] += prmt(b, 0u, 0x4342u);
-        }
-      } else if (BM == 1) {
-#pragma unroll
-        for (int i = 0; i < V; i++) {
-          mx[2 * i] = __vmaxs2(mx[2 * i], prmt(w[u][i], 0u, INS ? 0x9180u : 0x4140u));          // bytes 0, 1 sign- / zero-extended to 16 bits
-          mx[2 * i + 1] = __vmaxs2(mx[2 * i + 1], prmt(w[u][i], 0u, INS ? 0xB3A2u : 0x4342u));  // bytes 2, 3
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-          const uint32_t sh = w[u][j >> 2] >> (8 * (j & 3));
-          const int32_t a = INS ? (int32_t)(int8_t)sh : (int32_t)(sh & 0xFFu);
-          const uint32_t pair = (j & 2) ? wq[u][j >> 2].y : wq[u][j >> 2].x;
-          acc[j] += ((j & 1) ? ((int32_t)pair >> 16) : (int32_t)(int16_t)(pair & 0xFFFFu)) * a;
-        }
+      for (int kx = 0; kx < KS; kx++) {
+        const int x = x0 + kx;
+        const bool ok = yok && x >= 0 && x < p.IX;
+        chanwise_load<V>(row + (size_t)(ok ? x : 0) * p.in_word_bytes, ok, w[ky * KS + kx]);
       }
     }
+#pragma unroll
+    for (int u = T; u < TC; u++)
+#pragma unroll
+      for (int i = 0; i < V; i++) w[u][i] = 0u;
+#pragma unroll
+    for (int t0 = 0; t0 < T; t0 += 4) {
+      uint32_t wc[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int i = 0; i < V; i++) wc[u][i] = w[t0 + u][i];
+      chanwise_consume<V, BM, INS>(p, wc, t0, T - t0 < 4 ? T - t0 : 4, ch0, acc, mx);
+    }
+  } else {
+    // taps in (ky, kx) order, four at a time: the loads of a chunk are issued together (what these units need is bytes in flight)
+    int ky = 0, kx = 0;
+    for (int t0 = 0; t0 < taps; t0 += 4) {
+      uint32_t w[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int y = y0 + ky * p.DY, x = x0 + kx * p.DX;
+        const bool ok = t0 + u < taps && y >= 0 && y < p.IY && x >= 0 && x < p.IX;
+        chanwise_load<V>(in + ((size_t)(ok ? y : 0) * p.IX + (ok ? x : 0)) * p.in_word_bytes, ok, w[u]);
+        if (++kx == p.KX) { kx = 0; ++ky; }
+      }
+      chanwise_consume<V, BM, INS>(p, w, t0, taps - t0 < 4 ? taps - t0 : 4, ch0, acc, mx);
     }
   }
   if (BM == 1) {
@@ -239,21 +279,27 @@ __global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p)
   }
 }
 
+template <int V, int KS>
+static void launch_bytes_k(const ChanParams& q, dim3 grid, cudaStream_t st) {
+  const int bm = q.mode == CW_DWCONV ? (q.wt4 ? 3 : 0) : q.mode == CW_POOL_MAX ? 1 : 2;
+  if (q.in_signed) {
+    if (bm == 0) chanwise_bytes_kernel<V, 0, true, 0><<<grid, 256, 0, st>>>(q);  // (16-bit weights: the rolled form keeps the registers down)
+    else if (bm == 1) chanwise_bytes_kernel<V, 1, true, KS><<<grid, 256, 0, st>>>(q);
+    else if (bm == 2) chanwise_bytes_kernel<V, 2, true, KS><<<grid, 256, 0, st>>>(q);
+    else chanwise_bytes_kernel<V, 3, true, KS><<<grid, 256, 0, st>>>(q);
+  } else {
+    if (bm == 0) chanwise_bytes_kernel<V, 0, false, 0><<<grid, 256, 0, st>>>(q);
+    else if (bm == 1) chanwise_bytes_kernel<V, 1, false, KS><<<grid, 256, 0, st>>>(q);
+    else if (bm == 2) chanwise_bytes_kernel<V, 2, false, KS><<<grid, 256, 0, st>>>(q);
+    else chanwise_bytes_kernel<V, 3, false, KS><<<grid, 256, 0, st>>>(q);
+  }
+}
 template <int V>
 static void launch_bytes(const ChanParams& q, dim3 grid, cudaStream_t st) {
-  const int bm = q.mode == CW_DWCONV ? (q.wt4 ? 3 : 0) : q.mode == CW_POOL_MAX ? 1 : 2;
-  if (bm == 3) {
-    if (q.in_signed) chanwise_bytes_kernel<V, 3, true><<<grid, 256, 0, st>>>(q);
-    else chanwise_bytes_kernel<V, 3, false><<<grid, 256, 0, st>>>(q);
-  } else if (q.in_signed) {
-    if (bm == 0) chanwise_bytes_kernel<V, 0, true><<<grid, 256, 0, st>>>(q);
-    else if (bm == 1) chanwise_bytes_kernel<V, 1, true><<<grid, 256, 0, st>>>(q);
-    else chanwise_bytes_kernel<V, 2, true><<<grid, 256, 0, st>>>(q);
-  } else {
-    if (bm == 0) chanwise_bytes_kernel<V, 0, false><<<grid, 256, 0, st>>>(q);
-    else if (bm == 1) chanwise_bytes_kernel<V, 1, false><<<grid, 256, 0, st>>>(q);
-    else chanwise_bytes_kernel<V, 2, false><<<grid, 256, 0, st>>>(q);
-  }
+  const int ks = (q.KX == q.KY && q.DX == 1 && q.DY == 1 && (q.KX == 2 || q.KX == 3)) ? q.KX : 0;
+  if (ks == 2) launch_bytes_k<V, 2>(q, grid, st);
+  else if (ks == 3) launch_bytes_k<V, 3>(q, grid, st);
+  else launch_bytes_k<V, 0>(q, grid, st);
 }
 
 // AddStreams_Batch on byte lanes (8-bit operands, 8- or 16-bit sums): 16 lanes per thread
