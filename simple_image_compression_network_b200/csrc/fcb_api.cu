@@ -607,7 +607,7 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   if (engine == ENG_IMAD && !force_imad && g.kind == FCB_KIND_CONV && g.weight_kind == FCB_W_FIXED && sym_pad &&
       g.w_bits <= 8 && g.in_bits == 8 && g.K <= 128 && g.OFM <= 256 && g.pool <= 2 && g.SX == g.SY) {
     Geom g2 = g;
-    g2.C = 128; g2.KX = g2.KY = 1; g2.K = 128; g2.IX = g.OX; g2.IY = g.OY; g2.SX = g2.SY = 1; g2.PAD = 0;
+    g2.C = 128; g2.KX = g2.KY = 1; g2.K = 128; g2.IX = g.OX; g2.IY = g.OY; g2.SX = g2.SY = 1; g2.PAD = 0; g2.pad_l = g2.pad_r = g2.pad_u = g2.pad_d = 0;
     g2.in_word_bytes = 128; g2.in_img_bytes = (size_t)128 * g.OX * g.OY;
     std::vector<int32_t> W2((size_t)g.OFM * 128, 0);
     for (int ch = 0; ch < g.OFM; ch++)

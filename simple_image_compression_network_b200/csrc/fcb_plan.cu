@@ -95,8 +95,7 @@ int umma_eligible(const Geom& g) {
   if (g.KX * g.KY > 32) return 0;
   if ((uint64_t)g.K * 255ull * 128ull >= (1ull << 31)) return 0;  // exact int32 accumulation
   if (g.pool > 2) return 0;
-  if (g.pad_l != g.pad_r || g.pad_u != g.pad_d || g.pad_l != g.pad_u) return 0;  // asymmetric FMPadding: universal engine
-  if (g.kind == FCB_KIND_DECONV522) return g.pool == 1;
+  if (g.kind == FCB_KIND_DECONV522) return g.pool == 1;  // (its padding is fixed: derive_geom)
   if (g.SX != g.SY) return 0;
   // stride 1: a partial last channel chunk is zero-filled by TMA (it then multiplies the next tap's weights by 0);
   // stride 2: the parity view packs two pixels per row, so chunks must not straddle pixels
@@ -118,7 +117,7 @@ int umma_plan_create(const Geom& g, const std::vector<int32_t>& W, const EpiPara
   if ((rc = upload(&P->d_w, w8))) return rc;
 #ifdef FCB_EXPERIMENT
   const char* v1only = exp_env("FCB_UMMA_V1");
-  if (v1only && v1only[0] == '1') {
+  if (v1only && v1only[0] == '1' && g.pad_l == g.pad_r && g.pad_u == g.pad_d && g.pad_l == g.pad_u && g.DX == 1 && g.DY == 1) {  // (v1: symmetric padding only)
     rc = umma_v1_create(g, P->d_w, epi, P->num_sms, &P->v1);
     if (rc) return rc;
     snprintf(P->desc, sizeof(P->desc), "v1 per-tap TMA");

@@ -1211,7 +1211,9 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   if (!deconv) {
     for (int ky = 0; ky < g.KY; ky++)
       for (int kx = 0; kx < g.KX; kx++) {
-        const int dx = kx * g.DX - g.PAD, dy = ky * g.DY - g.PAD;  // (a dilated tap is just another plane offset)
+        // FMPadding_nonsquare's left / up share (streamtools.h:374-379): the right / down zeros are TMA out-of-bounds fill like the
+        // rest, so an asymmetric split only moves the tap offsets (a dilated tap is just another plane offset as well)
+        const int dx = kx * g.DX - g.pad_l, dy = ky * g.DY - g.pad_u;
         taps.push_back({fdiv(dx, s), fdiv(dy, s), dx - fdiv(dx, s) * s, dy - fdiv(dy, s) * s, ky * g.KX + kx, 0});
       }
   } else {

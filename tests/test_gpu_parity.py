@@ -474,6 +474,38 @@ def _direct_descs(seed, count):
     return out
 
 
+@pytest.mark.parametrize("style", [1, 2])
+def test_asymmetric_padding_on_the_tensor_plan(style, fcb_lib, oracle_mod):
+    """FMPadding_nonsquare with odd Padding_x / Padding_y (streamtools.h:361-406: the extra zero goes left / up for PaddingStyle 2, right /
+    down for 1) on channel-heavy layers: the resident-planes tensor plan moves its tap offsets by the left / up share and leaves the
+    rest to the TMA out-of-bounds fill -- stride 1 and 2, bias+ReLU and pooled thresholds, against the oracle and the universal engine."""
+    from simple_image_compression_network_b200.desc import ACT_BIAS_RELU, ACT_THRESHOLDS, KIND_CONV, LayerDesc
+    rng = np.random.default_rng(40 + style)
+    on_tensor = 0
+    for i in range(10):
+        s = 1 + i % 2
+        c = 128 if s == 2 else int(rng.choice([32, 128, 256])); ofm = int(rng.choice([32, 128, 192]))
+        k = int(rng.choice([2, 3, 4, 5]))
+        px, py = int(rng.integers(0, k)), int(rng.integers(0, k))
+        x = 2 * int(rng.integers(k, 24)); y = 2 * int(rng.integers(k, 9))
+        if (x + px - k) % s or (y + py - k) % s:
+            px += (x + px - k) % s; py += (y + py - k) % s
+        thr = i % 3 == 2 and s == 1
+        kw = dict(act_kind=ACT_THRESHOLDS, acc_bits=24, acc_signed=1, out_bits=8, num_th=255, pool=2 if ((x + px - k + 1) % 2 == 0 and (y + py - k + 1) % 2 == 0) else 0) \
+            if thr else dict(act_kind=ACT_BIAS_RELU, acc_bits=8, acc_signed=0, out_bits=8)
+        d = LayerDesc(kind=KIND_CONV, kernel_x=k, kernel_y=k, ifm_ch=c, ofm_ch=ofm, ifm_x=x, ifm_y=y, stride_x=s, stride_y=s, pad=0, simd=16, pe=16,
+                      in_bits=8, w_bits=4, pad_style=style, pad_x_total=px, pad_y_total=py, **kw)
+        inp = cases.make_inputs(d, seed_shift=style * 50 + i, num_reps=2, relu_range=True)
+        L = _layer(d, inp)
+        on_tensor += L.engine == "umma_i8"  # (a shape without a tensor plan, e.g. an even kernel at stride 2, takes the universal engine)
+        got = L.run(inp["in_words"], 2)
+        want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], inp["bias"], num_reps=2)
+        assert np.array_equal(got, want), f"case {i} {d} [{L.plan}]: {_diff(got, want)}"
+        L2 = _layer(dataclasses.replace(d, engine_hint=ENGINE_IMAD), inp)
+        assert np.array_equal(L2.run(inp["in_words"], 2), want), f"case {i} {d} [imad]"
+    assert on_tensor >= 6, on_tensor
+
+
 @pytest.mark.parametrize("seed", [7, 8])
 def test_direct_engine_kernels_match_oracle(seed, fcb_lib, oracle_mod):
     """The three inner loops of the universal engine (fcb_direct.cu): IDP.4A (lanes <= 8 bits, weights <= 8 bits), IDP.2A (lanes of
