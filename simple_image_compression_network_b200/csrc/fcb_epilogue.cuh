@@ -102,7 +102,7 @@ __device__ __forceinline__ int32_t lds_s32(uint32_t saddr) {
 }
 // top_saddr: shared-space byte address of this channel's column of the top table; row_shift: log2(bytes per table row);
 // gshift: log2(G).  32-bit shared addressing and shifts keep a level at ~5 instructions per output.
-template <int N>
+template <int N, bool WRAP = true>  // WRAP = false: the caller already holds TA-wrapped values (pooled epilogue)
 __device__ __forceinline__ void activate_thr_hybrid(const EpiParams& e, uint32_t top_saddr, int row_shift, int top_levels, int gshift,
                                                     const int32_t* __restrict__ row_cm /*global row of the channel*/,
                                                     const int32_t (&acc)[N], uint32_t (&out)[N]) {
@@ -112,7 +112,7 @@ __device__ __forceinline__ void activate_thr_hybrid(const EpiParams& e, uint32_t
   uint32_t posb[N];
   const uint32_t base = top_saddr - (1u << row_shift);  // row (j - 1) holds sorted index j * G - 1
 #pragma unroll
-  for (int i = 0; i < N; i++) { a[i] = wrap_ta(acc[i], e.acc_bits, e.acc_signed); posb[i] = base; }
+  for (int i = 0; i < N; i++) { a[i] = WRAP ? wrap_ta(acc[i], e.acc_bits, e.acc_signed) : acc[i]; posb[i] = base; }
   const bool strict = (e.cmp == FCB_CMP_LESS) || (e.cmp == FCB_CMP_GREATER_EQUAL);
   uint32_t stepb = (uint32_t)(((e.thr_n + 1) >> 1) >> gshift) << row_shift;  // warp-uniform
 #pragma unroll 1

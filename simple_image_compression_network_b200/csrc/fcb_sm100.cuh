@@ -72,7 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0 = 0;
   for (uint32_t n = 1; !mbar_try_wait_sleep(bar, parity); ++n) {
-    if ((n & 15) == 0) {  // bounded: a protocol bug must end in a trap, not a hung GPU
+    if ((n & 255) == 0) {  // bounded: a protocol bug must end in a trap, not a hung GPU
       if (!t0) t0 = globaltimer_ns();
       else if (globaltimer_ns() - t0 > 4000000000ull) __trap();
     }

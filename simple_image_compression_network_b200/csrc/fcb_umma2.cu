@@ -1094,15 +1094,28 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     tmem_ld8(taddr + (uint32_t)((rr + 1) * p.P + xb + 8), vb[1]);
                   }
                   tmem_ld_wait();
+                  if (p.epi.acc_bits >= 32) {
+                    // the create-time range analysis found the sums inside TA (fcb_api.cu): no wrap, three max instructions per output
+                    // (one uniform branch here instead of predicated shifts on every accumulator)
 #pragma unroll
-                  for (int g2 = 0; g2 < 2; g2++) {
+                    for (int g2 = 0; g2 < 2; g2++) {
 #pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                      int32_t m0 = wrap_ta((int32_t)va[g2][2 * w], p.epi.acc_bits, p.epi.acc_signed);
-                      m0 = max(m0, wrap_ta((int32_t)va[g2][2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
-                      m0 = max(m0, wrap_ta((int32_t)vb[g2][2 * w], p.epi.acc_bits, p.epi.acc_signed));
-                      m0 = max(m0, wrap_ta((int32_t)vb[g2][2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
-                      m8[4 * g2 + w] = (g2 == 0 || second) ? m0 : 0;
+                      for (int w = 0; w < 4; w++) {
+                        const int32_t m0 = max(max((int32_t)va[g2][2 * w], (int32_t)va[g2][2 * w + 1]), max((int32_t)vb[g2][2 * w], (int32_t)vb[g2][2 * w + 1]));
+                        m8[4 * g2 + w] = (g2 == 0 || second) ? m0 : 0;
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int g2 = 0; g2 < 2; g2++) {
+#pragma unroll
+                      for (int w = 0; w < 4; w++) {
+                        int32_t m0 = wrap_ta((int32_t)va[g2][2 * w], p.epi.acc_bits, p.epi.acc_signed);
+                        m0 = max(m0, wrap_ta((int32_t)va[g2][2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
+                        m0 = max(m0, wrap_ta((int32_t)vb[g2][2 * w], p.epi.acc_bits, p.epi.acc_signed));
+                        m0 = max(m0, wrap_ta((int32_t)vb[g2][2 * w + 1], p.epi.acc_bits, p.epi.acc_signed));
+                        m8[4 * g2 + w] = (g2 == 0 || second) ? m0 : 0;
+                      }
                     }
                   }
                   if (DBG(16)) {
@@ -1121,7 +1134,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   } else if (use_lut) {
                     activate_thr_lut<8>(p.epi, top_s, row_shift, lut_s, lut_lo, lut_sh, m8, pooled);
                   } else if (THRP || hybrid) {
-                    activate_thr_hybrid<8>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, m8, pooled);
+                    activate_thr_hybrid<8, false>(p.epi, top_s, row_shift, p.thr_top, gshift, row_cm, m8, pooled);  // (m8 is TA-wrapped above)
                   } else {
                     activate_thrN<8>(p.epi, tbl, tstride, m8, pooled);
                   }
