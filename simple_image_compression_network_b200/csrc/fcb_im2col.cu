@@ -54,30 +54,38 @@ int launch_im2col(const Im2colParams& p, int n_images, cudaStream_t st) {
 }
 
 // ---- 1-bit activations -> {-1,+1} bytes (tensor-core form of the xnor layer) -----------------------------------------
+// A thread expands 16 channels of one pixel of the (padded) frame: two input bytes in, one 16-byte store out (K = channels rounded
+// up to 16, so a pixel is K / 16 such groups).  Bit b -> byte 0x01 / 0xFF: the four bits of a nibble are spread to the low bits of
+// four bytes (t), and 0xFFFFFFFF - 0xFE * t leaves 0x01 where the bit was set and 0xFF where it was not (no borrow crosses a byte).
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t x) {
+  const uint32_t t = (x | (x << 7) | (x << 14) | (x << 21)) & 0x01010101u;
+  return 0xFFFFFFFFu - 0xFEu * t;
+}
 __global__ void __launch_bounds__(256) expand_bits_kernel(const Im2colParams p) {
   const int img = blockIdx.z, oy = blockIdx.y;
-  const int words_per_px = p.K >> 2;  // output u32 per pixel
+  const int groups = p.K >> 4;  // 16-channel groups per pixel
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.OX * words_per_px) return;
-  const int ox = idx / words_per_px, w = idx - ox * words_per_px;
+  if (idx >= p.OX * groups) return;
+  const int ox = idx / groups, g = idx - ox * groups;
   const int iy = oy - p.PAD, ix = ox - p.PAD;
   uint32_t bits = 0;  // a zero-padded border bit is an ordinary 0 activation
   if (iy >= 0 && iy < p.IY && ix >= 0 && ix < p.IX) {
     const uint8_t* word = p.in + (size_t)img * p.in_img_bytes + ((size_t)iy * p.IX + ix) * p.in_word_bytes;
-    bits = (uint32_t)(word[(4 * w) >> 3] >> ((4 * w) & 7)) & 0xFu;
+    bits = word[2 * g];
+    if (16 * g + 8 < p.C) bits |= (uint32_t)word[2 * g + 1] << 8;
   }
-  uint32_t out = 0;
+  uint32_t o[4];
 #pragma unroll
-  for (int b = 0; b < 4; b++) {
-    const int c = 4 * w + b;
-    const uint32_t v = c < p.C ? (((bits >> b) & 1u) ? 0x01u : 0xFFu) : 0u;  // channels beyond C: 0 (weights there are 0 too)
-    out |= v << (8 * b);
+  for (int j = 0; j < 4; j++) {
+    o[j] = expand_nibble((bits >> (4 * j)) & 0xFu);
+    const int c = 16 * g + 4 * j, left = p.C - c;  // channels beyond C: 0 (their weights are 0 too)
+    if (left < 4) o[j] &= left <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - left)));
   }
-  reinterpret_cast<uint32_t*>(p.out)[(((size_t)img * p.OY + oy) * p.OX + ox) * words_per_px + w] = out;
+  reinterpret_cast<uint4*>(p.out)[(((size_t)img * p.OY + oy) * p.OX + ox) * groups + g] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 int launch_expand_bits(const Im2colParams& p, int n_images, cudaStream_t st) {
-  const int per_row = p.OX * (p.K >> 2);
+  const int per_row = p.OX * (p.K >> 4);
   for (int n0 = 0; n0 < n_images; n0 += 65535) {
     Im2colParams q = p;
     const int nb = n_images - n0 < 65535 ? n_images - n0 : 65535;

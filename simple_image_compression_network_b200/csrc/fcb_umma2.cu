@@ -992,6 +992,42 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 dst += xstep4 + (wrapped ? wrap_delta : 0ll);
               }
             }
+          } else if (GEN && pk == 1 && p.epi.act_kind == FCB_ACT_THRESHOLDS && p.epi.thr_n == 1 && p.epi.out_bits == 1) {
+            // One threshold, 1-bit lanes: the bnn layers on the tensor path (ThresholdsActivation<.., 1, TA, ap_uint<1>>).  The
+            // threshold lives in a register, a pixel costs a compare and a ballot, and every lane derives the output word of
+            // ITS pixel (column c0 + lane) once per 32-column block instead of once per pixel.
+            const int32_t t0 = chv ? __ldg(p.epi.thr + ch) : 0;
+            const bool strict = (p.epi.cmp == FCB_CMP_LESS) || (p.epi.cmp == FCB_CMP_GREATER_EQUAL);
+            const bool less = (p.epi.cmp == FCB_CMP_LESS) || (p.epi.cmp == FCB_CMP_LESS_EQUAL);
+            const int nth = min(p.epi.num_th, 1);  // thr_finish: pos = min(pos, num_th)
+            const uint32_t bit0 = (uint32_t)(p.epi.act_val + (less ? 0 : p.epi.num_th)) & 1u;           // no threshold below the accumulator
+            const uint32_t bit1 = (uint32_t)(p.epi.act_val + (less ? nth : p.epi.num_th - nth)) & 1u;  // the threshold is below it
+            const bool wrap = p.epi.acc_bits < 32;
+            const int c0w = chbase + cb * 128 + q * 32;  // first channel of this warp
+            int rl = (col_lo + lane) / p.P, xl = (col_lo + lane) - rl * p.P;  // this lane's pixel of the block
+#pragma unroll 1
+            for (int c0 = col_lo; c0 < col_hi && c0 < vrows * p.P; c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32(taddr + (uint32_t)c0, v);
+              tmem_ld_wait();
+              uint32_t mine = 0;
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                const int32_t a = wrap ? wrap_ta((int32_t)v[j], p.epi.acc_bits, p.epi.acc_signed) : (int32_t)v[j];
+                const bool below = strict ? (t0 < a) : (t0 <= a);
+                const uint32_t bits = __ballot_sync(0xffffffffu, chv && ((below ? bit1 : bit0) != 0u));
+                if (lane == j) mine = bits;
+              }
+              if (xl < vcols && rl < vrows) {
+                uint8_t* dst = p.out + pm.word_off(rl, xl, 1) + (c0w >> 3);
+                if (c0w + 32 <= p.OFM && p.out_word_bytes >= 4) *reinterpret_cast<uint32_t*>(dst) = mine;
+                else
+                  for (int b = 0; b < 4; b++)
+                    if (c0w + 8 * b < p.OFM) dst[b] = (uint8_t)(mine >> (8 * b));
+              }
+              xl += 32;
+              while (xl >= p.P) { xl -= p.P; ++rl; }
+            }
           } else if (GEN && pk == 1) {
             int rr = col_lo / p.P, xo = col_lo - rr * p.P;
 #pragma unroll 1
