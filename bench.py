@@ -252,7 +252,9 @@ def run_configs(h: Harness, peaks, n_scale: float):
     """Every other BASELINE.json config, device-resident, timed like the headline (outside its timed region)."""
     import numpy as np
     import torch
+    import dataclasses
     from simple_image_compression_network_b200 import configs, synth, workloads as W
+    from simple_image_compression_network_b200.desc import ENGINE_XNOR_POPC
     from simple_image_compression_network_b200.layer import ConvLayer, Net, synth_fill
     sh = h.stream.cuda_stream
     out = []
@@ -298,7 +300,9 @@ def run_configs(h: Harness, peaks, n_scale: float):
         net_layers[i] = layer_entry(f"L{i}", configs.net_layer(i), n, 0xFF if i == 0 else 0x7F, bound)
     net_layers[1] = mk(configs.net_layer(1))
     # ---- config 3 (xnor-popcount) and config 4 (thresholds + pool)
-    layer_entry("config3_xnor_popc_64x64_3x3_128x96", W.config3(), 16384, 0xFF, "popc")
+    # config 3 twice: what FCB_ENGINE_AUTO runs (the +-1 int8 form on the tensor cores) and the XNOR/popc warp kernels north_star names
+    layer_entry("config3_xnor_64x64_3x3_128x96", W.config3(), 16384, 0xFF, "tensor")
+    layer_entry("config3_xnor_popc_engine_64x64_3x3_128x96", dataclasses.replace(W.config3(), engine_hint=ENGINE_XNOR_POPC), 16384, 0xFF, "popc")
     layer_entry("config4_thr255_pool_256x256_3x3_64x48", W.config4(), 4096, 0xFF, "tensor")
     layer_entry("wide_lanes_imad_s16xs8_64x64_3x3_96x64", W.imad16(), 2048, 0xFF, "alu")
     # ---- stacks: 5a = layers 0-3 of the reference net, 5b = 4 x [conv3x3 -> 255 thresholds -> pool], and the whole net

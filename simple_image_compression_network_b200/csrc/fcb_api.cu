@@ -523,8 +523,13 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
   // FCB_ENGINE_TENSOR on a 1-bit xnor layer: the layer on the tensor cores.  With a^ = 2a-1, w^ = 2w-1 in {-1,+1}:
   // sum_k [w_k == a_k] = (K + sum_k a^_k w^_k) / 2 (interpret.hpp:57-73), so thr < matches  <=>  2*thr - K < sum a^w^ :
   // bits are expanded to s8 (a zero-padded border bit is an ordinary 0 activation = -1), thresholds are remapped once,
-  // and the layer runs on umma_i8.  north_star names XNOR/popc as the implementation of this path, so that stays the default.
-  const bool want_xnor_tensor = g.weight_kind == FCB_W_BINARY_XNOR && (hint == FCB_ENGINE_TENSOR || env_is("FCB_XNOR_ENGINE", "tensor"));
+  // and the layer runs on umma_i8.
+  // FCB_ENGINE_AUTO takes this form for the shape class it was measured on -- one threshold, 1-bit lanes out, >= 32 channels in
+  // (config 3: 566 k img/s against 182 k on the popcount engine, profiles/r02_xnor_tensor.log) -- unless the experiment build says
+  // otherwise; FCB_ENGINE_XNOR_POPC keeps the XNOR/popc warp kernels north_star names.
+  const bool auto_xnor_tensor = hint == FCB_ENGINE_AUTO && L->epi.thr_n == 1 && g.out_bits == 1 && g.C >= 32 && !force_imad &&
+                                !env_is("FCB_XNOR_ENGINE", "popc");
+  const bool want_xnor_tensor = g.weight_kind == FCB_W_BINARY_XNOR && (hint == FCB_ENGINE_TENSOR || env_is("FCB_XNOR_ENGINE", "tensor") || auto_xnor_tensor);
   bool xnor_tensor_done = false;
   if (want_xnor_tensor && g.act_kind == FCB_ACT_THRESHOLDS && g.kind == FCB_KIND_CONV && dense_bits && g.SX == g.SY && g.SX == 1 && g.OFM <= 256 &&
       g.pool <= 2 && g.pad_l == g.pad_r && g.pad_u == g.pad_d && g.pad_l == g.pad_u && g.DX == 1 && g.DY == 1 &&

@@ -78,7 +78,7 @@ def test_umma_generations_agree(name, fcb_lib, oracle_mod, monkeypatch, exp_buil
 
 def test_expected_engines(fcb_lib):
     exp = {"c2d_e": "umma_i8", "c2d_g": "umma_i8", "dc_c": "umma_i8", "th_cfg4": "umma_i8", "c2d_c": "umma_i8", "c2d_a": "umma_i8", "dc_a": "imad", "dc_d": "umma_i8", "dc_e": "umma_i8", "dc_L4": "umma_i8", "c2d_b": "imad",
-           "xn_b": "xnor_popc", "xn_c": "xnor_popc", "xn_a": "imad", "c2d_L1band": "umma_i8"}
+           "xn_b": "umma_i8", "xn_c": "umma_i8", "xn_a": "imad", "c2d_L1band": "umma_i8"}
     for name, eng in exp.items():
         d = cases.CASES[name]
         inp = cases.make_inputs(d)
@@ -257,14 +257,18 @@ def test_analysis_stack_stage_shapes(fcb_lib, oracle_mod):
 
 @pytest.mark.parametrize("name,pad,pool", [("xn_a", 0, 0), ("xn_b", 0, 0), ("xn_c", 0, 0), ("xn_c", 1, 0), ("xn_b", 1, 2)])
 def test_xnor_on_tensor_cores(name, pad, pool, fcb_lib, oracle_mod):
-    """Opt-in (engine_hint = TENSOR) +-1 int8 form of the xnor layer (sum [w==a] = (K + sum a^w^)/2, thresholds remapped to 2t-K) against the
-    oracle and against the default popcount engine; pad > 0 checks that border bits act as ordinary 0 activations."""
+    """The +-1 int8 form of the xnor layer (sum [w==a] = (K + sum a^w^)/2, thresholds remapped to 2t-K; engine_hint = TENSOR, and what
+    AUTO picks for single-threshold 1-bit layers of >= 32 channels) against the oracle and against the popcount engine north_star names
+    (engine_hint = XNOR_POPC); pad > 0 checks that border bits act as ordinary 0 activations."""
     d = dataclasses.replace(cases.CASES[name], pad=pad, pool=pool)
     inp = cases.make_inputs(d, seed_shift=21, num_reps=2)
     want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], None, num_reps=2)
-    Lp = _layer(d, inp)
+    Lp = _layer(dataclasses.replace(d, engine_hint=ENGINE_XNOR_POPC if d.ifm_ch % 32 == 0 else ENGINE_IMAD), inp)
     assert Lp.engine in ("xnor_popc", "imad")
     assert np.array_equal(Lp.run(inp["in_words"], 2), want)
+    La = _layer(d, inp)
+    assert La.engine == ("umma_i8" if d.ifm_ch >= 32 else "imad"), La.plan
+    assert np.array_equal(La.run(inp["in_words"], 2), want)
     Lt = _layer(dataclasses.replace(d, engine_hint=ENGINE_TENSOR), inp)
     assert Lt.engine == "umma_i8" and "xnor as +-1" in Lt.plan, Lt.plan
     got = Lt.run(inp["in_words"], 2)

@@ -84,6 +84,9 @@ if __name__ == "__main__":
                 bench_layer("cfg3_xnor_tensor", dataclasses.replace(c3, engine_hint=ENGINE_TENSOR), a.images, 0xFF)
             elif nm == "cfg3":
                 bench_layer("cfg3_xnor", c3, a.images, 0xFF)
+            elif nm == "cfg3p":  # the XNOR/popc warp kernels (FCB_ENGINE_AUTO takes the tensor form for this shape class)
+                from simple_image_compression_network_b200.desc import ENGINE_XNOR_POPC
+                bench_layer("cfg3_xnor_popc", dataclasses.replace(c3, engine_hint=ENGINE_XNOR_POPC), a.images, 0xFF)
             elif nm == "cfg4n":
                 bench_layer("cfg4_thr_nopool", dataclasses.replace(c4, pool=0), a.images, 0xFF)
             elif nm == "cfg4":
