@@ -535,15 +535,25 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
       g.pool <= 2 && g.pad_l == g.pad_r && g.pad_u == g.pad_d && g.pad_l == g.pad_u && g.DX == 1 && g.DY == 1 &&
       (g.acc_bits >= 31 || g.K < (1 << (g.acc_bits - (g.acc_signed ? 1 : 0))))) {
     const int Cp = (g.C + 15) / 16 * 16;
+    // Pixel pairs (experiment build, FCB_XNOR_PAIR=1): with <= 64 channels a 128-byte K-block of the tensor kernel is half zeros.  The
+    // expansion can write, for frame pixel x, the bytes of pixels x and x+1 back to back (one "pair row"); the layer then has 2*Cp
+    // channels, ceil(KX / 2) horizontal taps and dilation 2 (tap kx' = kernel columns 2kx', 2kx'+1; zero weights past KX; odd KX keeps
+    // the output width): 6 K-blocks instead of 9 for a 3x3 kernel.  Bit-exact, but measured SLOWER on config 3 (440 k vs 540 k img/s,
+    // profiles/r02_xnor_tensor.log): the kernel is not MMA-bound there and the pair rows double the scratch and plane traffic.
+    const int pair = (Cp <= 64 && g.KX > 1 && (g.KX & 1) && exp_int("FCB_XNOR_PAIR", 0)) ? 2 : 1;
+    const int C2 = pair * Cp, KX2 = (g.KX + pair - 1) / pair;
     Geom g2 = g;
-    g2.C = Cp; g2.K = g.KX * g.KY * Cp; g2.IX = g.IX + 2 * g.PAD; g2.IY = g.IY + 2 * g.PAD; g2.PAD = 0;
+    g2.C = C2; g2.KX = KX2; g2.DX = pair; g2.K = KX2 * g.KY * C2; g2.IX = g.IX + 2 * g.PAD; g2.IY = g.IY + 2 * g.PAD; g2.PAD = 0;
     g2.pad_l = g2.pad_r = g2.pad_u = g2.pad_d = 0;
     g2.in_bits = 8; g2.in_signed = 1; g2.w_bits = 8; g2.weight_kind = FCB_W_FIXED; g2.acc_bits = 32; g2.acc_signed = 1;
-    g2.in_word_bytes = Cp; g2.in_img_bytes = (size_t)Cp * g2.IX * g2.IY;
+    g2.in_word_bytes = C2; g2.in_img_bytes = (size_t)C2 * g2.IX * g2.IY;
     std::vector<int32_t> W2((size_t)g.OFM * g2.K, 0);
     for (int ch = 0; ch < g.OFM; ch++)
-      for (int tap = 0; tap < g.KX * g.KY; tap++)
-        for (int c = 0; c < g.C; c++) W2[(size_t)ch * g2.K + tap * Cp + c] = W[(size_t)ch * g.K + tap * g.C + c] ? 1 : -1;
+      for (int ky = 0; ky < g.KY; ky++)
+        for (int kx = 0; kx < g.KX; kx++)
+          for (int c = 0; c < g.C; c++)
+            W2[(size_t)ch * g2.K + (size_t)(ky * KX2 + kx / pair) * C2 + (kx % pair) * Cp + c] =
+                W[(size_t)ch * g.K + (size_t)(ky * g.KX + kx) * g.C + c] ? 1 : -1;
     // t' = 2t - K in 64 bits: the remapped table must stay inside int32 (and below the INT32_MAX padding value)
     std::vector<std::vector<int32_t>> rows2 = thr_rows;
     bool remap_ok = true;
@@ -566,9 +576,10 @@ int fcb_layer_create(const fcb_layer_desc* desc, const void* weights, const void
         L->lower_bits = true;
         L->scratch_img_bytes = g2.in_img_bytes;
         Im2colParams& ip = L->ip;
-        ip.IX = g.IX; ip.IY = g.IY; ip.OX = g2.IX; ip.OY = g2.IY; ip.S = 1; ip.PAD = g.PAD; ip.K = Cp; ip.C = g.C; ip.KX = g.KX;
+        ip.IX = g.IX; ip.IY = g.IY; ip.OX = g2.IX; ip.OY = g2.IY; ip.S = pair; ip.PAD = g.PAD; ip.K = Cp; ip.C = g.C; ip.KX = g.KX;  // (S: pixels per row)
         ip.in_word_bytes = (int)g.in_word_bytes; ip.in_img_bytes = g.in_img_bytes;
-        snprintf(L->plan_desc, sizeof(L->plan_desc), "xnor as +-1 int8: bit expansion (C=%d -> %d B) + %s", g.C, Cp, umma_plan_describe(L->umma));
+        snprintf(L->plan_desc, sizeof(L->plan_desc), "xnor as +-1 int8: bit expansion (C=%d -> %d B%s) + %s", g.C, Cp,
+                 pair == 2 ? ", pixel pairs per row" : "", umma_plan_describe(L->umma));
         xnor_tensor_done = true;
       } else {
         L->umma = nullptr;

@@ -61,13 +61,19 @@ __device__ __forceinline__ uint32_t expand_nibble(uint32_t x) {
   const uint32_t t = (x | (x << 7) | (x << 14) | (x << 21)) & 0x01010101u;
   return 0xFFFFFFFFu - 0xFEu * t;
 }
+// p.S = pixels per output row (1, or 2: row x = the bytes of frame pixels x and x+1 back to back; past the frame's last column
+// the second half is zeros -- it only ever meets zero weights or discarded columns).
 __global__ void __launch_bounds__(256) expand_bits_kernel(const Im2colParams p) {
   const int img = blockIdx.z, oy = blockIdx.y;
-  const int groups = p.K >> 4;  // 16-channel groups per pixel
+  const int gpp = p.K >> 4, groups = gpp * p.S;  // 16-channel groups per pixel / per output row
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.OX * groups) return;
-  const int ox = idx / groups, g = idx - ox * groups;
-  const int iy = oy - p.PAD, ix = ox - p.PAD;
+  const int ox = idx / groups, gr = idx - ox * groups, half = gr / gpp, g = gr - half * gpp;
+  const int iy = oy - p.PAD, ix = ox + half - p.PAD;
+  if (ox + half >= p.OX) {  // (pair rows only) beyond the padded frame
+    reinterpret_cast<uint4*>(p.out)[(((size_t)img * p.OY + oy) * p.OX + ox) * groups + gr] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
   uint32_t bits = 0;  // a zero-padded border bit is an ordinary 0 activation
   if (iy >= 0 && iy < p.IY && ix >= 0 && ix < p.IX) {
     const uint8_t* word = p.in + (size_t)img * p.in_img_bytes + ((size_t)iy * p.IX + ix) * p.in_word_bytes;
@@ -81,16 +87,16 @@ __global__ void __launch_bounds__(256) expand_bits_kernel(const Im2colParams p) 
     const int c = 16 * g + 4 * j, left = p.C - c;  // channels beyond C: 0 (their weights are 0 too)
     if (left < 4) o[j] &= left <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - left)));
   }
-  reinterpret_cast<uint4*>(p.out)[(((size_t)img * p.OY + oy) * p.OX + ox) * groups + g] = make_uint4(o[0], o[1], o[2], o[3]);
+  reinterpret_cast<uint4*>(p.out)[(((size_t)img * p.OY + oy) * p.OX + ox) * groups + gr] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 int launch_expand_bits(const Im2colParams& p, int n_images, cudaStream_t st) {
-  const int per_row = p.OX * (p.K >> 4);
+  const int per_row = p.OX * (p.K >> 4) * p.S;
   for (int n0 = 0; n0 < n_images; n0 += 65535) {
     Im2colParams q = p;
     const int nb = n_images - n0 < 65535 ? n_images - n0 : 65535;
     q.in = p.in + (size_t)n0 * p.in_img_bytes;
-    q.out = p.out + (size_t)n0 * p.OX * p.OY * p.K;
+    q.out = p.out + (size_t)n0 * p.OX * p.OY * p.K * p.S;
     dim3 grid((per_row + 255) / 256, p.OY, nb);
     expand_bits_kernel<<<grid, 256, 0, st>>>(q);
     FCB_CUDA_OK(cudaGetLastError());
