@@ -419,7 +419,8 @@ def _random_descs(seed, count):
             c = int(rng.choice([32, 64, 128])); ofm = int(rng.choice([16, 64]))
             d = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=3, ifm_ch=c, ofm_ch=ofm, ifm_x=int(rng.integers(3, 40)), ifm_y=int(rng.integers(3, 12)),
                           stride_x=1, stride_y=1, pad=int(rng.integers(0, 2)), simd=32, pe=16, in_bits=1, w_bits=1, weight_kind=W_BINARY_XNOR,
-                          acc_bits=16, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=1, num_th=1)
+                          acc_bits=16, acc_signed=1, act_kind=ACT_THRESHOLDS, out_bits=1, num_th=1,
+                          engine_hint=ENGINE_XNOR_POPC if len(out) % 2 else 0)  # AUTO = the +-1 int8 tensor form; every other case: the popcount engine
         else:  # odd widths on the universal engine
             d = LayerDesc(kind=KIND_CONV, kernel_x=3, kernel_y=int(rng.choice([1, 3])), ifm_ch=int(rng.choice([2, 6, 10])), ofm_ch=int(rng.choice([3, 5, 12])),
                           ifm_x=int(rng.integers(3, 20)), ifm_y=int(rng.integers(3, 9)), stride_x=1, stride_y=1, pad=0, simd=2, pe=1,
