@@ -275,6 +275,21 @@ def test_xnor_on_tensor_cores(name, pad, pool, fcb_lib, oracle_mod):
     assert np.array_equal(got, want), f"{name} pad={pad} [{Lt.plan}]: {_diff(got, want)}"
 
 
+@pytest.mark.parametrize("name,pad", [("xn_b", 0), ("xn_c", 1)])
+def test_xnor_pixel_pair_rows(name, pad, fcb_lib, oracle_mod, monkeypatch, exp_build):
+    """Experiment build: the +-1 int8 form with two pixels per 128-byte K-block (FCB_XNOR_PAIR=1: 2*Cp channels, ceil(KX/2) taps, dilation 2).
+    Measured slower than one pixel per row and left off in the product; kept bit-exact."""
+    d = dataclasses.replace(cases.CASES[name], pad=pad)
+    inp = cases.make_inputs(d, seed_shift=23, num_reps=3)
+    want = oracle_mod.run_layer(d, inp["in_words"], inp["weights"], inp["thresholds"], None, num_reps=3)
+    exp_build()
+    monkeypatch.setenv("FCB_XNOR_PAIR", "1")
+    L = _layer(d, inp)
+    assert "pixel pairs" in L.plan, L.plan
+    got = L.run(inp["in_words"], 3)
+    assert np.array_equal(got, want), f"{name} [{L.plan}]: {_diff(got, want)}"
+
+
 def _thin_cases():
     from simple_image_compression_network_b200.desc import ACT_BIAS_RELU, ACT_THRESHOLDS, KIND_CONV, LayerDesc
 
