@@ -241,6 +241,11 @@ __global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p)
   }
   uint32_t r[N];
   const uint32_t omask = p.out_bits >= 32 ? 0xffffffffu : ((1u << p.out_bits) - 1u);
+  // accu / size (pool.hpp:151-154, C++ truncation) by multiply-high: |accu| <= 128 taps x 255 < 2^16 and size < 2^16, so
+  // floor(n / d) = umulhi(n, ceil(2^32 / d)) exactly (the error term n * e / 2^32 < 2^-16 < 1 / d); one division per thread for the constant
+  // the sum only needs the wrap to TA when taps x 255 can leave TA's range (a uniform branch instead of shifts on every lane)
+  const bool wrap_sum = BM == 2 && (long long)taps * 255 >= (1ll << (p.acc_bits - (p.acc_signed ? 1 : 0)));
+  const uint32_t div_m = (BM == 2 && p.mode == CW_POOL_AVG && p.size > 1) ? 0xFFFFFFFFu / (uint32_t)p.size + 1u : 0u;
 #pragma unroll
   for (int j = 0; j < N; j++) {
     if (BM == 0 || BM == 3) {
@@ -248,9 +253,15 @@ __global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p)
     } else {
       int32_t o = acc[j];
       if (BM == 2) {
-        o = wrap32(o, p.acc_bits, p.acc_signed);
-        // accu / size with C++ truncation; |accu| <= 128 taps x 255 < 2^24, so the float quotient truncates to the same integer
-        if (p.mode == CW_POOL_AVG) o = p.size ? (int32_t)((float)o / (float)p.size) : 0;
+        if (wrap_sum) o = wrap32(o, p.acc_bits, p.acc_signed);
+        if (p.mode == CW_POOL_AVG) {
+          if (p.size > 1) {
+            const int32_t q = (int32_t)__umulhi((uint32_t)abs(o), div_m);
+            o = o < 0 ? -q : q;
+          } else if (p.size == 0) {
+            o = 0;
+          }
+        }
         else if (p.mode == CW_POOL_QUANTAVG) o = o >> p.size;
       }
       r[j] = (uint32_t)o & omask;
