@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p)
   // accu / size (pool.hpp:151-154, C++ truncation) by multiply-high: |accu| <= 128 taps x 255 < 2^16 and size < 2^16, so
   // floor(n / d) = umulhi(n, ceil(2^32 / d)) exactly (the error term n * e / 2^32 < 2^-16 < 1 / d); one division per thread for the constant
   // the sum only needs the wrap to TA when taps x 255 can leave TA's range (a uniform branch instead of shifts on every lane)
-  const bool wrap_sum = BM == 2 && (long long)taps * 255 >= (1ll << (p.acc_bits - (p.acc_signed ? 1 : 0)));
+  const bool wrap_sum = BM == 2 && ((long long)taps * 255 >= (1ll << (p.acc_bits - (p.acc_signed ? 1 : 0))) || (INS && !p.acc_signed));  // (negative sums in an unsigned TA wrap too)
   const uint32_t div_m = (BM == 2 && p.mode == CW_POOL_AVG && p.size > 1) ? 0xFFFFFFFFu / (uint32_t)p.size + 1u : 0u;
 #pragma unroll
   for (int j = 0; j < N; j++) {

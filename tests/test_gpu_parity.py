@@ -725,7 +725,9 @@ def test_channelwise_byte_lane_forms(seed, fcb_lib, oracle_mod):
                       in_signed=ins, dilation_x=int(rng.choice([1, 1, 2])))
         if i % 2:
             fn = i // 2 % 4
-            d = LayerDesc(kind=KIND_POOL, w_bits=0, weight_kind=fn, acc_bits=int(rng.choice([8, 12, 16])), acc_signed=ins, act_kind=ACT_PASSTHROUGH,
+            # (sums also with TA's signedness different from the lanes': negative sums wrap in an unsigned TA; max needs them equal here)
+            tas = ins if fn == 0 or i % 3 else 1 - ins
+            d = LayerDesc(kind=KIND_POOL, w_bits=0, weight_kind=fn, acc_bits=int(rng.choice([8, 12, 16])), acc_signed=tas, act_kind=ACT_PASSTHROUGH,
                           out_bits=outb, act_val=int(rng.choice([2, 3, 4])), **common)
         else:
             thr = i % 4 == 0
