@@ -166,71 +166,10 @@ __device__ __forceinline__ void chanwise_load(const uint8_t* src, bool ok, uint3
 
 // KS: 2 / 3 = square window of that size with unit dilation, fully unrolled (all loads of the window issued first, tap addresses from
 // one row pointer per ky); 0 = any window, taps in (ky, kx) order four at a time.
-template <int V, int BM, bool INS, int KS>
-__global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p) {
-  constexpr int N = 4 * V;  // channels per thread
-  const int groups = p.C / N;
-  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (t >= (long long)p.OX * p.OY * groups) return;
-  const int g = (int)(t % groups), pix = (int)(t / groups);
-  const int oy = pix / p.OX, ox = pix - oy * p.OX, ch0 = g * N;
-  const uint8_t* in = p.in + (size_t)blockIdx.y * p.in_img_bytes + (size_t)ch0;
-  const int y0 = oy * p.SY - p.pad_u, x0 = ox * p.SX - p.pad_l;
-  int32_t acc[N];
-  uint32_t mx[N / 2];  // max and sums: two channels per register as 16-bit halves (VIMNMX.S16x2 / one IADD; byte lanes widen with one PRMT per pair)
-  {
-    // pool.hpp:98-102: the type's minimum, or min_value (maxpool.h:144-150); anything below -32768 is below every 8-bit tap
-    int32_t first = BM == 1 ? (p.has_init ? p.init : (p.acc_signed ? -(1 << (p.acc_bits - 1)) : 0)) : 0;
-    first = max(first, -32768);
-#pragma unroll
-    for (int j = 0; j < N; j++) acc[j] = 0;
-#pragma unroll
-    for (int j = 0; j < N / 2; j++) mx[j] = BM == 1 ? ((uint32_t)first & 0xFFFFu) * 0x10001u : 0u;
-  }
-  const int taps = p.KX * p.KY;
-  if constexpr (KS > 0) {
-    constexpr int T = KS * KS, TC = KS ? (T + 3) / 4 * 4 : 4;  // (KS = 0 never runs this branch; the array must still have a size)
-    uint32_t w[TC][V];
-#pragma unroll
-    for (int ky = 0; ky < KS; ky++) {
-      const int y = y0 + ky;
-      const bool yok = y >= 0 && y < p.IY;
-      const uint8_t* row = in + ((size_t)(yok ? y : 0) * p.IX) * p.in_word_bytes;
-#pragma unroll
-      for (int kx = 0; kx < KS; kx++) {
-        const int x = x0 + kx;
-        const bool ok = yok && x >= 0 && x < p.IX;
-        chanwise_load<V>(row + (size_t)(ok ? x : 0) * p.in_word_bytes, ok, w[ky * KS + kx]);
-      }
-    }
-#pragma unroll
-    for (int u = T; u < TC; u++)
-#pragma unroll
-      for (int i = 0; i < V; i++) w[u][i] = 0u;
-#pragma unroll
-    for (int t0 = 0; t0 < T; t0 += 4) {
-      uint32_t wc[4][V];
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-#pragma unroll
-        for (int i = 0; i < V; i++) wc[u][i] = w[t0 + u][i];
-      chanwise_consume<V, BM, INS>(p, wc, t0, T - t0 < 4 ? T - t0 : 4, ch0, acc, mx);
-    }
-  } else {
-    // taps in (ky, kx) order, four at a time: the loads of a chunk are issued together (what these units need is bytes in flight)
-    int ky = 0, kx = 0;
-    for (int t0 = 0; t0 < taps; t0 += 4) {
-      uint32_t w[4][V];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int y = y0 + ky * p.DY, x = x0 + kx * p.DX;
-        const bool ok = t0 + u < taps && y >= 0 && y < p.IY && x >= 0 && x < p.IX;
-        chanwise_load<V>(in + ((size_t)(ok ? y : 0) * p.IX + (ok ? x : 0)) * p.in_word_bytes, ok, w[u]);
-        if (++kx == p.KX) { kx = 0; ++ky; }
-      }
-      chanwise_consume<V, BM, INS>(p, w, t0, taps - t0 < 4 ? taps - t0 : 4, ch0, acc, mx);
-    }
-  }
+// accumulators -> activation / pool function result -> packed lanes -> one vector store (pixel `pix` of image blockIdx.y)
+template <int V, int BM, bool INS>
+__device__ __forceinline__ void chanwise_finish(const ChanParams& p, int32_t (&acc)[4 * V], uint32_t (&mx)[2 * V], int taps, int ch0, int pix) {
+  constexpr int N = 4 * V;
   if (BM == 1) {
 #pragma unroll
     for (int j = 0; j < N; j++) acc[j] = (j & 1) ? ((int32_t)mx[j >> 1] >> 16) : (int32_t)(int16_t)(mx[j >> 1] & 0xFFFFu);
@@ -290,27 +229,108 @@ __global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p)
   }
 }
 
-template <int V, int KS>
-static void launch_bytes_k(const ChanParams& q, dim3 grid, cudaStream_t st) {
+// KS: 2 / 3 = square window of that size with unit dilation, fully unrolled (all loads of the window issued first, tap addresses from
+// one row pointer per ky); 0 = any window, taps in (ky, kx) order four at a time.  VO = 2 (3x3 windows at vertical stride 1): a thread
+// owns two vertically adjacent outputs and loads the four input rows they share once (12 loads for two outputs instead of 18).
+template <int V, int BM, bool INS, int KS, int VO>
+__global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p) {
+  constexpr int N = 4 * V;  // channels per thread
+  const int groups = p.C / N, oyb = (p.OY + VO - 1) / VO;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)p.OX * oyb * groups) return;
+  const int g = (int)(t % groups), pix = (int)(t / groups);
+  const int oy = (pix / p.OX) * VO, ox = pix - (pix / p.OX) * p.OX, ch0 = g * N;
+  const uint8_t* in = p.in + (size_t)blockIdx.y * p.in_img_bytes + (size_t)ch0;
+  const int y0 = oy * p.SY - p.pad_u, x0 = ox * p.SX - p.pad_l;
+  int32_t acc[VO][N];
+  uint32_t mx[VO][N / 2];  // max and sums: two channels per register as 16-bit halves (VIMNMX.S16x2 / one IADD; byte lanes widen with one PRMT per pair)
+  {
+    // pool.hpp:98-102: the type's minimum, or min_value (maxpool.h:144-150); anything below -32768 is below every 8-bit tap
+    int32_t first = BM == 1 ? (p.has_init ? p.init : (p.acc_signed ? -(1 << (p.acc_bits - 1)) : 0)) : 0;
+    first = max(first, -32768);
+#pragma unroll
+    for (int vo = 0; vo < VO; vo++) {
+#pragma unroll
+      for (int j = 0; j < N; j++) acc[vo][j] = 0;
+#pragma unroll
+      for (int j = 0; j < N / 2; j++) mx[vo][j] = BM == 1 ? ((uint32_t)first & 0xFFFFu) * 0x10001u : 0u;
+    }
+  }
+  const int taps = p.KX * p.KY;
+  if constexpr (KS > 0) {
+    constexpr int T = KS * KS, ROWS = KS + VO - 1, TL = ROWS * KS, TC = KS ? (TL + 3) / 4 * 4 + 4 : 4;  // (KS = 0 never runs this branch)
+    uint32_t w[TC][V];
+#pragma unroll
+    for (int ky = 0; ky < ROWS; ky++) {
+      const int y = y0 + ky;
+      const bool yok = y >= 0 && y < p.IY;
+      const uint8_t* row = in + ((size_t)(yok ? y : 0) * p.IX) * p.in_word_bytes;
+#pragma unroll
+      for (int kx = 0; kx < KS; kx++) {
+        const int x = x0 + kx;
+        const bool ok = yok && x >= 0 && x < p.IX;
+        chanwise_load<V>(row + (size_t)(ok ? x : 0) * p.in_word_bytes, ok, w[ky * KS + kx]);
+      }
+    }
+#pragma unroll
+    for (int vo = 0; vo < VO; vo++) {
+#pragma unroll
+      for (int t0 = 0; t0 < T; t0 += 4) {
+        uint32_t wc[4][V];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int i = 0; i < V; i++) wc[u][i] = t0 + u < T ? w[vo * KS + t0 + u][i] : 0u;  // output vo starts KS taps (one row) further
+        chanwise_consume<V, BM, INS>(p, wc, t0, T - t0 < 4 ? T - t0 : 4, ch0, acc[vo], mx[vo]);
+      }
+    }
+  } else {
+    // taps in (ky, kx) order, four at a time: the loads of a chunk are issued together (what these units need is bytes in flight)
+    int ky = 0, kx = 0;
+    for (int t0 = 0; t0 < taps; t0 += 4) {
+      uint32_t w[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int y = y0 + ky * p.DY, x = x0 + kx * p.DX;
+        const bool ok = t0 + u < taps && y >= 0 && y < p.IY && x >= 0 && x < p.IX;
+        chanwise_load<V>(in + ((size_t)(ok ? y : 0) * p.IX + (ok ? x : 0)) * p.in_word_bytes, ok, w[u]);
+        if (++kx == p.KX) { kx = 0; ++ky; }
+      }
+      chanwise_consume<V, BM, INS>(p, w, t0, taps - t0 < 4 ? taps - t0 : 4, ch0, acc[0], mx[0]);
+    }
+  }
+#pragma unroll
+  for (int vo = 0; vo < VO; vo++)
+    if (oy + vo < p.OY) chanwise_finish<V, BM, INS>(p, acc[vo], mx[vo], taps, ch0, (oy + vo) * p.OX + ox);
+}
+
+template <int V, int KS, int VO>
+static void launch_bytes_k(const ChanParams& q, int nb, cudaStream_t st) {
+  const long long threads = (long long)q.OX * ((q.OY + VO - 1) / VO) * (q.C / (4 * V));
+  const dim3 grid((unsigned)((threads + 255) / 256), nb, 1);
   const int bm = q.mode == CW_DWCONV ? (q.wt4 ? 3 : 0) : q.mode == CW_POOL_MAX ? 1 : 2;
   if (q.in_signed) {
-    if (bm == 0) chanwise_bytes_kernel<V, 0, true, 0><<<grid, 256, 0, st>>>(q);  // (16-bit weights: the rolled form keeps the registers down)
-    else if (bm == 1) chanwise_bytes_kernel<V, 1, true, KS><<<grid, 256, 0, st>>>(q);
-    else if (bm == 2) chanwise_bytes_kernel<V, 2, true, KS><<<grid, 256, 0, st>>>(q);
-    else chanwise_bytes_kernel<V, 3, true, KS><<<grid, 256, 0, st>>>(q);
+    if (bm == 1) chanwise_bytes_kernel<V, 1, true, KS, VO><<<grid, 256, 0, st>>>(q);
+    else if (bm == 2) chanwise_bytes_kernel<V, 2, true, KS, VO><<<grid, 256, 0, st>>>(q);
+    else chanwise_bytes_kernel<V, 3, true, KS, VO><<<grid, 256, 0, st>>>(q);
   } else {
-    if (bm == 0) chanwise_bytes_kernel<V, 0, false, 0><<<grid, 256, 0, st>>>(q);
-    else if (bm == 1) chanwise_bytes_kernel<V, 1, false, KS><<<grid, 256, 0, st>>>(q);
-    else if (bm == 2) chanwise_bytes_kernel<V, 2, false, KS><<<grid, 256, 0, st>>>(q);
-    else chanwise_bytes_kernel<V, 3, false, KS><<<grid, 256, 0, st>>>(q);
+    if (bm == 1) chanwise_bytes_kernel<V, 1, false, KS, VO><<<grid, 256, 0, st>>>(q);
+    else if (bm == 2) chanwise_bytes_kernel<V, 2, false, KS, VO><<<grid, 256, 0, st>>>(q);
+    else chanwise_bytes_kernel<V, 3, false, KS, VO><<<grid, 256, 0, st>>>(q);
   }
 }
 template <int V>
-static void launch_bytes(const ChanParams& q, dim3 grid, cudaStream_t st) {
+static void launch_bytes(const ChanParams& q, int nb, cudaStream_t st) {
   const int ks = (q.KX == q.KY && q.DX == 1 && q.DY == 1 && (q.KX == 2 || q.KX == 3)) ? q.KX : 0;
-  if (ks == 2) launch_bytes_k<V, 2>(q, grid, st);
-  else if (ks == 3) launch_bytes_k<V, 3>(q, grid, st);
-  else launch_bytes_k<V, 0>(q, grid, st);
+  if (q.mode == CW_DWCONV && !q.wt4) {  // 16-bit weights: the rolled form keeps the registers down
+    const long long threads = (long long)q.OX * q.OY * (q.C / (4 * V));
+    const dim3 grid((unsigned)((threads + 255) / 256), nb, 1);
+    if (q.in_signed) chanwise_bytes_kernel<V, 0, true, 0, 1><<<grid, 256, 0, st>>>(q);
+    else chanwise_bytes_kernel<V, 0, false, 0, 1><<<grid, 256, 0, st>>>(q);
+  } else if (ks == 3 && q.SY == 1 && q.OY > 1 && q.mode != CW_DWCONV) launch_bytes_k<V, 3, 2>(q, nb, st);  // (depth-wise: 86 registers, measured slower)
+  else if (ks == 3) launch_bytes_k<V, 3, 1>(q, nb, st);
+  else if (ks == 2) launch_bytes_k<V, 2, 1>(q, nb, st);
+  else launch_bytes_k<V, 0, 1>(q, nb, st);
 }
 
 // AddStreams_Batch on byte lanes (8-bit operands, 8- or 16-bit sums): 16 lanes per thread
@@ -425,10 +445,8 @@ int launch_chanwise(const ChanParams& p, int n_images, cudaStream_t st) {
     q.in = p.in + (size_t)n0 * p.in_img_bytes;
     q.out = p.out + (size_t)n0 * p.out_img_bytes;
     if (V) {
-      const long long threads = (long long)p.OX * p.OY * (p.C / (4 * V));
-      const dim3 grid((unsigned)((threads + 255) / 256), nb, 1);
-      if (V == 4) launch_bytes<4>(q, grid, st);
-      else launch_bytes<1>(q, grid, st);
+      if (V == 4) launch_bytes<4>(q, nb, st);
+      else launch_bytes<1>(q, nb, st);
     } else
     chanwise_kernel<<<dim3(blocks, nb, 1), 256, 0, st>>>(q);
     FCB_CUDA_OK(cudaGetLastError());
