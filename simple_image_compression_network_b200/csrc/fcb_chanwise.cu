@@ -96,26 +96,33 @@ __device__ __forceinline__ int32_t dp4a_mixed(uint32_t a, uint32_t b, int32_t c)
   return d;
 }
 
+// Depth-wise with weights of at most 8 bits: the four taps of a chunk go through the dot-product unit.  Per word of four channels the
+// 4x4 bytes (tap x channel) are transposed with 8 PRMTs into one register per channel holding its four taps, and one IDP.4A per
+// channel multiplies them with that channel's four weights (wv: the [chunk][channel] words of table wt4, zero past the last tap):
+// 12 instructions per 16 MACs instead of ~70.
+template <int V, bool INS>
+__device__ __forceinline__ void chanwise_dw_chunk(const uint32_t (&w)[4][V], const uint4 (&wv)[V], int32_t (&acc)[4 * V]) {
+#pragma unroll
+  for (int i = 0; i < V; i++) {
+    const uint32_t lo01 = prmt(w[0][i], w[1][i], 0x5140u), hi01 = prmt(w[0][i], w[1][i], 0x7362u);
+    const uint32_t lo23 = prmt(w[2][i], w[3][i], 0x5140u), hi23 = prmt(w[2][i], w[3][i], 0x7362u);
+    acc[4 * i] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x5410u), wv[i].x, acc[4 * i]);
+    acc[4 * i + 1] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x7632u), wv[i].y, acc[4 * i + 1]);
+    acc[4 * i + 2] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x5410u), wv[i].z, acc[4 * i + 2]);
+    acc[4 * i + 3] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x7632u), wv[i].w, acc[4 * i + 3]);
+  }
+}
+
 // One chunk of up to four taps (cnt valid ones, t0 = index of the first) into the accumulators.  w[u][i]: word i (4 channels) of tap u,
 // zeros for FMPadding and past the last tap.
 template <int V, int BM, bool INS>
 __device__ __forceinline__ void chanwise_consume(const ChanParams& p, const uint32_t (&w)[4][V], int t0, int cnt, int ch0, int32_t (&acc)[4 * V],
                                                  uint32_t (&mx)[2 * V]) {
   if (BM == 3) {
-    // depth-wise with weights of at most 8 bits: the four taps of the chunk go through the dot-product unit.  Per word of four
-    // channels the 4x4 bytes (tap x channel) are transposed with 8 PRMTs into one register per channel holding its four taps, and
-    // one IDP.4A per channel multiplies them with that channel's four weights (table wt4: [chunk][channel] words, zero past the
-    // last tap): 12 instructions per 16 MACs instead of ~70.
+    uint4 wv[V];
 #pragma unroll
-    for (int i = 0; i < V; i++) {
-      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.wt4 + (size_t)(t0 >> 2) * p.Cpad + ch0) + i);
-      const uint32_t lo01 = prmt(w[0][i], w[1][i], 0x5140u), hi01 = prmt(w[0][i], w[1][i], 0x7362u);
-      const uint32_t lo23 = prmt(w[2][i], w[3][i], 0x5140u), hi23 = prmt(w[2][i], w[3][i], 0x7362u);
-      acc[4 * i] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x5410u), wv.x, acc[4 * i]);
-      acc[4 * i + 1] = dp4a_mixed<INS>(prmt(lo01, lo23, 0x7632u), wv.y, acc[4 * i + 1]);
-      acc[4 * i + 2] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x5410u), wv.z, acc[4 * i + 2]);
-      acc[4 * i + 3] = dp4a_mixed<INS>(prmt(hi01, hi23, 0x7632u), wv.w, acc[4 * i + 3]);
-    }
+    for (int i = 0; i < V; i++) wv[i] = __ldg(reinterpret_cast<const uint4*>(p.wt4 + (size_t)(t0 >> 2) * p.Cpad + ch0) + i);
+    chanwise_dw_chunk<V, INS>(w, wv, acc);
   } else {
 #pragma unroll
   for (int u = 0; u < 4; u++) {
@@ -185,6 +192,17 @@ __device__ __forceinline__ void chanwise_finish(const ChanParams& p, int32_t (&a
   // the sum only needs the wrap to TA when taps x 255 can leave TA's range (a uniform branch instead of shifts on every lane)
   const bool wrap_sum = BM == 2 && ((long long)taps * 255 >= (1ll << (p.acc_bits - (p.acc_signed ? 1 : 0))) || (INS && !p.acc_signed));  // (negative sums in an unsigned TA wrap too)
   const uint32_t div_m = (BM == 2 && p.mode == CW_POOL_AVG && p.size > 1) ? 0xFFFFFFFFu / (uint32_t)p.size + 1u : 0u;
+  if ((BM == 0 || BM == 3) && p.epi.act_kind == FCB_ACT_PASSTHROUGH) {
+    // PassThroughActivation (activations.hpp:127-134): the TA-wrapped sum, truncated to the output lane -- uniform branches instead of
+    // the generic activate() per channel (the finish is a third of this kernel's instructions otherwise)
+    if (p.epi.acc_bits < 32) {
+#pragma unroll
+      for (int j = 0; j < N; j++) r[j] = (uint32_t)wrap_ta(acc[j], p.epi.acc_bits, p.epi.acc_signed) & omask;
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; j++) r[j] = (uint32_t)acc[j] & omask;
+    }
+  } else
 #pragma unroll
   for (int j = 0; j < N; j++) {
     if (BM == 0 || BM == 3) {
@@ -273,15 +291,21 @@ __global__ void __launch_bounds__(256) chanwise_bytes_kernel(const ChanParams p)
       }
     }
 #pragma unroll
-    for (int vo = 0; vo < VO; vo++) {
+    for (int t0 = 0; t0 < T; t0 += 4) {
+      uint4 wv[V];  // (depth-wise: the chunk's weights are loaded once for all the thread's outputs)
+      if (BM == 3) {
 #pragma unroll
-      for (int t0 = 0; t0 < T; t0 += 4) {
+        for (int i = 0; i < V; i++) wv[i] = __ldg(reinterpret_cast<const uint4*>(p.wt4 + (size_t)(t0 >> 2) * p.Cpad + ch0) + i);
+      }
+#pragma unroll
+      for (int vo = 0; vo < VO; vo++) {
         uint32_t wc[4][V];
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
           for (int i = 0; i < V; i++) wc[u][i] = t0 + u < T ? w[vo * KS + t0 + u][i] : 0u;  // output vo starts KS taps (one row) further
-        chanwise_consume<V, BM, INS>(p, wc, t0, T - t0 < 4 ? T - t0 : 4, ch0, acc[vo], mx[vo]);
+        if (BM == 3) chanwise_dw_chunk<V, INS>(wc, wv, acc[vo]);
+        else chanwise_consume<V, BM, INS>(p, wc, t0, T - t0 < 4 ? T - t0 : 4, ch0, acc[vo], mx[vo]);
       }
     }
   } else {
@@ -327,7 +351,7 @@ static void launch_bytes(const ChanParams& q, int nb, cudaStream_t st) {
     const dim3 grid((unsigned)((threads + 255) / 256), nb, 1);
     if (q.in_signed) chanwise_bytes_kernel<V, 0, true, 0, 1><<<grid, 256, 0, st>>>(q);
     else chanwise_bytes_kernel<V, 0, false, 0, 1><<<grid, 256, 0, st>>>(q);
-  } else if (ks == 3 && q.SY == 1 && q.OY > 1 && q.mode != CW_DWCONV) launch_bytes_k<V, 3, 2>(q, nb, st);  // (depth-wise: 86 registers, measured slower)
+  } else if (ks == 3 && q.SY == 1 && q.OY > 1) launch_bytes_k<V, 3, 2>(q, nb, st);
   else if (ks == 3) launch_bytes_k<V, 3, 1>(q, nb, st);
   else if (ks == 2) launch_bytes_k<V, 2, 1>(q, nb, st);
   else launch_bytes_k<V, 0, 1>(q, nb, st);
