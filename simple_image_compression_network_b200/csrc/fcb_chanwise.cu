@@ -202,6 +202,26 @@ __device__ __forceinline__ void chanwise_finish(const ChanParams& p, int32_t (&a
 #pragma unroll
       for (int j = 0; j < N; j++) r[j] = (uint32_t)acc[j] & omask;
     }
+  } else if ((BM == 0 || BM == 3) && p.epi.act_kind == FCB_ACT_THRESHOLDS) {
+    // ThresholdsActivation: the N channels' binary searches advance in lock step, so the N table loads of a level are in flight
+    // together (activate() per channel would chain N x log2(thr_n + 1) dependent loads)
+    const EpiParams& e = p.epi;
+    int32_t a[N];
+    int pos[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) { a[j] = wrap_ta(acc[j], e.acc_bits, e.acc_signed); pos[j] = 0; }
+    const bool strict = (e.cmp == FCB_CMP_LESS) || (e.cmp == FCB_CMP_GREATER_EQUAL);
+    const int32_t* __restrict__ t = e.thr + ch0;
+#pragma unroll 1
+    for (int step = (e.thr_n + 1) >> 1; step; step >>= 1) {
+      int32_t tv[N];
+#pragma unroll
+      for (int j = 0; j < N; j++) tv[j] = __ldg(t + (size_t)(pos[j] + step - 1) * e.thr_stride + j);
+#pragma unroll
+      for (int j = 0; j < N; j++) pos[j] += (strict ? (tv[j] < a[j]) : (tv[j] <= a[j])) ? step : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = thr_finish(e, pos[j]);
   } else
 #pragma unroll
   for (int j = 0; j < N; j++) {
