@@ -1318,6 +1318,21 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   // two channel blocks without shared-memory tables: one CTA group per block keeps 256 accumulator columns free, so the epilogue of
   // a tile overlaps the MMAs of the next (CB = 2 in one CTA fills all 512 columns: acc_stages = 1, epilogue serial with the MMAs)
   if (!thr && CB == 2 && !exp_env("FCB_U2_NO_CHB")) cands.push_back({0, 2, 0.0});
+  // two channel blocks, hybrid tables per CTA group (top D-2 levels of 128 channels: 32 KB, room for two plane sets and N = 256).
+  // The factor is calibrated, not derived: config 5b stage 4 473 k -> 530 k img/s against the whole-table chb = 2 form, config 4
+  // 430 k -> 504 k against the D-2 hybrid on N = 128 tiles (profiles/r02_thr_candidates.log), so it must win against both (2 x 36 < 2 x 40).
+  if (thr && CB == 2 && !exp_env("FCB_U2_NO_SMEM_THR") && !exp_env("FCB_U2_NO_CHB")) {
+    int D = 0;
+    while ((1 << D) < epi.thr_n + 1) D++;
+    if (D - 2 >= 1 && D >= 7 && exp_int("FCB_U2_CHB_HYB", 1)) cands.push_back({D - 2, 2, 36.0});
+  }
+  // Big tables (>= 127 thresholds) on one channel block: the whole table in shared memory is 8 plain levels, leaves room for one plane
+  // set only, and loses to the D-2 hybrid with double-buffered planes (config 5b stage 2 / 3: 65.9 k / 254 k vs 71.4 k / 279 k img/s,
+  // profiles/r02_thr_candidates.log).  Making room for the bucket LUT beside the table (N = 128 tiles, two weight stages) was measured
+  // too: 52 k / 187 k img/s -- the short tiles cost more than the cheaper search returns.
+  int Dfull = 0;
+  if (thr) while ((1 << Dfull) < epi.thr_n + 1) Dfull++;
+  bool best_lut = false;
   double best = 1e30;
   int bWT = 0, bR = 0, bNPX = 0, bWS = 0, thr_top = 0, thr_bytes = 0, chb = 1, CBe = CB;
   const int only_cand = exp_int("FCB_U2_CAND", -1);  // experiments: evaluate one candidate only
@@ -1362,14 +1377,17 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
           // per warp-level output (32 channels), counted with the padding of the 16-wide search batches
           // (profiles/r01_cfg4_epilogue_profile.txt)
           const double groups = g.pool == 2 ? (double)(R / 2) * ((WT + 15) / 16) * 8 : (double)((R * P + 31) / 32) * 32;
-          const double epi_clk = thr ? groups * nph * cbe * 4 * cd.epi_factor : (double)WT * R * nph * cbe * 7.0;
+          double ef = cd.epi_factor;
+          const bool with_lut = false;
+          if (thr && cd.thr_top == Dfull && Dfull >= 7 && cd.chb == 1) ef = 66.0;
+          const double epi_clk = thr ? groups * nph * cbe * 4 * ef : (double)WT * R * nph * cbe * 7.0;
           const double tile_clk = acc_st == 2 ? std::max(std::max(mma_clk, fill_clk), epi_clk) : std::max(mma_clk + epi_clk, fill_clk);
           const double ws_pen = WS >= 3 ? 1.0 : 1.05;
           // ties (e.g. 1x1 layers, where every WT is equally efficient) go to wide boxes: long contiguous TMA rows
           const double cost = tiles * tile_clk * ws_pen * (1.0 + 0.0005 * R) / ((double)PX * PY);
           if (cost < best * 0.999) {
             best = cost; bWT = WT; bR = R; bNPX = NPX; bWS = WS;
-            thr_top = cd.thr_top; thr_bytes = tb; chb = cd.chb; CBe = cbe;
+            thr_top = cd.thr_top; thr_bytes = tb; chb = cd.chb; CBe = cbe; best_lut = with_lut;
           }
         }
     }
@@ -1432,7 +1450,8 @@ int umma2_plan_create(const Geom& g, const int8_t* d_w, const EpiParams& epi, in
   }
   p.nplanes = np;
   p.set_bytes = off;
-  p.nsets = ((size_t)2 * off + (size_t)bWS * w_bytes + 4096 + (thr_bytes ? thr_bytes + 128 : 0) <= (size_t)227 * 1024 - 1024) ? 2 : 1;
+  const size_t lut_reserve = best_lut ? (size_t)CBe * 128 * 256 + 128 : 0;  // (the LUT the cost model counted on comes before a second plane set)
+  p.nsets = ((size_t)2 * off + (size_t)bWS * w_bytes + 4096 + (thr_bytes ? thr_bytes + 128 : 0) + lut_reserve <= (size_t)227 * 1024 - 1024) ? 2 : 1;
   p.nsets = std::max(1, std::min(p.nsets, exp_int("FCB_U2_NSETS", p.nsets)));
   off *= p.nsets;
   U->box_rows[0] = map_rows[0]; U->box_rows[1] = nmaps > 1 ? map_rows[1] : map_rows[0];
