@@ -12,6 +12,9 @@ from simple_image_compression_network_b200.layer import ConvLayer, Net, synth_fi
 if os.environ.get("FCB_EXP"):  # the experiment build (environment switches that bend plans): measurements only
     from simple_image_compression_network_b200 import _lib
     _lib.set_default(_lib.load(_lib.EXP_LIB_PATH))
+if os.environ.get("FCB_LIB"):  # any other build of the same sources (A/B of a compile-time choice)
+    from simple_image_compression_network_b200 import _lib
+    _lib.set_default(_lib.load(os.environ["FCB_LIB"]))
 
 
 def timed(fn, steps=5, warm=2):
