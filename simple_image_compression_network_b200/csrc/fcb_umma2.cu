@@ -204,6 +204,34 @@ __device__ __forceinline__ void build_row(uint32_t src, uint32_t dst, uint32_t m
   for (int j = 0; j < 2 * KS; j++) sts_v4(dst + (((uint32_t)j ^ m7) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
 
+// Two horizontally adjacent im2col rows of a 5x5 stride-2 window (the first layer of the reference net) at once: pixel x+1's
+// window starts two patch words after pixel x's, so the two rows share 3 of the 5 words of every window line.  Per window line
+// the thread reads 8 consecutive patch words as four 8-byte loads (src is 8-byte aligned: even pad, even x) instead of 2 x 5
+// single words: 20 loads for two rows instead of 50.  Row layout as build_row<4, 25>: 25 window words, the constant 1 of the bias
+// row, zeros.
+__device__ __forceinline__ void build_row_pair_5x5s2(uint32_t src, uint32_t line_step, uint32_t dst, uint32_t m7) {
+  uint32_t a[32], b[32];
+#pragma unroll
+  for (int ky = 0; ky < 5; ky++) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint2 v = lds_v2(src + (uint32_t)ky * line_step + 8u * (uint32_t)i);
+      w[2 * i] = v.x; w[2 * i + 1] = v.y;
+    }
+#pragma unroll
+    for (int kx = 0; kx < 5; kx++) { a[ky * 5 + kx] = w[kx]; b[ky * 5 + kx] = w[kx + 2]; }
+  }
+  a[25] = b[25] = 1u;
+#pragma unroll
+  for (int i = 26; i < 32; i++) a[i] = b[i] = 0u;
+  const uint32_t m7b = m7 + 1u;  // (m is even: the second row's swizzle phase is the next one, no wrap inside the pair)
+#pragma unroll
+  for (int j = 0; j < 8; j++) sts_v4(dst + (((uint32_t)j ^ m7) << 4), a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+#pragma unroll
+  for (int j = 0; j < 8; j++) sts_v4(dst + 128u + (((uint32_t)j ^ m7b) << 4), b[4 * j], b[4 * j + 1], b[4 * j + 2], b[4 * j + 3]);
+}
+
 // col2im of the thin-output transposed conv.  The byte tile is PIXEL-major: S[pixel][word][ch], one 4-byte word per tap
 // (word order dcol_word(), fcb_internal.h: taps grouped by input shift, sorted by output phase inside a group), pitch DCOL_PIX bytes
 // per pixel.  An input pixel's 2x2 output block is then 9 vector loads (one per shift: 4 x 16 B, 4 x 8 B, 1 x 4 B) and 21 packed
@@ -412,6 +440,9 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         asm volatile("" : "+r"(offs[i]));
       }
       const int npix = p.R * p.WT, ksteps = p.ksteps, bias_word = p.bias_word;
+      // the 5x5 stride-2 window with the bias row (L0): rows are built in pairs; needs 8-byte aligned window starts (even pad, even
+      // tile width) and an even number of pixels per tile line
+      const bool pair55 = bias_word == 25 && p.S == 2 && p.nw == 25 && p.toff[4] == 4 && p.toff[5] == p.BWp && !(p.pad & 1) && !(p.WT & 1) && !DBG(256);
       const uint32_t row_step = 4u * (uint32_t)(p.S * p.BWp), col_step = 4u * (uint32_t)p.S;
       uint32_t tile_it = 0;
       PROF_START();
@@ -426,6 +457,17 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const uint32_t xshift = (uint32_t)((p.S * ti.tx * p.WT - p.pad) & 3);
         const uint32_t patch = smem_u32(smem + p.patch_off + pb * p.patch_bytes) + 4u * xshift;
         const uint32_t rows = smem_u32(smem + set * p.set_bytes + p.planes[0].smem_off);
+        if (pair55) {
+          // rows 2j, 2j+1 (same tile line: WT is even), j = 32*bw + lane (+ 32*NB per pass)
+          int m = 2 * (32 * bw + lane);
+          int rr = m / p.WT, xo = m - rr * p.WT;
+          for (; m < (DBG(64) ? 0 : npix); m += 64 * NB) {
+            const uint32_t src = patch + (uint32_t)rr * row_step + (uint32_t)xo * col_step;
+            build_row_pair_5x5s2(src, 4u * (uint32_t)p.BWp, rows + 128u * (uint32_t)m, (uint32_t)m & 7u);
+            xo += 64 * NB;
+            while (xo >= p.WT) { xo -= p.WT; ++rr; }
+          }
+        } else {
         int rr = (32 * bw + lane) / p.WT, xo = (32 * bw + lane) - rr * p.WT;
         for (int m = 32 * bw + lane; m < (DBG(64) ? 0 : npix); m += 32 * NB) {
           uint32_t src = patch + (uint32_t)rr * row_step + (uint32_t)xo * col_step;
@@ -439,6 +481,7 @@ umma2_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           else build_row<1, -1>(src, dst, m7, offs);
           xo += 32 * NB;
           while (xo >= p.WT) { xo -= p.WT; ++rr; }
+        }
         }
         PROF_T(3);
         fence_proxy_async();
